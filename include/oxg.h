@@ -1,0 +1,239 @@
+/*
+ * oxg.h — C ABI of liboxg: the B200 (sm_100a) nearest-neighbour / validity backend
+ * for oxmpl's planners.
+ *
+ * This header is the single seam between oxmpl (Rust, via an `oxmpl-cuda` crate's
+ * `extern "C"` block — see INTEGRATION.md) and the CUDA kernels.  Every entry point
+ * cites the reference code it replaces (paths relative to the oxmpl v0.4.1 tree).
+ *
+ * Conventions
+ *  - All functions return 0 on success or a negative OXG_E_* code; the message for
+ *    the calling thread's last failure is oxg_last_error().  Nothing unwinds across
+ *    this boundary.
+ *  - A *state* is `dim = n_real + n_so2` f64 values: the RealVector block first,
+ *    then one angle (radians) per SO2 component.  Host state arrays are row-major
+ *    (`rows[i*dim + d]`), exactly the `Vec<f64>` of RealVectorState / the `value`
+ *    of SO2State.  On the device the store is structure-of-arrays.
+ *  - Indices are append order, identical to `tree.len()` / `roadmap.len()` at push
+ *    time in the reference.
+ *  - Arithmetic is IEEE-754 binary64, round-to-nearest, never fused, in the
+ *    reference's operation order; indices and booleans are bit-exact with the
+ *    reference's CPU loops, distances are bit-identical.
+ *  - Host-pointer entry points are synchronous: outputs are valid on return.
+ *    `_dev` entry points take device pointers, enqueue on the handle's stream and
+ *    return without synchronising (use oxg_store_sync / oxg_world_sync).
+ *  - A handle may be used from one host thread at a time.
+ *  - There is no CPU fallback: without a CUDA device every compute entry point
+ *    fails with OXG_E_CUDA.
+ */
+#ifndef OXG_H
+#define OXG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OXG_VERSION 100 /* 0.1.0 */
+
+/* ---- error codes ------------------------------------------------------- */
+#define OXG_OK 0
+#define OXG_E_NULL (-1)       /* required pointer was NULL                      */
+#define OXG_E_DIM (-2)        /* bad dimension / space descriptor               */
+#define OXG_E_CAPACITY (-3)   /* caller-provided output capacity too small      */
+#define OXG_E_CUDA (-4)       /* CUDA runtime error (incl. no device)           */
+#define OXG_E_RESOLUTION (-5) /* motion resolution <= 0 or NaN                  */
+#define OXG_E_ARG (-6)        /* other invalid argument                         */
+#define OXG_E_EMPTY (-7)      /* query against an empty store                   */
+#define OXG_E_ALLOC (-8)      /* host/device allocation failed                  */
+#define OXG_E_INTERNAL (-9)   /* unexpected C++ exception caught at the boundary */
+
+#define OXG_INVALID_INDEX 0xFFFFFFFFu
+
+/* ---- space descriptor ---------------------------------------------------
+ * Replaces the `SP: StateSpace` type parameter the planners are generic over
+ * (oxmpl/src/base/space.rs:78-145).  distance():
+ *   n_so2 == 0             -> RealVectorStateSpace::distance
+ *                             (oxmpl/src/base/spaces/real_vector_state_space.rs:137-155)
+ *   n_real == 0, n_so2 == 1 -> SO2StateSpace::distance
+ *                             (oxmpl/src/base/spaces/so2_state_space.rs:97-101)
+ *   otherwise (compound; not in the reference — SURVEY F2): left-to-right
+ *        acc = w_real * realvector_distance ; acc = acc + w_so2 * so2_distance_c  (c ascending)
+ *     with every product and sum separately rounded.
+ * interpolate(): RealVector block per real_vector_state_space.rs:161-186, each SO2
+ * component per so2_state_space.rs:107-122.
+ */
+typedef struct oxg_space_desc {
+  uint32_t n_real;
+  uint32_t n_so2;
+  double w_real; /* ignored unless compound */
+  double w_so2;  /* ignored unless compound */
+} oxg_space_desc;
+
+typedef struct oxg_store_s* oxg_store; /* GPU-resident SoA f64 state store */
+typedef struct oxg_world_s* oxg_world; /* declarative obstacle set          */
+
+/* ---- library / device ---------------------------------------------------- */
+int oxg_version(void);
+const char* oxg_last_error(void);
+int oxg_device_count(int* out_count);
+int oxg_set_device(int device);
+
+/* ---- state store ---------------------------------------------------------
+ * Replaces the planners' `Vec<Node<S>>` state storage: rrt.rs:24-27,61,
+ * rrt_star.rs:24-28, prm.rs:24-29.  append == `tree.push` (rrt.rs:213-217,
+ * prm.rs:140-141); clear == `Planner::setup` (rrt.rs:147, prm.rs:224).
+ * Parents / costs / adjacency stay with the caller.
+ */
+int oxg_store_create(const oxg_space_desc* space, uint64_t capacity, oxg_store* out);
+int oxg_store_destroy(oxg_store s);
+int oxg_store_clear(oxg_store s);
+int oxg_store_reserve(oxg_store s, uint64_t capacity);
+/* Appends n row-major states; *first_index receives the index of the first one. */
+int oxg_store_append(oxg_store s, const double* rows, uint64_t n, uint64_t* first_index);
+int oxg_store_size(oxg_store s, uint64_t* out_n);
+int oxg_store_read(oxg_store s, uint64_t first, uint64_t n, double* rows_out);
+int oxg_store_sync(oxg_store s);
+
+/* ---- nearest neighbour ----------------------------------------------------
+ * oxg_nn1: the 1-NN linear scan of rrt.rs:187-196, rrt_connect.rs:128-136,
+ * rrt_star.rs:199-208 for Q queries at once.  distance(stored, query); values
+ * compared after sqrt with strict `<`, so the lowest index wins ties.  `dist[q]`
+ * is the reference's `min_dist` (bit-identical; it feeds the steering division).
+ */
+int oxg_nn1(oxg_store s, const double* queries, uint64_t Q, uint32_t* idx, double* dist);
+
+/* oxg_knn: k nearest by (distance(query, stored), index) ascending.  Not in the
+ * reference — semantics pinned by oracle/ (k smallest by the reference's
+ * distance value, ties to the lowest index).  exclude_idx (nullable, one per query)
+ * removes that stored index from the candidates (self-exclusion by index).  Rows are
+ * padded with OXG_INVALID_INDEX / +inf when fewer than k candidates exist.
+ */
+int oxg_knn(oxg_store s, const double* queries, uint64_t Q, uint32_t k,
+            const uint32_t* exclude_idx, uint32_t* idx, double* dist);
+
+/* oxg_radius: the radius scans of rrt_star.rs:121-131 (find_neighbours),
+ * prm.rs:131-138 and prm.rs:249-256: all i with distance(query, stored_i) < r
+ * (strict), ascending i.  idx_limit (nullable, one per query) restricts query q
+ * to stored indices < idx_limit[q] (PRM's "node sees only earlier nodes").
+ * CSR output: offsets[Q+1]; idx (and dist, nullable) hold offsets[Q] entries.
+ * If offsets[Q] > cap the call fails with OXG_E_CAPACITY after filling offsets
+ * (so the caller can size the buffers and call again).
+ */
+int oxg_radius(oxg_store s, const double* queries, uint64_t Q, double r,
+               const uint32_t* idx_limit, uint64_t* offsets, uint32_t* idx,
+               uint64_t cap, double* dist);
+
+/* ---- declarative validity checker -----------------------------------------
+ * Implements `StateValidityChecker::is_valid` (oxmpl/src/base/validity.rs:39-48)
+ * for obstacle sets over the first `dim` (RealVector) coordinates of a state:
+ *   sphere  (dim+1 f64: centre, r):   valid iff sqrt(sum (x_i-c_i)^2) > r
+ *                                      (README.md:147-150; boundary is invalid)
+ *   aabb    (2*dim f64: lo, hi):       invalid iff for all i lo_i <= x_i <= hi_i
+ *                                      (oxmpl/tests/rrt_rvss_tests.rs:24-36; inclusive)
+ *   capsule (2*dim+1 f64: a, b, r):    valid iff dist(x, segment ab) > r, operation
+ *                                      order fixed by oracle/ (no reference form)
+ *   so2 interval (comp, lo, hi):       invalid iff lo <= normalise(theta_comp) <= hi
+ *                                      (oxmpl/tests/rrt_so2ss_tests.rs:17-27)
+ * A state is valid iff no obstacle marks it invalid.
+ */
+int oxg_world_create(uint32_t dim, const double* spheres, uint64_t n_spheres,
+                     const double* aabbs, uint64_t n_aabbs, const double* capsules,
+                     uint64_t n_capsules, oxg_world* out);
+int oxg_world_add_so2_interval(oxg_world w, uint32_t so2_component, double lo, double hi);
+int oxg_world_destroy(oxg_world w);
+int oxg_world_sync(oxg_world w);
+
+/* is_valid for Q row-major states (validity.rs:47). out[q] = 1 valid, 0 invalid. */
+int oxg_is_valid(oxg_world w, const oxg_space_desc* space, const double* states,
+                 uint64_t Q, uint8_t* out);
+
+/* ---- motion validity --------------------------------------------------------
+ * The planners' private `check_motion(from, to)` — rrt.rs:90-116,
+ * rrt_connect.rs:166-189, rrt_star.rs:76-104, prm.rs:161-187 — for E edges.
+ * `resolution` is the caller-computed `space.get_longest_valid_segment_length() * 0.1`
+ * (rrt.rs:97).  first_invalid_step (nullable): 0 if the motion is valid, else the
+ * 1-based step at which the sequential reference loop returns false (1 when
+ * num_steps <= 1 and `to` is invalid).
+ */
+int oxg_check_motion(oxg_world w, const oxg_space_desc* space, const double* from,
+                     const double* to, uint64_t E, double resolution, uint8_t* valid,
+                     uint32_t* first_invalid_step);
+
+/* Same, endpoints given as store indices (PRM: check_motion(q_rand, roadmap[i]),
+ * prm.rs:134; RRT* rewire rrt_star.rs:244,275). */
+int oxg_check_edges(oxg_world w, oxg_store s, const uint32_t* from_idx,
+                    const uint32_t* to_idx, uint64_t E, double resolution, uint8_t* valid);
+
+/* ---- batched PRM roadmap construction -----------------------------------------
+ * Replaces PRM::construct_roadmap's body (prm.rs:117-146) for a store pre-filled
+ * with the valid samples, in sample order.
+ *
+ * oxg_prm_build_radius — reference-faithful: node i connects to every j < i with
+ *   distance(q_i, q_j) < connection_radius && check_motion(q_i, q_j) (prm.rs:131-138).
+ *   Output is the lower-index adjacency in CSR form (ascending j per i), i.e. exactly
+ *   `new_node.edges` at push time; symmetrise to obtain `roadmap[i].edges`
+ *   (prm.rs:143-145).  Rows [row_begin,row_end) only (shard unit for multi-GPU);
+ *   offsets has (row_end-row_begin)+1 entries.
+ *
+ * oxg_prm_build_knn — count-bounded k-NN variant: for each
+ *   node i in [row_begin,row_end) its k nearest other nodes (oxg_knn semantics,
+ *   self excluded by index); every candidate edge {i,j} is motion-checked once as
+ *   check_motion(from = node max(i,j), to = node min(i,j)).  idx/dist/valid are
+ *   [rows][k]; valid is 1/0, and 0 for padded slots.
+ */
+typedef struct oxg_prm_stats {
+  uint64_t n_rows;          /* rows processed                                   */
+  uint64_t n_candidates;    /* directed candidate slots (non-padded)            */
+  uint64_t n_edges_checked; /* distinct motion checks executed                  */
+  uint64_t n_edges_valid;   /* of those, valid                                  */
+  double knn_ms;            /* device time of the neighbour phase               */
+  double edge_ms;           /* device time of the motion-check phase            */
+} oxg_prm_stats;
+
+int oxg_prm_build_radius(oxg_world w, oxg_store s, double connection_radius,
+                         double resolution, uint64_t row_begin, uint64_t row_end,
+                         uint64_t* offsets, uint32_t* idx, uint64_t cap,
+                         oxg_prm_stats* stats);
+
+int oxg_prm_build_knn(oxg_world w, oxg_store s, uint32_t k, double resolution,
+                      uint64_t row_begin, uint64_t row_end, uint32_t* idx, double* dist,
+                      uint8_t* valid, oxg_prm_stats* stats);
+
+/* ---- device-pointer pipeline (resident data; multi-GPU sharding) ----------------
+ * The same phases with device buffers, enqueued on the store's stream.
+ *  oxg_knn_rows_dev   : k-NN of stored rows [row_begin,row_end) against the whole
+ *                       store, self excluded; d_idx/d_dist are [rows][k] device.
+ *  oxg_prm_edges_dev  : given the complete d_idx_all [N][k] (after the all-gather),
+ *                       motion-checks the candidate edges owned by rows
+ *                       [row_begin,row_end) and writes d_valid_all[row][slot] for
+ *                       those rows: 1/0, or 2 = "owned by the mirror slot".
+ *  oxg_prm_resolve_dev: after d_valid_all is complete on this device, replaces every
+ *                       2 by the mirror slot's value.
+ */
+int oxg_knn_rows_dev(oxg_store s, uint64_t row_begin, uint64_t row_end, uint32_t k,
+                     uint32_t* d_idx, double* d_dist);
+int oxg_prm_edges_dev(oxg_world w, oxg_store s, const uint32_t* d_idx_all, uint32_t k,
+                      double resolution, uint64_t row_begin, uint64_t row_end,
+                      uint8_t* d_valid_all, uint64_t* d_counters /* 2 x u64: checked, valid */);
+int oxg_prm_resolve_dev(oxg_store s, const uint32_t* d_idx_all, uint32_t k,
+                        uint8_t* d_valid_all);
+/* The CUDA stream of a store (cudaStream_t as void*), so callers can order their
+ * own work (NCCL collectives, torch ops) after the library's. */
+int oxg_store_stream(oxg_store s, void** out_stream);
+
+/* ---- measurement helpers ----------------------------------------------------------
+ * oxg_fp64_peak: measures this GPU's unfused FP64 issue rate (independent DADD/DMUL
+ * chains, no FMA) — the roofline denominator for the batched k-NN / validity kernels
+ * (SURVEY §8d).  Returns operations per second.
+ * oxg_kernel_launches: number of liboxg kernel launches since the counter was reset.
+ */
+int oxg_fp64_peak(double* out_ops_per_s, double* out_ms);
+uint64_t oxg_kernel_launches(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OXG_H */

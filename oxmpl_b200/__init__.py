@@ -1,0 +1,22 @@
+"""oxmpl_b200 — B200 (sm_100a) nearest-neighbour / validity backend for oxmpl's planners.
+
+The product is ``liboxg.so`` (hand-written CUDA behind the C ABI in ``include/oxg.h``);
+this package is the thin host-side binding.  Importing it requires the built library —
+there is no CPU fallback.
+"""
+from .api import (  # noqa: F401
+    INVALID_INDEX,
+    Space,
+    StateStore,
+    World,
+    device_count,
+    fp64_peak,
+    kernel_launches,
+    motion_resolution,
+    prm_build_knn,
+    prm_build_radius,
+    real_vector_max_extent,
+)
+from ._lib import OxgError, PrmStats, SpaceDesc  # noqa: F401
+
+__version__ = "0.1.0"

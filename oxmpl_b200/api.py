@@ -1,0 +1,328 @@
+"""numpy-facing wrappers over the C ABI (include/oxg.h).
+
+These are the calls a user (or the parity tests) makes; each one is a single liboxg entry
+point with host buffers.  Names follow the reference's domain: a *store* holds the planner's
+tree / roadmap states (``Vec<Node<S>>`` in rrt.rs:61, prm.rs:58), a *world* is a declarative
+``StateValidityChecker`` (oxmpl/src/base/validity.rs:39-48).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import PrmStats, SpaceDesc, check, lib
+
+INVALID_INDEX = _lib.OXG_INVALID_INDEX
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _f64(a, shape_last=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape_last is not None and (a.ndim != 2 or a.shape[1] != shape_last):
+        raise ValueError(f"expected an array of shape (n, {shape_last}), got {a.shape}")
+    return a
+
+
+@dataclass(frozen=True)
+class Space:
+    """Mirror of ``oxg_space_desc``: a RealVector block of ``n_real`` coordinates followed by
+    ``n_so2`` angles.  ``Space.real_vector(d)`` is RealVectorStateSpace
+    (real_vector_state_space.rs), ``Space.so2()`` is SO2StateSpace (so2_state_space.rs),
+    ``Space.compound(d, 1)`` is the SE2-style composition (not in the reference)."""
+
+    n_real: int
+    n_so2: int = 0
+    w_real: float = 1.0
+    w_so2: float = 1.0
+
+    @staticmethod
+    def real_vector(dim: int) -> "Space":
+        return Space(dim, 0)
+
+    @staticmethod
+    def so2() -> "Space":
+        return Space(0, 1)
+
+    @staticmethod
+    def compound(n_real: int, n_so2: int, w_real: float = 1.0, w_so2: float = 0.5) -> "Space":
+        return Space(n_real, n_so2, w_real, w_so2)
+
+    @property
+    def dim(self) -> int:
+        return self.n_real + self.n_so2
+
+    def desc(self) -> SpaceDesc:
+        return SpaceDesc(self.n_real, self.n_so2, self.w_real, self.w_so2)
+
+
+def real_vector_max_extent(bounds) -> float:
+    """RealVectorStateSpace::get_maximum_extent (real_vector_state_space.rs:103-118).
+    Python floats are IEEE binary64 and ``math.sqrt`` is correctly rounded, so this is
+    bit-identical to the Rust."""
+    if any((not math.isfinite(lo)) or (not math.isfinite(hi)) for lo, hi in bounds):
+        return 1.0
+    s = 0.0
+    for lo, hi in bounds:
+        d = hi - lo
+        s = s + d * d
+    return math.sqrt(s)
+
+
+def motion_resolution(extent: float, fraction: float = 0.05) -> float:
+    """``space.get_longest_valid_segment_length() * 0.1`` (real_vector_state_space.rs:251-253,
+    rrt.rs:97); fraction defaults to 0.05 (real_vector_state_space.rs:98)."""
+    return (extent * fraction) * 0.1
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    code = lib.oxg_device_count(C.byref(n))
+    return n.value if code == 0 else 0
+
+
+def fp64_peak():
+    """(unfused FP64 add|mul operations per second, kernel ms) measured on the current GPU."""
+    ops = C.c_double(0.0)
+    ms = C.c_double(0.0)
+    check(lib.oxg_fp64_peak(C.byref(ops), C.byref(ms)))
+    return ops.value, ms.value
+
+
+def kernel_launches(reset: bool = False) -> int:
+    return int(lib.oxg_kernel_launches(1 if reset else 0))
+
+
+class StateStore:
+    """GPU-resident SoA f64 state store (replaces ``Vec<Node<S>>``)."""
+
+    def __init__(self, space: Space, capacity: int = 0):
+        self.space = space
+        self._desc = space.desc()
+        self._h = C.c_void_p()
+        check(lib.oxg_store_create(C.byref(self._desc), capacity, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.oxg_store_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def clear(self):
+        check(lib.oxg_store_clear(self._h))
+
+    def reserve(self, capacity: int):
+        check(lib.oxg_store_reserve(self._h, capacity))
+
+    def append(self, rows) -> int:
+        rows = _f64(np.atleast_2d(rows), self.space.dim)
+        first = C.c_uint64(0)
+        check(lib.oxg_store_append(self._h, _ptr(rows), rows.shape[0], C.byref(first)))
+        return first.value
+
+    def append_ptr(self, host_ptr: int, n: int) -> int:
+        """Append n row-major states from a raw host address (e.g. pinned memory)."""
+        first = C.c_uint64(0)
+        check(lib.oxg_store_append(self._h, C.c_void_p(host_ptr), n, C.byref(first)))
+        return first.value
+
+    def __len__(self) -> int:
+        n = C.c_uint64(0)
+        check(lib.oxg_store_size(self._h, C.byref(n)))
+        return n.value
+
+    def read(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        if n is None:
+            n = len(self) - first
+        out = np.empty((n, self.space.dim), dtype=np.float64)
+        check(lib.oxg_store_read(self._h, first, n, _ptr(out)))
+        return out
+
+    def sync(self):
+        check(lib.oxg_store_sync(self._h))
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        check(lib.oxg_store_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    # -- nearest neighbour ---------------------------------------------------------
+    def nn1(self, queries):
+        """1-NN scan of rrt.rs:187-196 for each query row -> (idx u32[Q], dist f64[Q])."""
+        q = _f64(np.atleast_2d(queries), self.space.dim)
+        idx = np.empty(q.shape[0], dtype=np.uint32)
+        dist = np.empty(q.shape[0], dtype=np.float64)
+        check(lib.oxg_nn1(self._h, _ptr(q), q.shape[0], _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def knn(self, queries, k: int, exclude=None):
+        q = _f64(np.atleast_2d(queries), self.space.dim)
+        idx = np.empty((q.shape[0], k), dtype=np.uint32)
+        dist = np.empty((q.shape[0], k), dtype=np.float64)
+        ex = None if exclude is None else np.ascontiguousarray(exclude, dtype=np.uint32)
+        check(lib.oxg_knn(self._h, _ptr(q), q.shape[0], k, _ptr(ex), _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def radius(self, queries, r: float, idx_limit=None, want_dist: bool = False):
+        """Radius scan of rrt_star.rs:121-131 / prm.rs:131-138 -> CSR (offsets, idx[, dist])."""
+        q = _f64(np.atleast_2d(queries), self.space.dim)
+        Q = q.shape[0]
+        lim = None if idx_limit is None else np.ascontiguousarray(idx_limit, dtype=np.uint32)
+        offsets = np.zeros(Q + 1, dtype=np.uint64)
+        cap = max(1024, 64 * Q)
+        while True:
+            idx = np.empty(cap, dtype=np.uint32)
+            dist = np.empty(cap, dtype=np.float64) if want_dist else None
+            code = lib.oxg_radius(
+                self._h, _ptr(q), Q, float(r), _ptr(lim), _ptr(offsets), _ptr(idx), cap, _ptr(dist)
+            )
+            if code == _lib.OXG_E_CAPACITY:
+                cap = int(offsets[Q])
+                continue
+            check(code)
+            break
+        n = int(offsets[Q])
+        if want_dist:
+            return offsets, idx[:n].copy(), dist[:n].copy()
+        return offsets, idx[:n].copy()
+
+
+class World:
+    """Declarative obstacle set implementing ``StateValidityChecker::is_valid``.
+
+    spheres: (n, dim+1) rows ``[centre..., r]``; aabbs: (n, 2*dim) rows ``[lo..., hi...]``;
+    capsules: (n, 2*dim+1) rows ``[a..., b..., r]``."""
+
+    def __init__(self, dim: int, spheres=None, aabbs=None, capsules=None, so2_intervals=()):
+        self.dim = dim
+        sp = _f64(spheres, dim + 1) if spheres is not None and len(spheres) else None
+        bx = _f64(aabbs, 2 * dim) if aabbs is not None and len(aabbs) else None
+        cp = _f64(capsules, 2 * dim + 1) if capsules is not None and len(capsules) else None
+        self._h = C.c_void_p()
+        check(
+            lib.oxg_world_create(
+                dim,
+                _ptr(sp), 0 if sp is None else sp.shape[0],
+                _ptr(bx), 0 if bx is None else bx.shape[0],
+                _ptr(cp), 0 if cp is None else cp.shape[0],
+                C.byref(self._h),
+            )
+        )
+        for comp, lo, hi in so2_intervals:
+            check(lib.oxg_world_add_so2_interval(self._h, comp, float(lo), float(hi)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.oxg_world_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def is_valid(self, space: Space, states) -> np.ndarray:
+        st = _f64(np.atleast_2d(states), space.dim)
+        out = np.empty(st.shape[0], dtype=np.uint8)
+        d = space.desc()
+        check(lib.oxg_is_valid(self._h, C.byref(d), _ptr(st), st.shape[0], _ptr(out)))
+        return out
+
+    def check_motion(self, space: Space, frm, to, resolution: float, want_first_invalid=False):
+        """Batched ``check_motion(from, to)`` (rrt.rs:90-116)."""
+        a = _f64(np.atleast_2d(frm), space.dim)
+        b = _f64(np.atleast_2d(to), space.dim)
+        if a.shape != b.shape:
+            raise ValueError("from/to shape mismatch")
+        E = a.shape[0]
+        valid = np.empty(E, dtype=np.uint8)
+        first = np.empty(E, dtype=np.uint32) if want_first_invalid else None
+        d = space.desc()
+        check(
+            lib.oxg_check_motion(
+                self._h, C.byref(d), _ptr(a), _ptr(b), E, float(resolution), _ptr(valid), _ptr(first)
+            )
+        )
+        return (valid, first) if want_first_invalid else valid
+
+    def check_edges(self, store: StateStore, from_idx, to_idx, resolution: float) -> np.ndarray:
+        fi = np.ascontiguousarray(from_idx, dtype=np.uint32)
+        ti = np.ascontiguousarray(to_idx, dtype=np.uint32)
+        valid = np.empty(fi.shape[0], dtype=np.uint8)
+        check(
+            lib.oxg_check_edges(
+                self._h, store.handle, _ptr(fi), _ptr(ti), fi.shape[0], float(resolution), _ptr(valid)
+            )
+        )
+        return valid
+
+
+def _stats_dict(st: PrmStats) -> dict:
+    return {name: getattr(st, name) for name, _ in PrmStats._fields_}
+
+
+def prm_build_knn(world: World, store: StateStore, k: int, resolution: float, row_begin: int = 0,
+                  row_end: int | None = None):
+    """k-NN PRM rows -> (idx[rows,k], dist[rows,k], valid[rows,k], stats)."""
+    if row_end is None:
+        row_end = len(store)
+    rows = row_end - row_begin
+    idx = np.empty((rows, k), dtype=np.uint32)
+    dist = np.empty((rows, k), dtype=np.float64)
+    valid = np.empty((rows, k), dtype=np.uint8)
+    st = PrmStats()
+    check(
+        lib.oxg_prm_build_knn(
+            world.handle, store.handle, k, float(resolution), row_begin, row_end, _ptr(idx),
+            _ptr(dist), _ptr(valid), C.byref(st),
+        )
+    )
+    return idx, dist, valid, _stats_dict(st)
+
+
+def prm_build_radius(world: World, store: StateStore, connection_radius: float, resolution: float,
+                     row_begin: int = 0, row_end: int | None = None):
+    """Reference-faithful radius PRM rows -> CSR (offsets, idx) of ``new_node.edges``
+    (prm.rs:131-138), plus stats."""
+    if row_end is None:
+        row_end = len(store)
+    rows = row_end - row_begin
+    offsets = np.zeros(rows + 1, dtype=np.uint64)
+    cap = max(1024, 32 * rows)
+    st = PrmStats()
+    while True:
+        idx = np.empty(cap, dtype=np.uint32)
+        code = lib.oxg_prm_build_radius(
+            world.handle, store.handle, float(connection_radius), float(resolution), row_begin,
+            row_end, _ptr(offsets), _ptr(idx), cap, C.byref(st),
+        )
+        if code == _lib.OXG_E_CAPACITY:
+            cap = int(offsets[rows])
+            continue
+        check(code)
+        break
+    return offsets, idx[: int(offsets[rows])].copy(), _stats_dict(st)

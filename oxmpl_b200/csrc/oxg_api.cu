@@ -1,0 +1,442 @@
+// oxg_api.cu — library plumbing: errors, device selection, the SoA state store and the
+// declarative world.  See include/oxg.h for the contract of each entry point.
+#include <cstdarg>
+#include <vector>
+
+#include "oxg_internal.cuh"
+#include "oxg_math.cuh"
+
+namespace oxg {
+
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int validate_space(const oxg_space_desc* sp) {
+  if (!sp) {
+    set_error("space descriptor is NULL");
+    return OXG_E_NULL;
+  }
+  uint32_t dim = sp->n_real + sp->n_so2;
+  if (dim == 0 || dim > (uint32_t)kMaxDim || sp->n_so2 > 16) {
+    set_error("unsupported space: n_real=%u n_so2=%u (need 1 <= dim <= %d, n_so2 <= 16)", sp->n_real,
+              sp->n_so2, kMaxDim);
+    return OXG_E_DIM;
+  }
+  return OXG_OK;
+}
+
+// max{x >= 0 : sqrt(x) <= r}.  Host mirror of sqrt_le_threshold_dev.
+double sqrt_le_threshold(double r) {
+  if (!(r == r)) return INFINITY;  // "sqrt(d2) > NaN" is always false -> every state hits
+  if (r < 0.0) return -1.0;
+  if (std::isinf(r)) return INFINITY;
+  double x = r * r;
+  if (std::isinf(x)) x = 1.7976931348623157e308;
+  while (std::sqrt(x) > r && x > 0.0) x = std::nextafter(x, 0.0);
+  for (;;) {
+    double nx = std::nextafter(x, INFINITY);
+    if (!std::isinf(nx) && std::sqrt(nx) <= r)
+      x = nx;
+    else
+      break;
+  }
+  return x;
+}
+
+// max{x >= 0 : sqrt(x) < r}; -1 if there is none (r <= 0 or NaN).
+double sqrt_lt_threshold(double r) {
+  if (!(r == r) || r <= 0.0) return -1.0;
+  if (std::isinf(r)) return 1.7976931348623157e308;
+  double x = sqrt_le_threshold(r);  // sqrt(x) <= r
+  while (x >= 0.0 && std::sqrt(x) >= r) {
+    if (x == 0.0) return -1.0;
+    x = std::nextafter(x, 0.0);
+  }
+  return x;
+}
+
+// Row-major [n][dim] -> SoA columns, appended at `first`.
+__global__ void scatter_rows_kernel(const double* __restrict__ rows, uint64_t n, uint32_t dim,
+                                    double* __restrict__ data, uint64_t pitch, uint64_t first) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t total = n * dim;
+  for (; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t i = t / dim;
+    uint32_t d = (uint32_t)(t - i * dim);
+    data[(uint64_t)d * pitch + first + i] = rows[t];
+  }
+}
+
+__global__ void gather_rows_kernel(const double* __restrict__ data, uint64_t pitch, uint64_t first,
+                                   uint64_t n, uint32_t dim, double* __restrict__ rows) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t total = n * dim;
+  for (; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t i = t / dim;
+    uint32_t d = (uint32_t)(t - i * dim);
+    rows[t] = data[(uint64_t)d * pitch + first + i];
+  }
+}
+
+static uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
+
+static int store_grow(oxg_store_s* s, uint64_t capacity) {
+  if (capacity <= s->pitch) return OXG_OK;
+  uint64_t new_pitch = round_up(std::max<uint64_t>(capacity, 1024), 32);
+  double* nd = nullptr;
+  cudaError_t e = cudaMalloc(&nd, sizeof(double) * new_pitch * s->dim);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaMalloc of %llu x %u f64 store failed: %s", (unsigned long long)new_pitch, s->dim,
+              cudaGetErrorString(e));
+    return OXG_E_ALLOC;
+  }
+  if (s->d_data && s->size > 0) {
+    for (uint32_t d = 0; d < s->dim; ++d)
+      OXG_CUDA_TRY(cudaMemcpyAsync(nd + (uint64_t)d * new_pitch, s->d_data + (uint64_t)d * s->pitch,
+                                   sizeof(double) * s->size, cudaMemcpyDeviceToDevice, s->stream));
+    OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  }
+  if (s->d_data) cudaFree(s->d_data);
+  s->d_data = nd;
+  s->pitch = new_pitch;
+  return OXG_OK;
+}
+
+}  // namespace oxg
+
+using namespace oxg;
+
+extern "C" {
+
+int oxg_version(void) { return OXG_VERSION; }
+
+const char* oxg_last_error(void) { return g_err; }
+
+int oxg_device_count(int* out_count) {
+  if (!out_count) {
+    set_error("out_count is NULL");
+    return OXG_E_NULL;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *out_count = 0;
+    set_error("cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    return OXG_E_CUDA;
+  }
+  *out_count = n;
+  return OXG_OK;
+}
+
+int oxg_set_device(int device) {
+  OXG_CUDA_TRY(cudaSetDevice(device));
+  return OXG_OK;
+}
+
+uint64_t oxg_kernel_launches(int reset) {
+  if (reset) return g_launches.exchange(0);
+  return g_launches.load();
+}
+
+// ------------------------------------------------------------------ store
+int oxg_store_create(const oxg_space_desc* space, uint64_t capacity, oxg_store* out) {
+  OXG_API_BEGIN
+  if (!out) {
+    set_error("out is NULL");
+    return OXG_E_NULL;
+  }
+  *out = nullptr;
+  OXG_TRY(validate_space(space));
+  if (capacity > 0xFFFFFFF0ull) {
+    set_error("capacity %llu exceeds the u32 index range", (unsigned long long)capacity);
+    return OXG_E_ARG;
+  }
+  int dev = 0;
+  OXG_CUDA_TRY(cudaGetDevice(&dev));
+  oxg_store_s* s = new oxg_store_s();
+  s->space = *space;
+  s->dim = space->n_real + space->n_so2;
+  s->device = dev;
+  cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev2);
+  if (e != cudaSuccess) {
+    set_error("stream/event creation failed: %s", cudaGetErrorString(e));
+    delete s;
+    return OXG_E_CUDA;
+  }
+  int r = store_grow(s, capacity);
+  if (r != OXG_OK) {
+    oxg_store_destroy(s);
+    return r;
+  }
+  *out = s;
+  return OXG_OK;
+  OXG_API_END
+}
+
+int oxg_store_destroy(oxg_store s) {
+  if (!s) return OXG_OK;
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->d_data) cudaFree(s->d_data);
+  for (auto& b : s->buf) b.release();
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->ev2) cudaEventDestroy(s->ev2);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return OXG_OK;
+}
+
+int oxg_store_clear(oxg_store s) {
+  if (!s) {
+    set_error("store is NULL");
+    return OXG_E_NULL;
+  }
+  s->size = 0;
+  return OXG_OK;
+}
+
+int oxg_store_reserve(oxg_store s, uint64_t capacity) {
+  OXG_API_BEGIN
+  if (!s) {
+    set_error("store is NULL");
+    return OXG_E_NULL;
+  }
+  if (capacity > 0xFFFFFFF0ull) {
+    set_error("capacity %llu exceeds the u32 index range", (unsigned long long)capacity);
+    return OXG_E_ARG;
+  }
+  return store_grow(s, capacity);
+  OXG_API_END
+}
+
+int oxg_store_append(oxg_store s, const double* rows, uint64_t n, uint64_t* first_index) {
+  OXG_API_BEGIN
+  if (!s || (!rows && n > 0)) {
+    set_error("store or rows is NULL");
+    return OXG_E_NULL;
+  }
+  if (first_index) *first_index = s->size;
+  if (n == 0) return OXG_OK;
+  if (s->size + n > 0xFFFFFFF0ull) {
+    set_error("store would exceed the u32 index range");
+    return OXG_E_CAPACITY;
+  }
+  if (s->size + n > s->pitch) OXG_TRY(store_grow(s, std::max(s->size + n, s->pitch * 2)));
+  size_t bytes = sizeof(double) * n * s->dim;
+  OXG_TRY(s->buf[B_STAGE].ensure(bytes));
+  OXG_CUDA_TRY(cudaMemcpyAsync(s->buf[B_STAGE].p, rows, bytes, cudaMemcpyHostToDevice, s->stream));
+  uint64_t total = n * s->dim;
+  int threads = 256;
+  int blocks = (int)std::min<uint64_t>((total + threads - 1) / threads, 148 * 16);
+  scatter_rows_kernel<<<blocks, threads, 0, s->stream>>>(s->buf[B_STAGE].as<double>(), n, s->dim, s->d_data,
+                                                         s->pitch, s->size);
+  OXG_LAUNCH_CHECK();
+  // the caller may reuse `rows` immediately
+  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  s->size += n;
+  return OXG_OK;
+  OXG_API_END
+}
+
+int oxg_store_size(oxg_store s, uint64_t* out_n) {
+  if (!s || !out_n) {
+    set_error("store or out_n is NULL");
+    return OXG_E_NULL;
+  }
+  *out_n = s->size;
+  return OXG_OK;
+}
+
+int oxg_store_read(oxg_store s, uint64_t first, uint64_t n, double* rows_out) {
+  OXG_API_BEGIN
+  if (!s || (!rows_out && n > 0)) {
+    set_error("store or rows_out is NULL");
+    return OXG_E_NULL;
+  }
+  if (first + n > s->size) {
+    set_error("read range [%llu, %llu) exceeds store size %llu", (unsigned long long)first,
+              (unsigned long long)(first + n), (unsigned long long)s->size);
+    return OXG_E_ARG;
+  }
+  if (n == 0) return OXG_OK;
+  size_t bytes = sizeof(double) * n * s->dim;
+  OXG_TRY(s->buf[B_STAGE].ensure(bytes));
+  uint64_t total = n * s->dim;
+  int threads = 256;
+  int blocks = (int)std::min<uint64_t>((total + threads - 1) / threads, 148 * 16);
+  gather_rows_kernel<<<blocks, threads, 0, s->stream>>>(s->d_data, s->pitch, first, n, s->dim,
+                                                        s->buf[B_STAGE].as<double>());
+  OXG_LAUNCH_CHECK();
+  OXG_CUDA_TRY(cudaMemcpyAsync(rows_out, s->buf[B_STAGE].p, bytes, cudaMemcpyDeviceToHost, s->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return OXG_OK;
+  OXG_API_END
+}
+
+int oxg_store_sync(oxg_store s) {
+  if (!s) {
+    set_error("store is NULL");
+    return OXG_E_NULL;
+  }
+  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return OXG_OK;
+}
+
+int oxg_store_stream(oxg_store s, void** out_stream) {
+  if (!s || !out_stream) {
+    set_error("store or out_stream is NULL");
+    return OXG_E_NULL;
+  }
+  *out_stream = (void*)s->stream;
+  return OXG_OK;
+}
+
+// ------------------------------------------------------------------ world
+static int upload(double** dst, const std::vector<double>& h, cudaStream_t st) {
+  *dst = nullptr;
+  if (h.empty()) return OXG_OK;
+  OXG_CUDA_TRY(cudaMalloc((void**)dst, sizeof(double) * h.size()));
+  OXG_CUDA_TRY(cudaMemcpyAsync(*dst, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, st));
+  return OXG_OK;
+}
+
+int oxg_world_create(uint32_t dim, const double* spheres, uint64_t n_spheres, const double* aabbs,
+                     uint64_t n_aabbs, const double* capsules, uint64_t n_capsules, oxg_world* out) {
+  OXG_API_BEGIN
+  if (!out) {
+    set_error("out is NULL");
+    return OXG_E_NULL;
+  }
+  *out = nullptr;
+  if ((n_spheres && !spheres) || (n_aabbs && !aabbs) || (n_capsules && !capsules)) {
+    set_error("obstacle array is NULL with a non-zero count");
+    return OXG_E_NULL;
+  }
+  if (dim > (uint32_t)kMaxDim || (dim == 0 && (n_spheres || n_aabbs || n_capsules))) {
+    set_error("unsupported world dimension %u", dim);
+    return OXG_E_DIM;
+  }
+  if (n_spheres > 0x7FFFFFFFull || n_aabbs > 0x7FFFFFFFull || n_capsules > 0x7FFFFFFFull) {
+    set_error("too many obstacles");
+    return OXG_E_ARG;
+  }
+  int dev = 0;
+  OXG_CUDA_TRY(cudaGetDevice(&dev));
+  oxg_world_s* w = new oxg_world_s();
+  w->dim = dim;
+  w->device = dev;
+  w->n_spheres = n_spheres;
+  w->n_aabbs = n_aabbs;
+  w->n_capsules = n_capsules;
+  w->sphere_stride = (dim + 1 + 1) & ~1u;
+  w->aabb_stride = 2 * dim;
+  w->capsule_stride = (2 * dim + 2 + 1) & ~1u;
+  cudaError_t e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    delete w;
+    return OXG_E_CUDA;
+  }
+  std::vector<double> hs(n_spheres * w->sphere_stride, 0.0);
+  for (uint64_t i = 0; i < n_spheres; ++i) {
+    const double* src = spheres + i * (dim + 1);
+    double* dst = hs.data() + i * w->sphere_stride;
+    for (uint32_t d = 0; d < dim; ++d) dst[d] = src[d];
+    dst[dim] = sqrt_le_threshold(src[dim]);
+  }
+  std::vector<double> ha(aabbs, aabbs + n_aabbs * 2 * dim);
+  std::vector<double> hc(n_capsules * w->capsule_stride, 0.0);
+  for (uint64_t i = 0; i < n_capsules; ++i) {
+    const double* a = capsules + i * (2 * dim + 1);
+    const double* b = a + dim;
+    double* dst = hc.data() + i * w->capsule_stride;
+    double den = 0.0;
+    for (uint32_t d = 0; d < dim; ++d) {
+      double ab = b[d] - a[d];
+      double m = ab * ab;
+      den = (d == 0) ? m : den + m;
+      dst[d] = a[d];
+      dst[dim + d] = ab;
+    }
+    dst[2 * dim] = den;
+    dst[2 * dim + 1] = sqrt_le_threshold(a[2 * dim]);
+  }
+  int r = upload(&w->d_spheres, hs, w->stream);
+  if (r == OXG_OK) r = upload(&w->d_aabbs, ha, w->stream);
+  if (r == OXG_OK) r = upload(&w->d_capsules, hc, w->stream);
+  if (r == OXG_OK && cudaStreamSynchronize(w->stream) != cudaSuccess) {
+    set_error("world upload failed");
+    r = OXG_E_CUDA;
+  }
+  if (r != OXG_OK) {
+    oxg_world_destroy(w);
+    return r;
+  }
+  *out = w;
+  return OXG_OK;
+  OXG_API_END
+}
+
+int oxg_world_add_so2_interval(oxg_world w, uint32_t so2_component, double lo, double hi) {
+  OXG_API_BEGIN
+  if (!w) {
+    set_error("world is NULL");
+    return OXG_E_NULL;
+  }
+  if (w->n_so2 >= 16 || so2_component >= 16) {
+    set_error("at most 16 SO2 intervals / components are supported");
+    return OXG_E_ARG;
+  }
+  w->h_so2_comp[w->n_so2] = so2_component;
+  w->h_so2_lohi[2 * w->n_so2] = lo;
+  w->h_so2_lohi[2 * w->n_so2 + 1] = hi;
+  w->n_so2 += 1;
+  if (!w->d_so2_comp) {
+    OXG_CUDA_TRY(cudaMalloc((void**)&w->d_so2_comp, sizeof(uint32_t) * 16));
+    OXG_CUDA_TRY(cudaMalloc((void**)&w->d_so2_lohi, sizeof(double) * 32));
+  }
+  OXG_CUDA_TRY(cudaMemcpyAsync(w->d_so2_comp, w->h_so2_comp, sizeof(uint32_t) * 16,
+                               cudaMemcpyHostToDevice, w->stream));
+  OXG_CUDA_TRY(cudaMemcpyAsync(w->d_so2_lohi, w->h_so2_lohi, sizeof(double) * 32,
+                               cudaMemcpyHostToDevice, w->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(w->stream));
+  return OXG_OK;
+  OXG_API_END
+}
+
+int oxg_world_destroy(oxg_world w) {
+  if (!w) return OXG_OK;
+  if (w->stream) cudaStreamSynchronize(w->stream);
+  if (w->d_spheres) cudaFree(w->d_spheres);
+  if (w->d_aabbs) cudaFree(w->d_aabbs);
+  if (w->d_capsules) cudaFree(w->d_capsules);
+  if (w->d_so2_comp) cudaFree(w->d_so2_comp);
+  if (w->d_so2_lohi) cudaFree(w->d_so2_lohi);
+  for (auto& b : w->buf) b.release();
+  if (w->stream) cudaStreamDestroy(w->stream);
+  delete w;
+  return OXG_OK;
+}
+
+int oxg_world_sync(oxg_world w) {
+  if (!w) {
+    set_error("world is NULL");
+    return OXG_E_NULL;
+  }
+  OXG_CUDA_TRY(cudaStreamSynchronize(w->stream));
+  return OXG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+// oxg_internal.cuh — shared declarations for liboxg (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/oxg.h"
+
+namespace oxg {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define OXG_CUDA_TRY(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::oxg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                       __LINE__);                                                       \
+      return OXG_E_CUDA;                                                                \
+    }                                                                                   \
+  } while (0)
+
+#define OXG_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != OXG_OK) return _r; \
+  } while (0)
+
+// Checks the launch and counts it (bench.py reports the count as gpu_launches).
+#define OXG_LAUNCH_CHECK()                                                                     \
+  do {                                                                                         \
+    ::oxg::g_launches.fetch_add(1, std::memory_order_relaxed);                                 \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess) {                                                                   \
+      ::oxg::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__,   \
+                       __LINE__);                                                              \
+      return OXG_E_CUDA;                                                                       \
+    }                                                                                          \
+  } while (0)
+
+#define OXG_API_BEGIN try {
+#define OXG_API_END                                         \
+  }                                                         \
+  catch (const std::bad_alloc&) {                           \
+    ::oxg::set_error("host allocation failed");             \
+    return OXG_E_ALLOC;                                     \
+  }                                                         \
+  catch (const std::exception& e) {                         \
+    ::oxg::set_error("internal error: %s", e.what());       \
+    return OXG_E_INTERNAL;                                  \
+  }                                                         \
+  catch (...) {                                             \
+    ::oxg::set_error("internal error: unknown exception");  \
+    return OXG_E_INTERNAL;                                  \
+  }
+
+// ---------------------------------------------------------------- device buffers
+// A growable device allocation (never shrinks); contents are not preserved by ensure().
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return OXG_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+      p = nullptr;
+      return OXG_E_CUDA;
+    }
+    cap = want;
+    return OXG_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+// Named device scratch arenas of a store (each grows on demand, never shrinks).
+enum StoreBuf {
+  B_STAGE = 0,  // row-major upload / download staging for append & read
+  B_QUERY,      // uploaded query rows / edge endpoints
+  B_TMP,        // cub temporary storage
+  B_PIDX,       // k-NN partial lists (idx) / radius hit indices
+  B_PDIST,      // k-NN partial lists (dist) / radius hit distances
+  B_COUNTS,     // radius per-(query, slice) counts
+  B_OFFSETS,    // radius scanned offsets
+  B_OIDX,       // final k-NN indices for host download
+  B_ODIST,      // final k-NN distances for host download
+  B_AUX,        // exclusion lists / index limits / per-query CSR offsets
+  B_AUX2,       // edge lists, flags
+  B_AUX3,
+  B_COUNT
+};
+
+constexpr int kMaxDim = 32;     // generic (runtime-dimension) kernels keep states in local arrays
+constexpr int kMaxFastDim = 16; // RealVector fast paths are instantiated for D = 1..16
+constexpr uint32_t kMaxK = 64;
+
+}  // namespace oxg
+
+// ---------------------------------------------------------------- handles
+struct oxg_store_s {
+  oxg_space_desc space;
+  uint32_t dim = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  double* d_data = nullptr;  // SoA: coordinate d of state i at d_data[d * pitch + i]
+  uint64_t pitch = 0;        // elements; multiple of 32 (256-byte aligned columns)
+  uint64_t size = 0;
+  oxg::DevBuf buf[oxg::B_COUNT];  // named scratch arenas, see enum StoreBuf
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+};
+
+struct oxg_world_s {
+  uint32_t dim = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // Array-of-structs per primitive so a warp-uniform obstacle read is one contiguous burst.
+  //   sphere : [c_0..c_{dim-1}, U]                stride sphere_stride (even)
+  //   aabb   : [lo_0..lo_{dim-1}, hi_0..hi_{dim-1}] stride 2*dim
+  //   capsule: [a_0.., ab_0.., den, U]             stride capsule_stride (even)
+  // U = max{x : sqrt(x) <= r}: "sqrt(d2) > r" is evaluated as "d2 > U" (exactly equivalent).
+  double* d_spheres = nullptr;
+  double* d_aabbs = nullptr;
+  double* d_capsules = nullptr;
+  uint64_t n_spheres = 0, n_aabbs = 0, n_capsules = 0;
+  uint32_t sphere_stride = 0, aabb_stride = 0, capsule_stride = 0;
+  // SO2 interval obstacles (host copy kept so add() can re-upload)
+  uint32_t n_so2 = 0;
+  uint32_t h_so2_comp[16];
+  double h_so2_lohi[32];
+  uint32_t* d_so2_comp = nullptr;
+  double* d_so2_lohi = nullptr;
+  oxg::DevBuf buf[4];
+};
+
+namespace oxg {
+
+// View of a world passed by value to kernels.
+struct WorldView {
+  const double* spheres;
+  const double* aabbs;
+  const double* capsules;
+  const uint32_t* so2_comp;
+  const double* so2_lohi;
+  uint32_t n_spheres, n_aabbs, n_capsules, n_so2;
+  uint32_t sphere_stride, aabb_stride, capsule_stride;
+  uint32_t dim;
+};
+inline WorldView world_view(const oxg_world_s* w) {
+  WorldView v;
+  v.spheres = w->d_spheres;
+  v.aabbs = w->d_aabbs;
+  v.capsules = w->d_capsules;
+  v.so2_comp = w->d_so2_comp;
+  v.so2_lohi = w->d_so2_lohi;
+  v.n_spheres = (uint32_t)w->n_spheres;
+  v.n_aabbs = (uint32_t)w->n_aabbs;
+  v.n_capsules = (uint32_t)w->n_capsules;
+  v.n_so2 = w->n_so2;
+  v.sphere_stride = w->sphere_stride;
+  v.aabb_stride = w->aabb_stride;
+  v.capsule_stride = w->capsule_stride;
+  v.dim = w->dim;
+  return v;
+}
+
+// Where a batch of states lives: coordinate d of state i at p[i * stride_i + d * stride_d].
+//   row-major host upload : stride_i = dim, stride_d = 1
+//   SoA store             : stride_i = 1,   stride_d = pitch
+struct StateView {
+  const double* p;
+  uint64_t stride_i;
+  uint64_t stride_d;
+};
+inline StateView store_view(const oxg_store_s* s) { return StateView{s->d_data, 1, s->pitch}; }
+inline StateView rows_view(const double* p, uint32_t dim) { return StateView{p, dim, 1}; }
+
+// Host-side exact thresholds (std::sqrt is correctly rounded, as is CUDA's sqrt.rn.f64).
+//   sqrt_le_threshold(r) = max{x >= 0 : sqrt(x) <= r}   (-1 if none, +inf if r = +inf)
+//   sqrt_lt_threshold(r) = max{x >= 0 : sqrt(x) <  r}   (-1 if none)
+double sqrt_le_threshold(double r);
+double sqrt_lt_threshold(double r);
+
+int validate_space(const oxg_space_desc* sp);
+inline bool is_pure_rv(const oxg_space_desc& sp) { return sp.n_so2 == 0; }
+
+// internal entry points shared between translation units
+int nn_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclude_mode,
+                  const uint32_t* d_exclude, uint64_t self_base, bool stored_first,
+                  uint32_t* d_idx, double* d_dist);
+// E_dev (nullable): the edge count is read from device memory at kernel start (E is then
+// only an upper bound used to size the grid), so a producer kernel can feed the check without
+// a host round-trip.
+int motion_check_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t stream,
+                        StateView from, StateView to, const uint32_t* d_from_idx,
+                        const uint32_t* d_to_idx, uint64_t E, const uint64_t* E_dev,
+                        double resolution, uint8_t* d_valid, uint32_t* d_first_invalid);
+int is_valid_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t stream,
+                    StateView st, uint64_t Q, uint8_t* d_out);
+int nn_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double r, const uint32_t* d_idx_limit,
+                     bool limit_self, uint64_t self_base, bool want_dist, uint64_t* total);
+int nn_radius_nsplit(const oxg_store_s* s, uint64_t Q);
+int nn_radius_offsets(oxg_store_s* s, uint64_t Q, uint64_t* d_out);
+
+}  // namespace oxg

@@ -1,0 +1,183 @@
+// oxg_math.cuh — device arithmetic in the reference's operation order.
+//
+// Every function here restates a piece of oxmpl's f64 arithmetic with explicitly
+// rounded, never-fused operations (__dadd_rn / __dsub_rn / __dmul_rn; the library is
+// also compiled with -fmad=false).  sqrt(), '/' and fmod() on doubles are IEEE
+// correctly-rounded / exact in CUDA, as they are in Rust's std on the CPU.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace oxg {
+
+#define OXG_PI 3.14159265358979323846264338327950288
+#define OXG_DEV __device__ __forceinline__
+
+// Dimension that is a compile-time constant when DT > 0, else a runtime value.
+template <int DT>
+struct DimOf {
+  OXG_DEV static int get(int rt) { return DT > 0 ? DT : rt; }
+};
+
+// f64::rem_euclid (Rust core): r = self % rhs; if r < 0.0 { r + rhs.abs() } else { r }
+OXG_DEV double rem_euclid_dev(double v, double rhs) {
+  double r = fmod(v, rhs);
+  if (r < 0.0) r = __dadd_rn(r, fabs(rhs));
+  return r;
+}
+
+// SO2State::normalise — oxmpl/src/base/states/so2_state.rs:55-59
+OXG_DEV double so2_normalise_dev(double v) {
+  return __dsub_rn(rem_euclid_dev(__dadd_rn(v, OXG_PI), __dmul_rn(2.0, OXG_PI)), OXG_PI);
+}
+
+// SO2StateSpace::distance — oxmpl/src/base/spaces/so2_state_space.rs:97-101
+OXG_DEV double so2_distance_dev(double a, double b) {
+  double diff = __dsub_rn(a, b);
+  diff = __dsub_rn(rem_euclid_dev(__dadd_rn(diff, OXG_PI), __dmul_rn(2.0, OXG_PI)), OXG_PI);
+  return fabs(diff);
+}
+
+// SO2StateSpace::interpolate — so2_state_space.rs:107-122
+OXG_DEV double so2_interpolate_dev(double from, double to, double t) {
+  double diff = __dsub_rn(so2_normalise_dev(to), so2_normalise_dev(from));
+  if (diff > OXG_PI) {
+    diff = __dsub_rn(diff, __dmul_rn(2.0, OXG_PI));
+  } else if (diff < -OXG_PI) {
+    diff = __dadd_rn(diff, __dmul_rn(2.0, OXG_PI));
+  }
+  double v = __dadd_rn(from, __dmul_rn(diff, t));
+  return so2_normalise_dev(v);
+}
+
+// Sum of squared differences, RealVectorStateSpace::distance's pre-sqrt value —
+// oxmpl/src/base/spaces/real_vector_state_space.rs:148-153 (left fold; 0.0 + x*x == x*x).
+template <int DT>
+OXG_DEV double rv_sumsq_dev(const double* a, const double* b, int n_rt) {
+  const int n = DimOf<DT>::get(n_rt);
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    double d = __dsub_rn(a[i], b[i]);
+    double m = __dmul_rn(d, d);
+    s = (i == 0) ? m : __dadd_rn(s, m);
+  }
+  return s;
+}
+
+// Space distance for runtime descriptors (see include/oxg.h, oxg_space_desc).
+OXG_DEV double space_distance_dev(uint32_t n_real, uint32_t n_so2, double w_real, double w_so2,
+                                  const double* a, const double* b) {
+  if (n_so2 == 0) return sqrt(rv_sumsq_dev<0>(a, b, (int)n_real));
+  if (n_real == 0 && n_so2 == 1) return so2_distance_dev(a[0], b[0]);
+  double acc = 0.0;
+  bool have = false;
+  if (n_real > 0) {
+    acc = __dmul_rn(w_real, sqrt(rv_sumsq_dev<0>(a, b, (int)n_real)));
+    have = true;
+  }
+  for (uint32_t c = 0; c < n_so2; ++c) {
+    double term = __dmul_rn(w_so2, so2_distance_dev(a[n_real + c], b[n_real + c]));
+    acc = have ? __dadd_rn(acc, term) : term;
+    have = true;
+  }
+  return acc;
+}
+
+// Rust `x.ceil() as usize`: saturating, NaN -> 0.
+OXG_DEV unsigned long long ceil_as_usize_dev(double x) {
+  double c = ceil(x);
+  if (!(c == c)) return 0ull;
+  if (c <= 0.0) return 0ull;
+  if (c >= 18446744073709551615.0) return 0xFFFFFFFFFFFFFFFFull;
+  return (unsigned long long)c;
+}
+
+// next / previous representable double for x >= +0 (bit pattern arithmetic).
+OXG_DEV double next_up_nonneg(double x) {
+  return __longlong_as_double(__double_as_longlong(x) + 1);
+}
+OXG_DEV double next_down_pos(double x) {
+  return __longlong_as_double(__double_as_longlong(x) - 1);
+}
+
+// max{x >= 0 : sqrt(x) <= s} for s >= 0 (s = +inf -> +inf).  "sqrt(d2) <= s" <=> "d2 <= U".
+// The preimage of one double under the correctly-rounded sqrt holds 1-3 doubles, and
+// fl(s*s) is within one of them, so both loops run a handful of iterations.
+OXG_DEV double sqrt_le_threshold_dev(double s) {
+  if (!(s == s) || s < 0.0) return -1.0;
+  double x = __dmul_rn(s, s);
+  if (x == __longlong_as_double(0x7FF0000000000000ll)) {
+    if (s == x) return x;                       // s = +inf
+    x = __longlong_as_double(0x7FEFFFFFFFFFFFFFll);  // DBL_MAX
+  }
+  while (sqrt(x) > s && x > 0.0) x = next_down_pos(x);
+  for (;;) {
+    double nx = next_up_nonneg(x);
+    if (nx == nx && sqrt(nx) <= s)
+      x = nx;
+    else
+      break;
+  }
+  return x;
+}
+
+// ----------------------------------------------------------------- validity predicates
+// World layouts are described in oxg_internal.cuh (oxg_world_s).
+
+// sphere: valid iff sqrt(sum (x_i - c_i)^2) > r   (README.md:147-150)  <=>  sumsq > U
+template <int DT>
+OXG_DEV bool sphere_hit_dev(const double* x, const double* __restrict__ sph, int dim_rt) {
+  const int dim = DimOf<DT>::get(dim_rt);
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < dim; ++i) {
+    double d = __dsub_rn(x[i], __ldg(sph + i));
+    double m = __dmul_rn(d, d);
+    s = (i == 0) ? m : __dadd_rn(s, m);
+  }
+  return !(s > __ldg(sph + dim));
+}
+
+// aabb: invalid iff all_i lo_i <= x_i <= hi_i   (oxmpl/tests/rrt_rvss_tests.rs:24-36)
+template <int DT>
+OXG_DEV bool aabb_hit_dev(const double* x, const double* __restrict__ box, int dim_rt) {
+  const int dim = DimOf<DT>::get(dim_rt);
+  bool inside = true;
+#pragma unroll
+  for (int i = 0; i < dim; ++i) {
+    double lo = __ldg(box + i), hi = __ldg(box + dim + i);
+    inside = inside && (x[i] >= lo) && (x[i] <= hi);
+  }
+  return inside;
+}
+
+// capsule: valid iff dist(x, segment) > r, operation order as in oracle/oxg_oracle.cpp
+// (capsule_valid).  ab_i and den are precomputed at world creation with the same roundings.
+template <int DT>
+OXG_DEV bool capsule_hit_dev(const double* x, const double* __restrict__ cap, int dim_rt) {
+  const int dim = DimOf<DT>::get(dim_rt);
+  double num = 0.0;
+#pragma unroll
+  for (int i = 0; i < dim; ++i) {
+    double ap = __dsub_rn(x[i], __ldg(cap + i));
+    double m = __dmul_rn(ap, __ldg(cap + dim + i));
+    num = (i == 0) ? m : __dadd_rn(num, m);
+  }
+  double den = __ldg(cap + 2 * dim);
+  double t = (den > 0.0) ? __ddiv_rn(num, den) : 0.0;
+  if (t < 0.0) t = 0.0;
+  if (t > 1.0) t = 1.0;
+  double d2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < dim; ++i) {
+    double c = __dadd_rn(__ldg(cap + i), __dmul_rn(__ldg(cap + dim + i), t));
+    double e = __dsub_rn(x[i], c);
+    double m = __dmul_rn(e, e);
+    d2 = (i == 0) ? m : __dadd_rn(d2, m);
+  }
+  return !(d2 > __ldg(cap + 2 * dim + 1));
+}
+
+}  // namespace oxg

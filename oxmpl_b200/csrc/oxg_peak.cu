@@ -1,0 +1,65 @@
+// oxg_peak.cu — measures the roofline denominator of the batched k-NN / validity kernels:
+// the issue rate of UNFUSED FP64 adds and multiplies (the reference never contracts a*b+c,
+// so DFMA's two-flops-per-issue datasheet figure is not reachable by this workload).
+#include <algorithm>
+
+#include "oxg_internal.cuh"
+
+namespace oxg {
+
+constexpr int PEAK_CHAINS = 8;
+
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* __restrict__ out, double a, double b,
+                                                        int iters) {
+  double x[PEAK_CHAINS];
+#pragma unroll
+  for (int c = 0; c < PEAK_CHAINS; ++c) x[c] = a * (double)(threadIdx.x + c + 1);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < PEAK_CHAINS; ++c) {
+      x[c] = __dmul_rn(x[c], b);
+      x[c] = __dadd_rn(x[c], a);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < PEAK_CHAINS; ++c) s = __dadd_rn(s, x[c]);
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace oxg
+
+using namespace oxg;
+
+extern "C" int oxg_fp64_peak(double* out_ops_per_s, double* out_ms) {
+  OXG_API_BEGIN
+  if (!out_ops_per_s) {
+    set_error("out_ops_per_s is NULL");
+    return OXG_E_NULL;
+  }
+  const int blocks = 148 * 8, threads = 256, iters = 16384;
+  double* d_out = nullptr;
+  OXG_CUDA_TRY(cudaMalloc((void**)&d_out, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  OXG_CUDA_TRY(cudaEventCreate(&e0));
+  OXG_CUDA_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    OXG_CUDA_TRY(cudaEventRecord(e0, 0));
+    fp64_peak_kernel<<<blocks, threads>>>(d_out, 1e-9, 1.0000001, iters);
+    OXG_LAUNCH_CHECK();
+    OXG_CUDA_TRY(cudaEventRecord(e1, 0));
+    OXG_CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    OXG_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  const double ops = (double)blocks * threads * (double)iters * PEAK_CHAINS * 2.0;
+  *out_ops_per_s = ops / (best * 1e-3);
+  if (out_ms) *out_ms = best;
+  return OXG_OK;
+  OXG_API_END
+}

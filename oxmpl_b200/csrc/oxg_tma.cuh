@@ -1,0 +1,58 @@
+// oxg_tma.cuh — minimal mbarrier + bulk-copy (TMA engine, non-tensor form) wrappers.
+//
+// The store is structure-of-arrays, so a tile of TILE consecutive states is D contiguous
+// runs of TILE f64 — exactly what the 1-D bulk copy moves (SASS: UBLKCP).  One elected
+// thread arms an mbarrier with the byte count and issues the copies; every consumer thread
+// waits on the barrier's phase parity.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace oxg {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
+               : "memory");
+}
+
+// Makes the barrier initialisation visible to the async proxy (the copy engine).
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+
+// global -> shared bulk copy; `bytes` multiple of 16, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                              uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "OXG_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra OXG_DONE;\n"
+      "bra OXG_WAIT;\n"
+      "OXG_DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+}  // namespace oxg

@@ -1,0 +1,335 @@
+// oxg_validity.cu — declarative StateValidityChecker and the interpolated motion check.
+//
+// is_valid   : oxmpl/src/base/validity.rs:39-48 with the obstacle semantics of the reference's
+//              own fixtures (README.md:147-150 sphere, oxmpl/tests/rrt_rvss_tests.rs:24-36 AABB,
+//              oxmpl/tests/rrt_so2ss_tests.rs:17-27 SO2 interval) plus the oracle-defined capsule.
+// check_motion: rrt.rs:90-116 (= rrt_connect.rs:166-189, rrt_star.rs:76-104, prm.rs:161-187).
+//
+// Mapping.  A group of L lanes owns one edge; lane g evaluates steps g+1, g+1+L, ... so the
+// interpolation steps of an edge run in parallel, and a group ballot after each round of L
+// steps gives the early exit and the exact index of the first invalid step (all earlier rounds
+// were valid, and within a round the lowest set bit is the first).  Every lane walks the
+// obstacle list in the same order, so obstacle reads are warp-uniform (one burst per primitive,
+// served by L1/L2) and the FP64 pipe is the bound.  The boolean result does not depend on the
+// evaluation order, so it is bit-identical to the sequential reference loop.
+#include <algorithm>
+
+#include "oxg_internal.cuh"
+#include "oxg_math.cuh"
+
+namespace oxg {
+
+struct SpaceP {
+  uint32_t n_real, n_so2;
+  double w_real, w_so2;
+};
+
+// valid iff no obstacle marks the state invalid.  x holds n_real coordinates then n_so2 angles.
+template <int DT>
+__device__ __forceinline__ bool state_valid_dev(const WorldView& w, const double* x, int n_real_rt) {
+  const int dim = DimOf<DT>::get(n_real_rt);
+  for (uint32_t i = 0; i < w.n_spheres; ++i)
+    if (sphere_hit_dev<DT>(x, w.spheres + (size_t)i * w.sphere_stride, dim)) return false;
+  for (uint32_t i = 0; i < w.n_aabbs; ++i)
+    if (aabb_hit_dev<DT>(x, w.aabbs + (size_t)i * w.aabb_stride, dim)) return false;
+  for (uint32_t i = 0; i < w.n_capsules; ++i)
+    if (capsule_hit_dev<DT>(x, w.capsules + (size_t)i * w.capsule_stride, dim)) return false;
+  if (DT == 0) {  // fast RealVector instantiations have no SO2 components
+    for (uint32_t i = 0; i < w.n_so2; ++i) {
+      double v = so2_normalise_dev(x[dim + w.so2_comp[i]]);
+      if (v >= w.so2_lohi[2 * i] && v <= w.so2_lohi[2 * i + 1]) return false;
+    }
+  }
+  return true;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(128) is_valid_kernel(const WorldView w, const SpaceP sp,
+                                                       const StateView st, uint64_t Q,
+                                                       uint8_t* __restrict__ out) {
+  constexpr int XN = DT > 0 ? DT : kMaxDim;
+  const int n_real = DimOf<DT>::get((int)sp.n_real);
+  const int dim = DT > 0 ? DT : (int)(sp.n_real + sp.n_so2);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Q;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    double x[XN];
+#pragma unroll
+    for (int d = 0; d < dim; ++d) x[d] = st.p[i * st.stride_i + (uint64_t)d * st.stride_d];
+    out[i] = state_valid_dev<DT>(w, x, n_real) ? 1 : 0;
+  }
+}
+
+struct MotionParams {
+  WorldView w;
+  SpaceP sp;
+  StateView from, to;
+  const uint32_t* from_idx;  // nullable: endpoint e is row from_idx[e] of `from`
+  const uint32_t* to_idx;
+  uint64_t E;
+  const uint64_t* E_dev;  // nullable: actual edge count in device memory
+  double resolution;
+  uint8_t* valid;
+  uint32_t* first_invalid;  // nullable
+};
+
+template <int DT, int L>
+__global__ void __launch_bounds__(128) motion_kernel(const MotionParams p) {
+  constexpr int XN = DT > 0 ? DT : kMaxDim;
+  const int n_real = DimOf<DT>::get((int)p.sp.n_real);
+  const int n_so2 = DT > 0 ? 0 : (int)p.sp.n_so2;
+  const int dim = n_real + n_so2;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lane_g = lane % L;
+  const unsigned group_shift = lane - lane_g;
+  const unsigned group_mask = (L == 32) ? 0xFFFFFFFFu : (((1u << L) - 1u) << group_shift);
+  const uint64_t gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) / L;
+
+  const uint64_t E = p.E_dev ? *p.E_dev : p.E;
+  for (uint64_t e = gid; e < E; e += ngroups) {
+    const uint64_t fi = p.from_idx ? p.from_idx[e] : e;
+    const uint64_t ti = p.to_idx ? p.to_idx[e] : e;
+    double from[XN], to[XN], x[XN];
+#pragma unroll
+    for (int d = 0; d < dim; ++d) {
+      from[d] = p.from.p[fi * p.from.stride_i + (uint64_t)d * p.from.stride_d];
+      to[d] = p.to.p[ti * p.to.stride_i + (uint64_t)d * p.to.stride_d];
+    }
+    // dist = space.distance(from, to); num_steps = ceil(dist / resolution) as usize  (rrt.rs:95-97)
+    double dist;
+    if (DT > 0)
+      dist = sqrt(rv_sumsq_dev<DT>(from, to, n_real));
+    else
+      dist = space_distance_dev(p.sp.n_real, p.sp.n_so2, p.sp.w_real, p.sp.w_so2, from, to);
+    unsigned long long n = ceil_as_usize_dev(__ddiv_rn(dist, p.resolution));
+    unsigned long long first_bad = 0;
+    if (n > (1ull << 32)) {
+      first_bad = 0xFFFFFFFFull;  // the reference loop would not terminate in practice
+    } else {
+      const bool single = n <= 1;   // `if num_steps <= 1 { return vc.is_valid(to); }` (rrt.rs:99-101)
+      const unsigned long long nn = single ? 1ull : n;
+      const double nf = (double)n;
+      for (unsigned long long base = 0; base < nn; base += L) {
+        const unsigned long long i = base + lane_g + 1;
+        bool bad = false;
+        if (i <= nn) {
+          if (single) {
+#pragma unroll
+            for (int d = 0; d < dim; ++d) x[d] = to[d];
+          } else {
+            const double t = __ddiv_rn((double)i, nf);  // `i as f64 / num_steps as f64` (rrt.rs:105)
+#pragma unroll
+            for (int d = 0; d < n_real; ++d)
+              x[d] = __dadd_rn(from[d], __dmul_rn(__dsub_rn(to[d], from[d]), t));
+            for (int c = 0; c < n_so2; ++c)
+              x[n_real + c] = so2_interpolate_dev(from[n_real + c], to[n_real + c], t);
+          }
+          bad = !state_valid_dev<DT>(p.w, x, n_real);
+        }
+        const unsigned b = (__ballot_sync(group_mask, bad) & group_mask) >> group_shift;
+        if (b) {
+          first_bad = base + (unsigned long long)(__ffs(b) - 1) + 1ull;
+          break;
+        }
+      }
+    }
+    if (lane_g == 0) {
+      p.valid[e] = first_bad == 0 ? 1 : 0;
+      if (p.first_invalid)
+        p.first_invalid[e] = first_bad > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)first_bad;
+    }
+  }
+}
+
+#define OXG_DISPATCH_DT(D_RT, CALL)                     \
+  switch (D_RT) {                                       \
+    case 1: { constexpr int DD = 1; CALL; } break;      \
+    case 2: { constexpr int DD = 2; CALL; } break;      \
+    case 3: { constexpr int DD = 3; CALL; } break;      \
+    case 4: { constexpr int DD = 4; CALL; } break;      \
+    case 5: { constexpr int DD = 5; CALL; } break;      \
+    case 6: { constexpr int DD = 6; CALL; } break;      \
+    case 7: { constexpr int DD = 7; CALL; } break;      \
+    case 8: { constexpr int DD = 8; CALL; } break;      \
+    case 9: { constexpr int DD = 9; CALL; } break;      \
+    case 10: { constexpr int DD = 10; CALL; } break;    \
+    case 11: { constexpr int DD = 11; CALL; } break;    \
+    case 12: { constexpr int DD = 12; CALL; } break;    \
+    case 13: { constexpr int DD = 13; CALL; } break;    \
+    case 14: { constexpr int DD = 14; CALL; } break;    \
+    case 15: { constexpr int DD = 15; CALL; } break;    \
+    case 16: { constexpr int DD = 16; CALL; } break;    \
+    default: { constexpr int DD = 0; CALL; } break;     \
+  }
+
+static int check_world_space(const oxg_world_s* w, const oxg_space_desc& sp) {
+  const bool has_rn = w->n_spheres || w->n_aabbs || w->n_capsules;
+  if (has_rn && w->dim != sp.n_real) {
+    set_error("world dimension %u does not match the space's RealVector block (%u)", w->dim,
+              sp.n_real);
+    return OXG_E_DIM;
+  }
+  for (uint32_t i = 0; i < w->n_so2; ++i)
+    if (w->h_so2_comp[i] >= sp.n_so2) {
+      set_error("SO2 interval refers to component %u but the space has %u", w->h_so2_comp[i],
+                sp.n_so2);
+      return OXG_E_DIM;
+    }
+  return OXG_OK;
+}
+
+static inline int fast_dim(const oxg_space_desc& sp) {
+  return (sp.n_so2 == 0 && sp.n_real <= (uint32_t)kMaxFastDim) ? (int)sp.n_real : 0;
+}
+
+int is_valid_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t stream,
+                    StateView st, uint64_t Q, uint8_t* d_out) {
+  OXG_TRY(check_world_space(w, sp));
+  if (Q == 0) return OXG_OK;
+  WorldView wv = world_view(w);
+  SpaceP spp{sp.n_real, sp.n_so2, sp.w_real, sp.w_so2};
+  int threads = 128;
+  unsigned blocks = (unsigned)std::min<uint64_t>((Q + threads - 1) / threads, 148ull * 32);
+  OXG_DISPATCH_DT(fast_dim(sp),
+                  (is_valid_kernel<DD><<<blocks, threads, 0, stream>>>(wv, spp, st, Q, d_out)));
+  OXG_LAUNCH_CHECK();
+  return OXG_OK;
+}
+
+int motion_check_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t stream,
+                        StateView from, StateView to, const uint32_t* d_from_idx,
+                        const uint32_t* d_to_idx, uint64_t E, const uint64_t* E_dev,
+                        double resolution, uint8_t* d_valid, uint32_t* d_first_invalid) {
+  OXG_TRY(check_world_space(w, sp));
+  if (!(resolution > 0.0)) {
+    set_error("motion resolution must be > 0 (got %g): the reference loop would not terminate",
+              resolution);
+    return OXG_E_RESOLUTION;
+  }
+  if (E == 0) return OXG_OK;
+  MotionParams p;
+  p.w = world_view(w);
+  p.sp = SpaceP{sp.n_real, sp.n_so2, sp.w_real, sp.w_so2};
+  p.from = from;
+  p.to = to;
+  p.from_idx = d_from_idx;
+  p.to_idx = d_to_idx;
+  p.E = E;
+  p.E_dev = E_dev;
+  p.resolution = resolution;
+  p.valid = d_valid;
+  p.first_invalid = d_first_invalid;
+  const int threads = 128;
+  // few edges: a whole warp per edge; many edges: 4 lanes per edge keeps lanes busy at the
+  // typical 4-12 steps per edge.
+  const bool wide = E < 148ull * 64;
+  const int L = wide ? 32 : 4;
+  unsigned blocks = (unsigned)std::min<uint64_t>((E * L + threads - 1) / threads, 148ull * 16);
+  if (wide) {
+    OXG_DISPATCH_DT(fast_dim(sp), (motion_kernel<DD, 32><<<blocks, threads, 0, stream>>>(p)));
+  } else {
+    OXG_DISPATCH_DT(fast_dim(sp), (motion_kernel<DD, 4><<<blocks, threads, 0, stream>>>(p)));
+  }
+  OXG_LAUNCH_CHECK();
+  return OXG_OK;
+}
+
+}  // namespace oxg
+
+using namespace oxg;
+
+extern "C" {
+
+int oxg_is_valid(oxg_world w, const oxg_space_desc* space, const double* states, uint64_t Q,
+                 uint8_t* out) {
+  OXG_API_BEGIN
+  if (!w || (Q > 0 && (!states || !out))) {
+    set_error("NULL argument");
+    return OXG_E_NULL;
+  }
+  OXG_TRY(validate_space(space));
+  if (Q == 0) return OXG_OK;
+  uint32_t dim = space->n_real + space->n_so2;
+  size_t bytes = sizeof(double) * Q * dim;
+  OXG_TRY(w->buf[0].ensure(bytes));
+  OXG_TRY(w->buf[1].ensure(Q));
+  OXG_CUDA_TRY(cudaMemcpyAsync(w->buf[0].p, states, bytes, cudaMemcpyHostToDevice, w->stream));
+  OXG_TRY(is_valid_device(w, *space, w->stream, rows_view(w->buf[0].as<double>(), dim), Q,
+                          w->buf[1].as<uint8_t>()));
+  OXG_CUDA_TRY(cudaMemcpyAsync(out, w->buf[1].p, Q, cudaMemcpyDeviceToHost, w->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(w->stream));
+  return OXG_OK;
+  OXG_API_END
+}
+
+int oxg_check_motion(oxg_world w, const oxg_space_desc* space, const double* from, const double* to,
+                     uint64_t E, double resolution, uint8_t* valid, uint32_t* first_invalid_step) {
+  OXG_API_BEGIN
+  if (!w || (E > 0 && (!from || !to || !valid))) {
+    set_error("NULL argument");
+    return OXG_E_NULL;
+  }
+  OXG_TRY(validate_space(space));
+  if (!(resolution > 0.0)) {
+    set_error("motion resolution must be > 0 (got %g): the reference loop would not terminate",
+              resolution);
+    return OXG_E_RESOLUTION;
+  }
+  if (E == 0) return OXG_OK;
+  uint32_t dim = space->n_real + space->n_so2;
+  size_t bytes = sizeof(double) * E * dim;
+  OXG_TRY(w->buf[0].ensure(bytes));
+  OXG_TRY(w->buf[1].ensure(bytes));
+  OXG_TRY(w->buf[2].ensure(E));
+  OXG_TRY(w->buf[3].ensure(E * sizeof(uint32_t)));
+  OXG_CUDA_TRY(cudaMemcpyAsync(w->buf[0].p, from, bytes, cudaMemcpyHostToDevice, w->stream));
+  OXG_CUDA_TRY(cudaMemcpyAsync(w->buf[1].p, to, bytes, cudaMemcpyHostToDevice, w->stream));
+  OXG_TRY(motion_check_device(w, *space, w->stream, rows_view(w->buf[0].as<double>(), dim),
+                              rows_view(w->buf[1].as<double>(), dim), nullptr, nullptr, E, nullptr,
+                              resolution, w->buf[2].as<uint8_t>(),
+                              first_invalid_step ? w->buf[3].as<uint32_t>() : nullptr));
+  OXG_CUDA_TRY(cudaMemcpyAsync(valid, w->buf[2].p, E, cudaMemcpyDeviceToHost, w->stream));
+  if (first_invalid_step)
+    OXG_CUDA_TRY(cudaMemcpyAsync(first_invalid_step, w->buf[3].p, E * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, w->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(w->stream));
+  return OXG_OK;
+  OXG_API_END
+}
+
+int oxg_check_edges(oxg_world w, oxg_store s, const uint32_t* from_idx, const uint32_t* to_idx,
+                    uint64_t E, double resolution, uint8_t* valid) {
+  OXG_API_BEGIN
+  if (!w || !s || (E > 0 && (!from_idx || !to_idx || !valid))) {
+    set_error("NULL argument");
+    return OXG_E_NULL;
+  }
+  if (!(resolution > 0.0)) {
+    set_error("motion resolution must be > 0 (got %g): the reference loop would not terminate",
+              resolution);
+    return OXG_E_RESOLUTION;
+  }
+  if (E == 0) return OXG_OK;
+  for (uint64_t e = 0; e < E; ++e)
+    if (from_idx[e] >= s->size || to_idx[e] >= s->size) {
+      set_error("edge %llu refers to a state outside the store (size %llu)", (unsigned long long)e,
+                (unsigned long long)s->size);
+      return OXG_E_ARG;
+    }
+  OXG_TRY(s->buf[B_AUX].ensure(E * sizeof(uint32_t)));
+  OXG_TRY(s->buf[B_AUX2].ensure(E * sizeof(uint32_t)));
+  OXG_TRY(s->buf[B_AUX3].ensure(E));
+  OXG_CUDA_TRY(cudaMemcpyAsync(s->buf[B_AUX].p, from_idx, E * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                               s->stream));
+  OXG_CUDA_TRY(cudaMemcpyAsync(s->buf[B_AUX2].p, to_idx, E * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                               s->stream));
+  OXG_TRY(motion_check_device(w, s->space, s->stream, store_view(s), store_view(s),
+                              s->buf[B_AUX].as<uint32_t>(), s->buf[B_AUX2].as<uint32_t>(), E,
+                              nullptr, resolution, s->buf[B_AUX3].as<uint8_t>(), nullptr));
+  OXG_CUDA_TRY(cudaMemcpyAsync(valid, s->buf[B_AUX3].p, E, cudaMemcpyDeviceToHost, s->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return OXG_OK;
+  OXG_API_END
+}
+
+}  // extern "C"

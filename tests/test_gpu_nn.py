@@ -1,0 +1,219 @@
+"""GPU parity: nn1 / knn / radius through the C ABI vs the CPU oracle (bit-exact)."""
+import numpy as np
+import pytest
+
+from conftest import uniform_states
+
+pytestmark = pytest.mark.gpu
+
+
+def _adversarial(seed, n, d):
+    """Duplicates, an integer lattice (mass exact ties) and 1-ulp near-ties."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 4, size=(n, d)).astype(np.float64)      # lattice: many exact ties
+    dup = base[rng.integers(0, n, size=n // 4)]                      # exact duplicates
+    near = base[: n // 4] + 0.0
+    near[:, 0] = np.nextafter(near[:, 0] + 0.5, np.inf)              # 1-ulp perturbations
+    near2 = base[: n // 4] + 0.0
+    near2[:, 0] = near2[:, 0] + 0.5
+    pts = np.vstack([base, dup, near, near2])
+    rng.shuffle(pts)
+    return np.ascontiguousarray(pts)
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 6, 7, 14, 16])
+@pytest.mark.parametrize("n", [1, 5, 127, 128, 129, 1000, 20011])
+def test_nn1_knn_radius_uniform(oxg, orc, d, n):
+    rows = uniform_states(100 + d, n, [0.0] * d, [1.0] * d)
+    queries = uniform_states(200 + d, 67, [0.0] * d, [1.0] * d)
+    sp_o = orc.space(d)
+    with oxg.StateStore(oxg.Space.real_vector(d)) as st:
+        assert st.append(rows) == 0
+        assert len(st) == n
+        np.testing.assert_array_equal(st.read(), rows)
+        idx, dist = st.nn1(queries)
+        oi, od = orc.nn1(sp_o, rows, queries)
+        np.testing.assert_array_equal(idx, oi)
+        np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+        for k in (1, 3, 10):
+            idx, dist = st.knn(queries, k)
+            oi, od = orc.knn(sp_o, rows, queries, k)
+            np.testing.assert_array_equal(idx, oi)
+            np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+        r = 0.3 * np.sqrt(d)
+        off, ridx, rdist = st.radius(queries, r, want_dist=True)
+        ooff, oidx, odist = orc.radius(sp_o, rows, queries, r, want_dist=True)
+        np.testing.assert_array_equal(off, ooff)
+        np.testing.assert_array_equal(ridx, oidx)
+        np.testing.assert_array_equal(rdist.view(np.uint64), odist.view(np.uint64))
+
+
+@pytest.mark.parametrize("d", [2, 3, 7])
+def test_adversarial_ties(oxg, orc, d):
+    rows = _adversarial(7 + d, 2000, d)
+    queries = np.vstack([rows[:200], _adversarial(99, 100, d)])
+    sp_o = orc.space(d)
+    with oxg.StateStore(oxg.Space.real_vector(d)) as st:
+        st.append(rows)
+        idx, dist = st.nn1(queries)
+        oi, od = orc.nn1(sp_o, rows, queries)
+        np.testing.assert_array_equal(idx, oi)
+        np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+        idx, dist = st.knn(queries, 10)
+        oi, od = orc.knn(sp_o, rows, queries, 10)
+        np.testing.assert_array_equal(idx, oi)
+        np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+        # self-exclusion by index, not by zero distance (duplicates stay)
+        ex = np.arange(200, dtype=np.uint32)
+        idx, dist = st.knn(rows[:200], 5, exclude=ex)
+        oi, od = orc.knn(sp_o, rows, rows[:200], 5, exclude=ex)
+        np.testing.assert_array_equal(idx, oi)
+        np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+        for r in (0.5, 1.0, np.nextafter(1.0, 2.0), 1.5):
+            off, ridx = st.radius(queries, r)
+            ooff, oidx = orc.radius(sp_o, rows, queries, r)
+            np.testing.assert_array_equal(off, ooff)
+            np.testing.assert_array_equal(ridx, oidx)
+
+
+def test_sqrt_collapse_tie(oxg, orc):
+    """Two stored states whose squared distances differ by an ulp but whose sqrt is equal:
+    the reference compares after sqrt, so the LOWER index must win (SURVEY hard part 1)."""
+    rng = np.random.default_rng(3)
+    pairs = []
+    while len(pairs) < 64:
+        a = rng.random(2) + 0.5
+        b = a.copy()
+        b[0] = np.nextafter(b[0], np.inf)
+        da = a[0] * a[0] + a[1] * a[1]
+        db = b[0] * b[0] + b[1] * b[1]
+        if da != db and np.sqrt(da) == np.sqrt(db):
+            pairs.append((a, b))
+    sp_o = orc.space(2)
+    q = np.zeros((1, 2))
+    for a, b in pairs:
+        rows = np.array([b, a, [5.0, 5.0]])      # the farther-in-d2 state has the LOWER index
+        with oxg.StateStore(oxg.Space.real_vector(2)) as st:
+            st.append(rows)
+            idx, dist = st.nn1(q)
+            oi, od = orc.nn1(sp_o, rows, q)
+            assert oi[0] == 0                     # reference: tie after sqrt -> first index
+            np.testing.assert_array_equal(idx, oi)
+            np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+            idx, dist = st.knn(q, 2)
+            oi, od = orc.knn(sp_o, rows, q, 2)
+            np.testing.assert_array_equal(idx, oi)
+            off, ridx = st.radius(q, float(np.sqrt(b[0] * b[0] + b[1] * b[1])))
+            ooff, oidx = orc.radius(sp_o, rows, q, float(np.sqrt(b[0] * b[0] + b[1] * b[1])))
+            np.testing.assert_array_equal(off, ooff)
+            np.testing.assert_array_equal(ridx, oidx)
+
+
+def test_radius_idx_limit_and_empty(oxg, orc):
+    d = 3
+    rows = uniform_states(5, 3000, [0.0] * d, [1.0] * d)
+    sp_o = orc.space(d)
+    with oxg.StateStore(oxg.Space.real_vector(d)) as st:
+        st.append(rows)
+        lim = np.arange(0, 3000, 7, dtype=np.uint32)
+        q = rows[lim]
+        off, ridx = st.radius(q, 0.2, idx_limit=lim)
+        ooff, oidx = orc.radius(sp_o, rows, q, 0.2, idx_limit=lim)
+        np.testing.assert_array_equal(off, ooff)
+        np.testing.assert_array_equal(ridx, oidx)
+        off, ridx = st.radius(q, 0.0)            # strict '<': nothing, not even self
+        assert off[-1] == 0 and ridx.size == 0
+        off, ridx = st.radius(q[:3], np.inf)
+        assert off[-1] == 3 * 3000
+
+
+def test_incremental_append_matches_tree_growth(oxg, orc):
+    """append one state at a time (tree.push) and query in between, as RRT does."""
+    d = 2
+    rows = uniform_states(11, 300, [-10.0] * d, [10.0] * d)
+    qs = uniform_states(12, 300, [-10.0] * d, [10.0] * d)
+    sp_o = orc.space(d)
+    with oxg.StateStore(oxg.Space.real_vector(d), capacity=4) as st:
+        for i in range(300):
+            assert st.append(rows[i]) == i
+            if i % 17 == 0 or i < 5:
+                idx, dist = st.nn1(qs[i])
+                oi, od = orc.nn1(sp_o, rows[: i + 1], qs[i])
+                assert idx[0] == oi[0] and dist[0] == od[0]
+        st.clear()
+        assert len(st) == 0
+        st.append(rows[:10])
+        idx, _ = st.nn1(qs[:5])
+        oi, _ = orc.nn1(sp_o, rows[:10], qs[:5])
+        np.testing.assert_array_equal(idx, oi)
+
+
+@pytest.mark.parametrize("space_kind", ["so2", "se2", "rv20"])
+def test_generic_spaces(oxg, orc, space_kind):
+    rng = np.random.default_rng(21)
+    if space_kind == "so2":
+        sp, sp_o = oxg.Space.so2(), orc.space(0, 1)
+        rows = rng.uniform(-4 * np.pi, 4 * np.pi, size=(777, 1))
+        qs = rng.uniform(-4 * np.pi, 4 * np.pi, size=(50, 1))
+        r = 0.3
+    elif space_kind == "se2":
+        sp, sp_o = oxg.Space.compound(2, 1, 1.0, 0.5), orc.space(2, 1, 1.0, 0.5)
+        rows = np.hstack([rng.uniform(0, 100, (1500, 2)), rng.uniform(-np.pi, np.pi, (1500, 1))])
+        qs = np.hstack([rng.uniform(0, 100, (60, 2)), rng.uniform(-np.pi, np.pi, (60, 1))])
+        r = 8.0
+    else:
+        sp, sp_o = oxg.Space.real_vector(20), orc.space(20)
+        rows = rng.random((900, 20))
+        qs = rng.random((40, 20))
+        r = 1.5
+    with oxg.StateStore(sp) as st:
+        st.append(rows)
+        idx, dist = st.nn1(qs)
+        oi, od = orc.nn1(sp_o, rows, qs)
+        np.testing.assert_array_equal(idx, oi)
+        np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+        idx, dist = st.knn(qs, 7)
+        oi, od = orc.knn(sp_o, rows, qs, 7)
+        np.testing.assert_array_equal(idx, oi)
+        np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+        off, ridx, rdist = st.radius(qs, r, want_dist=True)
+        ooff, oidx, odist = orc.radius(sp_o, rows, qs, r, want_dist=True)
+        np.testing.assert_array_equal(off, ooff)
+        np.testing.assert_array_equal(ridx, oidx)
+        np.testing.assert_array_equal(rdist.view(np.uint64), odist.view(np.uint64))
+
+
+def test_large_batch_two_queries_per_thread(oxg, orc):
+    """Q large enough to take the 2-queries-per-thread kernel; checked on a sample."""
+    d, n, Q = 7, 30000, 160000
+    rows = uniform_states(31, n, [0.0] * d, [1.0] * d)
+    qs = uniform_states(32, Q, [0.0] * d, [1.0] * d)
+    sp_o = orc.space(d)
+    with oxg.StateStore(oxg.Space.real_vector(d)) as st:
+        st.append(rows)
+        idx, dist = st.knn(qs, 10)
+        sel = np.r_[0:300, Q - 300:Q, 75000:75300]
+        oi, od = orc.knn(sp_o, rows, qs[sel], 10)
+        np.testing.assert_array_equal(idx[sel], oi)
+        np.testing.assert_array_equal(dist[sel].view(np.uint64), od.view(np.uint64))
+        # properties over the full batch: sorted by (dist, idx), no duplicates per row
+        assert np.all(np.diff(dist, axis=1) >= 0)
+        tie = np.diff(dist, axis=1) == 0
+        assert np.all(np.diff(idx.astype(np.int64), axis=1)[tie] > 0)
+
+
+def test_errors(oxg):
+    from oxmpl_b200 import OxgError
+
+    with oxg.StateStore(oxg.Space.real_vector(3)) as st:
+        with pytest.raises(OxgError) as e:
+            st.nn1(np.zeros((1, 3)))
+        assert e.value.code == -7  # OXG_E_EMPTY
+        st.append(np.zeros((4, 3)))
+        with pytest.raises(OxgError):
+            st.knn(np.zeros((1, 3)), 0)
+        with pytest.raises(OxgError):
+            st.knn(np.zeros((1, 3)), 1000)
+    with pytest.raises(OxgError) as e:
+        oxg.StateStore(oxg.Space(0, 0))
+    assert e.value.code == -2  # OXG_E_DIM

@@ -1,0 +1,128 @@
+"""GPU parity: is_valid / check_motion / check_edges through the C ABI vs the CPU oracle."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import uniform_states
+from oxmpl_b200 import worlds
+
+pytestmark = pytest.mark.gpu
+
+
+def _world_pair(oxg, orc, dim, spheres=None, aabbs=None, capsules=None, so2=()):
+    gw = oxg.World(dim, spheres=spheres, aabbs=aabbs, capsules=capsules, so2_intervals=so2)
+    ow, keep = orc.world(dim, spheres=spheres, aabbs=aabbs, capsules=capsules, so2_intervals=so2)
+    return gw, ow, keep
+
+
+def test_readme_circle_boundary_and_wall_fixture(oxg, orc):
+    """Operator strictness of the reference's own fixtures."""
+    sp, sp_o = oxg.Space.real_vector(2), orc.space(2)
+    # README circle: valid iff sqrt(x^2 + y^2) > 2.0 (README.md:147-150) — boundary invalid
+    gw, ow, keep = _world_pair(oxg, orc, 2, spheres=worlds.CONFIG1["spheres"])
+    pts = np.array([[2.0, 0.0], [np.nextafter(2.0, 3.0), 0.0], [np.nextafter(2.0, 0.0), 0.0],
+                    [0.0, -2.0], [1.2, 1.6], [3.0, 4.0], [0.0, 0.0], [-5.0, -5.0]])
+    got = gw.is_valid(sp, pts)
+    np.testing.assert_array_equal(got, orc.is_valid(ow, sp_o, pts))
+    np.testing.assert_array_equal(got, [0, 1, 0, 0, 0, 1, 0, 1])
+    gw.close()
+    # wall: invalid iff lo <= x <= hi on all faces, inclusive (oxmpl/tests/rrt_rvss_tests.rs:24-36)
+    gw, ow, keep = _world_pair(oxg, orc, 2, aabbs=worlds.WALL["aabbs"])
+    pts = np.array([[4.75, 2.0], [5.25, 8.0], [np.nextafter(4.75, 0.0), 5.0], [5.0, 5.0],
+                    [5.0, np.nextafter(8.0, 9.0)], [1.0, 5.0]])
+    got = gw.is_valid(sp, pts)
+    np.testing.assert_array_equal(got, orc.is_valid(ow, sp_o, pts))
+    np.testing.assert_array_equal(got, [0, 0, 1, 0, 1, 1])
+    gw.close()
+
+
+@pytest.mark.parametrize("dim", [2, 3, 6, 7, 14])
+def test_is_valid_and_motion_random_worlds(oxg, orc, dim):
+    lo, hi = [-1.0] * dim, [1.0] * dim
+    spheres, aabbs, capsules = worlds.calibrated_obstacles(dim, dim, 40, 25, 33)
+    sp, sp_o = oxg.Space.real_vector(dim), orc.space(dim)
+    gw, ow, keep = _world_pair(oxg, orc, dim, spheres, aabbs, capsules)
+    states = uniform_states(50 + dim, 20000, lo, hi)
+    np.testing.assert_array_equal(gw.is_valid(sp, states), orc.is_valid(ow, sp_o, states))
+    res = oxg.motion_resolution(oxg.real_vector_max_extent(list(zip(lo, hi))))
+    assert res == orc.resolution(orc.rv_max_extent(lo, hi))
+    frm = uniform_states(60 + dim, 6000, lo, hi)
+    rng = np.random.default_rng(70 + dim)
+    to = frm + rng.normal(scale=0.25, size=frm.shape) * rng.random((6000, 1))
+    to[:50] = frm[:50]                                  # zero-length: num_steps = 0 -> is_valid(to)
+    to[50:100] = frm[50:100] + 1e-4                     # one step
+    v, first = gw.check_motion(sp, frm, to, res, want_first_invalid=True)
+    ov, ofirst = orc.check_motion(ow, sp_o, frm, to, res)
+    np.testing.assert_array_equal(v, ov)
+    np.testing.assert_array_equal(first, ofirst)
+    assert 0 < v.sum() < v.size                          # the world is neither empty nor solid
+    # the few-edges launch shape (a warp per edge) must agree too
+    v2, f2 = gw.check_motion(sp, frm[:97], to[:97], res, want_first_invalid=True)
+    np.testing.assert_array_equal(v2, ov[:97])
+    np.testing.assert_array_equal(f2, ofirst[:97])
+    # index-pair form against a store
+    with oxg.StateStore(sp) as st:
+        st.append(np.vstack([frm[:3000], to[:3000]]))
+        fi = np.arange(3000, dtype=np.uint32)
+        ti = fi + 3000
+        np.testing.assert_array_equal(gw.check_edges(st, fi, ti, res), ov[:3000])
+    gw.close()
+
+
+def test_motion_direction_and_so2(oxg, orc):
+    """SO2 / compound spaces: argument order matters (SURVEY hard part 3)."""
+    rng = np.random.default_rng(5)
+    # pure SO2 with the forbidden-angle interval (oxmpl/tests/rrt_so2ss_tests.rs:17-27)
+    sp, sp_o = oxg.Space.so2(), orc.space(0, 1)
+    gw, ow, keep = _world_pair(oxg, orc, 0, so2=[worlds.SO2_FORBIDDEN["interval"]])
+    a = rng.uniform(-3 * math.pi, 3 * math.pi, (4000, 1))
+    b = rng.uniform(-3 * math.pi, 3 * math.pi, (4000, 1))
+    np.testing.assert_array_equal(gw.is_valid(sp, a), orc.is_valid(ow, sp_o, a))
+    res = (math.pi * 0.05) * 0.1                    # so2_state_space.rs:77-79,168-170; rrt.rs:97
+    for x, y in ((a, b), (b, a)):
+        v, f = gw.check_motion(sp, x, y, res, want_first_invalid=True)
+        ov, of = orc.check_motion(ow, sp_o, x, y, res)
+        np.testing.assert_array_equal(v, ov)
+        np.testing.assert_array_equal(f, of)
+    gw.close()
+    # SE2-style compound: AABBs over (x, y), angle free
+    sp, sp_o = oxg.Space.compound(2, 1, 1.0, 0.5), orc.space(2, 1, 1.0, 0.5)
+    boxes = worlds.aabb_world(9, [0, 0], [100, 100], 300, 1.0, 5.0)
+    gw, ow, keep = _world_pair(oxg, orc, 2, aabbs=boxes)
+    a = np.hstack([rng.uniform(0, 100, (5000, 2)), rng.uniform(-math.pi, math.pi, (5000, 1))])
+    b = a + np.hstack([rng.normal(scale=2.0, size=(5000, 2)), rng.normal(scale=1.0, size=(5000, 1))])
+    np.testing.assert_array_equal(gw.is_valid(sp, a), orc.is_valid(ow, sp_o, a))
+    for x, y in ((a, b), (b, a)):
+        v, f = gw.check_motion(sp, x, y, 0.7, want_first_invalid=True)
+        ov, of = orc.check_motion(ow, sp_o, x, y, 0.7)
+        np.testing.assert_array_equal(v, ov)
+        np.testing.assert_array_equal(f, of)
+    gw.close()
+
+
+def test_resolution_rejected(oxg):
+    from oxmpl_b200 import OxgError
+
+    sp = oxg.Space.real_vector(2)
+    with oxg.World(2, spheres=worlds.CONFIG1["spheres"]) as gw:
+        for bad in (0.0, -1.0, float("nan")):
+            with pytest.raises(OxgError) as e:
+                gw.check_motion(sp, [[0.0, 0.0]], [[1.0, 1.0]], bad)
+            assert e.value.code == -5  # OXG_E_RESOLUTION
+
+
+def test_config1_step_count(oxg, orc):
+    """Config-1 arithmetic: extent 28.28..., resolution 0.1414..., a 0.5-long edge has 4 steps
+    (SURVEY §8a row A6): an obstacle that only the 3rd interpolated state touches must be found
+    at step 3."""
+    sp, sp_o = oxg.Space.real_vector(2), orc.space(2)
+    res = oxg.motion_resolution(oxg.real_vector_max_extent([(-10.0, 10.0), (-10.0, 10.0)]))
+    assert res == 0.14142135623730953
+    frm, to = np.array([[3.0, 3.0]]), np.array([[3.5, 3.0]])
+    sph = np.array([[3.375, 3.0, 0.01]])
+    gw, ow, keep = _world_pair(oxg, orc, 2, spheres=sph)
+    v, f = gw.check_motion(sp, frm, to, res, want_first_invalid=True)
+    ov, of = orc.check_motion(ow, sp_o, frm, to, res)
+    assert (v[0], f[0]) == (0, 3) == (ov[0], of[0])
+    gw.close()
