@@ -450,10 +450,15 @@ static int launch_knn_rv(const ScanParams& p, dim3 grid, cudaStream_t st) {
 template <int D>
 static int launch_radius_rv(const ScanParams& p, dim3 grid, bool fill, cudaStream_t st) {
   size_t smem = sizeof(double) * NN_STAGES * D * NN_TILE + sizeof(uint64_t) * NN_STAGES;
-  if (fill)
+  if (fill) {
+    OXG_CUDA_TRY(cudaFuncSetAttribute(radius_rv_kernel<D, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     radius_rv_kernel<D, true><<<grid, NN_THREADS, smem, st>>>(p);
-  else
+  } else {
+    OXG_CUDA_TRY(cudaFuncSetAttribute(radius_rv_kernel<D, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     radius_rv_kernel<D, false><<<grid, NN_THREADS, smem, st>>>(p);
+  }
   OXG_LAUNCH_CHECK();
   return OXG_OK;
 }
