@@ -1,0 +1,74 @@
+"""The C-ABI library loads and exports every symbol include/oxg.h declares; without a CUDA
+device the compute entry points fail loudly (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "oxg.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(oxg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound():
+    from oxmpl_b200 import _lib
+
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    raw = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in oxg.h but not exported by liboxg.so"
+    # the Python binding covers the whole header, nothing more
+    assert sorted(_lib.SIGNATURES) == declared
+
+
+def test_version_and_error_channel():
+    from oxmpl_b200 import _lib
+
+    assert _lib.lib.oxg_version() == 100
+    n = C.c_int(-1)
+    code = _lib.lib.oxg_device_count(C.byref(n))
+    assert code in (0, _lib.OXG_E_CUDA)
+    assert _lib.lib.oxg_device_count(None) == _lib.OXG_E_NULL
+    assert b"NULL" in _lib.lib.oxg_last_error()
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU the product path must refuse to run, not fall back."""
+    import oxmpl_b200 as oxg
+
+    if oxg.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(oxg.OxgError) as e:
+        oxg.StateStore(oxg.Space.real_vector(3))
+    assert e.value.code == -4  # OXG_E_CUDA
+    with pytest.raises(oxg.OxgError):
+        oxg.World(2, spheres=np.array([[0.0, 0.0, 1.0]]))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "oxmpl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                # comments may cite the oracle's definition; code may not include, import,
+                # link, dlopen or call it
+                bad = re.search(r'#include\s*[<"][^>"]*oracle|liboxg_oracle|from oracle|'
+                                r'import oracle|\borc_[a-z0-9_]+\s*\(', text)
+                assert bad is None, f"{f} uses the oracle: {bad.group(0)}"
+
+
+def test_host_resolution_helpers_match_config1():
+    import oxmpl_b200 as oxg
+
+    ext = oxg.real_vector_max_extent([(-10.0, 10.0), (-10.0, 10.0)])
+    assert ext == 28.284271247461902
+    assert oxg.motion_resolution(ext) == 0.14142135623730953
+    assert oxg.real_vector_max_extent([(0.0, float("inf"))]) == 1.0
