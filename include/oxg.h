@@ -231,6 +231,10 @@ int oxg_store_stream(oxg_store s, void** out_stream);
  * oxg_kernel_launches: number of liboxg kernel launches since the counter was reset.
  */
 int oxg_fp64_peak(double* out_ops_per_s, double* out_ms);
+/* oxg_fp32_peak: FP32 pipe rate with the certified pre-filter's instruction mix (packed
+ * subtract + packed FMA, FADD2/FFMA2), in lane-instructions per second (an FMA counts once;
+ * the mix's flop rate is 1.5x this figure). */
+int oxg_fp32_peak(double* out_ops_per_s, double* out_ms);
 uint64_t oxg_kernel_launches(int reset);
 
 #ifdef __cplusplus

@@ -10,6 +10,7 @@ from .api import (  # noqa: F401
     StateStore,
     World,
     device_count,
+    fp32_peak,
     fp64_peak,
     kernel_launches,
     motion_resolution,

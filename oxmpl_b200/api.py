@@ -95,6 +95,14 @@ def fp64_peak():
     return ops.value, ms.value
 
 
+def fp32_peak():
+    """(FP32 lane-instructions per second of the pre-filter's FADD2+FFMA2 mix, kernel ms)."""
+    ops = C.c_double(0.0)
+    ms = C.c_double(0.0)
+    check(lib.oxg_fp32_peak(C.byref(ops), C.byref(ms)))
+    return ops.value, ms.value
+
+
 def kernel_launches(reset: bool = False) -> int:
     return int(lib.oxg_kernel_launches(1 if reset else 0))
 

@@ -62,16 +62,30 @@ double sqrt_lt_threshold(double r) {
   return x;
 }
 
-// Row-major [n][dim] -> SoA columns, appended at `first`.
+// Row-major [n][dim] -> SoA columns, appended at `first`.  Also maintains the f32 mirror used
+// by the certified pre-filter and the running max |coordinate| (as f64 bits; |x| >= +0 so the
+// bit patterns order like the values, and NaN sorts above +inf, which disables the filter).
 __global__ void scatter_rows_kernel(const double* __restrict__ rows, uint64_t n, uint32_t dim,
-                                    double* __restrict__ data, uint64_t pitch, uint64_t first) {
+                                    double* __restrict__ data, float* __restrict__ data32,
+                                    uint64_t pitch, uint64_t first,
+                                    unsigned long long* __restrict__ maxabs) {
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t total = n * dim;
+  unsigned long long m = 0ull;
   for (; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t i = t / dim;
     uint32_t d = (uint32_t)(t - i * dim);
-    data[(uint64_t)d * pitch + first + i] = rows[t];
+    double v = rows[t];
+    data[(uint64_t)d * pitch + first + i] = v;
+    data32[(uint64_t)d * pitch + first + i] = __double2float_rn(v);
+    unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v));
+    m = b > m ? b : m;
   }
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long x = __shfl_down_sync(0xFFFFFFFFu, m, o);
+    m = x > m ? x : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(maxabs, m);
 }
 
 __global__ void gather_rows_kernel(const double* __restrict__ data, uint64_t pitch, uint64_t first,
@@ -98,14 +112,29 @@ static int store_grow(oxg_store_s* s, uint64_t capacity) {
               cudaGetErrorString(e));
     return OXG_E_ALLOC;
   }
+  float* nd32 = nullptr;
+  e = cudaMalloc(&nd32, sizeof(float) * new_pitch * s->dim);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(nd);
+    set_error("cudaMalloc of %llu x %u f32 store mirror failed: %s", (unsigned long long)new_pitch,
+              s->dim, cudaGetErrorString(e));
+    return OXG_E_ALLOC;
+  }
   if (s->d_data && s->size > 0) {
-    for (uint32_t d = 0; d < s->dim; ++d)
+    for (uint32_t d = 0; d < s->dim; ++d) {
       OXG_CUDA_TRY(cudaMemcpyAsync(nd + (uint64_t)d * new_pitch, s->d_data + (uint64_t)d * s->pitch,
                                    sizeof(double) * s->size, cudaMemcpyDeviceToDevice, s->stream));
+      OXG_CUDA_TRY(cudaMemcpyAsync(nd32 + (uint64_t)d * new_pitch,
+                                   s->d_data32 + (uint64_t)d * s->pitch, sizeof(float) * s->size,
+                                   cudaMemcpyDeviceToDevice, s->stream));
+    }
     OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
   }
   if (s->d_data) cudaFree(s->d_data);
+  if (s->d_data32) cudaFree(s->d_data32);
   s->d_data = nd;
+  s->d_data32 = nd32;
   s->pitch = new_pitch;
   return OXG_OK;
 }
@@ -175,6 +204,13 @@ int oxg_store_create(const oxg_space_desc* space, uint64_t capacity, oxg_store* 
     delete s;
     return OXG_E_CUDA;
   }
+  if (cudaMalloc((void**)&s->d_maxabs, sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemsetAsync(s->d_maxabs, 0, sizeof(unsigned long long), s->stream) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("store allocation failed");
+    oxg_store_destroy(s);
+    return OXG_E_ALLOC;
+  }
   int r = store_grow(s, capacity);
   if (r != OXG_OK) {
     oxg_store_destroy(s);
@@ -189,6 +225,8 @@ int oxg_store_destroy(oxg_store s) {
   if (!s) return OXG_OK;
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->d_data) cudaFree(s->d_data);
+  if (s->d_data32) cudaFree(s->d_data32);
+  if (s->d_maxabs) cudaFree(s->d_maxabs);
   for (auto& b : s->buf) b.release();
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -204,6 +242,7 @@ int oxg_store_clear(oxg_store s) {
     return OXG_E_NULL;
   }
   s->size = 0;
+  OXG_CUDA_TRY(cudaMemsetAsync(s->d_maxabs, 0, sizeof(unsigned long long), s->stream));
   return OXG_OK;
 }
 
@@ -240,8 +279,9 @@ int oxg_store_append(oxg_store s, const double* rows, uint64_t n, uint64_t* firs
   uint64_t total = n * s->dim;
   int threads = 256;
   int blocks = (int)std::min<uint64_t>((total + threads - 1) / threads, 148 * 16);
-  scatter_rows_kernel<<<blocks, threads, 0, s->stream>>>(s->buf[B_STAGE].as<double>(), n, s->dim, s->d_data,
-                                                         s->pitch, s->size);
+  scatter_rows_kernel<<<blocks, threads, 0, s->stream>>>(s->buf[B_STAGE].as<double>(), n, s->dim,
+                                                         s->d_data, s->d_data32, s->pitch, s->size,
+                                                         s->d_maxabs);
   OXG_LAUNCH_CHECK();
   // the caller may reuse `rows` immediately
   OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));

@@ -129,6 +129,9 @@ struct oxg_store_s {
   int device = 0;
   cudaStream_t stream = nullptr;
   double* d_data = nullptr;  // SoA: coordinate d of state i at d_data[d * pitch + i]
+  float* d_data32 = nullptr; // the same states rounded to f32 (round-to-nearest), same layout:
+                             // input of the certified FP32 pre-filter, never of a result
+  unsigned long long* d_maxabs = nullptr;  // bits of max |coordinate| over the store (NaN sorts high)
   uint64_t pitch = 0;        // elements; multiple of 32 (256-byte aligned columns)
   uint64_t size = 0;
   oxg::DevBuf buf[oxg::B_COUNT];  // named scratch arenas, see enum StoreBuf

@@ -16,9 +16,20 @@
 // the rare survivors take the slow path: sqrt, then the lexicographic (distance, index) test.
 // d2 >= +0 always, so the filter is a signed 64-bit integer compare of the bit patterns
 // (NaN patterns compare above +inf or negative and are rejected in the slow path).
+//
+// Certified FP32 pre-filter (knn_rv_f32_kernel, radius_rv_f32_kernel).  3D FP64 operations per
+// pair at 64 lanes/clk/SM is the floor of the all-FP64 kernel, and all but ~1e-4 of the pairs
+// are rejected by a wide margin.  So each pair is first evaluated in FP32 from the store's f32
+// mirror (D packed subtracts + D packed FMAs, FADD2/FFMA2) and compared with a per-query
+// threshold T32 that dominates U by a rigorous bound on the FP32 evaluation error
+// (filter_threshold_dev).  A pair is discarded only if  a32 > T32, which PROVES d2 > U; every
+// other pair (including anything NaN/overflowed) is recomputed from the f64 store in the
+// reference's operation order and takes the exact path above.  Results are unchanged bit for
+// bit; only certain rejections get cheaper.
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "oxg_internal.cuh"
@@ -35,6 +46,8 @@ enum { EXCL_NONE = 0, EXCL_ARRAY = 1, EXCL_SELF = 2 };
 
 struct ScanParams {
   const double* db;   // SoA store
+  const float* db32;  // f32 mirror of the store (same pitch), filter input only
+  const unsigned long long* maxabs;  // bits of max |coordinate| over the store
   uint64_t pitch;
   uint32_t n_db;
   StateView q;        // queries
@@ -237,6 +250,281 @@ __global__ void __launch_bounds__(NN_THREADS) knn_rv_kernel(const ScanParams p) 
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Certified FP32 pre-filter
+// ---------------------------------------------------------------------------------------
+constexpr int F_TILE = 256;   // stored states per pipeline stage (f32 mirror)
+constexpr int F_STAGES = 3;
+
+// Threshold for the FP32 evaluation a32 = fl32-chain( sum_d fma(df_d, df_d, .) ), df_d =
+// fl32(fl32(q_d) - fl32(p_d)), such that   d2 <= U  (the exact FP64 admission test)  implies
+// a32 <= T32.   With u = 2^-24, M >= every |q_d|, |p_d|, t_d = q_d - p_d, S = sum t_d^2:
+//   * inputs: |fl32(x) - x| <= u|x| (+ 2^-150 when subnormal), so
+//     df_d = t_d + e_d with |e_d| <= 2uM(1+u) + u|t_d| (1+2u)  <=  a + 2u|t_d|,  a := 4uM + 1e-37
+//   * sum df_d^2 <= S(1 + 4u + 8u^2) + 2a sqrt(D S) + 2 D a^2          (Cauchy-Schwarz)
+//   * the FP32 FMA chain adds at most a factor (1+u)^D <= 1 + D 2^-22 and 2^-149 per step
+//   * the FP64 chain loses at most a factor (1 - (D+2) 2^-53):  S <= U (1 + 1e-12)
+// The constants below are deliberately generous (1e-5 relative); the filter's selectivity is
+// decided by U, which is thousands of times smaller than a typical d2.
+__device__ __forceinline__ float filter_threshold_dev(long long ubits, double M, int D) {
+  const float inf = __int_as_float(0x7F800000);
+  if (ubits < 0) return -1.0f;  // nothing is admitted; a32 >= 0 > -1 discards, NaN still passes
+  const double U = __longlong_as_double(ubits);
+  if (!(U < 1.0e300)) return inf;
+  const double a = M * 2.384185791015625e-07 + 1e-37;  // 2^-22 M
+  const double S = U * 1.00001;
+  double T = S + 2.0 * a * sqrt((double)D * S) + 2.0 * (double)D * a * a + 1e-35;
+  T = T * (1.0 + (double)D * 2.384185791015625e-07);
+  if (!(T == T)) return inf;
+  return __double2float_ru(T);  // rounds up; overflows to +inf
+}
+
+__device__ __forceinline__ float2 sub2(float q, float2 p) {  // (q - p.x, q - p.y): one FADD2
+  float2 qq = make_float2(q, q), r;
+  asm("sub.f32x2 %0, %1, %2;"
+      : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+      : "l"(*reinterpret_cast<unsigned long long*>(&qq)),
+        "l"(*reinterpret_cast<unsigned long long*>(&p)));
+  return r;
+}
+
+template <int D>
+__device__ __forceinline__ double exact_sumsq_global(const ScanParams& p, uint32_t qi, uint32_t j,
+                                                     double* maxq) {
+  double s = 0.0, mq = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double qd = p.q.p[(uint64_t)qi * p.q.stride_i + (uint64_t)d * p.q.stride_d];
+    const double pd = p.db[(uint64_t)d * p.pitch + j];
+    mq = fmax(mq, fabs(qd));  // fmax drops NaN; a NaN query is caught by the d2 == d2 test
+    const double df = __dsub_rn(qd, pd);
+    const double m = __dmul_rn(df, df);
+    s = (d == 0) ? m : __dadd_rn(s, m);
+  }
+  *maxq = mq;
+  return s;
+}
+
+// Upper bound of max{x : sqrt(x) <= sw} (sw >= 0): sqrt(x) <= sw after rounding implies
+// x < sw^2 (1 + 2^-53)^2, so fl_up(sw*sw) (1 + 2^-50) dominates it.  Tiny values (where sw*sw
+// is subnormal and the relative bound fails) take the exact routine.  Used only to gate the
+// exact (sqrt, index) comparison, so any upper bound is correct.
+__device__ __forceinline__ double sqrt_le_upper_dev(double sw) {
+  const double u = __dmul_ru(sw, sw);
+  if (!(u > 1.0e-290)) return sqrt_le_threshold_dev(sw);
+  return __dadd_ru(u, __dmul_ru(u, 8.8817841970012523e-16));  // 2^-50
+}
+
+constexpr int CAND_CAP = 16;  // deferred candidates per query (u32 indices, shared memory)
+
+// Exact path of the pairs the FP32 filter could not discard, run for all of a query's deferred
+// candidates at once (the whole warp drains together, so the lanes stay converged).  Each
+// candidate is recomputed from the f64 store in the reference's operation order and goes
+// through the exact (distance, index) comparison.  Returns the query's new FP32 threshold.
+template <int D>
+__device__ __noinline__ float knn_drain_f32(const ScanParams& p, uint32_t qi, uint32_t n_end,
+                                            uint32_t excl, const uint32_t* cand, int ncand,
+                                            int stride, double* sl, uint32_t* il, int* have_p,
+                                            long long* ubits_p, float t32) {
+  if (ncand == 0) return t32;
+  const int k = (int)p.k;
+  double q[D], mq = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    q[d] = p.q.p[(uint64_t)qi * p.q.stride_i + (uint64_t)d * p.q.stride_d];
+    mq = fmax(mq, fabs(q[d]));  // fmax drops NaN; a NaN query fails the d2 == d2 test below
+  }
+  int have = *have_p;
+  long long ub = *ubits_p;
+  bool changed = false;
+  for (int c = 0; c < ncand; ++c) {
+    const uint32_t j = cand[c * stride];
+    if (j >= n_end || j == excl) continue;
+    double d2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double df = __dsub_rn(q[d], p.db[(uint64_t)d * p.pitch + j]);
+      const double m = __dmul_rn(df, df);
+      d2 = (d == 0) ? m : __dadd_rn(d2, m);
+    }
+    if (!(__double_as_longlong(d2) <= ub) || !(d2 == d2)) continue;
+    if (list_insert(sl, il, stride, k, have, sqrt(d2), j)) {
+      changed = true;
+      if (have == k) ub = __double_as_longlong(sqrt_le_upper_dev(sl[(k - 1) * stride]));
+    }
+  }
+  if (changed) {
+    *have_p = have;
+    if (have == k) {
+      *ubits_p = ub;
+      const double ms = __longlong_as_double((long long)*p.maxabs);
+      const double M = (ms > mq || !(ms == ms)) ? ms : mq;
+      t32 = filter_threshold_dev(ub, M, D);
+    }
+  }
+  return t32;
+}
+
+// Issues the D bulk copies of one f32 tile (called by one thread).
+template <int D>
+__device__ __forceinline__ void issue_tile32(const ScanParams& p, float* stage, uint64_t* bar,
+                                             uint32_t base, uint32_t cnt) {
+  uint32_t cnt_pad = (cnt + 3u) & ~3u;  // 16-byte granules; pad elements are index-checked
+  uint32_t bytes = cnt_pad * 4u;
+  mbar_arrive_expect_tx(bar, bytes * D);
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+    bulk_copy_g2s(stage + d * F_TILE, p.db32 + (uint64_t)d * p.pitch + base, bytes, bar);
+}
+
+// k-NN (k = 1 is the planners' 1-NN) with the FP32 pre-filter.
+// grid = (ceil(Q / (NN_THREADS*QPT)), nsplit)
+template <int D, int QPT>
+__global__ void __launch_bounds__(NN_THREADS) knn_rv_f32_kernel(const ScanParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NQ = NN_THREADS * QPT;
+  float* tiles = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + F_STAGES * D * F_TILE);
+  double* s_list = reinterpret_cast<double*>(bars + F_STAGES);
+  long long* s_ubits = reinterpret_cast<long long*>(s_list + (size_t)p.k * NQ);
+  uint32_t* i_list = reinterpret_cast<uint32_t*>(s_ubits + NQ);
+  int* s_have = reinterpret_cast<int*>(i_list + (size_t)p.k * NQ);
+  uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_have + NQ);  // [CAND_CAP][NQ]
+
+  const int tid = threadIdx.x;
+  const int k = (int)p.k;
+  const float inf32 = __int_as_float(0x7F800000);
+  float qf[QPT][D];
+  float t32[QPT];
+  uint32_t qi[QPT], excl[QPT];
+  int ncand[QPT];
+#pragma unroll
+  for (int a = 0; a < QPT; ++a) {
+    qi[a] = blockIdx.x * NQ + a * NN_THREADS + tid;
+    const bool ok = qi[a] < p.Q;
+    const uint32_t qq = ok ? qi[a] : 0u;
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+      qf[a][d] = __double2float_rn(p.q.p[(uint64_t)qq * p.q.stride_i + (uint64_t)d * p.q.stride_d]);
+    excl[a] = OXG_INVALID_INDEX;
+    if (p.exclude_mode == EXCL_ARRAY) excl[a] = p.exclude[qq];
+    if (p.exclude_mode == EXCL_SELF) excl[a] = p.self_base + qq;
+    t32[a] = ok ? inf32 : -1.0f;
+    s_ubits[a * NN_THREADS + tid] = ok ? 0x7FF0000000000000ll : -1ll;
+    s_have[a * NN_THREADS + tid] = 0;
+    qi[a] = qq;
+    ncand[a] = 0;
+  }
+
+  const uint32_t n0 = blockIdx.y * p.split_len;
+  const uint32_t n1 = min(p.n_db, n0 + p.split_len);
+  const uint32_t ntiles = (n1 > n0) ? (n1 - n0 + F_TILE - 1) / F_TILE : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < F_STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (uint32_t t = 0; t < (uint32_t)(F_STAGES - 1) && t < ntiles; ++t) {
+      uint32_t base = n0 + t * F_TILE;
+      issue_tile32<D>(p, tiles + (t % F_STAGES) * D * F_TILE, &bars[t % F_STAGES], base,
+                      min((uint32_t)F_TILE, n1 - base));
+    }
+  }
+
+  for (uint32_t t = 0; t < ntiles; ++t) {
+    if (tid == 0) {
+      uint32_t tn = t + F_STAGES - 1;
+      if (tn < ntiles) {
+        uint32_t base = n0 + tn * F_TILE;
+        issue_tile32<D>(p, tiles + (tn % F_STAGES) * D * F_TILE, &bars[tn % F_STAGES], base,
+                        min((uint32_t)F_TILE, n1 - base));
+      }
+    }
+    mbar_wait(&bars[t % F_STAGES], (t / F_STAGES) & 1u);
+    const float* sp = tiles + (t % F_STAGES) * D * F_TILE;
+    const uint32_t base = n0 + t * F_TILE;
+    const int cnt = (int)min((uint32_t)F_TILE, n1 - base);
+#pragma unroll 1
+    for (int j = 0; j < cnt; j += 4) {
+      float4 pv[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) pv[d] = *reinterpret_cast<const float4*>(sp + d * F_TILE + j);
+      float2 acc[QPT][2];
+      bool any = false;
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float2 d01 = sub2(qf[a][d], make_float2(pv[d].x, pv[d].y));
+          const float2 d23 = sub2(qf[a][d], make_float2(pv[d].z, pv[d].w));
+          if (d == 0) {
+            acc[a][0] = __fmul2_rn(d01, d01);
+            acc[a][1] = __fmul2_rn(d23, d23);
+          } else {
+            acc[a][0] = __ffma2_rn(d01, d01, acc[a][0]);
+            acc[a][1] = __ffma2_rn(d23, d23, acc[a][1]);
+          }
+        }
+        any = any || !(acc[a][0].x > t32[a]) || !(acc[a][0].y > t32[a]) ||
+              !(acc[a][1].x > t32[a]) || !(acc[a][1].y > t32[a]);
+      }
+      if (any) {
+#pragma unroll
+        for (int a = 0; a < QPT; ++a) {
+          const float av[4] = {acc[a][0].x, acc[a][0].y, acc[a][1].x, acc[a][1].y};
+          const int li = a * NN_THREADS + tid;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (av[e] > t32[a]) continue;
+            if (ncand[a] == CAND_CAP) {  // buffer full: drain this query now
+              t32[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ,
+                                        s_list + li, i_list + li, &s_have[li], &s_ubits[li], t32[a]);
+              ncand[a] = 0;
+              if (av[e] > t32[a]) continue;
+            }
+            s_cand[li + ncand[a] * NQ] = base + j + e;
+            ++ncand[a];
+          }
+        }
+      }
+    }
+    // tile boundary: if any lane of the warp holds deferred candidates, the warp drains together
+    {
+      bool pend = false;
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) pend = pend || ncand[a] > 0;
+      if (__any_sync(0xFFFFFFFFu, pend)) {
+#pragma unroll
+        for (int a = 0; a < QPT; ++a) {
+          const int li = a * NN_THREADS + tid;
+          t32[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ, s_list + li,
+                                    i_list + li, &s_have[li], &s_ubits[li], t32[a]);
+          ncand[a] = 0;
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with this stage before it is refilled
+  }
+
+#pragma unroll
+  for (int a = 0; a < QPT; ++a) {
+    const uint32_t q_out = blockIdx.x * NQ + a * NN_THREADS + tid;
+    if (q_out >= p.Q) continue;
+    const int li = a * NN_THREADS + tid;
+    const int have = s_have[li];
+    uint64_t o = ((uint64_t)blockIdx.y * p.Q + q_out) * (uint64_t)k;
+    const double* sl = s_list + li;
+    const uint32_t* il = i_list + li;
+    for (int e = 0; e < k; ++e) {
+      bool f = e < have;
+      p.out_idx[o + e] = f ? il[e * NQ] : OXG_INVALID_INDEX;
+      p.out_dist[o + e] = f ? sl[e * NQ] : __longlong_as_double(0x7FF0000000000000ll);
+    }
+  }
+}
+
 // Merges the nsplit partial lists of each query (each ascending by (dist, idx)).
 __global__ void knn_merge_kernel(const uint32_t* __restrict__ part_idx,
                                  const double* __restrict__ part_dist, uint32_t Q, uint32_t k,
@@ -348,6 +636,138 @@ __global__ void __launch_bounds__(NN_THREADS) radius_rv_kernel(const ScanParams 
   if (!FILL && ok) p.counts[(uint64_t)qi * p.nsplit + blockIdx.y] = count;
 }
 
+// Radius scan with the FP32 pre-filter; same two-pass scheme as radius_rv_kernel.  The radius
+// threshold is fixed, so T32 is computed once per query.  QPT queries per thread.
+template <int D, bool FILL, int QPT>
+__global__ void __launch_bounds__(NN_THREADS) radius_rv_f32_kernel(const ScanParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NQ = NN_THREADS * QPT;
+  float* tiles = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + F_STAGES * D * F_TILE);
+  __shared__ uint32_t s_maxlim;
+
+  const int tid = threadIdx.x;
+  float qf[QPT][D];
+  float t32[QPT];
+  uint32_t qi[QPT], lim[QPT], count[QPT];
+  uint64_t cursor[QPT];
+  uint32_t maxlim = 0;
+  const double ms = __longlong_as_double((long long)*p.maxabs);
+#pragma unroll
+  for (int a = 0; a < QPT; ++a) {
+    qi[a] = blockIdx.x * NQ + a * NN_THREADS + tid;
+    const bool ok = qi[a] < p.Q;
+    const uint32_t qq = ok ? qi[a] : 0u;
+    double mq = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double v = p.q.p[(uint64_t)qq * p.q.stride_i + (uint64_t)d * p.q.stride_d];
+      mq = fmax(mq, fabs(v));
+      qf[a][d] = __double2float_rn(v);
+    }
+    lim[a] = p.n_db;
+    if (p.idx_limit) lim[a] = min(lim[a], p.idx_limit[qq]);
+    if (p.limit_self) lim[a] = min(lim[a], p.self_base + qq);
+    if (!ok) lim[a] = 0;
+    maxlim = max(maxlim, lim[a]);
+    const double M = (ms > mq || !(ms == ms)) ? ms : mq;
+    t32[a] = ok ? filter_threshold_dev(p.r_bits, M, D) : -1.0f;
+    cursor[a] = 0;
+    if (FILL && ok) cursor[a] = p.counts[(uint64_t)qi[a] * p.nsplit + blockIdx.y];
+    count[a] = 0;
+    qi[a] = qq;
+  }
+
+  if (tid == 0) s_maxlim = 0;
+  __syncthreads();
+  atomicMax(&s_maxlim, maxlim);
+  if (tid == 0) {
+    for (int s = 0; s < F_STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const uint32_t n0 = blockIdx.y * p.split_len;
+  const uint32_t n1 = min(min(p.n_db, s_maxlim), n0 + p.split_len);
+  const uint32_t ntiles = (n1 > n0) ? (n1 - n0 + F_TILE - 1) / F_TILE : 0;
+
+  if (tid == 0) {
+    for (uint32_t t = 0; t < (uint32_t)(F_STAGES - 1) && t < ntiles; ++t) {
+      uint32_t base = n0 + t * F_TILE;
+      issue_tile32<D>(p, tiles + (t % F_STAGES) * D * F_TILE, &bars[t % F_STAGES], base,
+                      min((uint32_t)F_TILE, n1 - base));
+    }
+  }
+  for (uint32_t t = 0; t < ntiles; ++t) {
+    if (tid == 0) {
+      uint32_t tn = t + F_STAGES - 1;
+      if (tn < ntiles) {
+        uint32_t base = n0 + tn * F_TILE;
+        issue_tile32<D>(p, tiles + (tn % F_STAGES) * D * F_TILE, &bars[tn % F_STAGES], base,
+                        min((uint32_t)F_TILE, n1 - base));
+      }
+    }
+    mbar_wait(&bars[t % F_STAGES], (t / F_STAGES) & 1u);
+    const float* sp = tiles + (t % F_STAGES) * D * F_TILE;
+    const uint32_t base = n0 + t * F_TILE;
+    const int cnt = (int)min((uint32_t)F_TILE, n1 - base);
+#pragma unroll 1
+    for (int j = 0; j < cnt; j += 4) {
+      float4 pv[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) pv[d] = *reinterpret_cast<const float4*>(sp + d * F_TILE + j);
+      float2 acc[QPT][2];
+      bool any = false;
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float2 d01 = sub2(qf[a][d], make_float2(pv[d].x, pv[d].y));
+          const float2 d23 = sub2(qf[a][d], make_float2(pv[d].z, pv[d].w));
+          if (d == 0) {
+            acc[a][0] = __fmul2_rn(d01, d01);
+            acc[a][1] = __fmul2_rn(d23, d23);
+          } else {
+            acc[a][0] = __ffma2_rn(d01, d01, acc[a][0]);
+            acc[a][1] = __ffma2_rn(d23, d23, acc[a][1]);
+          }
+        }
+        any = any || !(acc[a][0].x > t32[a]) || !(acc[a][0].y > t32[a]) ||
+              !(acc[a][1].x > t32[a]) || !(acc[a][1].y > t32[a]);
+      }
+      if (any) {
+#pragma unroll
+        for (int a = 0; a < QPT; ++a) {
+          const float av[4] = {acc[a][0].x, acc[a][0].y, acc[a][1].x, acc[a][1].y};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (av[e] > t32[a]) continue;
+            const uint32_t jj = base + j + e;
+            if (jj >= n1 || jj >= lim[a]) continue;
+            double mq;
+            const double s = exact_sumsq_global<D>(p, qi[a], jj, &mq);
+            if (__double_as_longlong(s) <= p.r_bits && s == s) {
+              if (FILL) {
+                p.hit_idx[cursor[a] + count[a]] = jj;
+                if (p.hit_dist) p.hit_dist[cursor[a] + count[a]] = sqrt(s);
+              }
+              ++count[a];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (!FILL) {
+#pragma unroll
+    for (int a = 0; a < QPT; ++a) {
+      const uint32_t q_out = blockIdx.x * NQ + a * NN_THREADS + tid;
+      if (q_out < p.Q) p.counts[(uint64_t)q_out * p.nsplit + blockIdx.y] = count[a];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Generic spaces (SO2, compound R^n x SO2, or RealVector with D > 16): runtime dimensions,
 // full distance per pair in the reference's order, stored states read through the L1/L2 as
@@ -447,6 +867,56 @@ static int launch_knn_rv(const ScanParams& p, dim3 grid, cudaStream_t st) {
   return OXG_OK;
 }
 
+template <int D, int QPT>
+static size_t knn_f32_smem_bytes(uint32_t k) {
+  return sizeof(float) * F_STAGES * D * F_TILE + sizeof(uint64_t) * F_STAGES +
+         (size_t)NN_THREADS * QPT * ((size_t)k * (sizeof(double) + sizeof(uint32_t)) +
+                                     sizeof(long long) + sizeof(int) + CAND_CAP * sizeof(uint32_t));
+}
+
+template <int D, int QPT>
+static int launch_knn_rv_f32(const ScanParams& p, dim3 grid, cudaStream_t st) {
+  size_t smem = knn_f32_smem_bytes<D, QPT>(p.k);
+  OXG_CUDA_TRY(cudaFuncSetAttribute(knn_rv_f32_kernel<D, QPT>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  knn_rv_f32_kernel<D, QPT><<<grid, NN_THREADS, smem, st>>>(p);
+  OXG_LAUNCH_CHECK();
+  return OXG_OK;
+}
+
+// Tuning / A-B switches read once from the environment (measurement aids, not a fallback:
+// both settings run hand-written sm_100a kernels and give bit-identical results).
+//   OXG_KNN_FILTER=0  use the all-FP64 scan kernels (no FP32 pre-filter)
+//   OXG_KNN_QPT=1|2   force the queries-per-thread of the batched k-NN kernel
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+static bool use_f32_filter() {
+  static const bool on = env_int("OXG_KNN_FILTER", 1) != 0;
+  return on;
+}
+static int forced_qpt() {
+  static const int q = env_int("OXG_KNN_QPT", 0);
+  return q;
+}
+
+template <int D, int QPT>
+static int launch_radius_rv_f32(const ScanParams& p, dim3 grid, bool fill, cudaStream_t st) {
+  size_t smem = sizeof(float) * F_STAGES * D * F_TILE + sizeof(uint64_t) * F_STAGES;
+  if (fill) {
+    OXG_CUDA_TRY(cudaFuncSetAttribute(radius_rv_f32_kernel<D, true, QPT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    radius_rv_f32_kernel<D, true, QPT><<<grid, NN_THREADS, smem, st>>>(p);
+  } else {
+    OXG_CUDA_TRY(cudaFuncSetAttribute(radius_rv_f32_kernel<D, false, QPT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    radius_rv_f32_kernel<D, false, QPT><<<grid, NN_THREADS, smem, st>>>(p);
+  }
+  OXG_LAUNCH_CHECK();
+  return OXG_OK;
+}
+
 template <int D>
 static int launch_radius_rv(const ScanParams& p, dim3 grid, bool fill, cudaStream_t st) {
   size_t smem = sizeof(double) * NN_STAGES * D * NN_TILE + sizeof(uint64_t) * NN_STAGES;
@@ -488,14 +958,15 @@ static uint32_t round_up_u32(uint32_t v, uint32_t m) { return (v + m - 1) / m * 
 
 // Chooses how many slices of the store each query tile is split into, so that small query
 // batches still fill the GPU.
-static void choose_split(uint32_t n_db, uint64_t qtiles, uint32_t* nsplit, uint32_t* split_len) {
+static void choose_split(uint32_t n_db, uint64_t qtiles, uint32_t tile, uint32_t* nsplit,
+                         uint32_t* split_len) {
   const uint64_t target_ctas = 148ull * 6;
   uint64_t want = (target_ctas + qtiles - 1) / qtiles;
-  uint64_t max_split = std::max<uint64_t>(1, n_db / (NN_TILE * 4));
+  uint64_t max_split = std::max<uint64_t>(1, n_db / (tile * 4));
   uint64_t ns = std::min<uint64_t>(std::min<uint64_t>(want, max_split), 2048);
   if (ns < 1) ns = 1;
-  uint32_t len = round_up_u32((uint32_t)((n_db + ns - 1) / ns), NN_TILE);
-  if (len == 0) len = NN_TILE;
+  uint32_t len = round_up_u32((uint32_t)((n_db + ns - 1) / ns), tile);
+  if (len == 0) len = tile;
   *split_len = len;
   *nsplit = std::max<uint32_t>(1, (n_db + len - 1) / len);
 }
@@ -529,12 +1000,20 @@ int nn_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclu
   p.exclude = d_exclude;
   p.self_base = (uint32_t)self_base;
 
+  p.db32 = s->d_data32;
+  p.maxabs = s->d_maxabs;
   const bool fast = is_pure_rv(s->space) && s->dim <= (uint32_t)kMaxFastDim;
-  // two queries per thread once there is enough work to fill the machine that way
-  const bool qpt2 = fast && Q >= 2ull * 148 * NN_THREADS * 2 && k <= 32;
-  const uint32_t nq_per_cta = NN_THREADS * (qpt2 ? 2 : 1);
+  const bool f32 = fast && use_f32_filter();
+  // several queries per thread once there is enough work to fill the machine that way
+  int qpt = 1;
+  if (fast && Q >= 2ull * 148 * NN_THREADS * 2 && k <= 32) qpt = 2;
+  if (fast && forced_qpt() > 0) {
+    qpt = forced_qpt() >= 2 ? 2 : 1;
+    if (qpt == 2 && k > 32) qpt = 1;
+  }
+  const uint32_t nq_per_cta = NN_THREADS * qpt;
   const uint64_t qtiles = (Q + nq_per_cta - 1) / nq_per_cta;
-  choose_split(p.n_db, qtiles, &p.nsplit, &p.split_len);
+  choose_split(p.n_db, qtiles, f32 ? F_TILE : NN_TILE, &p.nsplit, &p.split_len);
 
   uint32_t* part_idx = d_idx;
   double* part_dist = d_dist;
@@ -549,9 +1028,17 @@ int nn_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclu
   p.out_dist = part_dist;
   dim3 grid((unsigned)qtiles, p.nsplit);
 
-  if (fast) {
+  if (f32) {
     int r = OXG_E_INTERNAL;
-    if (qpt2) {
+    if (qpt == 2) {
+      OXG_DISPATCH_D(s->dim, r = (launch_knn_rv_f32<DD, 2>(p, grid, s->stream)));
+    } else {
+      OXG_DISPATCH_D(s->dim, r = (launch_knn_rv_f32<DD, 1>(p, grid, s->stream)));
+    }
+    OXG_TRY(r);
+  } else if (fast) {
+    int r = OXG_E_INTERNAL;
+    if (qpt == 2) {
       OXG_DISPATCH_D(s->dim, r = (launch_knn_rv<DD, 2>(p, grid, s->stream)));
     } else {
       OXG_DISPATCH_D(s->dim, r = (launch_knn_rv<DD, 1>(p, grid, s->stream)));
@@ -584,6 +1071,24 @@ int nn_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclu
   return OXG_OK;
 }
 
+struct RadiusPlan {
+  bool fast, f32;
+  int qpt;
+  uint32_t nsplit, split_len;
+  uint64_t qtiles;
+};
+static RadiusPlan radius_plan(const oxg_store_s* s, uint64_t Q) {
+  RadiusPlan pl;
+  pl.fast = is_pure_rv(s->space) && s->dim <= (uint32_t)kMaxFastDim;
+  pl.f32 = pl.fast && use_f32_filter();
+  pl.qpt = (pl.f32 && Q >= 2ull * 148 * NN_THREADS * 2) ? 2 : 1;
+  const uint64_t per_cta = (uint64_t)NN_THREADS * pl.qpt;
+  pl.qtiles = std::max<uint64_t>((Q + per_cta - 1) / per_cta, 1);
+  choose_split(std::max<uint32_t>((uint32_t)s->size, 1), pl.qtiles, pl.f32 ? F_TILE : NN_TILE,
+               &pl.nsplit, &pl.split_len);
+  return pl;
+}
+
 // Radius scan of Q device-resident queries; results left in the store's scratch arenas:
 //   per-(query, slice) exclusive offsets in B_OFFSETS, idx in B_PIDX, dist in B_PDIST.
 // *total receives offsets[Q].  Synchronises the stream (the total is needed on the host).
@@ -597,6 +1102,8 @@ int nn_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double r, const ui
   ScanParams p;
   memset(&p, 0, sizeof(p));
   p.db = s->d_data;
+  p.db32 = s->d_data32;
+  p.maxabs = s->d_maxabs;
   p.pitch = s->pitch;
   p.n_db = (uint32_t)s->size;
   p.q = q;
@@ -612,8 +1119,9 @@ int nn_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double r, const ui
   } else {
     memcpy(&p.r_bits, &thr, sizeof(double));
   }
-  const uint64_t qtiles = (Q + NN_THREADS - 1) / NN_THREADS;
-  choose_split(std::max<uint32_t>(p.n_db, 1), std::max<uint64_t>(qtiles, 1), &p.nsplit, &p.split_len);
+  const RadiusPlan pl = radius_plan(s, Q);
+  p.nsplit = pl.nsplit;
+  p.split_len = pl.split_len;
 
   size_t ncounts = (size_t)Q * p.nsplit + 1;
   OXG_TRY(s->buf[B_OFFSETS].ensure(ncounts * sizeof(uint64_t)));
@@ -627,8 +1135,7 @@ int nn_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double r, const ui
     return OXG_OK;
   }
   p.counts = counts;
-  dim3 grid((unsigned)qtiles, p.nsplit);
-  const bool fast = is_pure_rv(s->space) && s->dim <= (uint32_t)kMaxFastDim;
+  dim3 grid((unsigned)pl.qtiles, p.nsplit);
   GenericParams g;
   g.n_real = s->space.n_real;
   g.n_so2 = s->space.n_so2;
@@ -636,15 +1143,30 @@ int nn_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double r, const ui
   g.w_so2 = s->space.w_so2;
   g.stored_first = 0;
   g.radius = r;
-  if (fast) {
-    int rr = OXG_E_INTERNAL;
-    OXG_DISPATCH_D(s->dim, rr = (launch_radius_rv<DD>(p, grid, false, s->stream)));
-    OXG_TRY(rr);
-  } else {
+  auto launch = [&](bool fill) -> int {
+    if (pl.f32) {
+      int rr = OXG_E_INTERNAL;
+      if (pl.qpt == 2) {
+        OXG_DISPATCH_D(s->dim, rr = (launch_radius_rv_f32<DD, 2>(p, grid, fill, s->stream)));
+      } else {
+        OXG_DISPATCH_D(s->dim, rr = (launch_radius_rv_f32<DD, 1>(p, grid, fill, s->stream)));
+      }
+      return rr;
+    }
+    if (pl.fast) {
+      int rr = OXG_E_INTERNAL;
+      OXG_DISPATCH_D(s->dim, rr = (launch_radius_rv<DD>(p, grid, fill, s->stream)));
+      return rr;
+    }
     g.s = p;
-    scan_generic_kernel<1><<<grid, NN_THREADS, 0, s->stream>>>(g);
+    if (fill)
+      scan_generic_kernel<2><<<grid, NN_THREADS, 0, s->stream>>>(g);
+    else
+      scan_generic_kernel<1><<<grid, NN_THREADS, 0, s->stream>>>(g);
     OXG_LAUNCH_CHECK();
-  }
+    return OXG_OK;
+  };
+  OXG_TRY(launch(false));
   // exclusive scan of the (query-major, slice-minor) counts; the trailing zero makes
   // offsets[Q*nsplit] the total.
   size_t tmp_bytes = 0;
@@ -665,15 +1187,7 @@ int nn_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double r, const ui
   p.counts = offsets;
   p.hit_idx = s->buf[B_PIDX].as<uint32_t>();
   p.hit_dist = want_dist ? s->buf[B_PDIST].as<double>() : nullptr;
-  if (fast) {
-    int rr = OXG_E_INTERNAL;
-    OXG_DISPATCH_D(s->dim, rr = (launch_radius_rv<DD>(p, grid, true, s->stream)));
-    OXG_TRY(rr);
-  } else {
-    g.s = p;
-    scan_generic_kernel<2><<<grid, NN_THREADS, 0, s->stream>>>(g);
-    OXG_LAUNCH_CHECK();
-  }
+  OXG_TRY(launch(true));
   return OXG_OK;
 }
 
@@ -684,13 +1198,7 @@ __global__ void pick_offsets_kernel(const uint64_t* __restrict__ scanned, uint64
   if (q <= Q) out[q] = scanned[q * nsplit];
 }
 
-int nn_radius_nsplit(const oxg_store_s* s, uint64_t Q) {
-  uint32_t nsplit, split_len;
-  const uint64_t qtiles = (Q + NN_THREADS - 1) / NN_THREADS;
-  choose_split(std::max<uint32_t>((uint32_t)s->size, 1), std::max<uint64_t>(qtiles, 1), &nsplit,
-               &split_len);
-  return (int)nsplit;
-}
+int nn_radius_nsplit(const oxg_store_s* s, uint64_t Q) { return (int)radius_plan(s, Q).nsplit; }
 
 // Compacts B_OFFSETS (per-slice offsets) into per-query CSR offsets in `d_out` (Q+1 entries).
 int nn_radius_offsets(oxg_store_s* s, uint64_t Q, uint64_t* d_out) {

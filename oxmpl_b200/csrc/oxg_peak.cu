@@ -27,9 +27,66 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* __restrict__ out
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// FP32 pipe rate with the pre-filter's instruction mix: one packed subtract (FADD2) and one
+// packed FMA (FFMA2) per pair of lanes, independent chains.
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float2* __restrict__ out, float a, float b,
+                                                        int iters) {
+  float2 x[PEAK_CHAINS];
+#pragma unroll
+  for (int c = 0; c < PEAK_CHAINS; ++c)
+    x[c] = make_float2(a * (float)(threadIdx.x + c + 1), a * (float)(threadIdx.x + c + 2));
+  const float2 bb = make_float2(b, b), aa = make_float2(a, a);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < PEAK_CHAINS; ++c) {
+      float2 d = __fadd2_rn(x[c], aa);
+      x[c] = __ffma2_rn(d, bb, x[c]);
+    }
+  }
+  float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < PEAK_CHAINS; ++c) s = __fadd2_rn(s, x[c]);
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace oxg
 
 using namespace oxg;
+
+// Lane-instructions per second of the FADD2+FFMA2 mix (a packed instruction counts as two
+// lane-instructions; an FMA counts once).  Flop rate of the mix = 1.5 x this figure.
+extern "C" int oxg_fp32_peak(double* out_ops_per_s, double* out_ms) {
+  OXG_API_BEGIN
+  if (!out_ops_per_s) {
+    set_error("out_ops_per_s is NULL");
+    return OXG_E_NULL;
+  }
+  const int blocks = 148 * 8, threads = 256, iters = 16384;
+  float2* d_out = nullptr;
+  OXG_CUDA_TRY(cudaMalloc((void**)&d_out, sizeof(float2) * blocks * threads));
+  cudaEvent_t e0, e1;
+  OXG_CUDA_TRY(cudaEventCreate(&e0));
+  OXG_CUDA_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    OXG_CUDA_TRY(cudaEventRecord(e0, 0));
+    fp32_peak_kernel<<<blocks, threads>>>(d_out, 1e-9f, 1.0000001f, iters);
+    OXG_LAUNCH_CHECK();
+    OXG_CUDA_TRY(cudaEventRecord(e1, 0));
+    OXG_CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    OXG_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  const double ops = (double)blocks * threads * (double)iters * PEAK_CHAINS * 2.0 * 2.0;
+  *out_ops_per_s = ops / (best * 1e-3);
+  if (out_ms) *out_ms = best;
+  return OXG_OK;
+  OXG_API_END
+}
 
 extern "C" int oxg_fp64_peak(double* out_ops_per_s, double* out_ms) {
   OXG_API_BEGIN

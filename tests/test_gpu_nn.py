@@ -217,3 +217,69 @@ def test_errors(oxg):
     with pytest.raises(OxgError) as e:
         oxg.StateStore(oxg.Space(0, 0))
     assert e.value.code == -2  # OXG_E_DIM
+
+
+def _scaled_sets(d):
+    """Inputs that stress the certified FP32 pre-filter: it must never change a result, only
+    skip certain rejections (csrc/oxg_nn.cu, filter_threshold_dev)."""
+    rng = np.random.default_rng(77 + d)
+    u = rng.random((3000, d))
+    q = rng.random((64, d))
+    mixed = np.array([10.0 ** rng.integers(-6, 7) for _ in range(d)])
+    return {
+        "offset_1e7": (1.0e7 + u, 1.0e7 + q, 0.4),          # all f32 images collide
+        "offset_1e15": (1.0e15 + 64.0 * u, 1.0e15 + 64.0 * q, 30.0),
+        "tiny_1e-30": (1e-30 * u, 1e-30 * q, 0.3e-30),
+        "f32_subnormal_1e-42": (1e-42 * u, 1e-42 * q, 0.3e-42),
+        "huge_1e200": (1e200 * u, 1e200 * q, 0.3e200),        # f32 overflow -> inf / NaN
+        "f64_near_overflow_1e153": (1e153 * u, 1e153 * q, 0.3e153),
+        "mixed_scales": (u * mixed, q * mixed, 0.3 * float(np.linalg.norm(mixed))),
+        "negative_box": (-5.0 + 10.0 * u, -5.0 + 10.0 * q, 2.5),
+    }
+
+
+@pytest.mark.parametrize("d", [2, 7])
+def test_fp32_prefilter_never_changes_results(oxg, orc, d):
+    sp_o = orc.space(d)
+    for name, (rows, queries, r) in _scaled_sets(d).items():
+        rows = np.ascontiguousarray(rows)
+        queries = np.ascontiguousarray(queries)
+        with oxg.StateStore(oxg.Space.real_vector(d)) as st:
+            st.append(rows)
+            idx, dist = st.nn1(queries)
+            oi, od = orc.nn1(sp_o, rows, queries)
+            np.testing.assert_array_equal(idx, oi, err_msg=name)
+            np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64), err_msg=name)
+            idx, dist = st.knn(queries, 5)
+            oi, od = orc.knn(sp_o, rows, queries, 5)
+            np.testing.assert_array_equal(idx, oi, err_msg=name)
+            np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64), err_msg=name)
+            off, ridx, rdist = st.radius(queries, r, want_dist=True)
+            ooff, oidx, odist = orc.radius(sp_o, rows, queries, r, want_dist=True)
+            np.testing.assert_array_equal(off, ooff, err_msg=name)
+            np.testing.assert_array_equal(ridx, oidx, err_msg=name)
+            np.testing.assert_array_equal(rdist.view(np.uint64), odist.view(np.uint64),
+                                          err_msg=name)
+
+
+def test_store_clear_resets_filter_scale(oxg, orc):
+    """max |coordinate| is tracked per store for the filter bound; clear() must reset it and a
+    later append of huge values must widen it again."""
+    d = 3
+    sp_o = orc.space(d)
+    small = uniform_states(1, 500, [0.0] * d, [1.0] * d)
+    huge = 1e12 + 1e3 * uniform_states(2, 500, [0.0] * d, [1.0] * d)
+    q = uniform_states(3, 40, [0.0] * d, [1.0] * d)
+    with oxg.StateStore(oxg.Space.real_vector(d)) as st:
+        st.append(huge)
+        st.clear()
+        st.append(small)
+        idx, dist = st.knn(q, 3)
+        oi, od = orc.knn(sp_o, small, q, 3)
+        np.testing.assert_array_equal(idx, oi)
+        st.append(huge)
+        both = np.vstack([small, huge])
+        idx, dist = st.knn(np.vstack([q, huge[:10]]), 3)
+        oi, od = orc.knn(sp_o, both, np.vstack([q, huge[:10]]), 3)
+        np.testing.assert_array_equal(idx, oi)
+        np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
