@@ -202,6 +202,64 @@ int oxg_prm_build_knn(oxg_world w, oxg_store s, uint32_t k, double resolution,
                       uint64_t row_begin, uint64_t row_end, uint32_t* idx, double* dist,
                       uint8_t* valid, oxg_prm_stats* stats);
 
+/* ---- fused sequential planners ---------------------------------------------------------
+ * The bodies of RRT::solve (rrt.rs:158-227), RRTConnect::solve (rrt_connect.rs:227-309 with
+ * extend :121-159) and RRTStar::solve (rrt_star.rs:171-290) as ONE persistent kernel each:
+ * 1-NN scan, steering (rrt.rs:200-208), check_motion, append, goal test and — for RRT* —
+ * find_neighbours, choose-parent and rewire run on the device for a whole sample stream, so a
+ * planner pays one launch per solve instead of several launches and a D2H sync per iteration.
+ *
+ *  - `tree` must hold the start state at index 0 (what Planner::setup pushes, rrt.rs:147-155);
+ *    RRT-Connect's goal tree must hold the goal state (rrt_connect.rs:201-216).  On return the
+ *    stores hold the grown trees (oxg_store_read); parents[i] is Node::parent_index (-1 = None),
+ *    costs[i] is Node::cost (RRT*).  Calling again on the same stores continues the same trees.
+ *  - `samples` is the pre-drawn stream of q_rand (row-major, n_samples x dim): the reference
+ *    draws `random_bool(goal_bias) ? goal.sample_goal : space.sample_uniform` once per iteration
+ *    independently of the tree (rrt.rs:177-184), so the caller draws the same sequence up front.
+ *  - The goal is the ball `distance(state, goal_target) <= goal_radius`
+ *    (CircularGoalRegion::is_satisfied, oxmpl/tests/rrt_rvss_tests.rs:46-50); goal_target NULL or
+ *    goal_radius < 0 disables the goal test.
+ *  - The reference loops until a wall-clock timeout; here a solve ends when it is solved, the
+ *    stream is consumed, a tree holds max_nodes states, or timeout_s (if > 0) elapses.
+ * status: 0 solved, 1 stream exhausted, 2 tree full, 3 timeout (PlanningError::Timeout).
+ */
+typedef struct oxg_plan_params {
+  double max_distance;  /* RRT::new(max_distance, ..) rrt.rs:75, rrt_connect.rs:86, rrt_star.rs:65 */
+  double search_radius; /* RRTStar::new(.., .., search_radius); ignored by RRT / RRT-Connect        */
+  double resolution;    /* space.get_longest_valid_segment_length() * 0.1 (rrt.rs:97)                */
+  double goal_radius;
+  double timeout_s;
+  uint64_t max_nodes;   /* capacity of each tree                                                     */
+  int32_t stop_at_goal; /* RRT*: 0 = keep optimising after the goal is first reached                 */
+  int32_t reserved;
+} oxg_plan_params;
+
+typedef struct oxg_plan_result {
+  uint64_t n_nodes[2];             /* tree sizes ([1]: RRT-Connect's goal tree)                      */
+  uint64_t iters;                  /* samples consumed                                               */
+  uint64_t motion_checks;          /* check_motion calls the sequential reference makes              */
+  uint64_t motion_checks_executed; /* evaluated here (RRT* checks a superset in parallel)            */
+  int64_t goal_node[2];            /* RRT / RRT*: node that satisfied the goal; RRT-Connect: the
+                                      joined nodes (start tree, goal tree), [1] = -1 when the start
+                                      tree reached the goal itself (rrt_connect.rs:271-274)          */
+  int32_t solved;
+  int32_t status;
+  double device_ms;
+  int32_t ctas;                    /* CTAs of the persistent grid                                    */
+  int32_t reserved;
+} oxg_plan_result;
+
+int oxg_rrt_solve(oxg_world w, oxg_store tree, const oxg_plan_params* params,
+                  const double* goal_target, const double* samples, uint64_t n_samples,
+                  int64_t* parents /* nullable, max_nodes entries */, oxg_plan_result* out);
+int oxg_rrt_connect_solve(oxg_world w, oxg_store start_tree, oxg_store goal_tree,
+                          const oxg_plan_params* params, const double* goal_target,
+                          const double* samples, uint64_t n_samples, int64_t* start_parents,
+                          int64_t* goal_parents, oxg_plan_result* out);
+int oxg_rrt_star_solve(oxg_world w, oxg_store tree, const oxg_plan_params* params,
+                       const double* goal_target, const double* samples, uint64_t n_samples,
+                       int64_t* parents, double* costs, oxg_plan_result* out);
+
 /* ---- device-pointer pipeline (resident data; multi-GPU sharding) ----------------
  * The same phases with device buffers, enqueued on the store's stream.
  *  oxg_knn_rows_dev   : k-NN of stored rows [row_begin,row_end) against the whole

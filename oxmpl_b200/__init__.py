@@ -17,7 +17,10 @@ from .api import (  # noqa: F401
     prm_build_knn,
     prm_build_radius,
     real_vector_max_extent,
+    rrt_connect_solve,
+    rrt_solve,
+    rrt_star_solve,
 )
-from ._lib import OxgError, PrmStats, SpaceDesc  # noqa: F401
+from ._lib import OxgError, PlanParams, PlanResult, PrmStats, SpaceDesc  # noqa: F401
 
 __version__ = "0.1.0"

@@ -62,6 +62,38 @@ class PrmStats(C.Structure):
     ]
 
 
+class PlanParams(C.Structure):
+    """struct oxg_plan_params."""
+
+    _fields_ = [
+        ("max_distance", C.c_double),
+        ("search_radius", C.c_double),
+        ("resolution", C.c_double),
+        ("goal_radius", C.c_double),
+        ("timeout_s", C.c_double),
+        ("max_nodes", C.c_uint64),
+        ("stop_at_goal", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class PlanResult(C.Structure):
+    """struct oxg_plan_result."""
+
+    _fields_ = [
+        ("n_nodes", C.c_uint64 * 2),
+        ("iters", C.c_uint64),
+        ("motion_checks", C.c_uint64),
+        ("motion_checks_executed", C.c_uint64),
+        ("goal_node", C.c_int64 * 2),
+        ("solved", C.c_int32),
+        ("status", C.c_int32),
+        ("device_ms", C.c_double),
+        ("ctas", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 _vp = C.c_void_p
 _u64 = C.c_uint64
 _u32 = C.c_uint32
@@ -103,6 +135,18 @@ SIGNATURES = {
     "oxg_prm_build_knn": (
         C.c_int,
         [_vp, _vp, _u32, _dbl, _u64, _u64, _pu32, _pd, _pu8, C.POINTER(PrmStats)],
+    ),
+    "oxg_rrt_solve": (
+        C.c_int,
+        [_vp, _vp, C.POINTER(PlanParams), _pd, _pd, _u64, _vp, C.POINTER(PlanResult)],
+    ),
+    "oxg_rrt_connect_solve": (
+        C.c_int,
+        [_vp, _vp, _vp, C.POINTER(PlanParams), _pd, _pd, _u64, _vp, _vp, C.POINTER(PlanResult)],
+    ),
+    "oxg_rrt_star_solve": (
+        C.c_int,
+        [_vp, _vp, C.POINTER(PlanParams), _pd, _pd, _u64, _vp, _vp, C.POINTER(PlanResult)],
     ),
     "oxg_knn_rows_dev": (C.c_int, [_vp, _u64, _u64, _u32, _pu32, _pd]),
     "oxg_prm_edges_dev": (C.c_int, [_vp, _vp, _pu32, _u32, _dbl, _u64, _u64, _pu8, _pu64]),

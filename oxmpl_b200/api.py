@@ -334,3 +334,74 @@ def prm_build_radius(world: World, store: StateStore, connection_radius: float, 
         check(code)
         break
     return offsets, idx[: int(offsets[rows])].copy(), _stats_dict(st)
+
+
+# -- fused sequential planners ---------------------------------------------------------------
+PLAN_STATUS = {0: "solved", 1: "samples_exhausted", 2: "tree_full", 3: "timeout"}
+
+
+def _plan_params(max_distance, resolution, max_nodes, goal_radius, search_radius=0.0,
+                 timeout_s=0.0, stop_at_goal=True):
+    return _lib.PlanParams(float(max_distance), float(search_radius), float(resolution),
+                           float(goal_radius), float(timeout_s), int(max_nodes),
+                           1 if stop_at_goal else 0, 0)
+
+
+def _plan_result(res) -> dict:
+    return {
+        "n_nodes": (int(res.n_nodes[0]), int(res.n_nodes[1])),
+        "iters": int(res.iters),
+        "motion_checks": int(res.motion_checks),
+        "motion_checks_executed": int(res.motion_checks_executed),
+        "goal_node": (int(res.goal_node[0]), int(res.goal_node[1])),
+        "solved": bool(res.solved),
+        "status": PLAN_STATUS.get(int(res.status), int(res.status)),
+        "device_ms": float(res.device_ms),
+        "ctas": int(res.ctas),
+    }
+
+
+def rrt_solve(world: World, tree: StateStore, samples, max_distance: float, resolution: float,
+              max_nodes: int, goal_target=None, goal_radius: float = -1.0, timeout_s: float = 0.0):
+    """RRT::solve (rrt.rs:158-227) over a pre-drawn sample stream, as one persistent kernel.
+    `tree` must hold the start state.  Returns (parents i64[n], result dict)."""
+    s = _f64(np.atleast_2d(samples), tree.space.dim)
+    g = None if goal_target is None else _f64(goal_target)
+    prm = _plan_params(max_distance, resolution, max_nodes, goal_radius, timeout_s=timeout_s)
+    parents = np.full(max_nodes, -1, dtype=np.int64)
+    res = _lib.PlanResult()
+    check(lib.oxg_rrt_solve(world.handle, tree.handle, C.byref(prm), _ptr(g), _ptr(s), s.shape[0],
+                            _ptr(parents), C.byref(res)))
+    return parents[: int(res.n_nodes[0])].copy(), _plan_result(res)
+
+
+def rrt_connect_solve(world: World, start_tree: StateStore, goal_tree: StateStore, samples,
+                      max_distance: float, resolution: float, max_nodes: int, goal_target=None,
+                      goal_radius: float = -1.0, timeout_s: float = 0.0):
+    """RRTConnect::solve (rrt_connect.rs:227-309).  Returns (start_parents, goal_parents, result)."""
+    s = _f64(np.atleast_2d(samples), start_tree.space.dim)
+    g = None if goal_target is None else _f64(goal_target)
+    prm = _plan_params(max_distance, resolution, max_nodes, goal_radius, timeout_s=timeout_s)
+    pa = np.full(max_nodes, -1, dtype=np.int64)
+    pb = np.full(max_nodes, -1, dtype=np.int64)
+    res = _lib.PlanResult()
+    check(lib.oxg_rrt_connect_solve(world.handle, start_tree.handle, goal_tree.handle, C.byref(prm),
+                                    _ptr(g), _ptr(s), s.shape[0], _ptr(pa), _ptr(pb), C.byref(res)))
+    return pa[: int(res.n_nodes[0])].copy(), pb[: int(res.n_nodes[1])].copy(), _plan_result(res)
+
+
+def rrt_star_solve(world: World, tree: StateStore, samples, max_distance: float,
+                   search_radius: float, resolution: float, max_nodes: int, goal_target=None,
+                   goal_radius: float = -1.0, stop_at_goal: bool = True, timeout_s: float = 0.0):
+    """RRTStar::solve (rrt_star.rs:171-290).  Returns (parents, costs, result)."""
+    s = _f64(np.atleast_2d(samples), tree.space.dim)
+    g = None if goal_target is None else _f64(goal_target)
+    prm = _plan_params(max_distance, resolution, max_nodes, goal_radius, search_radius, timeout_s,
+                       stop_at_goal)
+    parents = np.full(max_nodes, -1, dtype=np.int64)
+    costs = np.zeros(max_nodes, dtype=np.float64)
+    res = _lib.PlanResult()
+    check(lib.oxg_rrt_star_solve(world.handle, tree.handle, C.byref(prm), _ptr(g), _ptr(s),
+                                 s.shape[0], _ptr(parents), _ptr(costs), C.byref(res)))
+    n = int(res.n_nodes[0])
+    return parents[:n].copy(), costs[:n].copy(), _plan_result(res)

@@ -99,6 +99,40 @@ __global__ void gather_rows_kernel(const double* __restrict__ data, uint64_t pit
   }
 }
 
+// f32 mirror + max |coordinate| for states [first, first+n) written directly into the SoA
+// columns by a device kernel (the fused planners append on the device).
+__global__ void mirror_rows_kernel(const double* __restrict__ data, float* __restrict__ data32,
+                                   uint64_t pitch, uint64_t first, uint64_t n, uint32_t dim,
+                                   unsigned long long* __restrict__ maxabs) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t total = n * dim;
+  unsigned long long m = 0ull;
+  for (; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t d = (uint32_t)(t / n);
+    uint64_t i = first + (t - (uint64_t)d * n);
+    double v = data[(uint64_t)d * pitch + i];
+    data32[(uint64_t)d * pitch + i] = __double2float_rn(v);
+    unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v));
+    m = b > m ? b : m;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long x = __shfl_down_sync(0xFFFFFFFFu, m, o);
+    m = x > m ? x : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(maxabs, m);
+}
+
+int store_refresh_mirror(oxg_store_s* s, uint64_t first, uint64_t n) {
+  if (n == 0) return OXG_OK;
+  uint64_t total = n * s->dim;
+  int threads = 256;
+  int blocks = (int)std::min<uint64_t>((total + threads - 1) / threads, 148 * 16);
+  mirror_rows_kernel<<<blocks, threads, 0, s->stream>>>(s->d_data, s->d_data32, s->pitch, first, n,
+                                                        s->dim, s->d_maxabs);
+  OXG_LAUNCH_CHECK();
+  return OXG_OK;
+}
+
 static uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
 
 static int store_grow(oxg_store_s* s, uint64_t capacity) {
@@ -242,6 +276,7 @@ int oxg_store_clear(oxg_store s) {
     return OXG_E_NULL;
   }
   s->size = 0;
+  s->n_planned = 0;
   OXG_CUDA_TRY(cudaMemsetAsync(s->d_maxabs, 0, sizeof(unsigned long long), s->stream));
   return OXG_OK;
 }

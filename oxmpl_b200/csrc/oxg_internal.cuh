@@ -88,6 +88,31 @@ struct DevBuf {
     cap = want;
     return OXG_OK;
   }
+  // Grows like ensure() but keeps the first `keep` bytes (ordered on `st`).
+  int ensure_keep(size_t bytes, size_t keep, cudaStream_t st) {
+    if (bytes <= cap) return OXG_OK;
+    void* np = nullptr;
+    size_t want = bytes + bytes / 2 + 256;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+      return OXG_E_CUDA;
+    }
+    if (p && keep) {
+      e = cudaMemcpyAsync(np, p, keep < cap ? keep : cap, cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        cudaFree(np);
+        set_error("device copy failed: %s", cudaGetErrorString(e));
+        return OXG_E_CUDA;
+      }
+    }
+    if (p) cudaFree(p);
+    p = np;
+    cap = want;
+    return OXG_OK;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -113,6 +138,9 @@ enum StoreBuf {
   B_AUX,        // exclusion lists / index limits / per-query CSR offsets
   B_AUX2,       // edge lists, flags
   B_AUX3,
+  B_PARENT,     // planner trees: parent index of every node (i64, -1 = root)
+  B_COST,       // RRT*: cost-to-come of every node (f64)
+  B_PLAN,       // planner kernels: control block, barrier scratch, per-CTA neighbour lists
   B_COUNT
 };
 
@@ -134,6 +162,7 @@ struct oxg_store_s {
   unsigned long long* d_maxabs = nullptr;  // bits of max |coordinate| over the store (NaN sorts high)
   uint64_t pitch = 0;        // elements; multiple of 32 (256-byte aligned columns)
   uint64_t size = 0;
+  uint64_t n_planned = 0;    // nodes whose B_PARENT / B_COST entries are valid
   oxg::DevBuf buf[oxg::B_COUNT];  // named scratch arenas, see enum StoreBuf
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 };
@@ -228,6 +257,7 @@ int is_valid_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t
 int nn_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double r, const uint32_t* d_idx_limit,
                      bool limit_self, uint64_t self_base, bool want_dist, uint64_t* total);
 int nn_radius_nsplit(const oxg_store_s* s, uint64_t Q);
+int store_refresh_mirror(oxg_store_s* s, uint64_t first, uint64_t n);
 int nn_radius_offsets(oxg_store_s* s, uint64_t Q, uint64_t* d_out);
 
 }  // namespace oxg
