@@ -1,0 +1,108 @@
+//! Raw `extern "C"` declarations of include/oxg.h (one-to-one; keep in sync with the header —
+//! tests/test_abi.py checks the header against the built library).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct oxg_space_desc {
+    pub n_real: u32,
+    pub n_so2: u32,
+    pub w_real: f64,
+    pub w_so2: f64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct oxg_prm_stats {
+    pub n_rows: u64,
+    pub n_candidates: u64,
+    pub n_edges_checked: u64,
+    pub n_edges_valid: u64,
+    pub knn_ms: f64,
+    pub edge_ms: f64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct oxg_plan_params {
+    pub max_distance: f64,
+    pub search_radius: f64,
+    pub resolution: f64,
+    pub goal_radius: f64,
+    pub timeout_s: f64,
+    pub max_nodes: u64,
+    pub stop_at_goal: i32,
+    pub reserved: i32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct oxg_plan_result {
+    pub n_nodes: [u64; 2],
+    pub iters: u64,
+    pub motion_checks: u64,
+    pub motion_checks_executed: u64,
+    pub goal_node: [i64; 2],
+    pub solved: i32,
+    pub status: i32,
+    pub device_ms: f64,
+    pub ctas: i32,
+    pub reserved: i32,
+}
+
+pub type oxg_store = *mut c_void;
+pub type oxg_world = *mut c_void;
+
+pub const OXG_OK: c_int = 0;
+pub const OXG_E_CAPACITY: c_int = -3;
+
+extern "C" {
+    pub fn oxg_last_error() -> *const c_char;
+    pub fn oxg_device_count(out_count: *mut c_int) -> c_int;
+    pub fn oxg_set_device(device: c_int) -> c_int;
+
+    pub fn oxg_store_create(space: *const oxg_space_desc, capacity: u64, out: *mut oxg_store) -> c_int;
+    pub fn oxg_store_destroy(s: oxg_store) -> c_int;
+    pub fn oxg_store_clear(s: oxg_store) -> c_int;
+    pub fn oxg_store_append(s: oxg_store, rows: *const f64, n: u64, first_index: *mut u64) -> c_int;
+    pub fn oxg_store_size(s: oxg_store, out_n: *mut u64) -> c_int;
+    pub fn oxg_store_read(s: oxg_store, first: u64, n: u64, rows_out: *mut f64) -> c_int;
+
+    pub fn oxg_nn1(s: oxg_store, queries: *const f64, q: u64, idx: *mut u32, dist: *mut f64) -> c_int;
+    pub fn oxg_knn(s: oxg_store, queries: *const f64, q: u64, k: u32, exclude_idx: *const u32,
+                   idx: *mut u32, dist: *mut f64) -> c_int;
+    pub fn oxg_radius(s: oxg_store, queries: *const f64, q: u64, r: f64, idx_limit: *const u32,
+                      offsets: *mut u64, idx: *mut u32, cap: u64, dist: *mut f64) -> c_int;
+
+    pub fn oxg_world_create(dim: u32, spheres: *const f64, n_spheres: u64, aabbs: *const f64,
+                            n_aabbs: u64, capsules: *const f64, n_capsules: u64,
+                            out: *mut oxg_world) -> c_int;
+    pub fn oxg_world_add_so2_interval(w: oxg_world, so2_component: u32, lo: f64, hi: f64) -> c_int;
+    pub fn oxg_world_destroy(w: oxg_world) -> c_int;
+    pub fn oxg_is_valid(w: oxg_world, space: *const oxg_space_desc, states: *const f64, q: u64,
+                        out: *mut u8) -> c_int;
+    pub fn oxg_check_motion(w: oxg_world, space: *const oxg_space_desc, from: *const f64,
+                            to: *const f64, e: u64, resolution: f64, valid: *mut u8,
+                            first_invalid_step: *mut u32) -> c_int;
+    pub fn oxg_check_edges(w: oxg_world, s: oxg_store, from_idx: *const u32, to_idx: *const u32,
+                           e: u64, resolution: f64, valid: *mut u8) -> c_int;
+
+    pub fn oxg_prm_build_radius(w: oxg_world, s: oxg_store, connection_radius: f64, resolution: f64,
+                                row_begin: u64, row_end: u64, offsets: *mut u64, idx: *mut u32,
+                                cap: u64, stats: *mut oxg_prm_stats) -> c_int;
+    pub fn oxg_prm_build_knn(w: oxg_world, s: oxg_store, k: u32, resolution: f64, row_begin: u64,
+                             row_end: u64, idx: *mut u32, dist: *mut f64, valid: *mut u8,
+                             stats: *mut oxg_prm_stats) -> c_int;
+
+    pub fn oxg_rrt_solve(w: oxg_world, tree: oxg_store, params: *const oxg_plan_params,
+                         goal_target: *const f64, samples: *const f64, n_samples: u64,
+                         parents: *mut i64, out: *mut oxg_plan_result) -> c_int;
+    pub fn oxg_rrt_connect_solve(w: oxg_world, start_tree: oxg_store, goal_tree: oxg_store,
+                                 params: *const oxg_plan_params, goal_target: *const f64,
+                                 samples: *const f64, n_samples: u64, start_parents: *mut i64,
+                                 goal_parents: *mut i64, out: *mut oxg_plan_result) -> c_int;
+    pub fn oxg_rrt_star_solve(w: oxg_world, tree: oxg_store, params: *const oxg_plan_params,
+                              goal_target: *const f64, samples: *const f64, n_samples: u64,
+                              parents: *mut i64, costs: *mut f64, out: *mut oxg_plan_result) -> c_int;
+}

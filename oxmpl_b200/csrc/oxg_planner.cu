@@ -116,6 +116,10 @@ struct PlanShared {
   uint32_t e_nb[NBR_CAP];    // edge -> neighbour slot
   uint32_t e_pre[NBR_CAP + 1];
   uint32_t cta_off[160];
+  // single-CTA runs keep the hit flags here instead of in global memory
+  uint32_t hit_ext[2];
+  uint32_t hit_cp[NBR_CAP];
+  uint32_t hit_rw[NBR_CAP];
 };
 
 // ------------------------------------------------------------------------------- arithmetic
@@ -242,6 +246,7 @@ __device__ __forceinline__ void cta_slice(uint32_t n, uint32_t* lo, uint32_t* hi
 // distance(stored, target) with strict-< / lowest-index selection (rrt.rs:187-196).
 // `pend_idx` (if < n) is the index whose state is still only in sh.pend (appended after the last
 // barrier).
+template <bool MULTI>
 __device__ void phase_scan(const PlanParams& P, PlanShared& sh, const TreeView& T, uint32_t n,
                            const double* target, uint32_t pend_idx) {
   uint32_t lo, hi;
@@ -249,6 +254,7 @@ __device__ void phase_scan(const PlanParams& P, PlanShared& sh, const TreeView& 
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   double bd = inf;
   uint32_t bi = OXG_INVALID_INDEX;
+#pragma unroll 4
   for (uint32_t i = lo + threadIdx.x; i < hi; i += PL_THREADS) {
     const double d = (i == pend_idx) ? dist_ab(P, sm(sh.pend), sm(target))
                                      : dist_ab(P, node(T, i), sm(target));
@@ -277,18 +283,29 @@ __device__ void phase_scan(const PlanParams& P, PlanShared& sh, const TreeView& 
         bd = sh.red_d[wv];
         bi = sh.red_i[wv];
       }
-    P.cta_best_dist[blockIdx.x] = bd;
-    P.cta_best_idx[blockIdx.x] = bi;
+    if (MULTI) {
+      P.cta_best_dist[blockIdx.x] = bd;
+      P.cta_best_idx[blockIdx.x] = bi;
+    } else {
+      sh.bc_d[0] = bd;
+      sh.bc_u[0] = bi;
+    }
   }
 }
 
 // Phase B head: reduce the per-CTA bests, load q_near, steer (rrt.rs:200-208).  Leaves
 // sh.q_near, sh.q_new; returns (near, min_dist, reached).
+template <bool MULTI>
 __device__ void phase_steer(const PlanParams& P, PlanShared& sh, const TreeView& T,
                             const double* target, uint32_t pend_idx, uint32_t* near_out,
                             double* min_dist_out, bool* reached_out) {
   const int dim = (int)(P.n_real + P.n_so2);
-  if (threadIdx.x < 32) {
+  if (!MULTI) {
+    if (threadIdx.x == 0 && sh.bc_u[0] == OXG_INVALID_INDEX) {
+      sh.bc_u[0] = 0;  // every distance was NaN: the reference keeps index 0
+      sh.bc_d[0] = __longlong_as_double(0x7FF8000000000000ll);
+    }
+  } else if (threadIdx.x < 32) {
     const double inf = __longlong_as_double(0x7FF0000000000000ll);
     double bd = inf;
     uint32_t bi = OXG_INVALID_INDEX;
@@ -372,33 +389,40 @@ __device__ void motion_tasks(const PlanParams& P, PlanShared& sh, const TreeView
   }
   double* x = sh.wx[warp];
   for (uint32_t c = c0; c < n_oc; c += cstep) {
-    for (uint32_t s = s0; s < NS; s += sstep) {
-      // edge of state s: largest e with pre[e] <= s
-      uint32_t lo = 0, hi = E;
-      while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (pre[mid] <= s) lo = mid; else hi = mid;
+    uint32_t e = 0, skip_e = OXG_INVALID_INDEX, tick = 0, cur_e = OXG_INVALID_INDEX;
+    double o = 0.0;  // this lane's coordinate of the edge's far endpoint (reloaded per edge)
+    for (uint32_t s = s0; s < NS; s += sstep, ++tick) {
+      while (pre[e + 1] <= s) ++e;  // edge of state s (s only grows)
+      if (e == skip_e) continue;
+      // early exit: a hit recorded by any warp ends the edge; the flag lives in L2, so it is
+      // polled only every 8th task (a stale miss costs work, never a result)
+      if ((tick & 7u) == 7u && *reinterpret_cast<volatile uint32_t*>(&hit[e])) {
+        skip_e = e;
+        continue;
       }
-      const uint32_t e = lo;
-      if (*reinterpret_cast<volatile uint32_t*>(&hit[e])) continue;
       const uint32_t ns = e_nb ? steps[e_nb[e]] : steps[e];
       const uint32_t i = s - pre[e] + 1;
       if ((int)lane < dim) {
-        double o;
-        if (other_sm) {
-          o = other_sm[lane];
-        } else {
-          const uint32_t j = sh.nb_idx[e_nb[e]];
-          o = __ldcg(&T.data[(uint64_t)lane * T.pitch + j]);
+        if (e != cur_e) {
+          if (other_sm) {
+            o = other_sm[lane];
+          } else {
+            const uint32_t j = sh.nb_idx[e_nb[e]];
+            o = __ldcg(&T.data[(uint64_t)lane * T.pitch + j]);
+          }
         }
         const double f = fixed_is_to ? o : fixed[lane];
         const double t = fixed_is_to ? fixed[lane] : o;
         // `if num_steps <= 1 { return is_valid(to) }`; step i of n: t = i / n (rrt.rs:99-105)
         x[lane] = (ns <= 1) ? t : interp_coord(P, lane, f, t, __ddiv_rn((double)i, (double)ns));
       }
+      cur_e = e;
       __syncwarp();
       const bool h = chunk_hit(P, c, lane, x);
-      if (__any_sync(0xFFFFFFFFu, h) && lane == 0) atomicOr(&hit[e], 1u);
+      if (__any_sync(0xFFFFFFFFu, h)) {
+        if (lane == 0) atomicOr(&hit[e], 1u);
+        skip_e = e;
+      }
       __syncwarp();
     }
   }
@@ -406,14 +430,16 @@ __device__ void motion_tasks(const PlanParams& P, PlanShared& sh, const TreeView
 
 // RRT* find_neighbours (rrt_star.rs:121-131): all i < n with distance(q_new, tree[i]) <
 // search_radius, ascending.  Each CTA writes the ordered hits of its slice.
+template <bool MULTI>
 __device__ void phase_radius(const PlanParams& P, PlanShared& sh, const TreeView& T, uint32_t n,
                              uint32_t pend_idx) {
   uint32_t lo, hi;
   cta_slice(n, &lo, &hi);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t run = 0;
-  uint32_t* out_i = P.nbr_idx + (size_t)blockIdx.x * P.nbr_capc;
-  double* out_d = P.nbr_dist + (size_t)blockIdx.x * P.nbr_capc;
+  uint32_t* out_i = MULTI ? P.nbr_idx + (size_t)blockIdx.x * P.nbr_capc : sh.nb_idx;
+  double* out_d = MULTI ? P.nbr_dist + (size_t)blockIdx.x * P.nbr_capc : sh.nb_dist;
+  const uint32_t cap = MULTI ? P.nbr_capc : (uint32_t)NBR_CAP;
   for (uint32_t base = lo; base < hi; base += PL_THREADS) {
     const uint32_t i = base + threadIdx.x;
     bool h = false;
@@ -434,7 +460,7 @@ __device__ void phase_radius(const PlanParams& P, PlanShared& sh, const TreeView
     }
     if (h) {
       const uint32_t pos = off + __popc(b & ((1u << lane) - 1u));
-      if (pos < P.nbr_capc) {
+      if (pos < cap) {
         out_i[pos] = i;
         out_d[pos] = d;
       }
@@ -442,7 +468,12 @@ __device__ void phase_radius(const PlanParams& P, PlanShared& sh, const TreeView
     run += tot;
     __syncthreads();
   }
-  if (threadIdx.x == 0) P.nbr_cnt[blockIdx.x] = run;
+  if (threadIdx.x == 0) {
+    if (MULTI)
+      P.nbr_cnt[blockIdx.x] = run;
+    else
+      sh.bc_u[1] = run;
+  }
 }
 
 // ------------------------------------------------------------------------------- the kernel
@@ -455,12 +486,22 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
   const uint32_t tid = threadIdx.x;
   const uint32_t gtid = blockIdx.x * PL_THREADS + tid, gthreads = gridDim.x * PL_THREADS;
 
+  uint32_t* const hit_ext = MULTI ? P.hit_ext : sh.hit_ext;
+  uint32_t* const hit_cp = MULTI ? P.hit_cp : sh.hit_cp;
+  uint32_t* const hit_rw = MULTI ? P.hit_rw : sh.hit_rw;
+  if (!MULTI) {
+    if (tid < 2) sh.hit_ext[tid] = 0u;
+    __syncthreads();
+  }
+  auto flag = [](const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); };
+
   uint32_t n[2] = {P.n_init[0], P.n_init[1]};
   uint32_t pend_idx = OXG_INVALID_INDEX;  // index (in pend_tree) of the state still only in sh.pend
   int pend_tree = 0;
   unsigned long long it = 0, mc_ref = 0, mc_exec = 0, ext_count = 0;
   int solved = 0, status = ST_SAMPLES;
   long long node0 = -1, node1 = -1;
+  double q_next = ((int)tid < dim && P.n_samples > 0) ? P.samples[tid] : 0.0;
   unsigned long long t_start = 0;
   if (P.timeout_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 
@@ -472,10 +513,10 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
     const uint32_t pidx = (pend_tree == t) ? pend_idx : OXG_INVALID_INDEX;
     const unsigned par = (unsigned)(ext_count & 1ull);
     ++ext_count;
-    phase_scan(P, sh, T, n[t], target, pidx);
+    phase_scan<MULTI>(P, sh, T, n[t], target, pidx);
     grid_barrier<MULTI>(grid);
-    if (gtid == 0) P.hit_ext[par ^ 1u] = 0u;  // the other parity's flag: next extend's
-    phase_steer(P, sh, T, target, pidx, near_out, min_dist_out, reached_out);
+    if (gtid == 0) hit_ext[par ^ 1u] = 0u;  // the other parity's flag: next extend's
+    phase_steer<MULTI>(P, sh, T, target, pidx, near_out, min_dist_out, reached_out);
     // check_motion(q_near, q_new)
     const double dist = dist_ab(P, sm(sh.q_near), sm(sh.q_new));
     const unsigned long long ns64 = motion_steps(dist, P.resolution);
@@ -490,7 +531,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
     }
     __syncthreads();
     motion_tasks(P, sh, T, 1, sh.q_new, true, sh.q_near, sh.nb_ns, sh.e_pre, nullptr,
-                 P.hit_ext + par);
+                 hit_ext + par);
     if (count_ref) {
       ++mc_ref;
       ++mc_exec;
@@ -498,13 +539,13 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
     if (MODE == MODE_STAR) {
       // the radius scan and the flag reset ride in the same phase
       for (uint32_t u = gtid; u < (uint32_t)NBR_CAP; u += gthreads) {
-        P.hit_cp[u] = 0u;
-        P.hit_rw[u] = 0u;
+        hit_cp[u] = 0u;
+        hit_rw[u] = 0u;
       }
-      phase_radius(P, sh, T, n[t], pidx);
+      phase_radius<MULTI>(P, sh, T, n[t], pidx);
     }
     grid_barrier<MULTI>(grid);
-    const bool valid = __ldcg(&P.hit_ext[par]) == 0u;
+    const bool valid = flag(hit_ext + par) == 0u;
     return valid;
   };
 
@@ -549,9 +590,11 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
         if (now - t_start > P.timeout_ns) P.ctrl->stop = 1;
       }
     }
-    if ((int)tid < dim) sh.q_rand[tid] = P.samples[it * (unsigned long long)dim + tid];
+    if ((int)tid < dim) sh.q_rand[tid] = q_next;
     __syncthreads();
     ++it;
+    if ((int)tid < dim && it < P.n_samples)  // prefetch the next sample off the critical path
+      q_next = P.samples[it * (unsigned long long)dim + tid];
 
     uint32_t near;
     double min_dist;
@@ -618,8 +661,8 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
         break;
       }
       if (!ok) continue;  // rrt_star.rs:221-223
-      // ---- gather the ordered neighbour list
-      if (tid < 32) {
+      // ---- gather the ordered neighbour list (a single CTA wrote it in place)
+      if (MULTI && tid < 32) {
         uint32_t run = 0;
         for (uint32_t c0 = 0; c0 < gridDim.x; c0 += 32) {
           const uint32_t c = c0 + tid;
@@ -640,7 +683,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
         status = ST_E_NEIGHBOURS;
         break;
       }
-      for (uint32_t c = 0; c < gridDim.x; ++c) {
+      for (uint32_t c = 0; MULTI && c < gridDim.x; ++c) {
         const uint32_t cnt = (c + 1 < gridDim.x ? sh.cta_off[c + 1] : m) - sh.cta_off[c];
         for (uint32_t u = tid; u < cnt; u += PL_THREADS) {
           sh.nb_idx[sh.cta_off[c] + u] = __ldcg(&P.nbr_idx[(size_t)c * P.nbr_capc + u]);
@@ -685,7 +728,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
         break;
       }
       if (E0 > 0) {
-        motion_tasks(P, sh, T, E0, sh.q_new, true, nullptr, sh.nb_ns, sh.e_pre, sh.e_nb, P.hit_cp);
+        motion_tasks(P, sh, T, E0, sh.q_new, true, nullptr, sh.nb_ns, sh.e_pre, sh.e_nb, hit_cp);
         mc_exec += E0;
         grid_barrier<MULTI>(grid);
       }
@@ -698,7 +741,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
           const uint32_t u = sh.e_nb[e];
           if (sh.nb_c[u] < min_cost) {
             ++ref;
-            if (__ldcg(&P.hit_cp[e]) == 0u) {
+            if (flag(hit_cp + e) == 0u) {
               min_cost = sh.nb_c[u];
               best = sh.nb_idx[u];
             }
@@ -749,13 +792,13 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
         break;
       }
       if (E1 > 0) {
-        motion_tasks(P, sh, T, E1, sh.q_new, false, nullptr, sh.nb_ns, sh.e_pre, sh.e_nb, P.hit_rw);
+        motion_tasks(P, sh, T, E1, sh.q_new, false, nullptr, sh.nb_ns, sh.e_pre, sh.e_nb, hit_rw);
         mc_exec += E1;
         mc_ref += E1;
         grid_barrier<MULTI>(grid);
         if (blockIdx.x == 0) {
           for (uint32_t e = tid; e < E1; e += PL_THREADS) {
-            if (__ldcg(&P.hit_rw[e]) == 0u) {
+            if (flag(hit_rw + e) == 0u) {
               const uint32_t u = sh.e_nb[e];
               const uint32_t j = sh.nb_idx[u];
               T.parent[j] = (long long)new_idx;

@@ -27,7 +27,7 @@ def config3(n_nodes, n_spheres, cpu_prefix):
     dim = 6
     lo, hi = [-1.0] * dim, [1.0] * dim
     start, goal = [-0.9] * dim, [0.9] * dim
-    sph = worlds.sphere_world(3, lo, hi, n_spheres, 0.12, 0.22, keep_clear=[start, goal])
+    sph = worlds.sphere_world(3, lo, hi, n_spheres, 0.22, 0.32, keep_clear=[start, goal])
     sp = oxg.Space.real_vector(dim)
     res = res_of(lo, hi)
     n_samples = int(n_nodes * 1.6)
@@ -73,7 +73,7 @@ def config3(n_nodes, n_spheres, cpu_prefix):
                     "prefix_gpu_ms": r["device_ms"],
                     "prefix_gpu_iters_per_s": cpu_prefix / (r["device_ms"] * 1e-3),
                     "prefix_bit_identical": bool(same)})
-    print(json.dumps(out), flush=True)
+    return out
 
 
 def config2(n_samples):
@@ -99,18 +99,18 @@ def config2(n_samples):
         same = (np.array_equal(ta.read().view(np.uint64), o["start_tree"].view(np.uint64))
                 and np.array_equal(tb.read().view(np.uint64), o["goal_tree"].view(np.uint64))
                 and np.array_equal(pa, o["start_parents"]) and np.array_equal(pb, o["goal_parents"]))
-    print(json.dumps({"config": "2: RRT-Connect R2xSO2, 1000 AABBs", "iters": r["iters"],
+    return ({"config": "2: RRT-Connect R2xSO2, 1000 AABBs", "iters": r["iters"],
                       "solved": r["solved"], "nodes": r["n_nodes"], "gpu_ms": r["device_ms"],
                       "gpu_us_per_iter": r["device_ms"] * 1e3 / max(r["iters"], 1),
                       "cpu_s": cpu_s, "cpu_us_per_iter": cpu_s * 1e6 / max(o["iters"], 1),
-                      "bit_identical": bool(same), "ctas": r["ctas"]}), flush=True)
+                      "bit_identical": bool(same), "ctas": r["ctas"]})
 
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "3"
     if which == "2":
-        config2(int(sys.argv[2]) if len(sys.argv) > 2 else 30000)
+        print(json.dumps(config2(int(sys.argv[2]) if len(sys.argv) > 2 else 30000)), flush=True)
     else:
-        config3(int(sys.argv[2]) if len(sys.argv) > 2 else 200000,
-                int(sys.argv[3]) if len(sys.argv) > 3 else 10000,
-                int(sys.argv[4]) if len(sys.argv) > 4 else 3000)
+        print(json.dumps(config3(int(sys.argv[2]) if len(sys.argv) > 2 else 200000,
+                                 int(sys.argv[3]) if len(sys.argv) > 3 else 10000,
+                                 int(sys.argv[4]) if len(sys.argv) > 4 else 3000)), flush=True)
