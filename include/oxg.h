@@ -288,6 +288,9 @@ int oxg_store_stream(oxg_store s, void** out_stream);
  * (SURVEY §8d).  Returns operations per second.
  * oxg_kernel_launches: number of liboxg kernel launches since the counter was reset.
  */
+/* Device time (CUDA events on the store's stream) of the kernels of the most recent
+ * oxg_nn1 / oxg_knn call on this store, excluding the host<->device copies. */
+int oxg_store_last_scan_ms(oxg_store s, double* out_ms);
 int oxg_fp64_peak(double* out_ops_per_s, double* out_ms);
 /* oxg_fp32_peak: FP32 pipe rate with the certified pre-filter's instruction mix (packed
  * subtract + packed FMA, FADD2/FFMA2), in lane-instructions per second (an FMA counts once;

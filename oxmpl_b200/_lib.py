@@ -151,6 +151,7 @@ SIGNATURES = {
     "oxg_knn_rows_dev": (C.c_int, [_vp, _u64, _u64, _u32, _pu32, _pd]),
     "oxg_prm_edges_dev": (C.c_int, [_vp, _vp, _pu32, _u32, _dbl, _u64, _u64, _pu8, _pu64]),
     "oxg_prm_resolve_dev": (C.c_int, [_vp, _pu32, _u32, _pu8]),
+    "oxg_store_last_scan_ms": (C.c_int, [_vp, C.POINTER(_dbl)]),
     "oxg_fp64_peak": (C.c_int, [C.POINTER(_dbl), C.POINTER(_dbl)]),
     "oxg_fp32_peak": (C.c_int, [C.POINTER(_dbl), C.POINTER(_dbl)]),
     "oxg_kernel_launches": (_u64, [C.c_int]),

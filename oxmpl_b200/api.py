@@ -166,6 +166,12 @@ class StateStore:
     def sync(self):
         check(lib.oxg_store_sync(self._h))
 
+    def last_scan_ms(self) -> float:
+        """Device time of the kernels of the most recent nn1 / knn call (no copies)."""
+        ms = C.c_double(0.0)
+        check(lib.oxg_store_last_scan_ms(self._h, C.byref(ms)))
+        return ms.value
+
     def stream(self) -> int:
         s = C.c_void_p()
         check(lib.oxg_store_stream(self._h, C.byref(s)))

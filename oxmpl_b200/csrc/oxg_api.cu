@@ -99,6 +99,41 @@ __global__ void gather_rows_kernel(const double* __restrict__ data, uint64_t pit
   }
 }
 
+// Squared norm of states [first, first+n): column `dim` of the f32 mirror (input of the
+// dot-product form of the certified pre-filter) and the running maximum (maxabs[1], f64 bits).
+__global__ void norms_kernel(const double* __restrict__ data, float* __restrict__ data32,
+                             uint64_t pitch, uint64_t first, uint64_t n, uint32_t dim,
+                             unsigned long long* __restrict__ maxabs) {
+  unsigned long long m = 0ull;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = first + t;
+    double s = 0.0;
+    for (uint32_t d = 0; d < dim; ++d) {
+      const double v = data[(uint64_t)d * pitch + i];
+      s += v * v;
+    }
+    data32[(uint64_t)dim * pitch + i] = __double2float_rn(s);
+    unsigned long long b = (unsigned long long)__double_as_longlong(s);
+    m = b > m ? b : m;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long x = __shfl_down_sync(0xFFFFFFFFu, m, o);
+    m = x > m ? x : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(maxabs + 1, m);
+}
+
+static int launch_norms(oxg_store_s* s, uint64_t first, uint64_t n) {
+  if (n == 0) return OXG_OK;
+  int threads = 256;
+  int blocks = (int)std::min<uint64_t>((n + threads - 1) / threads, 148 * 16);
+  norms_kernel<<<blocks, threads, 0, s->stream>>>(s->d_data, s->d_data32, s->pitch, first, n, s->dim,
+                                                  s->d_maxabs);
+  OXG_LAUNCH_CHECK();
+  return OXG_OK;
+}
+
 // f32 mirror + max |coordinate| for states [first, first+n) written directly into the SoA
 // columns by a device kernel (the fused planners append on the device).
 __global__ void mirror_rows_kernel(const double* __restrict__ data, float* __restrict__ data32,
@@ -130,7 +165,7 @@ int store_refresh_mirror(oxg_store_s* s, uint64_t first, uint64_t n) {
   mirror_rows_kernel<<<blocks, threads, 0, s->stream>>>(s->d_data, s->d_data32, s->pitch, first, n,
                                                         s->dim, s->d_maxabs);
   OXG_LAUNCH_CHECK();
-  return OXG_OK;
+  return launch_norms(s, first, n);
 }
 
 static uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
@@ -147,7 +182,7 @@ static int store_grow(oxg_store_s* s, uint64_t capacity) {
     return OXG_E_ALLOC;
   }
   float* nd32 = nullptr;
-  e = cudaMalloc(&nd32, sizeof(float) * new_pitch * s->dim);
+  e = cudaMalloc(&nd32, sizeof(float) * new_pitch * (s->dim + 1));  // + the squared-norm column
   if (e != cudaSuccess) {
     cudaGetLastError();
     cudaFree(nd);
@@ -156,13 +191,13 @@ static int store_grow(oxg_store_s* s, uint64_t capacity) {
     return OXG_E_ALLOC;
   }
   if (s->d_data && s->size > 0) {
-    for (uint32_t d = 0; d < s->dim; ++d) {
+    for (uint32_t d = 0; d < s->dim; ++d)
       OXG_CUDA_TRY(cudaMemcpyAsync(nd + (uint64_t)d * new_pitch, s->d_data + (uint64_t)d * s->pitch,
                                    sizeof(double) * s->size, cudaMemcpyDeviceToDevice, s->stream));
+    for (uint32_t d = 0; d <= s->dim; ++d)
       OXG_CUDA_TRY(cudaMemcpyAsync(nd32 + (uint64_t)d * new_pitch,
                                    s->d_data32 + (uint64_t)d * s->pitch, sizeof(float) * s->size,
                                    cudaMemcpyDeviceToDevice, s->stream));
-    }
     OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
   }
   if (s->d_data) cudaFree(s->d_data);
@@ -238,8 +273,8 @@ int oxg_store_create(const oxg_space_desc* space, uint64_t capacity, oxg_store* 
     delete s;
     return OXG_E_CUDA;
   }
-  if (cudaMalloc((void**)&s->d_maxabs, sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMemsetAsync(s->d_maxabs, 0, sizeof(unsigned long long), s->stream) != cudaSuccess) {
+  if (cudaMalloc((void**)&s->d_maxabs, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemsetAsync(s->d_maxabs, 0, 2 * sizeof(unsigned long long), s->stream) != cudaSuccess) {
     cudaGetLastError();
     set_error("store allocation failed");
     oxg_store_destroy(s);
@@ -277,7 +312,7 @@ int oxg_store_clear(oxg_store s) {
   }
   s->size = 0;
   s->n_planned = 0;
-  OXG_CUDA_TRY(cudaMemsetAsync(s->d_maxabs, 0, sizeof(unsigned long long), s->stream));
+  OXG_CUDA_TRY(cudaMemsetAsync(s->d_maxabs, 0, 2 * sizeof(unsigned long long), s->stream));
   return OXG_OK;
 }
 
@@ -318,6 +353,7 @@ int oxg_store_append(oxg_store s, const double* rows, uint64_t n, uint64_t* firs
                                                          s->d_data, s->d_data32, s->pitch, s->size,
                                                          s->d_maxabs);
   OXG_LAUNCH_CHECK();
+  OXG_TRY(launch_norms(s, s->size, n));
   // the caller may reuse `rows` immediately
   OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
   s->size += n;

@@ -157,9 +157,11 @@ struct oxg_store_s {
   int device = 0;
   cudaStream_t stream = nullptr;
   double* d_data = nullptr;  // SoA: coordinate d of state i at d_data[d * pitch + i]
-  float* d_data32 = nullptr; // the same states rounded to f32 (round-to-nearest), same layout:
-                             // input of the certified FP32 pre-filter, never of a result
-  unsigned long long* d_maxabs = nullptr;  // bits of max |coordinate| over the store (NaN sorts high)
+  float* d_data32 = nullptr; // the same states rounded to f32 (round-to-nearest), same layout,
+                             // plus column `dim` = squared norm of each state: input of the
+                             // certified FP32 pre-filter, never of a result
+  unsigned long long* d_maxabs = nullptr;  // [0] bits of max |coordinate|, [1] bits of max
+                                           // squared norm over the store (NaN sorts high)
   uint64_t pitch = 0;        // elements; multiple of 32 (256-byte aligned columns)
   uint64_t size = 0;
   uint64_t n_planned = 0;    // nodes whose B_PARENT / B_COST entries are valid

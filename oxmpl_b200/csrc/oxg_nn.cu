@@ -55,6 +55,7 @@ struct ScanParams {
   uint32_t k;
   int exclude_mode;
   const uint32_t* exclude;
+  uint32_t exclude_one;  // few-query stream kernel: one excluded index (or OXG_INVALID_INDEX)
   uint32_t self_base;
   uint32_t split_len;  // stored states per blockIdx.y slice (multiple of NN_TILE)
   uint32_t nsplit;
@@ -316,23 +317,51 @@ __device__ __forceinline__ double sqrt_le_upper_dev(double sw) {
 }
 
 constexpr int CAND_CAP = 16;  // deferred candidates per query (u32 indices, shared memory)
+constexpr int DRAIN_EVERY = 8;  // tiles between scheduled warp-wide drains
+
+// Dot-product form of the pre-filter.  With g_d = -2 fl32(q_d), pn = fl32(|p|^2) and the FP32
+// FMA chain  A = fma(g_D, p_D, ... fma(g_1, p_1, pn)),  A approximates |p|^2 - 2 q.p = d2 - |q|^2
+// with  |A - (d2 - |q|^2)| <= gamma_{D+2} (2|p|^2 + |q|^2)  (one rounding per input, per FMA and
+// of pn; 2|q.p| <= |q|^2 + |p|^2).  So d2 <= U implies  A <= U - |q|^2 + B  with
+// B = gamma_{D+2} (2 Pmax + |q|^2),  Pmax = max squared norm over the store.  Half the FP32
+// work of the difference form (D FMAs per pair), but the bound grows with |p|^2 instead of
+// |p| sqrt(U): each warp watches its pass rate and falls back to the difference form when the
+// bound is too loose for its data (adaptive, results unaffected either way).
+__device__ __forceinline__ float filter_threshold_dot_dev(long long ubits, double Qn, double Pmax,
+                                                          int D) {
+  const float inf = __int_as_float(0x7F800000);
+  if (ubits < 0) return -inf;  // nothing is admitted (NaN evaluations still pass to the exact path)
+  const double U = __longlong_as_double(ubits);
+  const double W = 2.0 * Pmax + Qn;
+  if (!(U < 1.0e300) || !(W < 1.0e30)) return inf;
+  const double B = W * (double)(D + 2) * 1.1920928955078125e-07 * 1.0001 + 1e-30;  // 2^-23: 2x margin
+  const double T = U * (1.0 + 1e-9) - Qn + B + Qn * 1e-13;
+  if (!(T == T)) return inf;
+  return __double2float_ru(T);
+}
+
+struct FilterThr {
+  float diff;  // difference-form threshold (filter_threshold_dev)
+  float dot;   // dot-form threshold (filter_threshold_dot_dev)
+};
 
 // Exact path of the pairs the FP32 filter could not discard, run for all of a query's deferred
 // candidates at once (the whole warp drains together, so the lanes stay converged).  Each
 // candidate is recomputed from the f64 store in the reference's operation order and goes
-// through the exact (distance, index) comparison.  Returns the query's new FP32 threshold.
+// through the exact (distance, index) comparison.  Returns the query's new FP32 thresholds.
 template <int D>
-__device__ __noinline__ float knn_drain_f32(const ScanParams& p, uint32_t qi, uint32_t n_end,
-                                            uint32_t excl, const uint32_t* cand, int ncand,
-                                            int stride, double* sl, uint32_t* il, int* have_p,
-                                            long long* ubits_p, float t32) {
-  if (ncand == 0) return t32;
+__device__ __noinline__ FilterThr knn_drain_f32(const ScanParams& p, uint32_t qi, uint32_t n_end,
+                                                uint32_t excl, const uint32_t* cand, int ncand,
+                                                int stride, double* sl, uint32_t* il, int* have_p,
+                                                long long* ubits_p, FilterThr thr) {
+  if (ncand == 0) return thr;
   const int k = (int)p.k;
-  double q[D], mq = 0.0;
+  double q[D], mq = 0.0, qn = 0.0;
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     q[d] = p.q.p[(uint64_t)qi * p.q.stride_i + (uint64_t)d * p.q.stride_d];
     mq = fmax(mq, fabs(q[d]));  // fmax drops NaN; a NaN query fails the d2 == d2 test below
+    qn += q[d] * q[d];
   }
   int have = *have_p;
   long long ub = *ubits_p;
@@ -357,12 +386,13 @@ __device__ __noinline__ float knn_drain_f32(const ScanParams& p, uint32_t qi, ui
     *have_p = have;
     if (have == k) {
       *ubits_p = ub;
-      const double ms = __longlong_as_double((long long)*p.maxabs);
+      const double ms = __longlong_as_double((long long)p.maxabs[0]);
       const double M = (ms > mq || !(ms == ms)) ? ms : mq;
-      t32 = filter_threshold_dev(ub, M, D);
+      thr.diff = filter_threshold_dev(ub, M, D);
+      thr.dot = filter_threshold_dot_dev(ub, qn, __longlong_as_double((long long)p.maxabs[1]), D);
     }
   }
-  return t32;
+  return thr;
 }
 
 // Issues the D bulk copies of one f32 tile (called by one thread).
@@ -479,8 +509,9 @@ __global__ void __launch_bounds__(NN_THREADS) knn_rv_f32_kernel(const ScanParams
           for (int e = 0; e < 4; ++e) {
             if (av[e] > t32[a]) continue;
             if (ncand[a] == CAND_CAP) {  // buffer full: drain this query now
-              t32[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ,
-                                        s_list + li, i_list + li, &s_have[li], &s_ubits[li], t32[a]);
+              t32[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ, s_list + li,
+                                        i_list + li, &s_have[li], &s_ubits[li],
+                                        FilterThr{t32[a], 0.f}).diff;
               ncand[a] = 0;
               if (av[e] > t32[a]) continue;
             }
@@ -500,7 +531,8 @@ __global__ void __launch_bounds__(NN_THREADS) knn_rv_f32_kernel(const ScanParams
         for (int a = 0; a < QPT; ++a) {
           const int li = a * NN_THREADS + tid;
           t32[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ, s_list + li,
-                                    i_list + li, &s_have[li], &s_ubits[li], t32[a]);
+                                    i_list + li, &s_have[li], &s_ubits[li],
+                                    FilterThr{t32[a], 0.f}).diff;
           ncand[a] = 0;
         }
       }
@@ -522,6 +554,355 @@ __global__ void __launch_bounds__(NN_THREADS) knn_rv_f32_kernel(const ScanParams
       p.out_idx[o + e] = f ? il[e * NQ] : OXG_INVALID_INDEX;
       p.out_dist[o + e] = f ? sl[e * NQ] : __longlong_as_double(0x7FF0000000000000ll);
     }
+  }
+}
+
+// Issues the D+1 bulk copies (coordinates + squared norms) of one f32 tile.
+template <int D>
+__device__ __forceinline__ void issue_tile32n(const ScanParams& p, float* stage, uint64_t* bar,
+                                              uint32_t base, uint32_t cnt) {
+  uint32_t cnt_pad = (cnt + 3u) & ~3u;
+  uint32_t bytes = cnt_pad * 4u;
+  mbar_arrive_expect_tx(bar, bytes * (D + 1));
+#pragma unroll
+  for (int d = 0; d <= D; ++d)
+    bulk_copy_g2s(stage + d * F_TILE, p.db32 + (uint64_t)d * p.pitch + base, bytes, bar);
+}
+
+__device__ __forceinline__ float2 fma2_bcast(float g, float2 pv, float2 acc) {
+  return __ffma2_rn(make_float2(g, g), pv, acc);
+}
+
+// k-NN with the dot-form pre-filter and per-warp fallback to the difference form.
+// grid = (ceil(Q / (NN_THREADS*QPT)), nsplit)
+template <int D, int QPT>
+__global__ void __launch_bounds__(NN_THREADS) knn_rv_dot_kernel(const ScanParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NQ = NN_THREADS * QPT;
+  constexpr int COLS = D + 1;
+  float* tiles = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + F_STAGES * COLS * F_TILE);
+  double* s_list = reinterpret_cast<double*>(bars + F_STAGES);
+  long long* s_ubits = reinterpret_cast<long long*>(s_list + (size_t)p.k * NQ);
+  uint32_t* i_list = reinterpret_cast<uint32_t*>(s_ubits + NQ);
+  int* s_have = reinterpret_cast<int*>(i_list + (size_t)p.k * NQ);
+  uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_have + NQ);  // [CAND_CAP][NQ]
+
+  const int tid = threadIdx.x;
+  const int k = (int)p.k;
+  const float inf32 = __int_as_float(0x7F800000);
+  float qv[QPT][D];  // dot mode: -2 fl32(q_d); difference mode: fl32(q_d)
+  FilterThr thr[QPT];
+  uint32_t qi[QPT], excl[QPT];
+  int ncand[QPT];
+  bool dot_mode = true;  // warp-uniform
+#pragma unroll
+  for (int a = 0; a < QPT; ++a) {
+    qi[a] = blockIdx.x * NQ + a * NN_THREADS + tid;
+    const bool ok = qi[a] < p.Q;
+    const uint32_t qq = ok ? qi[a] : 0u;
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+      qv[a][d] = -2.0f * __double2float_rn(p.q.p[(uint64_t)qq * p.q.stride_i + (uint64_t)d * p.q.stride_d]);
+    excl[a] = OXG_INVALID_INDEX;
+    if (p.exclude_mode == EXCL_ARRAY) excl[a] = p.exclude[qq];
+    if (p.exclude_mode == EXCL_SELF) excl[a] = p.self_base + qq;
+    thr[a].diff = ok ? inf32 : -1.0f;
+    thr[a].dot = ok ? inf32 : -inf32;
+    s_ubits[a * NN_THREADS + tid] = ok ? 0x7FF0000000000000ll : -1ll;
+    s_have[a * NN_THREADS + tid] = 0;
+    qi[a] = qq;
+    ncand[a] = 0;
+  }
+
+  const uint32_t n0 = blockIdx.y * p.split_len;
+  const uint32_t n1 = min(p.n_db, n0 + p.split_len);
+  const uint32_t ntiles = (n1 > n0) ? (n1 - n0 + F_TILE - 1) / F_TILE : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < F_STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (uint32_t t = 0; t < (uint32_t)(F_STAGES - 1) && t < ntiles; ++t) {
+      uint32_t base = n0 + t * F_TILE;
+      issue_tile32n<D>(p, tiles + (t % F_STAGES) * COLS * F_TILE, &bars[t % F_STAGES], base,
+                       min((uint32_t)F_TILE, n1 - base));
+    }
+  }
+
+  for (uint32_t t = 0; t < ntiles; ++t) {
+    if (tid == 0) {
+      uint32_t tn = t + F_STAGES - 1;
+      if (tn < ntiles) {
+        uint32_t base = n0 + tn * F_TILE;
+        issue_tile32n<D>(p, tiles + (tn % F_STAGES) * COLS * F_TILE, &bars[tn % F_STAGES], base,
+                         min((uint32_t)F_TILE, n1 - base));
+      }
+    }
+    mbar_wait(&bars[t % F_STAGES], (t / F_STAGES) & 1u);
+    const float* sp = tiles + (t % F_STAGES) * COLS * F_TILE;
+    const uint32_t base = n0 + t * F_TILE;
+    const int cnt = (int)min((uint32_t)F_TILE, n1 - base);
+    int passed = 0;  // candidates this thread deferred in this tile
+#pragma unroll 1
+    for (int j = 0; j < cnt; j += 8) {
+      // 8 stored states per step: 4 independent packed accumulators per query
+      float2 acc[QPT][4];
+      bool any = false;
+      if (dot_mode) {
+        const float4 pn0 = *reinterpret_cast<const float4*>(sp + D * F_TILE + j);
+        const float4 pn1 = *reinterpret_cast<const float4*>(sp + D * F_TILE + j + 4);
+#pragma unroll
+        for (int a = 0; a < QPT; ++a) {
+          acc[a][0] = make_float2(pn0.x, pn0.y);
+          acc[a][1] = make_float2(pn0.z, pn0.w);
+          acc[a][2] = make_float2(pn1.x, pn1.y);
+          acc[a][3] = make_float2(pn1.z, pn1.w);
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float4 pv0 = *reinterpret_cast<const float4*>(sp + d * F_TILE + j);
+          const float4 pv1 = *reinterpret_cast<const float4*>(sp + d * F_TILE + j + 4);
+#pragma unroll
+          for (int a = 0; a < QPT; ++a) {
+            acc[a][0] = fma2_bcast(qv[a][d], make_float2(pv0.x, pv0.y), acc[a][0]);
+            acc[a][1] = fma2_bcast(qv[a][d], make_float2(pv0.z, pv0.w), acc[a][1]);
+            acc[a][2] = fma2_bcast(qv[a][d], make_float2(pv1.x, pv1.y), acc[a][2]);
+            acc[a][3] = fma2_bcast(qv[a][d], make_float2(pv1.z, pv1.w), acc[a][3]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float4 pv0 = *reinterpret_cast<const float4*>(sp + d * F_TILE + j);
+          const float4 pv1 = *reinterpret_cast<const float4*>(sp + d * F_TILE + j + 4);
+#pragma unroll
+          for (int a = 0; a < QPT; ++a) {
+            const float2 df[4] = {sub2(qv[a][d], make_float2(pv0.x, pv0.y)),
+                                  sub2(qv[a][d], make_float2(pv0.z, pv0.w)),
+                                  sub2(qv[a][d], make_float2(pv1.x, pv1.y)),
+                                  sub2(qv[a][d], make_float2(pv1.z, pv1.w))};
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              acc[a][g] = (d == 0) ? __fmul2_rn(df[g], df[g]) : __ffma2_rn(df[g], df[g], acc[a][g]);
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) {
+        const float tcur = dot_mode ? thr[a].dot : thr[a].diff;
+        // two short predicate chains instead of one long one
+        const bool h0 = !(acc[a][0].x > tcur) || !(acc[a][0].y > tcur) || !(acc[a][1].x > tcur) ||
+                        !(acc[a][1].y > tcur);
+        const bool h1 = !(acc[a][2].x > tcur) || !(acc[a][2].y > tcur) || !(acc[a][3].x > tcur) ||
+                        !(acc[a][3].y > tcur);
+        any = any || h0 || h1;
+      }
+      if (any) {
+#pragma unroll
+        for (int a = 0; a < QPT; ++a) {
+          const float av[8] = {acc[a][0].x, acc[a][0].y, acc[a][1].x, acc[a][1].y,
+                               acc[a][2].x, acc[a][2].y, acc[a][3].x, acc[a][3].y};
+          const int li = a * NN_THREADS + tid;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (av[e] > (dot_mode ? thr[a].dot : thr[a].diff)) continue;
+            if (ncand[a] == CAND_CAP) {  // buffer full: drain this query now
+              thr[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ,
+                                        s_list + li, i_list + li, &s_have[li], &s_ubits[li], thr[a]);
+              ncand[a] = 0;
+              if (av[e] > (dot_mode ? thr[a].dot : thr[a].diff)) continue;
+            }
+            s_cand[li + ncand[a] * NQ] = base + j + e;
+            ++ncand[a];
+            ++passed;
+          }
+        }
+      }
+    }
+    // Tile boundary.  The warp drains together (lanes stay converged) when some lane's buffer
+    // is getting full, every DRAIN_EVERY-th tile, and at the end: thresholds may lag a few
+    // tiles behind, which only lets a few more pairs through the filter.
+    {
+      bool pend = false, urgent = false;
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) {
+        pend = pend || ncand[a] > 0;
+        urgent = urgent || ncand[a] > CAND_CAP / 2;
+      }
+      const bool due = (t % DRAIN_EVERY) == DRAIN_EVERY - 1 || t + 1 == ntiles || t < 8;
+      if (__any_sync(0xFFFFFFFFu, urgent) || (due && __any_sync(0xFFFFFFFFu, pend))) {
+#pragma unroll
+        for (int a = 0; a < QPT; ++a) {
+          const int li = a * NN_THREADS + tid;
+          thr[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ, s_list + li,
+                                    i_list + li, &s_have[li], &s_ubits[li], thr[a]);
+          ncand[a] = 0;
+        }
+      }
+      // Adaptive fallback: once the lists have settled (a few tiles in), a warp that still
+      // defers more than ~2% of its pairs has a dot-form bound too loose for its data.
+      if (dot_mode && t >= 4) {
+        const int warp_passed = __reduce_add_sync(0xFFFFFFFFu, passed);
+        if (warp_passed > (32 * QPT * F_TILE) / 48) {
+          dot_mode = false;
+#pragma unroll
+          for (int a = 0; a < QPT; ++a)
+#pragma unroll
+            for (int d = 0; d < D; ++d) qv[a][d] = -0.5f * qv[a][d];  // exact: back to fl32(q_d)
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with this stage before it is refilled
+  }
+
+#pragma unroll
+  for (int a = 0; a < QPT; ++a) {
+    const uint32_t q_out = blockIdx.x * NQ + a * NN_THREADS + tid;
+    if (q_out >= p.Q) continue;
+    const int li = a * NN_THREADS + tid;
+    const int have = s_have[li];
+    uint64_t o = ((uint64_t)blockIdx.y * p.Q + q_out) * (uint64_t)k;
+    const double* sl = s_list + li;
+    const uint32_t* il = i_list + li;
+    for (int e = 0; e < k; ++e) {
+      bool f = e < have;
+      p.out_idx[o + e] = f ? il[e * NQ] : OXG_INVALID_INDEX;
+      p.out_dist[o + e] = f ? sl[e * NQ] : __longlong_as_double(0x7FF0000000000000ll);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Few-query 1-NN scan (the planners' per-iteration query through the C ABI, Q <= 8):
+// state-per-thread.  Every thread streams stored states straight from the f64 SoA columns
+// (coalesced, each byte of the store read exactly once: 8*D*N algorithmic bytes per batch) and
+// evaluates the QN queries held in registers.  This is the HBM-bound regime of SURVEY §8(d);
+// when the store fits the 126 MB L2 it is L2-bound.  Exactness: a state is admitted by
+// d2 <= U(best) (bit compare) and then compared as (sqrt(d2), index), exactly like the batched
+// kernel; per-CTA winners are merged by knn_merge_kernel.
+// ---------------------------------------------------------------------------------------
+constexpr int S1_THREADS = 256;
+
+template <int D, int QN>
+__global__ void __launch_bounds__(S1_THREADS) nn1_stream_kernel(const ScanParams p) {
+  __shared__ double s_d[QN][S1_THREADS / 32];
+  __shared__ uint32_t s_i[QN][S1_THREADS / 32];
+  double q[QN][D];
+  double best[QN];
+  uint32_t bi[QN];
+  long long ub[QN];
+#pragma unroll
+  for (int a = 0; a < QN; ++a) {
+    const uint32_t qq = (uint32_t)a < p.Q ? a : 0u;
+#pragma unroll
+    for (int d = 0; d < D; ++d) q[a][d] = p.q.p[(uint64_t)qq * p.q.stride_i + (uint64_t)d * p.q.stride_d];
+    best[a] = __longlong_as_double(0x7FF0000000000000ll);
+    bi[a] = OXG_INVALID_INDEX;
+    ub[a] = 0x7FF0000000000000ll;
+  }
+  const uint32_t stride = gridDim.x * S1_THREADS;
+#pragma unroll 2
+  for (uint32_t i = blockIdx.x * S1_THREADS + threadIdx.x; i < p.n_db; i += stride) {
+    double pt[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) pt[d] = __ldcs(p.db + (uint64_t)d * p.pitch + i);  // streamed once
+#pragma unroll
+    for (int a = 0; a < QN; ++a) {
+      // distance(stored, query): (stored - query)^2, the 1-NN call sites' argument order
+      double s = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const double df = __dsub_rn(pt[d], q[a][d]);
+        const double m = __dmul_rn(df, df);
+        s = (d == 0) ? m : __dadd_rn(s, m);
+      }
+      if (__double_as_longlong(s) <= ub[a] && s == s && i != p.exclude_one) {
+        const double r = sqrt(s);
+        if (r < best[a] || (r == best[a] && i < bi[a])) {
+          best[a] = r;
+          bi[a] = i;
+          ub[a] = __double_as_longlong(sqrt_le_upper_dev(r));
+        }
+      }
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int a = 0; a < QN; ++a) {
+    double bd = best[a];
+    uint32_t bx = bi[a];
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_down_sync(0xFFFFFFFFu, bd, o);
+      const uint32_t oi = __shfl_down_sync(0xFFFFFFFFu, bx, o);
+      if (od < bd || (od == bd && oi < bx)) {
+        bd = od;
+        bx = oi;
+      }
+    }
+    if (lane == 0) {
+      s_d[a][warp] = bd;
+      s_i[a][warp] = bx;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < QN && threadIdx.x < p.Q) {
+    const int a = threadIdx.x;
+    double bd = s_d[a][0];
+    uint32_t bx = s_i[a][0];
+    for (int wv = 1; wv < S1_THREADS / 32; ++wv)
+      if (s_d[a][wv] < bd || (s_d[a][wv] == bd && s_i[a][wv] < bx)) {
+        bd = s_d[a][wv];
+        bx = s_i[a][wv];
+      }
+    // partial list layout of knn_merge_kernel with k = 1: [slice][Q]
+    p.out_idx[(uint64_t)blockIdx.x * p.Q + a] = bx;
+    p.out_dist[(uint64_t)blockIdx.x * p.Q + a] = bd;
+  }
+}
+
+// Final reduction of the stream kernel's per-CTA winners: one CTA per query, (dist, idx) order.
+__global__ void __launch_bounds__(256) nn1_final_kernel(const uint32_t* __restrict__ part_idx,
+                                                        const double* __restrict__ part_dist,
+                                                        uint32_t Q, uint32_t nparts,
+                                                        uint32_t* __restrict__ out_idx,
+                                                        double* __restrict__ out_dist) {
+  __shared__ double s_d[8];
+  __shared__ uint32_t s_i[8];
+  const uint32_t qi = blockIdx.x;
+  double bd = __longlong_as_double(0x7FF0000000000000ll);
+  uint32_t bx = OXG_INVALID_INDEX;
+  for (uint32_t c = threadIdx.x; c < nparts; c += blockDim.x) {
+    const double d = part_dist[(uint64_t)c * Q + qi];
+    const uint32_t i = part_idx[(uint64_t)c * Q + qi];
+    if (d < bd || (d == bd && i < bx)) {
+      bd = d;
+      bx = i;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double od = __shfl_down_sync(0xFFFFFFFFu, bd, o);
+    const uint32_t oi = __shfl_down_sync(0xFFFFFFFFu, bx, o);
+    if (od < bd || (od == bd && oi < bx)) {
+      bd = od;
+      bx = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_d[threadIdx.x >> 5] = bd;
+    s_i[threadIdx.x >> 5] = bx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int wv = 1; wv < (int)(blockDim.x >> 5); ++wv)
+      if (s_d[wv] < bd || (s_d[wv] == bd && s_i[wv] < bx)) {
+        bd = s_d[wv];
+        bx = s_i[wv];
+      }
+    out_idx[qi] = bx;
+    out_dist[qi] = bd;
   }
 }
 
@@ -652,7 +1033,7 @@ __global__ void __launch_bounds__(NN_THREADS) radius_rv_f32_kernel(const ScanPar
   uint32_t qi[QPT], lim[QPT], count[QPT];
   uint64_t cursor[QPT];
   uint32_t maxlim = 0;
-  const double ms = __longlong_as_double((long long)*p.maxabs);
+  const double ms = __longlong_as_double((long long)p.maxabs[0]);
 #pragma unroll
   for (int a = 0; a < QPT; ++a) {
     qi[a] = blockIdx.x * NQ + a * NN_THREADS + tid;
@@ -884,9 +1265,36 @@ static int launch_knn_rv_f32(const ScanParams& p, dim3 grid, cudaStream_t st) {
   return OXG_OK;
 }
 
+template <int D>
+static int launch_nn1_stream(ScanParams p, uint32_t blocks, cudaStream_t st) {
+  if (p.Q <= 1) {
+    nn1_stream_kernel<D, 1><<<blocks, S1_THREADS, 0, st>>>(p);
+  } else if (p.Q <= 2) {
+    nn1_stream_kernel<D, 2><<<blocks, S1_THREADS, 0, st>>>(p);
+  } else if (p.Q <= 4) {
+    nn1_stream_kernel<D, 4><<<blocks, S1_THREADS, 0, st>>>(p);
+  } else {
+    nn1_stream_kernel<D, 8><<<blocks, S1_THREADS, 0, st>>>(p);
+  }
+  OXG_LAUNCH_CHECK();
+  return OXG_OK;
+}
+
+template <int D, int QPT>
+static int launch_knn_rv_dot(const ScanParams& p, dim3 grid, cudaStream_t st) {
+  size_t smem = knn_f32_smem_bytes<D, QPT>(p.k) + sizeof(float) * F_STAGES * F_TILE;  // + norm column
+  OXG_CUDA_TRY(cudaFuncSetAttribute(knn_rv_dot_kernel<D, QPT>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  knn_rv_dot_kernel<D, QPT><<<grid, NN_THREADS, smem, st>>>(p);
+  OXG_LAUNCH_CHECK();
+  return OXG_OK;
+}
+
 // Tuning / A-B switches read once from the environment (measurement aids, not a fallback:
 // both settings run hand-written sm_100a kernels and give bit-identical results).
 //   OXG_KNN_FILTER=0  use the all-FP64 scan kernels (no FP32 pre-filter)
+//   OXG_KNN_FORM=diff use the difference form of the pre-filter only (default: dot form with
+//                     per-warp fallback to the difference form)
 //   OXG_KNN_QPT=1|2   force the queries-per-thread of the batched k-NN kernel
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -894,6 +1302,13 @@ static int env_int(const char* name, int dflt) {
 }
 static bool use_f32_filter() {
   static const bool on = env_int("OXG_KNN_FILTER", 1) != 0;
+  return on;
+}
+static bool use_dot_form() {
+  static const bool on = [] {
+    const char* v = getenv("OXG_KNN_FORM");
+    return !(v && v[0] == 'd' && v[1] == 'i');
+  }();
   return on;
 }
 static int forced_qpt() {
@@ -1003,6 +1418,27 @@ int nn_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclu
   p.db32 = s->d_data32;
   p.maxabs = s->d_maxabs;
   const bool fast = is_pure_rv(s->space) && s->dim <= (uint32_t)kMaxFastDim;
+  if (fast && k == 1 && Q <= 8 && exclude_mode != EXCL_ARRAY) {
+    // few queries: stream the f64 store once, state-per-thread (HBM / L2 bound)
+    const uint32_t blocks =
+        (uint32_t)std::min<uint64_t>(((uint64_t)p.n_db + S1_THREADS - 1) / S1_THREADS, 148ull * 4);
+    p.exclude_one = (exclude_mode == EXCL_SELF) ? (uint32_t)self_base : OXG_INVALID_INDEX;
+    if (exclude_mode == EXCL_SELF && Q != 1) p.exclude_one = OXG_INVALID_INDEX;
+    if (!(exclude_mode == EXCL_SELF && Q != 1)) {
+      size_t npart = (size_t)blocks * Q;
+      OXG_TRY(s->buf[B_PIDX].ensure(npart * sizeof(uint32_t)));
+      OXG_TRY(s->buf[B_PDIST].ensure(npart * sizeof(double)));
+      p.out_idx = s->buf[B_PIDX].as<uint32_t>();
+      p.out_dist = s->buf[B_PDIST].as<double>();
+      int r = OXG_E_INTERNAL;
+      OXG_DISPATCH_D(s->dim, r = (launch_nn1_stream<DD>(p, blocks, s->stream)));
+      OXG_TRY(r);
+      nn1_final_kernel<<<(unsigned)Q, 256, 0, s->stream>>>(p.out_idx, p.out_dist, (uint32_t)Q, blocks,
+                                                          d_idx, d_dist);
+      OXG_LAUNCH_CHECK();
+      return OXG_OK;
+    }
+  }
   const bool f32 = fast && use_f32_filter();
   // several queries per thread once there is enough work to fill the machine that way
   int qpt = 1;
@@ -1028,7 +1464,15 @@ int nn_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclu
   p.out_dist = part_dist;
   dim3 grid((unsigned)qtiles, p.nsplit);
 
-  if (f32) {
+  if (f32 && use_dot_form() && Q >= 1024) {
+    int r = OXG_E_INTERNAL;
+    if (qpt == 2) {
+      OXG_DISPATCH_D(s->dim, r = (launch_knn_rv_dot<DD, 2>(p, grid, s->stream)));
+    } else {
+      OXG_DISPATCH_D(s->dim, r = (launch_knn_rv_dot<DD, 1>(p, grid, s->stream)));
+    }
+    OXG_TRY(r);
+  } else if (f32) {
     int r = OXG_E_INTERNAL;
     if (qpt == 2) {
       OXG_DISPATCH_D(s->dim, r = (launch_knn_rv_f32<DD, 2>(p, grid, s->stream)));
@@ -1251,8 +1695,10 @@ static int knn_host(oxg_store s, const double* queries, uint64_t Q, uint32_t k,
     OXG_CUDA_TRY(cudaMemcpyAsync(d_excl, exclude_idx, Q * sizeof(uint32_t), cudaMemcpyHostToDevice,
                                  s->stream));
   }
+  OXG_CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
   OXG_TRY(nn_knn_device(s, rows_view(s->buf[B_QUERY].as<double>(), s->dim), Q, k,
                         exclude_idx ? EXCL_ARRAY : EXCL_NONE, d_excl, 0, stored_first, d_idx, d_dist));
+  OXG_CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
   OXG_CUDA_TRY(cudaMemcpyAsync(idx, d_idx, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
   OXG_CUDA_TRY(cudaMemcpyAsync(dist, d_dist, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -1311,6 +1757,19 @@ int oxg_radius(oxg_store s, const double* queries, uint64_t Q, double r, const u
                                    cudaMemcpyDeviceToHost, s->stream));
   }
   OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return OXG_OK;
+  OXG_API_END
+}
+
+int oxg_store_last_scan_ms(oxg_store s, double* out_ms) {
+  OXG_API_BEGIN
+  if (!s || !out_ms) {
+    set_error("NULL argument");
+    return OXG_E_NULL;
+  }
+  float ms = 0.f;
+  OXG_CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+  *out_ms = ms;
   return OXG_OK;
   OXG_API_END
 }

@@ -219,12 +219,12 @@ def test_errors(oxg):
     assert e.value.code == -2  # OXG_E_DIM
 
 
-def _scaled_sets(d):
+def _scaled_sets(d, nq=64):
     """Inputs that stress the certified FP32 pre-filter: it must never change a result, only
     skip certain rejections (csrc/oxg_nn.cu, filter_threshold_dev)."""
     rng = np.random.default_rng(77 + d)
     u = rng.random((3000, d))
-    q = rng.random((64, d))
+    q = rng.random((nq, d))
     mixed = np.array([10.0 ** rng.integers(-6, 7) for _ in range(d)])
     return {
         "offset_1e7": (1.0e7 + u, 1.0e7 + q, 0.4),          # all f32 images collide
@@ -238,10 +238,13 @@ def _scaled_sets(d):
     }
 
 
+@pytest.mark.parametrize("nq", [64, 1100], ids=["diff_form", "dot_form"])
 @pytest.mark.parametrize("d", [2, 7])
-def test_fp32_prefilter_never_changes_results(oxg, orc, d):
+def test_fp32_prefilter_never_changes_results(oxg, orc, d, nq):
+    """64 queries take the difference-form kernel, >= 1024 the dot-form kernel (whose bound is
+    hopeless on the offset / mixed-scale sets: its warps must fall back, results unchanged)."""
     sp_o = orc.space(d)
-    for name, (rows, queries, r) in _scaled_sets(d).items():
+    for name, (rows, queries, r) in _scaled_sets(d, nq).items():
         rows = np.ascontiguousarray(rows)
         queries = np.ascontiguousarray(queries)
         with oxg.StateStore(oxg.Space.real_vector(d)) as st:
@@ -281,5 +284,28 @@ def test_store_clear_resets_filter_scale(oxg, orc):
         both = np.vstack([small, huge])
         idx, dist = st.knn(np.vstack([q, huge[:10]]), 3)
         oi, od = orc.knn(sp_o, both, np.vstack([q, huge[:10]]), 3)
+        np.testing.assert_array_equal(idx, oi)
+        np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+
+
+@pytest.mark.parametrize("q_count", [1, 2, 3, 5, 8])
+def test_few_query_stream_scan(oxg, orc, q_count):
+    """Q <= 8 takes the state-per-thread streaming kernel (the planners' per-iteration query)."""
+    for d, n in ((2, 1), (3, 300), (7, 70001), (14, 4097)):
+        rows = uniform_states(300 + d, n, [0.0] * d, [1.0] * d)
+        queries = uniform_states(400 + d, q_count, [0.0] * d, [1.0] * d)
+        with oxg.StateStore(oxg.Space.real_vector(d)) as st:
+            st.append(rows)
+            idx, dist = st.nn1(queries)
+            oi, od = orc.nn1(orc.space(d), rows, queries)
+            np.testing.assert_array_equal(idx, oi)
+            np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+            assert st.last_scan_ms() > 0.0
+    rows = _adversarial(5, 3000, 3)
+    queries = rows[:q_count] + 0.0
+    with oxg.StateStore(oxg.Space.real_vector(3)) as st:
+        st.append(rows)
+        idx, dist = st.nn1(queries)
+        oi, od = orc.nn1(orc.space(3), rows, queries)
         np.testing.assert_array_equal(idx, oi)
         np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
