@@ -415,6 +415,26 @@ int oxg_store_stream(oxg_store s, void** out_stream) {
 }
 
 // ------------------------------------------------------------------ world
+static int upload32(float** dst, const std::vector<float>& h, cudaStream_t st) {
+  *dst = nullptr;
+  if (h.empty()) return OXG_OK;
+  OXG_CUDA_TRY(cudaMalloc((void**)dst, sizeof(float) * h.size()));
+  OXG_CUDA_TRY(cudaMemcpyAsync(*dst, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice, st));
+  return OXG_OK;
+}
+
+// float >= v (round up) / float <= v (round down)
+static float f32_up(double v) {
+  float f = (float)v;
+  if ((double)f < v) f = std::nextafterf(f, INFINITY);
+  return f;
+}
+static float f32_down(double v) {
+  float f = (float)v;
+  if ((double)f > v) f = std::nextafterf(f, -INFINITY);
+  return f;
+}
+
 static int upload(double** dst, const std::vector<double>& h, cudaStream_t st) {
   *dst = nullptr;
   if (h.empty()) return OXG_OK;
@@ -484,9 +504,54 @@ int oxg_world_create(uint32_t dim, const double* spheres, uint64_t n_spheres, co
     dst[2 * dim] = den;
     dst[2 * dim + 1] = sqrt_le_threshold(a[2 * dim]);
   }
+  // ---- f32 mirrors for the certified pre-filter (see oxg_math.cuh, *_maybe_hit32)
+  w->sphere32_stride = (dim + 2 + 3) & ~3u;
+  w->capsule32_stride = (2 * dim + 3 + 3) & ~3u;
+  auto u1_of = [](double U) { return U >= 0.0 ? f32_up(U * 1.0001) : 0.0f; };
+  auto sq_of = [&](double U) {
+    return U >= 0.0 ? f32_up(std::sqrt((double)dim * U * 1.0001) * 1.0001) : 0.0f;
+  };
+  std::vector<float> hs32(n_spheres * w->sphere32_stride, 0.0f);
+  for (uint64_t i = 0; i < n_spheres; ++i) {
+    const double* src = hs.data() + i * w->sphere_stride;
+    float* dst = hs32.data() + i * w->sphere32_stride;
+    for (uint32_t d = 0; d < dim; ++d) {
+      dst[d] = (float)src[d];
+      w->wmax_spheres = std::fmax(w->wmax_spheres, std::fabs(src[d]));
+      if (!(src[d] == src[d])) w->wmax_spheres = INFINITY;
+    }
+    dst[dim] = u1_of(src[dim]);
+    dst[dim + 1] = sq_of(src[dim]);
+  }
+  std::vector<float> ha32(ha.size());
+  for (uint64_t i = 0; i < n_aabbs; ++i)
+    for (uint32_t d = 0; d < dim; ++d) {
+      ha32[i * 2 * dim + d] = f32_down(ha[i * 2 * dim + d]);
+      ha32[i * 2 * dim + dim + d] = f32_up(ha[i * 2 * dim + dim + d]);
+    }
+  std::vector<float> hc32(n_capsules * w->capsule32_stride, 0.0f);
+  for (uint64_t i = 0; i < n_capsules; ++i) {
+    const double* src = hc.data() + i * w->capsule_stride;
+    float* dst = hc32.data() + i * w->capsule32_stride;
+    for (uint32_t d = 0; d < dim; ++d) {
+      dst[d] = (float)src[d];
+      dst[dim + d] = (float)src[dim + d];
+      const double bd = capsules[i * (2 * dim + 1) + dim + d];
+      const double m = std::fmax(std::fmax(std::fabs(src[d]), std::fabs(src[dim + d])), std::fabs(bd));
+      w->wmax_capsules = std::fmax(w->wmax_capsules, m);
+      if (!(m == m)) w->wmax_capsules = INFINITY;
+    }
+    const double den = src[2 * dim];
+    dst[2 * dim] = den > 0.0 ? (float)(1.0 / den) : 0.0f;
+    dst[2 * dim + 1] = u1_of(src[2 * dim + 1]);
+    dst[2 * dim + 2] = sq_of(src[2 * dim + 1]);
+  }
   int r = upload(&w->d_spheres, hs, w->stream);
   if (r == OXG_OK) r = upload(&w->d_aabbs, ha, w->stream);
   if (r == OXG_OK) r = upload(&w->d_capsules, hc, w->stream);
+  if (r == OXG_OK) r = upload32(&w->d_spheres32, hs32, w->stream);
+  if (r == OXG_OK) r = upload32(&w->d_aabbs32, ha32, w->stream);
+  if (r == OXG_OK) r = upload32(&w->d_capsules32, hc32, w->stream);
   if (r == OXG_OK && cudaStreamSynchronize(w->stream) != cudaSuccess) {
     set_error("world upload failed");
     r = OXG_E_CUDA;
@@ -533,6 +598,9 @@ int oxg_world_destroy(oxg_world w) {
   if (w->d_spheres) cudaFree(w->d_spheres);
   if (w->d_aabbs) cudaFree(w->d_aabbs);
   if (w->d_capsules) cudaFree(w->d_capsules);
+  if (w->d_spheres32) cudaFree(w->d_spheres32);
+  if (w->d_aabbs32) cudaFree(w->d_aabbs32);
+  if (w->d_capsules32) cudaFree(w->d_capsules32);
   if (w->d_so2_comp) cudaFree(w->d_so2_comp);
   if (w->d_so2_lohi) cudaFree(w->d_so2_lohi);
   for (auto& b : w->buf) b.release();

@@ -181,6 +181,16 @@ struct oxg_world_s {
   double* d_spheres = nullptr;
   double* d_aabbs = nullptr;
   double* d_capsules = nullptr;
+  // f32 mirrors for the certified pre-filter of the validity kernels (never decide a result):
+  //   sphere : [c_0.., U1, sq]            U1 >= U(1+1e-4), sq >= sqrt(dim*U1)     stride sphere32_stride
+  //   aabb   : [lo_0.. (rounded down), hi_0.. (rounded up)]                        stride 2*dim
+  //   capsule: [a_0.., ab_0.., 1/den, U1, sq]                                      stride capsule32_stride
+  float* d_spheres32 = nullptr;
+  float* d_aabbs32 = nullptr;
+  float* d_capsules32 = nullptr;
+  uint32_t sphere32_stride = 0, capsule32_stride = 0;
+  double wmax_spheres = 0.0;   // max |centre coordinate|
+  double wmax_capsules = 0.0;  // max over |a_d|, |b_d|, |ab_d|
   uint64_t n_spheres = 0, n_aabbs = 0, n_capsules = 0;
   uint32_t sphere_stride = 0, aabb_stride = 0, capsule_stride = 0;
   // SO2 interval obstacles (host copy kept so add() can re-upload)
@@ -199,6 +209,11 @@ struct WorldView {
   const double* spheres;
   const double* aabbs;
   const double* capsules;
+  const float* spheres32;
+  const float* aabbs32;
+  const float* capsules32;
+  uint32_t sphere32_stride, capsule32_stride;
+  double wmax_spheres, wmax_capsules;
   const uint32_t* so2_comp;
   const double* so2_lohi;
   uint32_t n_spheres, n_aabbs, n_capsules, n_so2;
@@ -210,6 +225,13 @@ inline WorldView world_view(const oxg_world_s* w) {
   v.spheres = w->d_spheres;
   v.aabbs = w->d_aabbs;
   v.capsules = w->d_capsules;
+  v.spheres32 = w->d_spheres32;
+  v.aabbs32 = w->d_aabbs32;
+  v.capsules32 = w->d_capsules32;
+  v.sphere32_stride = w->sphere32_stride;
+  v.capsule32_stride = w->capsule32_stride;
+  v.wmax_spheres = w->wmax_spheres;
+  v.wmax_capsules = w->wmax_capsules;
   v.so2_comp = w->d_so2_comp;
   v.so2_lohi = w->d_so2_lohi;
   v.n_spheres = (uint32_t)w->n_spheres;

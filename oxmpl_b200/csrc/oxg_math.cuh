@@ -180,4 +180,93 @@ OXG_DEV bool capsule_hit_dev(const double* x, const double* __restrict__ cap, in
   return !(d2 > __ldg(cap + 2 * dim + 1));
 }
 
+// ----------------------------------------------------------------- certified FP32 pre-filters
+// "maybe hit" tests in FP32 from the world's f32 mirrors: they may only answer NO when a
+// rigorous bound on the FP32 evaluation error proves the exact FP64 predicate would answer NO
+// too; a YES is always followed by the exact predicate above.  Per-edge constants (EdgeTol)
+// carry the part of the bound that depends on the magnitude of the state's coordinates.
+//
+// Sphere (difference form, as the k-NN filter): with u = 2^-24, M >= |x_d|, |c_d|,
+// a = 4uM: d2_32 <= [S + 2a sqrt(D S) + 2 D a^2](1 + D 2^-22) whenever the exact sum S <= U.
+// Capsule: t32 is some point of [0,1], so the exact-arithmetic value at t32 is >= the true
+// minimum and exceeds it by |ab|^2 (t32 - t*)^2 <= (D+8)^2 u^2 (|ap| + M)^2; the evaluation of
+// e_d = x_d - a_d - ab_d t adds at most 8uM per coordinate.  Both are folded into
+// T = U1 + a2 * sq + ce with U1 >= U(1+1e-4), sq >= sqrt(D U1) from the mirror and a2, ce
+// from EdgeTol, every operation rounded up.
+struct EdgeTol {
+  float a2_s, ce_s;  // spheres
+  float a2_c, ce_c;  // capsules
+};
+
+// ms = max |coordinate| of the states this tolerance covers (both endpoints of an edge).
+OXG_DEV EdgeTol edge_tol_dev(double ms, double wmax_s, double wmax_c, int dim) {
+  EdgeTol t;
+  const float inf = __int_as_float(0x7F800000);
+  const double Ms = fmax(ms, wmax_s), Mc = fmax(ms, wmax_c);
+  if (!(Ms < 1.0e15) || !(ms == ms)) {
+    t.a2_s = inf;
+    t.ce_s = inf;
+  } else {
+    const double a = Ms * 2.384185791015625e-07 + 1e-37;  // 2^-22 M = 4uM
+    t.a2_s = __double2float_ru(2.0 * a * 1.0001);
+    t.ce_s = __double2float_ru((2.0 * dim * a * a + 1e-35) * 1.0001);
+  }
+  if (!(Mc < 1.0e15) || !(ms == ms)) {
+    t.a2_c = inf;
+    t.ce_c = inf;
+  } else {
+    const double a = Mc * 4.76837158203125e-07 + 1e-37;  // 2^-21 M = 8uM
+    t.a2_c = __double2float_ru(2.0 * a * 1.0001);
+    t.ce_c = __double2float_ru((2.0 * dim * a * a + 4e-10 * dim * Mc * Mc + 1e-35) * 1.0001);
+  }
+  return t;
+}
+
+template <int DT>
+OXG_DEV bool sphere_maybe_hit32(const float* xf, const float* __restrict__ sph, float a2, float ce,
+                                int dim_rt) {
+  const int dim = DimOf<DT>::get(dim_rt);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < dim; ++i) {
+    const float d = xf[i] - __ldg(sph + i);
+    s = __fmaf_rn(d, d, s);
+  }
+  const float T = __fmaf_ru(a2, __ldg(sph + dim + 1), __fadd_ru(__ldg(sph + dim), ce));
+  return !(s > T);
+}
+
+template <int DT>
+OXG_DEV bool aabb_maybe_hit32(const float* xf, const float* __restrict__ box, int dim_rt) {
+  const int dim = DimOf<DT>::get(dim_rt);
+  bool inside = true;
+#pragma unroll
+  for (int i = 0; i < dim; ++i)
+    inside = inside && !(xf[i] < __ldg(box + i)) && !(xf[i] > __ldg(box + dim + i));
+  return inside;
+}
+
+template <int DT>
+OXG_DEV bool capsule_maybe_hit32(const float* xf, const float* __restrict__ cap, float a2, float ce,
+                                 int dim_rt) {
+  const int dim = DimOf<DT>::get(dim_rt);
+  float ap[DT > 0 ? DT : 32];
+  float num = 0.f;
+#pragma unroll
+  for (int i = 0; i < dim; ++i) {
+    ap[i] = xf[i] - __ldg(cap + i);
+    num = __fmaf_rn(ap[i], __ldg(cap + dim + i), num);
+  }
+  float t = num * __ldg(cap + 2 * dim);
+  t = fminf(fmaxf(t, 0.f), 1.f);  // NaN -> 0: any t in [0,1] keeps the bound valid
+  float d2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < dim; ++i) {
+    const float e = __fmaf_rn(-t, __ldg(cap + dim + i), ap[i]);
+    d2 = __fmaf_rn(e, e, d2);
+  }
+  const float T = __fmaf_ru(a2, __ldg(cap + 2 * dim + 2), __fadd_ru(__ldg(cap + 2 * dim + 1), ce));
+  return !(d2 > T);
+}
+
 }  // namespace oxg

@@ -43,6 +43,26 @@ __device__ __forceinline__ bool state_valid_dev(const WorldView& w, const double
   return true;
 }
 
+// Same predicate with the certified FP32 pre-filter in front of every exact test (RealVector
+// fast paths).  xf = fl32(x); tol covers the magnitude of x.
+template <int DT>
+__device__ __forceinline__ bool state_valid_filtered_dev(const WorldView& w, const double* x,
+                                                         const float* xf, const EdgeTol& tol) {
+  for (uint32_t i = 0; i < w.n_spheres; ++i)
+    if (sphere_maybe_hit32<DT>(xf, w.spheres32 + (size_t)i * w.sphere32_stride, tol.a2_s, tol.ce_s, DT) &&
+        sphere_hit_dev<DT>(x, w.spheres + (size_t)i * w.sphere_stride, DT))
+      return false;
+  for (uint32_t i = 0; i < w.n_aabbs; ++i)
+    if (aabb_maybe_hit32<DT>(xf, w.aabbs32 + (size_t)i * w.aabb_stride, DT) &&
+        aabb_hit_dev<DT>(x, w.aabbs + (size_t)i * w.aabb_stride, DT))
+      return false;
+  for (uint32_t i = 0; i < w.n_capsules; ++i)
+    if (capsule_maybe_hit32<DT>(xf, w.capsules32 + (size_t)i * w.capsule32_stride, tol.a2_c, tol.ce_c, DT) &&
+        capsule_hit_dev<DT>(x, w.capsules + (size_t)i * w.capsule_stride, DT))
+      return false;
+  return true;
+}
+
 template <int DT>
 __global__ void __launch_bounds__(128) is_valid_kernel(const WorldView w, const SpaceP sp,
                                                        const StateView st, uint64_t Q,
@@ -55,7 +75,20 @@ __global__ void __launch_bounds__(128) is_valid_kernel(const WorldView w, const 
     double x[XN];
 #pragma unroll
     for (int d = 0; d < dim; ++d) x[d] = st.p[i * st.stride_i + (uint64_t)d * st.stride_d];
-    out[i] = state_valid_dev<DT>(w, x, n_real) ? 1 : 0;
+    if (DT > 0) {
+      float xf[XN];
+      double ms = 0.0;
+#pragma unroll
+      for (int d = 0; d < dim; ++d) {
+        xf[d] = __double2float_rn(x[d]);
+        ms = fmax(ms, fabs(x[d]));
+        if (!(x[d] == x[d])) ms = x[d];
+      }
+      const EdgeTol tol = edge_tol_dev(ms, w.wmax_spheres, w.wmax_capsules, DT);
+      out[i] = state_valid_filtered_dev<DT>(w, x, xf, tol) ? 1 : 0;
+    } else {
+      out[i] = state_valid_dev<DT>(w, x, n_real) ? 1 : 0;
+    }
   }
 }
 
@@ -103,6 +136,18 @@ __global__ void __launch_bounds__(128) motion_kernel(const MotionParams p) {
       dist = space_distance_dev(p.sp.n_real, p.sp.n_so2, p.sp.w_real, p.sp.w_so2, from, to);
     unsigned long long n = ceil_as_usize_dev(__ddiv_rn(dist, p.resolution));
     unsigned long long first_bad = 0;
+    EdgeTol tol;
+    if (DT > 0) {
+      // every interpolated coordinate lies between the endpoints' (up to one rounding, which the
+      // 1.0001 factors of the tolerance absorb)
+      double ms = 0.0;
+#pragma unroll
+      for (int d = 0; d < dim; ++d) {
+        ms = fmax(ms, fmax(fabs(from[d]), fabs(to[d])));
+        if (!(from[d] == from[d]) || !(to[d] == to[d])) ms = __longlong_as_double(0x7FF8000000000000ll);
+      }
+      tol = edge_tol_dev(ms * 1.0000001, p.w.wmax_spheres, p.w.wmax_capsules, DT);
+    }
     if (n > (1ull << 32)) {
       first_bad = 0xFFFFFFFFull;  // the reference loop would not terminate in practice
     } else {
@@ -124,7 +169,14 @@ __global__ void __launch_bounds__(128) motion_kernel(const MotionParams p) {
             for (int c = 0; c < n_so2; ++c)
               x[n_real + c] = so2_interpolate_dev(from[n_real + c], to[n_real + c], t);
           }
-          bad = !state_valid_dev<DT>(p.w, x, n_real);
+          if (DT > 0) {
+            float xf[XN];
+#pragma unroll
+            for (int d = 0; d < dim; ++d) xf[d] = __double2float_rn(x[d]);
+            bad = !state_valid_filtered_dev<DT>(p.w, x, xf, tol);
+          } else {
+            bad = !state_valid_dev<DT>(p.w, x, n_real);
+          }
         }
         const unsigned b = (__ballot_sync(group_mask, bad) & group_mask) >> group_shift;
         if (b) {
