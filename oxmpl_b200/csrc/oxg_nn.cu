@@ -569,6 +569,13 @@ __device__ __forceinline__ void issue_tile32n(const ScanParams& p, float* stage,
     bulk_copy_g2s(stage + d * F_TILE, p.db32 + (uint64_t)d * p.pitch + base, bytes, bar);
 }
 
+// min of three with NaN propagation (FMNMX3.NAN): a NaN evaluation must reach the exact path.
+__device__ __forceinline__ float min3_nan(float a, float b, float c) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 __device__ __forceinline__ float2 fma2_bcast(float g, float2 pv, float2 acc) {
   return __ffma2_rn(make_float2(g, g), pv, acc);
 }
@@ -693,12 +700,12 @@ __global__ void __launch_bounds__(NN_THREADS) knn_rv_dot_kernel(const ScanParams
 #pragma unroll
       for (int a = 0; a < QPT; ++a) {
         const float tcur = dot_mode ? thr[a].dot : thr[a].diff;
-        // two short predicate chains instead of one long one
-        const bool h0 = !(acc[a][0].x > tcur) || !(acc[a][0].y > tcur) || !(acc[a][1].x > tcur) ||
-                        !(acc[a][1].y > tcur);
-        const bool h1 = !(acc[a][2].x > tcur) || !(acc[a][2].y > tcur) || !(acc[a][3].x > tcur) ||
-                        !(acc[a][3].y > tcur);
-        any = any || h0 || h1;
+        // smallest of the 8 evaluations (3 x FMNMX3 + 1 FMNMX), one compare per query
+        const float m0 = min3_nan(acc[a][0].x, acc[a][0].y, acc[a][1].x);
+        const float m1 = min3_nan(acc[a][1].y, acc[a][2].x, acc[a][2].y);
+        const float m2 = min3_nan(acc[a][3].x, acc[a][3].y, m0);
+        const float m = min3_nan(m1, m2, m2);
+        any = any || !(m > tcur);
       }
       if (any) {
 #pragma unroll

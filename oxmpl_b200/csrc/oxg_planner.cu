@@ -97,11 +97,11 @@ struct PlanParams {
   double* nbr_dist;
   uint32_t nbr_capc;
   PlanCtrl* ctrl;
+  unsigned long long* barrier;  // grid barrier arrival counter (zeroed per launch)
 };
 
 struct PlanShared {
   double q_rand[kMaxDim], q_near[kMaxDim], q_new[kMaxDim], pend[kMaxDim];
-  double wx[PL_WARPS][kMaxDim];
   double red_d[PL_WARPS];
   double bc_d[4];
   uint32_t red_i[PL_WARPS];
@@ -213,10 +213,25 @@ __device__ __forceinline__ unsigned long long motion_steps(double dist, double r
 }
 
 // ------------------------------------------------------------------------------- barriers
+// Grid barrier of the cooperative launch (all CTAs are co-resident).  One monotonically
+// increasing arrival counter: barrier number g completes when it reaches g * gridDim.x.
+// Every datum that crosses CTAs in this kernel is read with ld.global.cg / volatile (L2), so
+// the barrier needs no L1 invalidation — which also keeps the obstacle set warm in L1 across
+// the several barriers of an iteration (cooperative_groups' grid.sync() flushes L1 each time).
 template <bool MULTI>
-__device__ __forceinline__ void grid_barrier(cg::grid_group& g) {
+__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long& gen) {
   if (MULTI) {
-    g.sync();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ++gen;
+      __threadfence();
+      atomicAdd(counter, 1ull);
+      const unsigned long long target = gen * gridDim.x;
+      while (*reinterpret_cast<volatile unsigned long long*>(counter) < target) {
+      }
+      __threadfence();
+    }
+    __syncthreads();
   } else {
     __syncthreads();
   }
@@ -361,69 +376,80 @@ __device__ void phase_steer(const PlanParams& P, PlanShared& sh, const TreeView&
 // Motion-check tasks.  Edge e (0 <= e < E) joins the fixed state `fixed` (shared memory) and
 // either `other_sm` (shared memory; E must be 1) or tree state nb_idx[e_nb[e]]; `fixed_is_to`
 // selects the direction (from = other, to = fixed) or (from = fixed, to = other).  Edge e has
-// ns = steps[e] reference steps and states e_pre[e]..e_pre[e+1]-1.  A warp task is one state
-// against one chunk of 32 obstacles; a hit sets hit[e].
-__device__ void motion_tasks(const PlanParams& P, PlanShared& sh, const TreeView& T, uint32_t E,
-                             const double* fixed, bool fixed_is_to, const double* other_sm,
-                             const uint32_t* steps, const uint32_t* pre, const uint32_t* e_nb,
-                             uint32_t* hit) {
+// ns = steps[e] reference steps and states pre[e]..pre[e+1]-1.
+//
+// Two stages per batch of states: (1) the CTA interpolates every state of the batch into shared
+// memory once (thread per coordinate; reference operation order), (2) each warp owns one chunk
+// of 32 obstacles (lane = obstacle) and sweeps the states of its group — no per-task search,
+// division or global load is left in the sweep.  A hit sets hit[e]; edges this warp already
+// knows to be hit are skipped, the global flag is polled only every 16th state.
+constexpr int PL_STATE_BYTES = 64 * 1024;
+
+__device__ void motion_tasks(const PlanParams& P, PlanShared& sh, double* st_buf, const TreeView& T,
+                             uint32_t E, const double* fixed, bool fixed_is_to,
+                             const double* other_sm, const uint32_t* steps, const uint32_t* pre,
+                             const uint32_t* e_nb, uint32_t* hit) {
   const uint32_t n_oc = world_chunks(P.w);
   if (n_oc == 0 || E == 0) return;
   const uint32_t NS = pre[E];
-  const int dim = (int)(P.n_real + P.n_so2);
+  const uint32_t dim = P.n_real + P.n_so2;
+  const uint32_t cap = (uint32_t)PL_STATE_BYTES / (dim * 8u + 4u);
+  uint32_t* st_edge = reinterpret_cast<uint32_t*>(st_buf + (size_t)cap * dim);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t gw = blockIdx.x * PL_WARPS + warp, GW = gridDim.x * PL_WARPS;
-  uint32_t c0, cstep, s0, sstep;
+  uint32_t c0, cstep, g0, groups;
   if (GW >= n_oc) {
-    const uint32_t groups = GW / n_oc;
+    groups = GW / n_oc;
     c0 = gw % n_oc;
     cstep = n_oc;  // one chunk per warp
-    s0 = gw / n_oc;
-    sstep = groups;
-    if (s0 >= groups) return;
+    g0 = gw / n_oc;
+    if (g0 >= groups) c0 = n_oc;  // idle warp (still takes part in the CTA barriers)
   } else {
     c0 = gw;
     cstep = GW;
-    s0 = 0;
-    sstep = 1;
+    g0 = 0;
+    groups = 1;
   }
-  double* x = sh.wx[warp];
-  for (uint32_t c = c0; c < n_oc; c += cstep) {
-    uint32_t e = 0, skip_e = OXG_INVALID_INDEX, tick = 0, cur_e = OXG_INVALID_INDEX;
-    double o = 0.0;  // this lane's coordinate of the edge's far endpoint (reloaded per edge)
-    for (uint32_t s = s0; s < NS; s += sstep, ++tick) {
-      while (pre[e + 1] <= s) ++e;  // edge of state s (s only grows)
-      if (e == skip_e) continue;
-      // early exit: a hit recorded by any warp ends the edge; the flag lives in L2, so it is
-      // polled only every 8th task (a stale miss costs work, never a result)
-      if ((tick & 7u) == 7u && *reinterpret_cast<volatile uint32_t*>(&hit[e])) {
-        skip_e = e;
-        continue;
+  for (uint32_t sb = 0; sb < NS; sb += cap) {
+    const uint32_t nb = min(cap, NS - sb);
+    __syncthreads();  // the previous batch (or the caller's use of st_buf) is finished
+    // ---- stage 1: interpolate states [sb, sb+nb)
+    for (uint32_t u = threadIdx.x; u < nb * dim; u += PL_THREADS) {
+      const uint32_t sl = u / dim, d = u - sl * dim, s_glob = sb + sl;
+      uint32_t lo = 0, hi = E;  // largest e with pre[e] <= s_glob
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pre[mid] <= s_glob) lo = mid; else hi = mid;
       }
+      const uint32_t e = lo;
       const uint32_t ns = e_nb ? steps[e_nb[e]] : steps[e];
-      const uint32_t i = s - pre[e] + 1;
-      if ((int)lane < dim) {
-        if (e != cur_e) {
-          if (other_sm) {
-            o = other_sm[lane];
-          } else {
-            const uint32_t j = sh.nb_idx[e_nb[e]];
-            o = __ldcg(&T.data[(uint64_t)lane * T.pitch + j]);
-          }
+      const uint32_t i = s_glob - pre[e] + 1;
+      const double o = other_sm ? other_sm[d]
+                                : __ldcg(&T.data[(uint64_t)d * T.pitch + sh.nb_idx[e_nb[e]]]);
+      const double f = fixed_is_to ? o : fixed[d];
+      const double t = fixed_is_to ? fixed[d] : o;
+      // `if num_steps <= 1 { return is_valid(to) }`; step i of n: t = i / n (rrt.rs:99-105)
+      st_buf[(size_t)sl * dim + d] =
+          (ns <= 1) ? t : interp_coord(P, d, f, t, __ddiv_rn((double)i, (double)ns));
+      if (d == 0) st_edge[sl] = e;
+    }
+    __syncthreads();
+    // ---- stage 2: obstacle chunk x state sweep
+    for (uint32_t c = c0; c < n_oc; c += cstep) {
+      uint32_t skip_e = OXG_INVALID_INDEX, tick = 0;
+      for (uint32_t sl = g0; sl < nb; sl += groups, ++tick) {
+        const uint32_t e = st_edge[sl];
+        if (e == skip_e) continue;
+        if ((tick & 15u) == 15u && *reinterpret_cast<volatile uint32_t*>(&hit[e])) {
+          skip_e = e;
+          continue;
         }
-        const double f = fixed_is_to ? o : fixed[lane];
-        const double t = fixed_is_to ? fixed[lane] : o;
-        // `if num_steps <= 1 { return is_valid(to) }`; step i of n: t = i / n (rrt.rs:99-105)
-        x[lane] = (ns <= 1) ? t : interp_coord(P, lane, f, t, __ddiv_rn((double)i, (double)ns));
+        const bool h = chunk_hit(P, c, lane, st_buf + (size_t)sl * dim);
+        if (__any_sync(0xFFFFFFFFu, h)) {
+          if (lane == 0) atomicOr(&hit[e], 1u);
+          skip_e = e;
+        }
       }
-      cur_e = e;
-      __syncwarp();
-      const bool h = chunk_hit(P, c, lane, x);
-      if (__any_sync(0xFFFFFFFFu, h)) {
-        if (lane == 0) atomicOr(&hit[e], 1u);
-        skip_e = e;
-      }
-      __syncwarp();
     }
   }
 }
@@ -476,12 +502,50 @@ __device__ void phase_radius(const PlanParams& P, PlanShared& sh, const TreeView
   }
 }
 
+// Ordered compaction of the selected neighbour slots into the edge list (e_nb, e_pre) by warp 0:
+// 32 slots per round, ballot for the positions, a shuffle scan for the state prefix.
+// nb_ns[u] == 0xFFFFFFFE marks a motion with too many steps (-> *bad).
+template <class Sel>
+__device__ __forceinline__ void compact_edges(PlanShared& sh, uint32_t m, Sel sel) {
+  if (threadIdx.x < 32) {
+    const uint32_t lane = threadIdx.x;
+    uint32_t E = 0, pre = 0;
+    bool bad = false;
+    for (uint32_t base = 0; base < m; base += 32) {
+      const uint32_t u = base + lane;
+      const bool sl = u < m && sel(u);
+      const uint32_t ns = sl ? sh.nb_ns[u] : 0u;
+      const uint32_t neff = sl ? ((ns <= 1u || ns == 0xFFFFFFFEu) ? 1u : ns) : 0u;
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, sl);
+      uint32_t incl = neff;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((int)lane >= o) incl += v;
+      }
+      if (sl) {
+        const uint32_t pos = E + __popc(b & ((1u << lane) - 1u));
+        sh.e_nb[pos] = u;
+        sh.e_pre[pos] = pre + incl - neff;
+      }
+      bad = bad || __any_sync(0xFFFFFFFFu, sl && ns == 0xFFFFFFFEu);
+      E += __popc(b);
+      pre += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (lane == 0) {
+      sh.e_pre[E] = pre;
+      sh.bc_u[2] = E;
+      sh.bc_i[0] = bad ? 1 : 0;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------- the kernel
 template <int MODE, bool MULTI>
 __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PlanShared& sh = *reinterpret_cast<PlanShared*>(smem_raw);
-  cg::grid_group grid = cg::this_grid();
+  double* const st_buf = reinterpret_cast<double*>(smem_raw + ((sizeof(PlanShared) + 15) & ~size_t(15)));
+  unsigned long long bar_gen = 0;  // barriers passed (tracked by thread 0)
   const int dim = (int)(P.n_real + P.n_so2);
   const uint32_t tid = threadIdx.x;
   const uint32_t gtid = blockIdx.x * PL_THREADS + tid, gthreads = gridDim.x * PL_THREADS;
@@ -514,7 +578,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
     const unsigned par = (unsigned)(ext_count & 1ull);
     ++ext_count;
     phase_scan<MULTI>(P, sh, T, n[t], target, pidx);
-    grid_barrier<MULTI>(grid);
+    grid_barrier<MULTI>(P.barrier, bar_gen);
     if (gtid == 0) hit_ext[par ^ 1u] = 0u;  // the other parity's flag: next extend's
     phase_steer<MULTI>(P, sh, T, target, pidx, near_out, min_dist_out, reached_out);
     // check_motion(q_near, q_new)
@@ -530,7 +594,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
       sh.nb_ns[0] = (uint32_t)ns64;
     }
     __syncthreads();
-    motion_tasks(P, sh, T, 1, sh.q_new, true, sh.q_near, sh.nb_ns, sh.e_pre, nullptr,
+    motion_tasks(P, sh, st_buf, T, 1, sh.q_new, true, sh.q_near, sh.nb_ns, sh.e_pre, nullptr,
                  hit_ext + par);
     if (count_ref) {
       ++mc_ref;
@@ -544,7 +608,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
       }
       phase_radius<MULTI>(P, sh, T, n[t], pidx);
     }
-    grid_barrier<MULTI>(grid);
+    grid_barrier<MULTI>(P.barrier, bar_gen);
     const bool valid = flag(hit_ext + par) == 0u;
     return valid;
   };
@@ -702,25 +766,10 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
         // check_motion(neighbour.state, q_new): dist = distance(from = nbr, to = new)
         const double dd = dist_ab(P, node(T, j), sm(sh.q_new));
         const unsigned long long ns64 = motion_steps(dd, P.resolution);
-        sh.nb_ns[u] = ns64 > MAX_STEPS ? 0xFFFFFFFFu : (uint32_t)ns64;
+        sh.nb_ns[u] = ns64 > MAX_STEPS ? 0xFFFFFFFEu : (uint32_t)ns64;
       }
       __syncthreads();
-      if (tid == 0) {
-        uint32_t E = 0, pre = 0;
-        int bad = 0;
-        for (uint32_t u = 0; u < m; ++u) {
-          if (sh.nb_c[u] < min_cost0) {  // superset of the lazily evaluated candidates
-            if (sh.nb_ns[u] == 0xFFFFFFFFu) bad = 1;
-            sh.e_nb[E] = u;
-            sh.e_pre[E] = pre;
-            pre += sh.nb_ns[u] <= 1 ? 1u : sh.nb_ns[u];
-            ++E;
-          }
-        }
-        sh.e_pre[E] = pre;
-        sh.bc_u[2] = E;
-        sh.bc_i[0] = bad;
-      }
+      compact_edges(sh, m, [&](uint32_t u) { return sh.nb_c[u] < min_cost0; });  // superset of the lazy loop's
       __syncthreads();
       const uint32_t E0 = sh.bc_u[2];
       if (sh.bc_i[0]) {
@@ -728,11 +777,14 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
         break;
       }
       if (E0 > 0) {
-        motion_tasks(P, sh, T, E0, sh.q_new, true, nullptr, sh.nb_ns, sh.e_pre, sh.e_nb, hit_cp);
+        motion_tasks(P, sh, st_buf, T, E0, sh.q_new, true, nullptr, sh.nb_ns, sh.e_pre, sh.e_nb, hit_cp);
         mc_exec += E0;
-        grid_barrier<MULTI>(grid);
+        grid_barrier<MULTI>(P.barrier, bar_gen);
       }
-      // sequential replay of the lazy selection
+      // sequential replay of the lazy selection (hit flags fetched in parallel first)
+      uint32_t* const hit_sm = reinterpret_cast<uint32_t*>(st_buf);
+      for (uint32_t e = tid; e < E0; e += PL_THREADS) hit_sm[e] = flag(hit_cp + e);
+      __syncthreads();
       if (tid == 0) {
         double min_cost = min_cost0;
         uint32_t best = near;
@@ -741,7 +793,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
           const uint32_t u = sh.e_nb[e];
           if (sh.nb_c[u] < min_cost) {
             ++ref;
-            if (flag(hit_cp + e) == 0u) {
+            if (hit_sm[e] == 0u) {
               min_cost = sh.nb_c[u];
               best = sh.nb_idx[u];
             }
@@ -769,22 +821,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
         sh.nb_ns[u] = cand ? (ns64 > MAX_STEPS ? 0xFFFFFFFEu : (uint32_t)ns64) : 0xFFFFFFFFu;
       }
       __syncthreads();
-      if (tid == 0) {
-        uint32_t E = 0, pre = 0;
-        int bad = 0;
-        for (uint32_t u = 0; u < m; ++u) {
-          if (sh.nb_ns[u] != 0xFFFFFFFFu) {
-            if (sh.nb_ns[u] == 0xFFFFFFFEu) bad = 1;
-            sh.e_nb[E] = u;
-            sh.e_pre[E] = pre;
-            pre += sh.nb_ns[u] <= 1 ? 1u : sh.nb_ns[u];
-            ++E;
-          }
-        }
-        sh.e_pre[E] = pre;
-        sh.bc_u[2] = E;
-        sh.bc_i[0] = bad;
-      }
+      compact_edges(sh, m, [&](uint32_t u) { return sh.nb_ns[u] != 0xFFFFFFFFu; });
       __syncthreads();
       const uint32_t E1 = sh.bc_u[2];
       if (sh.bc_i[0]) {
@@ -792,10 +829,10 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
         break;
       }
       if (E1 > 0) {
-        motion_tasks(P, sh, T, E1, sh.q_new, false, nullptr, sh.nb_ns, sh.e_pre, sh.e_nb, hit_rw);
+        motion_tasks(P, sh, st_buf, T, E1, sh.q_new, false, nullptr, sh.nb_ns, sh.e_pre, sh.e_nb, hit_rw);
         mc_exec += E1;
         mc_ref += E1;
-        grid_barrier<MULTI>(grid);
+        grid_barrier<MULTI>(P.barrier, bar_gen);
         if (blockIdx.x == 0) {
           for (uint32_t e = tid; e < E1; e += PL_THREADS) {
             if (flag(hit_rw + e) == 0u) {
@@ -858,7 +895,7 @@ int choose_ctas(uint64_t max_nodes, uint32_t dim, uint64_t n_obstacles, int sm_c
 
 template <int MODE>
 int launch_planner(const PlanParams& P, int G, cudaStream_t st) {
-  const size_t smem = sizeof(PlanShared);
+  const size_t smem = ((sizeof(PlanShared) + 15) & ~size_t(15)) + PL_STATE_BYTES + 64;
   PlanParams pp = P;
   void* args[] = {(void*)&pp};
   if (G > 1) {
@@ -992,6 +1029,7 @@ int plan_solve(oxg_world w, oxg_store t0, oxg_store t1, const oxg_plan_params* p
   const size_t o_hrw = take(sizeof(uint32_t) * NBR_CAP);
   const size_t o_goal = take(sizeof(double) * kMaxDim);
   const size_t o_cnt = take(sizeof(uint32_t) * G);
+  const size_t o_bar = take(sizeof(unsigned long long));
   const size_t zero_bytes = off;  // everything above starts zeroed
   size_t o_nidx = 0, o_ndist = 0;
   if (MODE == MODE_STAR) {
@@ -1044,6 +1082,7 @@ int plan_solve(oxg_world w, oxg_store t0, oxg_store t1, const oxg_plan_params* p
   P.nbr_dist = reinterpret_cast<double*>(base + o_ndist);
   P.nbr_capc = capc;
   P.ctrl = reinterpret_cast<PlanCtrl*>(base + o_ctrl);
+  P.barrier = reinterpret_cast<unsigned long long*>(base + o_bar);
 
   OXG_CUDA_TRY(cudaStreamSynchronize(w->stream));  // the world upload is complete
   OXG_CUDA_TRY(cudaEventRecord(s->ev0, st));

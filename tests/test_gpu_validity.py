@@ -126,3 +126,52 @@ def test_config1_step_count(oxg, orc):
     ov, of = orc.check_motion(ow, sp_o, frm, to, res)
     assert (v[0], f[0]) == (0, 3) == (ov[0], of[0])
     gw.close()
+
+
+@pytest.mark.parametrize("dim", [2, 7])
+@pytest.mark.parametrize("name,scale,offset", [
+    ("offset_1e6", 1.0, 1.0e6),          # f32 images of obstacles and states nearly collide
+    ("offset_1e12", 1.0, 1.0e12),
+    ("tiny_1e-20", 1e-20, 0.0),
+    ("huge_1e150", 1e150, 0.0),           # f32 overflow everywhere, f64 squares still finite
+    ("unit", 1.0, 0.0),
+])
+def test_validity_prefilter_never_changes_results(oxg, orc, dim, name, scale, offset):
+    """The FP32 pre-filter of the validity kernels (oxg_math.cuh, *_maybe_hit32) may only skip
+    exact tests whose outcome is certain: scaled / shifted worlds and states that sit exactly on
+    obstacle boundaries must give the oracle's booleans."""
+    spheres, aabbs, capsules = worlds.calibrated_obstacles(dim, dim, 24, 24, 24, p_each=0.02)
+
+    def tr(a, radius_col=None):
+        a = a.copy()
+        if radius_col is None:
+            return a * scale + offset
+        a[:, :radius_col] = a[:, :radius_col] * scale + offset
+        a[:, radius_col] = a[:, radius_col] * scale
+        return a
+
+    S, B, C = tr(spheres, dim), tr(aabbs), tr(capsules, 2 * dim)
+    sp, sp_o = oxg.Space.real_vector(dim), orc.space(dim)
+    gw, ow, keep = _world_pair(oxg, orc, dim, S, B, C)
+    states = uniform_states(90 + dim, 6000, [-1.0] * dim, [1.0] * dim) * scale + offset
+    # states exactly on boundaries: sphere surface along +e0, box faces and corners, capsule caps
+    on_sphere = S[:, :dim].copy()
+    on_sphere[:, 0] = on_sphere[:, 0] + S[:, dim]
+    on_box = np.vstack([B[:, :dim], B[:, dim:], 0.5 * (B[:, :dim] + B[:, dim:])])
+    on_cap = C[:, dim:2 * dim].copy()
+    on_cap[:, -1] = on_cap[:, -1] + C[:, 2 * dim]
+    states = np.ascontiguousarray(np.vstack([states, on_sphere, on_box, on_cap,
+                                             np.nextafter(on_sphere, np.inf),
+                                             np.nextafter(on_box, -np.inf)]))
+    got, want = gw.is_valid(sp, states), orc.is_valid(ow, sp_o, states)
+    np.testing.assert_array_equal(got, want, err_msg=name)
+    frm = states[:3000]
+    to = states[3000:6000]
+    res = 0.05 * scale
+    v, first = gw.check_motion(sp, frm, to, res, want_first_invalid=True)
+    ov, ofirst = orc.check_motion(ow, sp_o, frm, to, res)
+    np.testing.assert_array_equal(v, ov, err_msg=name)
+    np.testing.assert_array_equal(first, ofirst, err_msg=name)
+    if name in ("unit", "tiny_1e-20", "huge_1e150"):
+        assert 0 < want.sum() < want.size
+    gw.close()
