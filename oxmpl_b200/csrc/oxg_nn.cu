@@ -1156,6 +1156,293 @@ __global__ void __launch_bounds__(NN_THREADS) radius_rv_f32_kernel(const ScanPar
   }
 }
 
+// Radius scan with the dot-form pre-filter (per-warp fallback to the difference form), 8 stored
+// states per step; same two-pass scheme and output contract as radius_rv_f32_kernel.
+template <int D, bool FILL, int QPT>
+__global__ void __launch_bounds__(NN_THREADS) radius_rv_dot_kernel(const ScanParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NQ = NN_THREADS * QPT;
+  constexpr int COLS = D + 1;
+  float* tiles = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + F_STAGES * COLS * F_TILE);
+  __shared__ uint32_t s_maxlim;
+
+  const int tid = threadIdx.x;
+  float qv[QPT][D];  // dot mode: -2 fl32(q_d); difference mode: fl32(q_d)
+  FilterThr thr[QPT];
+  uint32_t qi[QPT], lim[QPT], count[QPT];
+  uint64_t cursor[QPT];
+  uint32_t maxlim = 0;
+  bool dot_mode = true;  // warp-uniform
+  const double ms = __longlong_as_double((long long)p.maxabs[0]);
+  const double pmax = __longlong_as_double((long long)p.maxabs[1]);
+  const float inf32 = __int_as_float(0x7F800000);
+#pragma unroll
+  for (int a = 0; a < QPT; ++a) {
+    qi[a] = blockIdx.x * NQ + a * NN_THREADS + tid;
+    const bool ok = qi[a] < p.Q;
+    const uint32_t qq = ok ? qi[a] : 0u;
+    double mq = 0.0, qn = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double v = p.q.p[(uint64_t)qq * p.q.stride_i + (uint64_t)d * p.q.stride_d];
+      mq = fmax(mq, fabs(v));
+      qn += v * v;
+      qv[a][d] = -2.0f * __double2float_rn(v);
+    }
+    lim[a] = p.n_db;
+    if (p.idx_limit) lim[a] = min(lim[a], p.idx_limit[qq]);
+    if (p.limit_self) lim[a] = min(lim[a], p.self_base + qq);
+    if (!ok) lim[a] = 0;
+    maxlim = max(maxlim, lim[a]);
+    const double M = (ms > mq || !(ms == ms)) ? ms : mq;
+    thr[a].diff = ok ? filter_threshold_dev(p.r_bits, M, D) : -1.0f;
+    thr[a].dot = ok ? filter_threshold_dot_dev(p.r_bits, qn, pmax, D) : -inf32;
+    cursor[a] = 0;
+    if (FILL && ok) cursor[a] = p.counts[(uint64_t)qi[a] * p.nsplit + blockIdx.y];
+    count[a] = 0;
+    qi[a] = qq;
+  }
+
+  if (tid == 0) s_maxlim = 0;
+  __syncthreads();
+  atomicMax(&s_maxlim, maxlim);
+  if (tid == 0) {
+    for (int s = 0; s < F_STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const uint32_t n0 = blockIdx.y * p.split_len;
+  const uint32_t n1 = min(min(p.n_db, s_maxlim), n0 + p.split_len);
+  const uint32_t ntiles = (n1 > n0) ? (n1 - n0 + F_TILE - 1) / F_TILE : 0;
+
+  if (tid == 0) {
+    for (uint32_t t = 0; t < (uint32_t)(F_STAGES - 1) && t < ntiles; ++t) {
+      uint32_t base = n0 + t * F_TILE;
+      issue_tile32n<D>(p, tiles + (t % F_STAGES) * COLS * F_TILE, &bars[t % F_STAGES], base,
+                       min((uint32_t)F_TILE, n1 - base));
+    }
+  }
+  for (uint32_t t = 0; t < ntiles; ++t) {
+    if (tid == 0) {
+      uint32_t tn = t + F_STAGES - 1;
+      if (tn < ntiles) {
+        uint32_t base = n0 + tn * F_TILE;
+        issue_tile32n<D>(p, tiles + (tn % F_STAGES) * COLS * F_TILE, &bars[tn % F_STAGES], base,
+                         min((uint32_t)F_TILE, n1 - base));
+      }
+    }
+    mbar_wait(&bars[t % F_STAGES], (t / F_STAGES) & 1u);
+    const float* sp = tiles + (t % F_STAGES) * COLS * F_TILE;
+    const uint32_t base = n0 + t * F_TILE;
+    const int cnt = (int)min((uint32_t)F_TILE, n1 - base);
+    int passed = 0;
+#pragma unroll 1
+    for (int j = 0; j < cnt; j += 8) {
+      float2 acc[QPT][4];
+      bool any = false;
+      if (dot_mode) {
+        const float4 pn0 = *reinterpret_cast<const float4*>(sp + D * F_TILE + j);
+        const float4 pn1 = *reinterpret_cast<const float4*>(sp + D * F_TILE + j + 4);
+#pragma unroll
+        for (int a = 0; a < QPT; ++a) {
+          acc[a][0] = make_float2(pn0.x, pn0.y);
+          acc[a][1] = make_float2(pn0.z, pn0.w);
+          acc[a][2] = make_float2(pn1.x, pn1.y);
+          acc[a][3] = make_float2(pn1.z, pn1.w);
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float4 pv0 = *reinterpret_cast<const float4*>(sp + d * F_TILE + j);
+          const float4 pv1 = *reinterpret_cast<const float4*>(sp + d * F_TILE + j + 4);
+#pragma unroll
+          for (int a = 0; a < QPT; ++a) {
+            acc[a][0] = fma2_bcast(qv[a][d], make_float2(pv0.x, pv0.y), acc[a][0]);
+            acc[a][1] = fma2_bcast(qv[a][d], make_float2(pv0.z, pv0.w), acc[a][1]);
+            acc[a][2] = fma2_bcast(qv[a][d], make_float2(pv1.x, pv1.y), acc[a][2]);
+            acc[a][3] = fma2_bcast(qv[a][d], make_float2(pv1.z, pv1.w), acc[a][3]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float4 pv0 = *reinterpret_cast<const float4*>(sp + d * F_TILE + j);
+          const float4 pv1 = *reinterpret_cast<const float4*>(sp + d * F_TILE + j + 4);
+#pragma unroll
+          for (int a = 0; a < QPT; ++a) {
+            const float2 df[4] = {sub2(qv[a][d], make_float2(pv0.x, pv0.y)),
+                                  sub2(qv[a][d], make_float2(pv0.z, pv0.w)),
+                                  sub2(qv[a][d], make_float2(pv1.x, pv1.y)),
+                                  sub2(qv[a][d], make_float2(pv1.z, pv1.w))};
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              acc[a][g] = (d == 0) ? __fmul2_rn(df[g], df[g]) : __ffma2_rn(df[g], df[g], acc[a][g]);
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) {
+        const float tcur = dot_mode ? thr[a].dot : thr[a].diff;
+        const float m0 = min3_nan(acc[a][0].x, acc[a][0].y, acc[a][1].x);
+        const float m1 = min3_nan(acc[a][1].y, acc[a][2].x, acc[a][2].y);
+        const float m2 = min3_nan(acc[a][3].x, acc[a][3].y, m0);
+        any = any || !(min3_nan(m1, m2, m2) > tcur);
+      }
+      if (any) {
+#pragma unroll
+        for (int a = 0; a < QPT; ++a) {
+          const float tcur = dot_mode ? thr[a].dot : thr[a].diff;
+          const float av[8] = {acc[a][0].x, acc[a][0].y, acc[a][1].x, acc[a][1].y,
+                               acc[a][2].x, acc[a][2].y, acc[a][3].x, acc[a][3].y};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (av[e] > tcur) continue;
+            ++passed;
+            const uint32_t jj = base + j + e;
+            if (jj >= n1 || jj >= lim[a]) continue;
+            double mq;
+            const double s = exact_sumsq_global<D>(p, qi[a], jj, &mq);
+            if (__double_as_longlong(s) <= p.r_bits && s == s) {
+              if (FILL) {
+                p.hit_idx[cursor[a] + count[a]] = jj;
+                if (p.hit_dist) p.hit_dist[cursor[a] + count[a]] = sqrt(s);
+              }
+              ++count[a];
+            }
+          }
+        }
+      }
+    }
+    if (dot_mode && t >= 1) {
+      const int warp_passed = __reduce_add_sync(0xFFFFFFFFu, passed);
+      if (warp_passed > (32 * QPT * F_TILE) / 48) {
+        dot_mode = false;
+#pragma unroll
+        for (int a = 0; a < QPT; ++a)
+#pragma unroll
+          for (int d = 0; d < D; ++d) qv[a][d] = -0.5f * qv[a][d];  // exact: back to fl32(q_d)
+      }
+    }
+    __syncthreads();
+  }
+  if (!FILL) {
+#pragma unroll
+    for (int a = 0; a < QPT; ++a) {
+      const uint32_t q_out = blockIdx.x * NQ + a * NN_THREADS + tid;
+      if (q_out < p.Q) p.counts[(uint64_t)q_out * p.nsplit + blockIdx.y] = count[a];
+    }
+  }
+}
+
+// Few-query radius scan (Q <= 8: RRT*'s find_neighbours and PRM's start connection through the
+// C ABI): state-per-thread over contiguous per-CTA slices of the f64 store, queries broadcast
+// from shared memory.  Same two-pass contract as the batched kernels: the count pass writes
+// counts[q * nsplit + slice], the fill pass writes the hits of each slice in ascending index
+// order (ballot + block prefix per round of S1_THREADS states).  The store is streamed once per
+// pass for all queries of the batch: HBM / L2 bound.
+constexpr int RS_MAXQ = 8;
+
+template <int D, bool FILL>
+__global__ void __launch_bounds__(S1_THREADS) radius_stream_kernel(const ScanParams p) {
+  __shared__ double s_q[RS_MAXQ][D];
+  __shared__ uint32_t s_lim[RS_MAXQ];
+  __shared__ uint32_t s_wcnt[RS_MAXQ][S1_THREADS / 32];
+  const uint32_t Q = p.Q;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < Q * D) {
+    const uint32_t a = threadIdx.x / D, d = threadIdx.x % D;
+    s_q[a][d] = p.q.p[(uint64_t)a * p.q.stride_i + (uint64_t)d * p.q.stride_d];
+  }
+  if (threadIdx.x < Q) {
+    uint32_t lim = p.n_db;
+    if (p.idx_limit) lim = min(lim, p.idx_limit[threadIdx.x]);
+    if (p.limit_self) lim = min(lim, p.self_base + threadIdx.x);
+    s_lim[threadIdx.x] = lim;
+  }
+  __syncthreads();
+  const uint32_t n0 = blockIdx.x * p.split_len;
+  const uint32_t n1 = min(p.n_db, n0 + p.split_len);
+  uint32_t run[RS_MAXQ];
+  uint64_t cursor[RS_MAXQ];
+#pragma unroll
+  for (int a = 0; a < RS_MAXQ; ++a) {
+    run[a] = 0;
+    cursor[a] = (FILL && (uint32_t)a < Q) ? p.counts[(uint64_t)a * p.nsplit + blockIdx.x] : 0;
+  }
+  for (uint32_t base = n0; base < n1; base += S1_THREADS) {
+    const uint32_t i = base + threadIdx.x;
+    double pt[D];
+    if (i < n1) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) pt[d] = __ldcs(p.db + (uint64_t)d * p.pitch + i);
+    }
+    uint32_t hits = 0;  // bit a: this state is inside query a's ball
+    double dist[RS_MAXQ];
+#pragma unroll
+    for (int a = 0; a < RS_MAXQ; ++a) {
+      if ((uint32_t)a >= Q) break;
+      bool h = false;
+      if (i < n1 && i < s_lim[a]) {
+        // distance(query, stored): radius call sites' argument order (rrt_star.rs:125, prm.rs:133)
+        double s = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const double df = __dsub_rn(s_q[a][d], pt[d]);
+          const double m = __dmul_rn(df, df);
+          s = (d == 0) ? m : __dadd_rn(s, m);
+        }
+        h = __double_as_longlong(s) <= p.r_bits && s == s;  // exactly sqrt(s) < r
+        dist[a] = s;
+      }
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, h);
+      if (FILL) {
+        if (lane == 0) s_wcnt[a][warp] = __popc(b);
+        if (h) hits |= 1u << a;
+      } else {
+        run[a] += (lane == 0) ? __popc(b) : 0u;
+      }
+    }
+    if (FILL) {
+      __syncthreads();
+#pragma unroll
+      for (int a = 0; a < RS_MAXQ; ++a) {
+        if ((uint32_t)a >= Q) break;
+        const bool h = (hits >> a) & 1u;
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, h);
+        uint32_t off = run[a], tot = 0;
+#pragma unroll
+        for (int wv = 0; wv < S1_THREADS / 32; ++wv) {
+          const uint32_t c = s_wcnt[a][wv];
+          if (wv < warp) off += c;
+          tot += c;
+        }
+        if (h) {
+          const uint64_t pos = cursor[a] + off + __popc(b & ((1u << lane) - 1u));
+          p.hit_idx[pos] = i;
+          if (p.hit_dist) p.hit_dist[pos] = sqrt(dist[a]);
+        }
+        run[a] += tot;
+      }
+      __syncthreads();
+    }
+  }
+  if (!FILL) {
+    // block total per query (lane 0 of each warp holds its warp's count)
+#pragma unroll
+    for (int a = 0; a < RS_MAXQ; ++a) {
+      if ((uint32_t)a >= Q) break;
+      if (lane == 0) s_wcnt[a][warp] = run[a];
+    }
+    __syncthreads();
+    if (threadIdx.x < Q) {
+      uint32_t tot = 0;
+      for (int wv = 0; wv < S1_THREADS / 32; ++wv) tot += s_wcnt[threadIdx.x][wv];
+      p.counts[(uint64_t)threadIdx.x * p.nsplit + blockIdx.x] = tot;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Generic spaces (SO2, compound R^n x SO2, or RealVector with D > 16): runtime dimensions,
 // full distance per pair in the reference's order, stored states read through the L1/L2 as
@@ -1334,6 +1621,22 @@ static int launch_radius_rv_f32(const ScanParams& p, dim3 grid, bool fill, cudaS
     OXG_CUDA_TRY(cudaFuncSetAttribute(radius_rv_f32_kernel<D, false, QPT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     radius_rv_f32_kernel<D, false, QPT><<<grid, NN_THREADS, smem, st>>>(p);
+  }
+  OXG_LAUNCH_CHECK();
+  return OXG_OK;
+}
+
+template <int D, int QPT>
+static int launch_radius_rv_dot(const ScanParams& p, dim3 grid, bool fill, cudaStream_t st) {
+  size_t smem = sizeof(float) * F_STAGES * (D + 1) * F_TILE + sizeof(uint64_t) * F_STAGES;
+  if (fill) {
+    OXG_CUDA_TRY(cudaFuncSetAttribute(radius_rv_dot_kernel<D, true, QPT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    radius_rv_dot_kernel<D, true, QPT><<<grid, NN_THREADS, smem, st>>>(p);
+  } else {
+    OXG_CUDA_TRY(cudaFuncSetAttribute(radius_rv_dot_kernel<D, false, QPT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    radius_rv_dot_kernel<D, false, QPT><<<grid, NN_THREADS, smem, st>>>(p);
   }
   OXG_LAUNCH_CHECK();
   return OXG_OK;
@@ -1523,7 +1826,7 @@ int nn_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclu
 }
 
 struct RadiusPlan {
-  bool fast, f32;
+  bool fast, f32, stream;
   int qpt;
   uint32_t nsplit, split_len;
   uint64_t qtiles;
@@ -1532,6 +1835,16 @@ static RadiusPlan radius_plan(const oxg_store_s* s, uint64_t Q) {
   RadiusPlan pl;
   pl.fast = is_pure_rv(s->space) && s->dim <= (uint32_t)kMaxFastDim;
   pl.f32 = pl.fast && use_f32_filter();
+  pl.stream = pl.fast && Q >= 1 && Q <= (uint64_t)RS_MAXQ;
+  if (pl.stream) {  // few queries: state-per-thread over contiguous per-CTA slices
+    const uint32_t n = std::max<uint32_t>((uint32_t)s->size, 1);
+    uint32_t ns = std::min<uint32_t>(std::max<uint32_t>(1, (n + 2047) / 2048), 148 * 4);
+    pl.split_len = round_up_u32((n + ns - 1) / ns, S1_THREADS);
+    pl.nsplit = (n + pl.split_len - 1) / pl.split_len;
+    pl.qpt = 1;
+    pl.qtiles = 1;
+    return pl;
+  }
   pl.qpt = (pl.f32 && Q >= 2ull * 148 * NN_THREADS * 2) ? 2 : 1;
   const uint64_t per_cta = (uint64_t)NN_THREADS * pl.qpt;
   pl.qtiles = std::max<uint64_t>((Q + per_cta - 1) / per_cta, 1);
@@ -1595,6 +1908,24 @@ int nn_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double r, const ui
   g.stored_first = 0;
   g.radius = r;
   auto launch = [&](bool fill) -> int {
+    if (pl.stream) {
+      if (fill) {
+        OXG_DISPATCH_D(s->dim, (radius_stream_kernel<DD, true><<<p.nsplit, S1_THREADS, 0, s->stream>>>(p)));
+      } else {
+        OXG_DISPATCH_D(s->dim, (radius_stream_kernel<DD, false><<<p.nsplit, S1_THREADS, 0, s->stream>>>(p)));
+      }
+      OXG_LAUNCH_CHECK();
+      return OXG_OK;
+    }
+    if (pl.f32 && use_dot_form() && Q >= 1024) {
+      int rr = OXG_E_INTERNAL;
+      if (pl.qpt == 2) {
+        OXG_DISPATCH_D(s->dim, rr = (launch_radius_rv_dot<DD, 2>(p, grid, fill, s->stream)));
+      } else {
+        OXG_DISPATCH_D(s->dim, rr = (launch_radius_rv_dot<DD, 1>(p, grid, fill, s->stream)));
+      }
+      return rr;
+    }
     if (pl.f32) {
       int rr = OXG_E_INTERNAL;
       if (pl.qpt == 2) {

@@ -309,3 +309,34 @@ def test_few_query_stream_scan(oxg, orc, q_count):
         oi, od = orc.nn1(orc.space(3), rows, queries)
         np.testing.assert_array_equal(idx, oi)
         np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+
+
+@pytest.mark.parametrize("q_count", [1, 2, 5, 8])
+def test_few_query_stream_radius(oxg, orc, q_count):
+    """Q <= 8 radius scans (find_neighbours / PRM start connection) take the state-per-thread
+    two-pass kernel: ascending indices, idx_limit, distances, empty results."""
+    for d, n in ((2, 1), (3, 777), (6, 70001), (14, 4097)):
+        rows = uniform_states(500 + d, n, [0.0] * d, [1.0] * d)
+        queries = uniform_states(600 + d, q_count, [0.0] * d, [1.0] * d)
+        sp_o = orc.space(d)
+        with oxg.StateStore(oxg.Space.real_vector(d)) as st:
+            st.append(rows)
+            for r in (0.0, 0.35 * np.sqrt(d), 10.0):
+                off, idx, dist = st.radius(queries, r, want_dist=True)
+                ooff, oidx, odist = orc.radius(sp_o, rows, queries, r, want_dist=True)
+                np.testing.assert_array_equal(off, ooff)
+                np.testing.assert_array_equal(idx, oidx)
+                np.testing.assert_array_equal(dist.view(np.uint64), odist.view(np.uint64))
+            lim = np.arange(q_count, dtype=np.uint32) * (n // 8)
+            off, idx = st.radius(queries, 0.4 * np.sqrt(d), idx_limit=lim)
+            ooff, oidx = orc.radius(sp_o, rows, queries, 0.4 * np.sqrt(d), idx_limit=lim)
+            np.testing.assert_array_equal(off, ooff)
+            np.testing.assert_array_equal(idx, oidx)
+    rows = _adversarial(6, 3000, 2)
+    with oxg.StateStore(oxg.Space.real_vector(2)) as st:
+        st.append(rows)
+        for r in (0.5, 1.0, np.nextafter(1.0, 2.0)):
+            off, idx = st.radius(rows[:q_count], r)
+            ooff, oidx = orc.radius(orc.space(2), rows, rows[:q_count], r)
+            np.testing.assert_array_equal(off, ooff)
+            np.testing.assert_array_equal(idx, oidx)
