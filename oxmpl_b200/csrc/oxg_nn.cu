@@ -318,6 +318,7 @@ __device__ __forceinline__ double sqrt_le_upper_dev(double sw) {
 
 constexpr int CAND_CAP = 16;  // deferred candidates per query (u32 indices, shared memory)
 constexpr int DRAIN_EVERY = 8;  // tiles between scheduled warp-wide drains
+constexpr int DOT_MIN_CTAS = 3; // CTAs per SM the dot kernel is compiled for (caps registers)
 
 // Dot-product form of the pre-filter.  With g_d = -2 fl32(q_d), pn = fl32(|p|^2) and the FP32
 // FMA chain  A = fma(g_D, p_D, ... fma(g_1, p_1, pn)),  A approximates |p|^2 - 2 q.p = d2 - |q|^2
@@ -352,8 +353,8 @@ struct FilterThr {
 template <int D>
 __device__ __noinline__ FilterThr knn_drain_f32(const ScanParams& p, uint32_t qi, uint32_t n_end,
                                                 uint32_t excl, const uint32_t* cand, int ncand,
-                                                int stride, double* sl, uint32_t* il, int* have_p,
-                                                long long* ubits_p, FilterThr thr) {
+                                                int cstride, int stride, double* sl, uint32_t* il,
+                                                int* have_p, long long* ubits_p, FilterThr thr) {
   if (ncand == 0) return thr;
   const int k = (int)p.k;
   double q[D], mq = 0.0, qn = 0.0;
@@ -367,7 +368,7 @@ __device__ __noinline__ FilterThr knn_drain_f32(const ScanParams& p, uint32_t qi
   long long ub = *ubits_p;
   bool changed = false;
   for (int c = 0; c < ncand; ++c) {
-    const uint32_t j = cand[c * stride];
+    const uint32_t j = cand[c * cstride];
     if (j >= n_end || j == excl) continue;
     double d2 = 0.0;
 #pragma unroll
@@ -509,8 +510,8 @@ __global__ void __launch_bounds__(NN_THREADS) knn_rv_f32_kernel(const ScanParams
           for (int e = 0; e < 4; ++e) {
             if (av[e] > t32[a]) continue;
             if (ncand[a] == CAND_CAP) {  // buffer full: drain this query now
-              t32[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ, s_list + li,
-                                        i_list + li, &s_have[li], &s_ubits[li],
+              t32[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ, NQ,
+                                        s_list + li, i_list + li, &s_have[li], &s_ubits[li],
                                         FilterThr{t32[a], 0.f}).diff;
               ncand[a] = 0;
               if (av[e] > t32[a]) continue;
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(NN_THREADS) knn_rv_f32_kernel(const ScanParams
 #pragma unroll
         for (int a = 0; a < QPT; ++a) {
           const int li = a * NN_THREADS + tid;
-          t32[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ, s_list + li,
+          t32[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ, NQ, s_list + li,
                                     i_list + li, &s_have[li], &s_ubits[li],
                                     FilterThr{t32[a], 0.f}).diff;
           ncand[a] = 0;
@@ -582,18 +583,122 @@ __device__ __forceinline__ float2 fma2_bcast(float g, float2 pv, float2 acc) {
 
 // k-NN with the dot-form pre-filter and per-warp fallback to the difference form.
 // grid = (ceil(Q / (NN_THREADS*QPT)), nsplit)
+// 16-byte shared-memory load from a 32-bit shared address (no generic-address conversion in
+// the inner loop).
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+
+// One tile of the filtered k-NN scan: 8 stored states per step, DOT selects the dot form
+// (columns 0..D-1 = coordinates, column D = squared norms) or the difference form.  Returns
+// the number of candidates this thread deferred.
+template <int D, int QPT, bool DOT>
+__device__ __forceinline__ int knn_scan_tile(const ScanParams& p, uint32_t sp_addr, int cnt,
+                                             uint32_t base, uint32_t n1, const float (&qv)[QPT][D],
+                                             FilterThr (&thr)[QPT], const uint32_t (&qi)[QPT],
+                                             const uint32_t (&excl)[QPT], int (&ncand)[QPT],
+                                             uint32_t* s_cand, double* const (&g_list)[QPT],
+                                             uint32_t* const (&g_ilist)[QPT], int* s_have,
+                                             long long* s_ubits, int tid) {
+  constexpr int NQ = NN_THREADS * QPT;
+  int passed = 0;
+#pragma unroll 1
+  for (int j = 0; j < cnt; j += 8) {
+    const uint32_t row = sp_addr + (uint32_t)j * 4u;
+    float2 acc[QPT][4];
+    if (DOT) {
+      const float4 pn0 = lds128(row + D * F_TILE * 4);
+      const float4 pn1 = lds128(row + D * F_TILE * 4 + 16);
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) {
+        acc[a][0] = make_float2(pn0.x, pn0.y);
+        acc[a][1] = make_float2(pn0.z, pn0.w);
+        acc[a][2] = make_float2(pn1.x, pn1.y);
+        acc[a][3] = make_float2(pn1.z, pn1.w);
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float4 pv0 = lds128(row + d * F_TILE * 4);
+        const float4 pv1 = lds128(row + d * F_TILE * 4 + 16);
+#pragma unroll
+        for (int a = 0; a < QPT; ++a) {
+          acc[a][0] = fma2_bcast(qv[a][d], make_float2(pv0.x, pv0.y), acc[a][0]);
+          acc[a][1] = fma2_bcast(qv[a][d], make_float2(pv0.z, pv0.w), acc[a][1]);
+          acc[a][2] = fma2_bcast(qv[a][d], make_float2(pv1.x, pv1.y), acc[a][2]);
+          acc[a][3] = fma2_bcast(qv[a][d], make_float2(pv1.z, pv1.w), acc[a][3]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float4 pv0 = lds128(row + d * F_TILE * 4);
+        const float4 pv1 = lds128(row + d * F_TILE * 4 + 16);
+#pragma unroll
+        for (int a = 0; a < QPT; ++a) {
+          const float2 df[4] = {sub2(qv[a][d], make_float2(pv0.x, pv0.y)),
+                                sub2(qv[a][d], make_float2(pv0.z, pv0.w)),
+                                sub2(qv[a][d], make_float2(pv1.x, pv1.y)),
+                                sub2(qv[a][d], make_float2(pv1.z, pv1.w))};
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            acc[a][g] = (d == 0) ? __fmul2_rn(df[g], df[g]) : __ffma2_rn(df[g], df[g], acc[a][g]);
+        }
+      }
+    }
+    bool any = false;
+#pragma unroll
+    for (int a = 0; a < QPT; ++a) {
+      const float tcur = DOT ? thr[a].dot : thr[a].diff;
+      // smallest of the 8 evaluations (FMNMX3 with NaN propagation), one compare per query
+      const float m0 = min3_nan(acc[a][0].x, acc[a][0].y, acc[a][1].x);
+      const float m1 = min3_nan(acc[a][1].y, acc[a][2].x, acc[a][2].y);
+      const float m2 = min3_nan(acc[a][3].x, acc[a][3].y, m0);
+      any = any || !(min3_nan(m1, m2, m2) > tcur);
+    }
+    if (any) {
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) {
+        const float av[8] = {acc[a][0].x, acc[a][0].y, acc[a][1].x, acc[a][1].y,
+                             acc[a][2].x, acc[a][2].y, acc[a][3].x, acc[a][3].y};
+        const int li = a * NN_THREADS + tid;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (av[e] > (DOT ? thr[a].dot : thr[a].diff)) continue;
+          if (ncand[a] == CAND_CAP) {  // buffer full: drain this query now
+            thr[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ, 1, g_list[a],
+                                      g_ilist[a], &s_have[li], &s_ubits[li], thr[a]);
+            ncand[a] = 0;
+            if (av[e] > (DOT ? thr[a].dot : thr[a].diff)) continue;
+          }
+          s_cand[li + ncand[a] * NQ] = base + j + e;
+          ++ncand[a];
+          ++passed;
+        }
+      }
+    }
+  }
+  return passed;
+}
+
 template <int D, int QPT>
-__global__ void __launch_bounds__(NN_THREADS) knn_rv_dot_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(NN_THREADS, DOT_MIN_CTAS) knn_rv_dot_kernel(const ScanParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NQ = NN_THREADS * QPT;
   constexpr int COLS = D + 1;
   float* tiles = reinterpret_cast<float*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + F_STAGES * COLS * F_TILE);
-  double* s_list = reinterpret_cast<double*>(bars + F_STAGES);
-  long long* s_ubits = reinterpret_cast<long long*>(s_list + (size_t)p.k * NQ);
-  uint32_t* i_list = reinterpret_cast<uint32_t*>(s_ubits + NQ);
-  int* s_have = reinterpret_cast<int*>(i_list + (size_t)p.k * NQ);
+  // The sorted (dist, idx) lists live in the output buffers themselves (global memory, one
+  // contiguous run per query, touched only by the rare exact path): shared memory is left to
+  // the tiles and the candidate buffers, which is what bounds the CTAs per SM.
+  long long* s_ubits = reinterpret_cast<long long*>(bars + F_STAGES);
+  int* s_have = reinterpret_cast<int*>(s_ubits + NQ);
   uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_have + NQ);  // [CAND_CAP][NQ]
+  double* g_list[QPT];
+  uint32_t* g_ilist[QPT];
 
   const int tid = threadIdx.x;
   const int k = (int)p.k;
@@ -618,6 +723,11 @@ __global__ void __launch_bounds__(NN_THREADS) knn_rv_dot_kernel(const ScanParams
     thr[a].dot = ok ? inf32 : -inf32;
     s_ubits[a * NN_THREADS + tid] = ok ? 0x7FF0000000000000ll : -1ll;
     s_have[a * NN_THREADS + tid] = 0;
+    {
+      const uint64_t o = ((uint64_t)blockIdx.y * p.Q + qq) * (uint64_t)p.k;
+      g_list[a] = p.out_dist + o;
+      g_ilist[a] = p.out_idx + o;
+    }
     qi[a] = qq;
     ncand[a] = 0;
   }
@@ -653,82 +763,13 @@ __global__ void __launch_bounds__(NN_THREADS) knn_rv_dot_kernel(const ScanParams
     const uint32_t base = n0 + t * F_TILE;
     const int cnt = (int)min((uint32_t)F_TILE, n1 - base);
     int passed = 0;  // candidates this thread deferred in this tile
-#pragma unroll 1
-    for (int j = 0; j < cnt; j += 8) {
-      // 8 stored states per step: 4 independent packed accumulators per query
-      float2 acc[QPT][4];
-      bool any = false;
-      if (dot_mode) {
-        const float4 pn0 = *reinterpret_cast<const float4*>(sp + D * F_TILE + j);
-        const float4 pn1 = *reinterpret_cast<const float4*>(sp + D * F_TILE + j + 4);
-#pragma unroll
-        for (int a = 0; a < QPT; ++a) {
-          acc[a][0] = make_float2(pn0.x, pn0.y);
-          acc[a][1] = make_float2(pn0.z, pn0.w);
-          acc[a][2] = make_float2(pn1.x, pn1.y);
-          acc[a][3] = make_float2(pn1.z, pn1.w);
-        }
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-          const float4 pv0 = *reinterpret_cast<const float4*>(sp + d * F_TILE + j);
-          const float4 pv1 = *reinterpret_cast<const float4*>(sp + d * F_TILE + j + 4);
-#pragma unroll
-          for (int a = 0; a < QPT; ++a) {
-            acc[a][0] = fma2_bcast(qv[a][d], make_float2(pv0.x, pv0.y), acc[a][0]);
-            acc[a][1] = fma2_bcast(qv[a][d], make_float2(pv0.z, pv0.w), acc[a][1]);
-            acc[a][2] = fma2_bcast(qv[a][d], make_float2(pv1.x, pv1.y), acc[a][2]);
-            acc[a][3] = fma2_bcast(qv[a][d], make_float2(pv1.z, pv1.w), acc[a][3]);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-          const float4 pv0 = *reinterpret_cast<const float4*>(sp + d * F_TILE + j);
-          const float4 pv1 = *reinterpret_cast<const float4*>(sp + d * F_TILE + j + 4);
-#pragma unroll
-          for (int a = 0; a < QPT; ++a) {
-            const float2 df[4] = {sub2(qv[a][d], make_float2(pv0.x, pv0.y)),
-                                  sub2(qv[a][d], make_float2(pv0.z, pv0.w)),
-                                  sub2(qv[a][d], make_float2(pv1.x, pv1.y)),
-                                  sub2(qv[a][d], make_float2(pv1.z, pv1.w))};
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              acc[a][g] = (d == 0) ? __fmul2_rn(df[g], df[g]) : __ffma2_rn(df[g], df[g], acc[a][g]);
-          }
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < QPT; ++a) {
-        const float tcur = dot_mode ? thr[a].dot : thr[a].diff;
-        // smallest of the 8 evaluations (3 x FMNMX3 + 1 FMNMX), one compare per query
-        const float m0 = min3_nan(acc[a][0].x, acc[a][0].y, acc[a][1].x);
-        const float m1 = min3_nan(acc[a][1].y, acc[a][2].x, acc[a][2].y);
-        const float m2 = min3_nan(acc[a][3].x, acc[a][3].y, m0);
-        const float m = min3_nan(m1, m2, m2);
-        any = any || !(m > tcur);
-      }
-      if (any) {
-#pragma unroll
-        for (int a = 0; a < QPT; ++a) {
-          const float av[8] = {acc[a][0].x, acc[a][0].y, acc[a][1].x, acc[a][1].y,
-                               acc[a][2].x, acc[a][2].y, acc[a][3].x, acc[a][3].y};
-          const int li = a * NN_THREADS + tid;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            if (av[e] > (dot_mode ? thr[a].dot : thr[a].diff)) continue;
-            if (ncand[a] == CAND_CAP) {  // buffer full: drain this query now
-              thr[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ,
-                                        s_list + li, i_list + li, &s_have[li], &s_ubits[li], thr[a]);
-              ncand[a] = 0;
-              if (av[e] > (dot_mode ? thr[a].dot : thr[a].diff)) continue;
-            }
-            s_cand[li + ncand[a] * NQ] = base + j + e;
-            ++ncand[a];
-            ++passed;
-          }
-        }
-      }
-    }
+    const uint32_t sp_addr = smem_u32(sp);
+    if (dot_mode)
+      passed = knn_scan_tile<D, QPT, true>(p, sp_addr, cnt, base, n1, qv, thr, qi, excl, ncand, s_cand,
+                                           g_list, g_ilist, s_have, s_ubits, tid);
+    else
+      passed = knn_scan_tile<D, QPT, false>(p, sp_addr, cnt, base, n1, qv, thr, qi, excl, ncand, s_cand,
+                                            g_list, g_ilist, s_have, s_ubits, tid);
     // Tile boundary.  The warp drains together (lanes stay converged) when some lane's buffer
     // is getting full, every DRAIN_EVERY-th tile, and at the end: thresholds may lag a few
     // tiles behind, which only lets a few more pairs through the filter.
@@ -744,8 +785,8 @@ __global__ void __launch_bounds__(NN_THREADS) knn_rv_dot_kernel(const ScanParams
 #pragma unroll
         for (int a = 0; a < QPT; ++a) {
           const int li = a * NN_THREADS + tid;
-          thr[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ, s_list + li,
-                                    i_list + li, &s_have[li], &s_ubits[li], thr[a]);
+          thr[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ, 1, g_list[a],
+                                    g_ilist[a], &s_have[li], &s_ubits[li], thr[a]);
           ncand[a] = 0;
         }
       }
@@ -765,19 +806,15 @@ __global__ void __launch_bounds__(NN_THREADS) knn_rv_dot_kernel(const ScanParams
     __syncthreads();  // everyone is done with this stage before it is refilled
   }
 
+  // pad the unused tail of each list (fewer than k candidates in the store)
 #pragma unroll
   for (int a = 0; a < QPT; ++a) {
     const uint32_t q_out = blockIdx.x * NQ + a * NN_THREADS + tid;
     if (q_out >= p.Q) continue;
-    const int li = a * NN_THREADS + tid;
-    const int have = s_have[li];
-    uint64_t o = ((uint64_t)blockIdx.y * p.Q + q_out) * (uint64_t)k;
-    const double* sl = s_list + li;
-    const uint32_t* il = i_list + li;
-    for (int e = 0; e < k; ++e) {
-      bool f = e < have;
-      p.out_idx[o + e] = f ? il[e * NQ] : OXG_INVALID_INDEX;
-      p.out_dist[o + e] = f ? sl[e * NQ] : __longlong_as_double(0x7FF0000000000000ll);
+    const int have = s_have[a * NN_THREADS + tid];
+    for (int e = have; e < k; ++e) {
+      g_ilist[a][e] = OXG_INVALID_INDEX;
+      g_list[a][e] = __longlong_as_double(0x7FF0000000000000ll);
     }
   }
 }
@@ -1576,7 +1613,8 @@ static int launch_nn1_stream(ScanParams p, uint32_t blocks, cudaStream_t st) {
 
 template <int D, int QPT>
 static int launch_knn_rv_dot(const ScanParams& p, dim3 grid, cudaStream_t st) {
-  size_t smem = knn_f32_smem_bytes<D, QPT>(p.k) + sizeof(float) * F_STAGES * F_TILE;  // + norm column
+  size_t smem = sizeof(float) * F_STAGES * (D + 1) * F_TILE + sizeof(uint64_t) * F_STAGES +
+                (size_t)NN_THREADS * QPT * (sizeof(long long) + sizeof(int) + CAND_CAP * sizeof(uint32_t));
   OXG_CUDA_TRY(cudaFuncSetAttribute(knn_rv_dot_kernel<D, QPT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   knn_rv_dot_kernel<D, QPT><<<grid, NN_THREADS, smem, st>>>(p);

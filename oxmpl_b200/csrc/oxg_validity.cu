@@ -193,6 +193,85 @@ __global__ void __launch_bounds__(128) motion_kernel(const MotionParams p) {
   }
 }
 
+// Few edges against a large world: one CTA per edge, threads spread over (step, obstacle) pairs
+// so that a single check_motion / is_valid call (the trait path, or an unfused planner
+// iteration) is not one thread walking thousands of obstacles.  first_invalid = the smallest
+// step with any hit (shared-memory atomicMin), identical to the sequential loop's answer.
+template <int DT>
+__global__ void __launch_bounds__(256) motion_small_kernel(const MotionParams p) {
+  constexpr int XN = DT > 0 ? DT : kMaxDim;
+  __shared__ unsigned int s_first;
+  const int n_real = DimOf<DT>::get((int)p.sp.n_real);
+  const int n_so2 = DT > 0 ? 0 : (int)p.sp.n_so2;
+  const int dim = n_real + n_so2;
+  const uint64_t e = blockIdx.x;
+  const uint64_t fi = p.from_idx ? p.from_idx[e] : e;
+  const uint64_t ti = p.to_idx ? p.to_idx[e] : e;
+  double from[XN], to[XN], x[XN];
+#pragma unroll
+  for (int d = 0; d < dim; ++d) {
+    from[d] = p.from.p[fi * p.from.stride_i + (uint64_t)d * p.from.stride_d];
+    to[d] = p.to.p[ti * p.to.stride_i + (uint64_t)d * p.to.stride_d];
+  }
+  double dist;
+  if (DT > 0)
+    dist = sqrt(rv_sumsq_dev<DT>(from, to, n_real));
+  else
+    dist = space_distance_dev(p.sp.n_real, p.sp.n_so2, p.sp.w_real, p.sp.w_so2, from, to);
+  const unsigned long long n = ceil_as_usize_dev(__ddiv_rn(dist, p.resolution));
+  if (threadIdx.x == 0) s_first = 0xFFFFFFFFu;
+  __syncthreads();
+  const WorldView& w = p.w;
+  const unsigned long long C = (unsigned long long)w.n_spheres + w.n_aabbs + w.n_capsules + w.n_so2;
+  if (n > (1ull << 32)) {
+    if (threadIdx.x == 0) s_first = 0xFFFFFFFEu;  // reported as 0xFFFFFFFF below
+  } else if (C > 0) {
+    const bool single = n <= 1;
+    const unsigned long long nn = single ? 1ull : n;
+    const double nf = (double)n;
+    const unsigned long long total = nn * C;
+    unsigned long long cur_step = 0;  // step whose state is in x[]
+    for (unsigned long long t = threadIdx.x; t < total; t += blockDim.x) {
+      const unsigned long long step = t / C + 1;
+      unsigned long long o = t - (step - 1) * C;
+      if (step >= s_first) continue;  // a hit at an earlier step is already known (benign race)
+      if (step != cur_step) {
+        cur_step = step;
+        if (single) {
+#pragma unroll
+          for (int d = 0; d < dim; ++d) x[d] = to[d];
+        } else {
+          const double tt = __ddiv_rn((double)step, nf);
+#pragma unroll
+          for (int d = 0; d < n_real; ++d)
+            x[d] = __dadd_rn(from[d], __dmul_rn(__dsub_rn(to[d], from[d]), tt));
+          for (int c = 0; c < n_so2; ++c)
+            x[n_real + c] = so2_interpolate_dev(from[n_real + c], to[n_real + c], tt);
+        }
+      }
+      bool hit;
+      if (o < w.n_spheres) {
+        hit = sphere_hit_dev<DT>(x, w.spheres + (size_t)o * w.sphere_stride, n_real);
+      } else if ((o -= w.n_spheres) < w.n_aabbs) {
+        hit = aabb_hit_dev<DT>(x, w.aabbs + (size_t)o * w.aabb_stride, n_real);
+      } else if ((o -= w.n_aabbs) < w.n_capsules) {
+        hit = capsule_hit_dev<DT>(x, w.capsules + (size_t)o * w.capsule_stride, n_real);
+      } else {
+        o -= w.n_capsules;
+        const double v = so2_normalise_dev(x[n_real + w.so2_comp[o]]);
+        hit = v >= w.so2_lohi[2 * o] && v <= w.so2_lohi[2 * o + 1];
+      }
+      if (hit) atomicMin(&s_first, (unsigned int)(step > 0xFFFFFFFDull ? 0xFFFFFFFDull : step));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int f = s_first;
+    p.valid[e] = f == 0xFFFFFFFFu ? 1 : 0;
+    if (p.first_invalid) p.first_invalid[e] = f == 0xFFFFFFFFu ? 0u : (f == 0xFFFFFFFEu ? 0xFFFFFFFFu : f);
+  }
+}
+
 #define OXG_DISPATCH_DT(D_RT, CALL)                     \
   switch (D_RT) {                                       \
     case 1: { constexpr int DD = 1; CALL; } break;      \
@@ -238,6 +317,25 @@ int is_valid_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t
                     StateView st, uint64_t Q, uint8_t* d_out) {
   OXG_TRY(check_world_space(w, sp));
   if (Q == 0) return OXG_OK;
+  const uint64_t n_obst = w->n_spheres + w->n_aabbs + w->n_capsules + w->n_so2;
+  if (Q <= 148ull * 4 && n_obst >= 64) {
+    // few states, large world: is_valid(x) == check_motion(x, x) (zero length: `to` only)
+    MotionParams p;
+    p.w = world_view(w);
+    p.sp = SpaceP{sp.n_real, sp.n_so2, sp.w_real, sp.w_so2};
+    p.from = st;
+    p.to = st;
+    p.from_idx = nullptr;
+    p.to_idx = nullptr;
+    p.E = Q;
+    p.E_dev = nullptr;
+    p.resolution = 1.0;
+    p.valid = d_out;
+    p.first_invalid = nullptr;
+    OXG_DISPATCH_DT(fast_dim(sp), (motion_small_kernel<DD><<<(unsigned)Q, 256, 0, stream>>>(p)));
+    OXG_LAUNCH_CHECK();
+    return OXG_OK;
+  }
   WorldView wv = world_view(w);
   SpaceP spp{sp.n_real, sp.n_so2, sp.w_real, sp.w_so2};
   int threads = 128;
@@ -271,6 +369,13 @@ int motion_check_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStre
   p.resolution = resolution;
   p.valid = d_valid;
   p.first_invalid = d_first_invalid;
+  const uint64_t n_obst = w->n_spheres + w->n_aabbs + w->n_capsules + w->n_so2;
+  if (E_dev == nullptr && E <= 148ull * 4 && n_obst >= 64) {
+    // few edges, large world: a CTA per edge over (step, obstacle) pairs
+    OXG_DISPATCH_DT(fast_dim(sp), (motion_small_kernel<DD><<<(unsigned)E, 256, 0, stream>>>(p)));
+    OXG_LAUNCH_CHECK();
+    return OXG_OK;
+  }
   const int threads = 128;
   // few edges: a whole warp per edge; many edges: 4 lanes per edge keeps lanes busy at the
   // typical 4-12 steps per edge.

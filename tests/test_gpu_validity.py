@@ -175,3 +175,38 @@ def test_validity_prefilter_never_changes_results(oxg, orc, dim, name, scale, of
     if name in ("unit", "tiny_1e-20", "huge_1e150"):
         assert 0 < want.sum() < want.size
     gw.close()
+
+
+@pytest.mark.parametrize("dim", [2, 7])
+def test_few_states_large_world(oxg, orc, dim):
+    """<= 592 states / edges against >= 64 obstacles take the CTA-per-edge kernel (the trait
+    path `is_valid(&state)` and an unfused planner iteration): booleans and first invalid step
+    must equal the sequential loop's."""
+    spheres, aabbs, capsules = worlds.calibrated_obstacles(dim + 20, dim, 120, 90, 110, p_each=0.004)
+    sp, sp_o = oxg.Space.real_vector(dim), orc.space(dim)
+    gw, ow, keep = _world_pair(oxg, orc, dim, spheres, aabbs, capsules)
+    for n in (1, 7, 300):
+        states = uniform_states(70 + n, n, [-1.0] * dim, [1.0] * dim)
+        np.testing.assert_array_equal(gw.is_valid(sp, states), orc.is_valid(ow, sp_o, states))
+        to = states + np.random.default_rng(n).normal(scale=0.3, size=states.shape)
+        to[0] = states[0]
+        for res in (0.02, 0.5, 100.0):
+            v, first = gw.check_motion(sp, states, to, res, want_first_invalid=True)
+            ov, ofirst = orc.check_motion(ow, sp_o, states, to, res)
+            np.testing.assert_array_equal(v, ov)
+            np.testing.assert_array_equal(first, ofirst)
+    gw.close()
+    # compound space with SO2 intervals through the generic (runtime-dimension) instantiation
+    spc, spc_o = oxg.Space.compound(2, 1, 1.0, 0.5), orc.space(2, 1, 1.0, 0.5)
+    boxes = worlds.aabb_world(3, [0.0, 0.0], [10.0, 10.0], 80, 0.3, 1.0)
+    gw2 = oxg.World(2, aabbs=boxes, so2_intervals=[(0, -0.4, 0.2)])
+    ow2, keep2 = orc.world(2, aabbs=boxes, so2_intervals=[(0, -0.4, 0.2)])
+    rng = np.random.default_rng(8)
+    a = np.column_stack([rng.uniform(0, 10, (200, 2)), rng.uniform(-3.1, 3.1, 200)])
+    b = np.column_stack([rng.uniform(0, 10, (200, 2)), rng.uniform(-3.1, 3.1, 200)])
+    np.testing.assert_array_equal(gw2.is_valid(spc, a), orc.is_valid(ow2, spc_o, a))
+    v, first = gw2.check_motion(spc, a, b, 0.3, want_first_invalid=True)
+    ov, ofirst = orc.check_motion(ow2, spc_o, a, b, 0.3)
+    np.testing.assert_array_equal(v, ov)
+    np.testing.assert_array_equal(first, ofirst)
+    gw2.close()
