@@ -226,8 +226,27 @@ template <int DT>
 OXG_DEV bool sphere_maybe_hit32(const float* xf, const float* __restrict__ sph, float a2, float ce,
                                 int dim_rt) {
   const int dim = DimOf<DT>::get(dim_rt);
-  float s = 0.f;
+  if (DT > 0) {
+    constexpr int NV = ((DT > 0 ? DT : 1) + 2 + 3) / 4;  // row stride is a multiple of 4 floats
+    float c[NV * 4];
 #pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(sph) + v);
+      c[4 * v] = t4.x;
+      c[4 * v + 1] = t4.y;
+      c[4 * v + 2] = t4.z;
+      c[4 * v + 3] = t4.w;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+      const float d = xf[i] - c[i];
+      s = __fmaf_rn(d, d, s);
+    }
+    const float T = __fmaf_ru(a2, c[DT + 1], __fadd_ru(c[DT], ce));
+    return !(s > T);
+  }
+  float s = 0.f;
   for (int i = 0; i < dim; ++i) {
     const float d = xf[i] - __ldg(sph + i);
     s = __fmaf_rn(d, d, s);
@@ -250,17 +269,45 @@ template <int DT>
 OXG_DEV bool capsule_maybe_hit32(const float* xf, const float* __restrict__ cap, float a2, float ce,
                                  int dim_rt) {
   const int dim = DimOf<DT>::get(dim_rt);
-  float ap[DT > 0 ? DT : 32];
-  float num = 0.f;
+  if (DT > 0) {
+    // one aligned 16-byte load per four mirror values (the row stride is a multiple of 4 floats)
+    constexpr int NV = (2 * (DT > 0 ? DT : 1) + 3 + 3) / 4;
+    float c[NV * 4];
 #pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(cap) + v);
+      c[4 * v] = t4.x;
+      c[4 * v + 1] = t4.y;
+      c[4 * v + 2] = t4.z;
+      c[4 * v + 3] = t4.w;
+    }
+    float ap[DT > 0 ? DT : 1];
+    float num = 0.f;
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+      ap[i] = xf[i] - c[i];
+      num = __fmaf_rn(ap[i], c[DT + i], num);
+    }
+    float t = num * c[2 * DT];
+    t = fminf(fmaxf(t, 0.f), 1.f);  // NaN -> 0: any t in [0,1] keeps the bound valid
+    float d2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+      const float e = __fmaf_rn(-t, c[DT + i], ap[i]);
+      d2 = __fmaf_rn(e, e, d2);
+    }
+    const float T = __fmaf_ru(a2, c[2 * DT + 2], __fadd_ru(c[2 * DT + 1], ce));
+    return !(d2 > T);
+  }
+  float ap[32];
+  float num = 0.f;
   for (int i = 0; i < dim; ++i) {
     ap[i] = xf[i] - __ldg(cap + i);
     num = __fmaf_rn(ap[i], __ldg(cap + dim + i), num);
   }
   float t = num * __ldg(cap + 2 * dim);
-  t = fminf(fmaxf(t, 0.f), 1.f);  // NaN -> 0: any t in [0,1] keeps the bound valid
+  t = fminf(fmaxf(t, 0.f), 1.f);
   float d2 = 0.f;
-#pragma unroll
   for (int i = 0; i < dim; ++i) {
     const float e = __fmaf_rn(-t, __ldg(cap + dim + i), ap[i]);
     d2 = __fmaf_rn(e, e, d2);
