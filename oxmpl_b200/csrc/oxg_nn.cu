@@ -317,7 +317,7 @@ __device__ __forceinline__ double sqrt_le_upper_dev(double sw) {
 }
 
 constexpr int CAND_CAP = 16;  // deferred candidates per query (u32 indices, shared memory)
-constexpr int DRAIN_EVERY = 8;  // tiles between scheduled warp-wide drains
+constexpr int DRAIN_EVERY = 16;  // tiles between scheduled warp-wide drains
 constexpr int DOT_MIN_CTAS = 3; // CTAs per SM the dot kernel is compiled for (caps registers)
 
 // Dot-product form of the pre-filter.  With g_d = -2 fl32(q_d), pn = fl32(|p|^2) and the FP32

@@ -340,3 +340,44 @@ def test_few_query_stream_radius(oxg, orc, q_count):
             ooff, oidx = orc.radius(orc.space(2), rows, rows[:q_count], r)
             np.testing.assert_array_equal(off, ooff)
             np.testing.assert_array_equal(idx, oidx)
+
+
+def test_randomised_shapes_against_oracle(oxg, orc):
+    """Seeded random (dim, N, Q, k, radius) combinations, including k > N, k = 64, Q = 0,
+    several store slices (small Q over a large N) and query batches that straddle the
+    kernel-selection thresholds (8 / 1024 queries)."""
+    rng = np.random.default_rng(2026)
+    for trial in range(28):
+        d = int(rng.integers(1, 17))
+        n = int(rng.choice([1, 2, 31, 257, 1500, 40_000]))
+        q = int(rng.choice([0, 1, 8, 9, 130, 1023, 1024, 2100]))
+        k = int(rng.choice([1, 2, 10, 33, 64]))
+        if q * n > 3e7:
+            q = max(1, int(3e7 // n))
+        lo = float(rng.choice([-3.0, 0.0, 100.0]))
+        rows = lo + rng.random((n, d)) * float(rng.choice([1.0, 7.5]))
+        queries = lo + rng.random((q, d)) * 7.5
+        sp_o = orc.space(d)
+        with oxg.StateStore(oxg.Space.real_vector(d)) as st:
+            st.append(rows)
+            msg = f"trial {trial}: d={d} n={n} q={q} k={k}"
+            if q == 0:
+                i0, d0 = st.knn(np.empty((0, d)), k)
+                assert i0.shape == (0, k) and d0.shape == (0, k)
+                off, idx = st.radius(np.empty((0, d)), 1.0)
+                assert off.tolist() == [0] and len(idx) == 0
+                continue
+            idx, dist = st.knn(queries, k)
+            oi, od = orc.knn(sp_o, rows, queries, k)
+            np.testing.assert_array_equal(idx, oi, err_msg=msg)
+            np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64), err_msg=msg)
+            idx, dist = st.nn1(queries)
+            oi, od = orc.nn1(sp_o, rows, queries)
+            np.testing.assert_array_equal(idx, oi, err_msg=msg)
+            np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64), err_msg=msg)
+            r = float(np.median(od)) * float(rng.choice([0.5, 1.0, 2.0]))
+            off, ridx, rdist = st.radius(queries, r, want_dist=True)
+            ooff, oidx, odist = orc.radius(sp_o, rows, queries, r, want_dist=True)
+            np.testing.assert_array_equal(off, ooff, err_msg=msg)
+            np.testing.assert_array_equal(ridx, oidx, err_msg=msg)
+            np.testing.assert_array_equal(rdist.view(np.uint64), odist.view(np.uint64), err_msg=msg)
