@@ -1,0 +1,222 @@
+"""Mirror of ``oxmpl_py.geometric`` on the GPU path: ``RRT``, ``RRTConnect``, ``RRTStar``,
+``PRM`` with the constructors and methods of oxmpl-py/src/geometric/*.rs
+(``RRT(max_distance, goal_bias, problem_definition)``, ``setup(validity)``,
+``solve(timeout_secs)`` -> ``Path``; ``PRM(timeout, connection_radius, problem_definition)``,
+``construct_roadmap()``).  ``setup`` takes a :class:`oxmpl_b200.base.GpuValidityChecker`
+instead of a Python callback — the point of the GPU path is that validity never re-enters the
+interpreter; a plain callable is rejected loudly (there is no CPU fallback)."""
+from __future__ import annotations
+
+import random
+import time
+from collections import deque
+
+import numpy as np
+
+from . import api
+from .base import GpuValidityChecker, Path, PlanningError, ProblemDefinition, RealVectorState
+
+
+def _checker(validity) -> GpuValidityChecker:
+    if not isinstance(validity, GpuValidityChecker):
+        raise TypeError("the GPU planners take a declarative GpuValidityChecker, not a Python "
+                        "callback (oxmpl_b200 has no CPU fallback)")
+    return validity
+
+
+class _TreePlanner:
+    chunk = 1 << 14
+    max_nodes = 1 << 20
+
+    def __init__(self, max_distance: float, goal_bias: float, problem_definition: ProblemDefinition,
+                 seed: int = 0):
+        self.max_distance = float(max_distance)
+        self.goal_bias = float(goal_bias)
+        self.pd = problem_definition
+        self.rng = random.Random(seed)
+        self.vc = None
+        self.tree = None
+
+    def setup(self, validity):
+        self.vc = _checker(validity)
+        self.tree = api.StateStore(self.pd.space._space(), capacity=1024)
+        self.tree.append(np.asarray([self.pd.start_state.values]))   # rrt.rs:147-155
+
+    def _stream(self, n):
+        # the reference's per-iteration draw (rrt.rs:177-184), n iterations ahead
+        pd, out = self.pd, np.empty((n, self.pd.space.dimension))
+        for i in range(n):
+            q = pd.goal.sample_goal() if self.rng.random() < self.goal_bias \
+                else pd.space.sample_uniform(self.rng)
+            out[i] = q.values
+        return out
+
+    def _resolution(self):
+        return self.pd.space.get_longest_valid_segment_length() * 0.1   # rrt.rs:97
+
+    def _trace(self, store, parents, node):
+        rows, out = store.read(), []
+        while node >= 0:
+            out.append(RealVectorState(rows[node]))
+            node = int(parents[node])
+        return out[::-1]
+
+
+class RRT(_TreePlanner):
+    """oxmpl_py.geometric.RRT (oxmpl-py/src/geometric/rrt.rs) over oxg_rrt_solve."""
+
+    def solve(self, timeout_secs: float) -> Path:
+        if self.vc is None:
+            raise PlanningError(PlanningError.UNINITIALISED)
+        t0 = time.perf_counter()
+        while True:
+            left = timeout_secs - (time.perf_counter() - t0)
+            if left <= 0:
+                raise PlanningError(PlanningError.TIMEOUT)
+            parents, r = api.rrt_solve(self.vc.world, self.tree, self._stream(self.chunk),
+                                       self.max_distance, self._resolution(), self.max_nodes,
+                                       goal_target=self.pd.goal.target.values,
+                                       goal_radius=self.pd.goal.radius, timeout_s=left)
+            if r["solved"]:
+                return Path(self._trace(self.tree, parents, r["goal_node"][0]))
+            if r["status"] in ("timeout", "tree_full"):
+                raise PlanningError(PlanningError.TIMEOUT)
+
+
+class RRTStar(_TreePlanner):
+    """oxmpl_py.geometric.RRTStar(max_distance, goal_bias, search_radius, problem_definition)."""
+
+    def __init__(self, max_distance, goal_bias, search_radius, problem_definition, seed: int = 0):
+        super().__init__(max_distance, goal_bias, problem_definition, seed)
+        self.search_radius = float(search_radius)
+
+    def solve(self, timeout_secs: float) -> Path:
+        if self.vc is None:
+            raise PlanningError(PlanningError.UNINITIALISED)
+        t0 = time.perf_counter()
+        while True:
+            left = timeout_secs - (time.perf_counter() - t0)
+            if left <= 0:
+                raise PlanningError(PlanningError.TIMEOUT)
+            parents, costs, r = api.rrt_star_solve(
+                self.vc.world, self.tree, self._stream(self.chunk), self.max_distance,
+                self.search_radius, self._resolution(), self.max_nodes,
+                goal_target=self.pd.goal.target.values, goal_radius=self.pd.goal.radius,
+                stop_at_goal=True, timeout_s=left)
+            if r["solved"]:
+                return Path(self._trace(self.tree, parents, r["goal_node"][0]))
+            if r["status"] in ("timeout", "tree_full"):
+                raise PlanningError(PlanningError.TIMEOUT)
+
+
+class RRTConnect(_TreePlanner):
+    """oxmpl_py.geometric.RRTConnect over oxg_rrt_connect_solve."""
+
+    def setup(self, validity):
+        super().setup(validity)
+        self.goal_tree = api.StateStore(self.pd.space._space(), capacity=1024)
+        self.goal_tree.append(np.asarray([self.pd.goal.sample_goal().values]))  # rrt_connect.rs:207-214
+
+    def solve(self, timeout_secs: float) -> Path:
+        if self.vc is None:
+            raise PlanningError(PlanningError.UNINITIALISED)
+        t0 = time.perf_counter()
+        while True:
+            left = timeout_secs - (time.perf_counter() - t0)
+            if left <= 0:
+                raise PlanningError(PlanningError.TIMEOUT)
+            pa, pb, r = api.rrt_connect_solve(
+                self.vc.world, self.tree, self.goal_tree, self._stream(self.chunk),
+                self.max_distance, self._resolution(), self.max_nodes,
+                goal_target=self.pd.goal.target.values, goal_radius=self.pd.goal.radius,
+                timeout_s=left)
+            if r["solved"]:
+                states = self._trace(self.tree, pa, r["goal_node"][0])
+                if r["goal_node"][1] >= 0:     # merge (rrt_connect.rs:288-304)
+                    states += self._trace(self.goal_tree, pb, r["goal_node"][1])[::-1][1:]
+                return Path(states)
+            if r["status"] in ("timeout", "tree_full"):
+                raise PlanningError(PlanningError.TIMEOUT)
+
+
+class PRM:
+    """oxmpl_py.geometric.PRM(timeout, connection_radius, problem_definition)
+    (oxmpl-py/src/geometric/prm.rs): construct_roadmap() via oxg_prm_build_radius in batches
+    (identical to the incremental build: node i only looks at nodes j < i), solve() = start
+    connection (radius scan + check_motion) + the reference's BFS (prm.rs:227-307)."""
+
+    batch = 1 << 13
+
+    def __init__(self, timeout: float, connection_radius: float, problem_definition: ProblemDefinition,
+                 seed: int = 0):
+        self.timeout = float(timeout)
+        self.connection_radius = float(connection_radius)
+        self.pd = problem_definition
+        self.rng = random.Random(seed)
+        self.vc = None
+        self.edges = []
+
+    def setup(self, validity):
+        self.vc = _checker(validity)
+        self.store = api.StateStore(self.pd.space._space(), capacity=1024)
+        self.edges = []                                       # prm.rs:224
+
+    def get_roadmap(self):
+        return self.edges
+
+    def construct_roadmap(self, max_samples: int | None = None):
+        if self.vc is None:
+            raise PlanningError(PlanningError.UNINITIALISED)
+        if self.edges:
+            return                                            # prm.rs:106-113
+        sp, res = self.pd.space, self.pd.space.get_longest_valid_segment_length() * 0.1
+        t0, drawn = time.perf_counter(), 0
+        while time.perf_counter() - t0 <= self.timeout and (max_samples is None or drawn < max_samples):
+            nb = self.batch if max_samples is None else min(self.batch, max_samples - drawn)
+            rows = np.array([sp.sample_uniform(self.rng).values for _ in range(nb)])
+            drawn += nb
+            keep = rows[self.vc.is_valid_batch(rows).astype(bool)]          # prm.rs:123
+            if not len(keep):
+                continue
+            first = self.store.append(keep)
+            off, idx, _ = api.prm_build_radius(self.vc.world, self.store, self.connection_radius,
+                                               res, first, first + len(keep))
+            self.edges.extend([] for _ in range(len(keep)))
+            for i in range(len(keep)):
+                for j in idx[int(off[i]):int(off[i + 1])]:
+                    self.edges[first + i].append(int(j))                    # prm.rs:135
+                    self.edges[int(j)].append(first + i)                    # prm.rs:143-145
+
+    def solve(self, timeout_secs: float) -> Path:
+        if self.vc is None:
+            raise PlanningError(PlanningError.UNINITIALISED)
+        if not self.edges:
+            raise PlanningError(PlanningError.UNSAMPLED)
+        start = self.pd.start_state
+        if not self.vc(start):
+            raise PlanningError(PlanningError.INVALID_START)
+        sp, res = self.pd.space, self.pd.space.get_longest_valid_segment_length() * 0.1
+        rows = self.store.read()
+        q = np.asarray([start.values])
+        off, nb = self.store.radius(q, self.connection_radius)              # prm.rs:249-256
+        ok = self.vc.world.check_motion(sp._space(), np.repeat(q, len(nb), axis=0), rows[nb], res) \
+            if len(nb) else np.empty(0, np.uint8)
+        start_conn = [int(j) for j, v in zip(nb, ok) if v]
+        goal = [self.pd.goal.is_satisfied(RealVectorState(r)) for r in rows]   # prm.rs:259-264
+        if not start_conn or not any(goal):
+            raise PlanningError(PlanningError.NO_SOLUTION)
+        parent = {j: None for j in start_conn}
+        queue = deque(start_conn)
+        while queue:                                                          # prm.rs:271-301
+            cur = queue.popleft()
+            if goal[cur]:
+                out = []
+                while cur is not None:
+                    out.append(RealVectorState(rows[cur]))
+                    cur = parent[cur]
+                return Path([start] + out[::-1])
+            for j in self.edges[cur]:
+                if j not in parent:
+                    parent[j] = cur
+                    queue.append(j)
+        raise PlanningError(PlanningError.NO_SOLUTION)
