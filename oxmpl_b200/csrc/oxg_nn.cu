@@ -318,6 +318,7 @@ __device__ __forceinline__ double sqrt_le_upper_dev(double sw) {
 
 constexpr int CAND_CAP = 16;  // deferred candidates per query (u32 indices, shared memory)
 constexpr int DRAIN_EVERY = 16;  // tiles between scheduled warp-wide drains
+constexpr int DOT_STAGES = 4;   // tile ring of the dot kernel (full/empty mbarrier pairs)
 constexpr int DOT_MIN_CTAS = 3; // CTAs per SM the dot kernel is compiled for (caps registers)
 
 // Dot-product form of the pre-filter.  With g_d = -2 fl32(q_d), pn = fl32(|p|^2) and the FP32
@@ -690,11 +691,12 @@ __global__ void __launch_bounds__(NN_THREADS, DOT_MIN_CTAS) knn_rv_dot_kernel(co
   constexpr int NQ = NN_THREADS * QPT;
   constexpr int COLS = D + 1;
   float* tiles = reinterpret_cast<float*>(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + F_STAGES * COLS * F_TILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + DOT_STAGES * COLS * F_TILE);  // full[S]
+  uint64_t* empty = bars + DOT_STAGES;  // empty[S]: one arrival per warp
   // The sorted (dist, idx) lists live in the output buffers themselves (global memory, one
   // contiguous run per query, touched only by the rare exact path): shared memory is left to
   // the tiles and the candidate buffers, which is what bounds the CTAs per SM.
-  long long* s_ubits = reinterpret_cast<long long*>(bars + F_STAGES);
+  long long* s_ubits = reinterpret_cast<long long*>(bars + 2 * DOT_STAGES);
   int* s_have = reinterpret_cast<int*>(s_ubits + NQ);
   uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_have + NQ);  // [CAND_CAP][NQ]
   double* g_list[QPT];
@@ -736,30 +738,41 @@ __global__ void __launch_bounds__(NN_THREADS, DOT_MIN_CTAS) knn_rv_dot_kernel(co
   const uint32_t n1 = min(p.n_db, n0 + p.split_len);
   const uint32_t ntiles = (n1 > n0) ? (n1 - n0 + F_TILE - 1) / F_TILE : 0;
 
+  // Producer / consumer pipeline without a CTA-wide barrier per tile: full[s] is completed by
+  // the bulk copies of a tile, empty[s] by one arrival per warp once the warp has finished the
+  // tile; the producer (thread 0) refills a stage only when all warps have left it.  Warps can
+  // drift up to DOT_STAGES-1 tiles apart, which absorbs the stalls of the exact path.
   if (tid == 0) {
-    for (int s = 0; s < F_STAGES; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < DOT_STAGES; ++s) {
+      mbar_init(&bars[s], 1);
+      mbar_init(&empty[s], NN_THREADS / 32);
+    }
     mbar_fence_init();
   }
   __syncthreads();
   if (tid == 0) {
-    for (uint32_t t = 0; t < (uint32_t)(F_STAGES - 1) && t < ntiles; ++t) {
+    for (uint32_t t = 0; t < (uint32_t)(DOT_STAGES - 1) && t < ntiles; ++t) {
       uint32_t base = n0 + t * F_TILE;
-      issue_tile32n<D>(p, tiles + (t % F_STAGES) * COLS * F_TILE, &bars[t % F_STAGES], base,
+      issue_tile32n<D>(p, tiles + (t % DOT_STAGES) * COLS * F_TILE, &bars[t % DOT_STAGES], base,
                        min((uint32_t)F_TILE, n1 - base));
     }
   }
 
   for (uint32_t t = 0; t < ntiles; ++t) {
     if (tid == 0) {
-      uint32_t tn = t + F_STAGES - 1;
+      uint32_t tn = t + DOT_STAGES - 1;
       if (tn < ntiles) {
+        const uint32_t st = tn % DOT_STAGES;
+        if (tn >= (uint32_t)DOT_STAGES)  // the stage's previous tile (tn - S) has been left by all warps
+          mbar_wait(&empty[st], ((tn / DOT_STAGES) - 1u) & 1u);
         uint32_t base = n0 + tn * F_TILE;
-        issue_tile32n<D>(p, tiles + (tn % F_STAGES) * COLS * F_TILE, &bars[tn % F_STAGES], base,
+        issue_tile32n<D>(p, tiles + st * COLS * F_TILE, &bars[st], base,
                          min((uint32_t)F_TILE, n1 - base));
       }
     }
-    mbar_wait(&bars[t % F_STAGES], (t / F_STAGES) & 1u);
-    const float* sp = tiles + (t % F_STAGES) * COLS * F_TILE;
+    __syncwarp();
+    mbar_wait(&bars[t % DOT_STAGES], (t / DOT_STAGES) & 1u);
+    const float* sp = tiles + (t % DOT_STAGES) * COLS * F_TILE;
     const uint32_t base = n0 + t * F_TILE;
     const int cnt = (int)min((uint32_t)F_TILE, n1 - base);
     int passed = 0;  // candidates this thread deferred in this tile
@@ -803,7 +816,8 @@ __global__ void __launch_bounds__(NN_THREADS, DOT_MIN_CTAS) knn_rv_dot_kernel(co
         }
       }
     }
-    __syncthreads();  // everyone is done with this stage before it is refilled
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[t % DOT_STAGES]);  // this warp has left the stage
   }
 
   // pad the unused tail of each list (fewer than k candidates in the store)
@@ -1613,7 +1627,7 @@ static int launch_nn1_stream(ScanParams p, uint32_t blocks, cudaStream_t st) {
 
 template <int D, int QPT>
 static int launch_knn_rv_dot(const ScanParams& p, dim3 grid, cudaStream_t st) {
-  size_t smem = sizeof(float) * F_STAGES * (D + 1) * F_TILE + sizeof(uint64_t) * F_STAGES +
+  size_t smem = sizeof(float) * DOT_STAGES * (D + 1) * F_TILE + sizeof(uint64_t) * 2 * DOT_STAGES +
                 (size_t)NN_THREADS * QPT * (sizeof(long long) + sizeof(int) + CAND_CAP * sizeof(uint32_t));
   OXG_CUDA_TRY(cudaFuncSetAttribute(knn_rv_dot_kernel<D, QPT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
