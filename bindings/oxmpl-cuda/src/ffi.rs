@@ -49,6 +49,7 @@ pub struct oxg_plan_result {
     pub device_ms: f64,
     pub ctas: i32,
     pub reserved: i32,
+    pub phase_ms: [f64; 8],
 }
 
 pub type oxg_store = *mut c_void;

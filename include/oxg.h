@@ -247,6 +247,11 @@ typedef struct oxg_plan_result {
   double device_ms;
   int32_t ctas;                    /* CTAs of the persistent grid                                    */
   int32_t reserved;
+  double phase_ms[8];              /* where the kernel's time went (CTA 0's clock): [0] 1-NN scans,
+                                      [1] barrier after the scan, [2] steer + motion check (+ RRT*
+                                      radius scan), [3] barrier, [4] RRT* choose-parent batch,
+                                      [5] RRT* barriers, [6] RRT* replay + append + rewire batch,
+                                      [7] everything else (loop control, append, goal test)         */
 } oxg_plan_result;
 
 int oxg_rrt_solve(oxg_world w, oxg_store tree, const oxg_plan_params* params,

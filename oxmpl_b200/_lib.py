@@ -91,6 +91,7 @@ class PlanResult(C.Structure):
         ("device_ms", C.c_double),
         ("ctas", C.c_int32),
         ("reserved", C.c_int32),
+        ("phase_ms", C.c_double * 8),
     ]
 
 

@@ -364,6 +364,7 @@ def _plan_result(res) -> dict:
         "status": PLAN_STATUS.get(int(res.status), int(res.status)),
         "device_ms": float(res.device_ms),
         "ctas": int(res.ctas),
+        "phase_ms": [float(x) for x in res.phase_ms],
     }
 
 

@@ -39,7 +39,7 @@ namespace cg = cooperative_groups;
 
 namespace oxg {
 
-constexpr int PL_THREADS = 256;
+constexpr int PL_THREADS = 512;
 constexpr int PL_WARPS = PL_THREADS / 32;
 constexpr int NBR_CAP = 2048;  // neighbours of one RRT* iteration (OXG_E_CAPACITY beyond)
 constexpr unsigned long long MAX_STEPS = 1ull << 24;  // steps of one motion (reference: unbounded)
@@ -70,6 +70,7 @@ struct PlanCtrl {
   int status;
   int stop;
   int pad;
+  unsigned long long phase_ns[8];  // time attribution (CTA 0, thread 0), see oxg_plan_result
 };
 
 struct PlanParams {
@@ -320,13 +321,22 @@ __device__ void phase_steer(const PlanParams& P, PlanShared& sh, const TreeView&
       sh.bc_u[0] = 0;  // every distance was NaN: the reference keeps index 0
       sh.bc_d[0] = __longlong_as_double(0x7FF8000000000000ll);
     }
-  } else if (threadIdx.x < 32) {
+  } else if (gridDim.x > 32) {
+    // one parallel round of L2 loads (a thread per CTA), then warp 0 reduces from shared memory
+    for (uint32_t c = threadIdx.x; c < gridDim.x; c += PL_THREADS) {
+      sh.nb_dist[c] = __ldcg(&P.cta_best_dist[c]);
+      sh.nb_idx[c] = __ldcg(&P.cta_best_idx[c]);
+    }
+    __syncthreads();
+  }
+  if (MULTI && threadIdx.x < 32) {
     const double inf = __longlong_as_double(0x7FF0000000000000ll);
     double bd = inf;
     uint32_t bi = OXG_INVALID_INDEX;
+    const bool direct = gridDim.x <= 32;  // a single round: read L2 directly, no staging barrier
     for (uint32_t c = threadIdx.x; c < gridDim.x; c += 32) {
-      const double d = __ldcg(&P.cta_best_dist[c]);
-      const uint32_t i = __ldcg(&P.cta_best_idx[c]);
+      const double d = direct ? __ldcg(&P.cta_best_dist[c]) : sh.nb_dist[c];
+      const uint32_t i = direct ? __ldcg(&P.cta_best_idx[c]) : sh.nb_idx[c];
       if (better(d, i, bd, bi)) {
         bd = d;
         bi = i;
@@ -565,6 +575,17 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
   unsigned long long it = 0, mc_ref = 0, mc_exec = 0, ext_count = 0;
   int solved = 0, status = ST_SAMPLES;
   long long node0 = -1, node1 = -1;
+  // phase attribution (CTA 0 / thread 0 only): ns spent between consecutive marks
+  unsigned long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ph_last = 0;
+  const bool timing = gtid == 0;
+  auto mark = [&](int slot) {
+    if (timing) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (ph_last) ph_acc[slot] += now - ph_last;
+      ph_last = now;
+    }
+  };
   double q_next = ((int)tid < dim && P.n_samples > 0) ? P.samples[tid] : 0.0;
   unsigned long long t_start = 0;
   if (P.timeout_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
@@ -577,8 +598,11 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
     const uint32_t pidx = (pend_tree == t) ? pend_idx : OXG_INVALID_INDEX;
     const unsigned par = (unsigned)(ext_count & 1ull);
     ++ext_count;
+    mark(7);  // everything since the previous mark that is not attributed elsewhere
     phase_scan<MULTI>(P, sh, T, n[t], target, pidx);
+    mark(0);  // 1-NN scan
     grid_barrier<MULTI>(P.barrier, bar_gen);
+    mark(1);  // barrier 1
     if (gtid == 0) hit_ext[par ^ 1u] = 0u;  // the other parity's flag: next extend's
     phase_steer<MULTI>(P, sh, T, target, pidx, near_out, min_dist_out, reached_out);
     // check_motion(q_near, q_new)
@@ -608,7 +632,9 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
       }
       phase_radius<MULTI>(P, sh, T, n[t], pidx);
     }
+    mark(2);  // steer + motion check (+ radius scan)
     grid_barrier<MULTI>(P.barrier, bar_gen);
+    mark(3);  // barrier 2
     const bool valid = flag(hit_ext + par) == 0u;
     return valid;
   };
@@ -726,11 +752,15 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
       }
       if (!ok) continue;  // rrt_star.rs:221-223
       // ---- gather the ordered neighbour list (a single CTA wrote it in place)
+      if (MULTI) {
+        for (uint32_t c = tid; c < gridDim.x; c += PL_THREADS) sh.e_nb[c] = __ldcg(&P.nbr_cnt[c]);
+        __syncthreads();
+      }
       if (MULTI && tid < 32) {
         uint32_t run = 0;
         for (uint32_t c0 = 0; c0 < gridDim.x; c0 += 32) {
           const uint32_t c = c0 + tid;
-          const uint32_t cnt = c < gridDim.x ? __ldcg(&P.nbr_cnt[c]) : 0u;
+          const uint32_t cnt = c < gridDim.x ? sh.e_nb[c] : 0u;
           uint32_t incl = cnt;
           for (int o = 1; o < 32; o <<= 1) {
             const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -747,11 +777,17 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
         status = ST_E_NEIGHBOURS;
         break;
       }
-      for (uint32_t c = 0; MULTI && c < gridDim.x; ++c) {
-        const uint32_t cnt = (c + 1 < gridDim.x ? sh.cta_off[c + 1] : m) - sh.cta_off[c];
-        for (uint32_t u = tid; u < cnt; u += PL_THREADS) {
-          sh.nb_idx[sh.cta_off[c] + u] = __ldcg(&P.nbr_idx[(size_t)c * P.nbr_capc + u]);
-          sh.nb_dist[sh.cta_off[c] + u] = __ldcg(&P.nbr_dist[(size_t)c * P.nbr_capc + u]);
+      if (MULTI) {
+        // one parallel round of L2 loads: slot u comes from the CTA c with cta_off[c] <= u
+        for (uint32_t u = tid; u < m; u += PL_THREADS) {
+          uint32_t lo = 0, hi = gridDim.x;
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sh.cta_off[mid] <= u) lo = mid; else hi = mid;
+          }
+          const uint32_t off = u - sh.cta_off[lo];
+          sh.nb_idx[u] = __ldcg(&P.nbr_idx[(size_t)lo * P.nbr_capc + off]);
+          sh.nb_dist[u] = __ldcg(&P.nbr_dist[(size_t)lo * P.nbr_capc + off]);
         }
       }
       __syncthreads();
@@ -779,7 +815,9 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
       if (E0 > 0) {
         motion_tasks(P, sh, st_buf, T, E0, sh.q_new, true, nullptr, sh.nb_ns, sh.e_pre, sh.e_nb, hit_cp);
         mc_exec += E0;
+        mark(4);  // neighbour gather + choose-parent candidates + their motion checks
         grid_barrier<MULTI>(P.barrier, bar_gen);
+        mark(5);  // barrier 3 / 4
       }
       // sequential replay of the lazy selection (hit flags fetched in parallel first)
       uint32_t* const hit_sm = reinterpret_cast<uint32_t*>(st_buf);
@@ -832,7 +870,9 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
         motion_tasks(P, sh, st_buf, T, E1, sh.q_new, false, nullptr, sh.nb_ns, sh.e_pre, sh.e_nb, hit_rw);
         mc_exec += E1;
         mc_ref += E1;
+        mark(6);  // replay, append, rewire candidates + their motion checks
         grid_barrier<MULTI>(P.barrier, bar_gen);
+        mark(5);
         if (blockIdx.x == 0) {
           for (uint32_t e = tid; e < E1; e += PL_THREADS) {
             if (flag(hit_rw + e) == 0u) {
@@ -866,6 +906,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
     c->node[1] = node1;
     c->solved = solved;
     c->status = status;
+    for (int i = 0; i < 8; ++i) c->phase_ns[i] = ph_acc[i];
   }
 }
 
@@ -1129,6 +1170,7 @@ int plan_solve(oxg_world w, oxg_store t0, oxg_store t1, const oxg_plan_params* p
   out->status = h.status;
   out->device_ms = ms;
   out->ctas = G;
+  for (int i = 0; i < 8; ++i) out->phase_ms[i] = (double)h.phase_ns[i] * 1e-6;
   if (h.status == ST_E_NEIGHBOURS) {
     set_error("more than %d states inside search_radius in one RRT* iteration", NBR_CAP);
     return OXG_E_CAPACITY;

@@ -52,7 +52,7 @@ def config3(n_nodes, n_spheres, cpu_prefix):
                     "motion_checks_ref": r["motion_checks"],
                     "motion_checks_executed": r["motion_checks_executed"],
                     "motion_checks_per_s": r["motion_checks"] / (r["device_ms"] * 1e-3),
-                    "ctas": r["ctas"]})
+                    "ctas": r["ctas"], "phase_ms": r["phase_ms"]})
     if cpu_prefix:
         sp_o = orc.space(dim)
         ow, keep = orc.world(dim, spheres=sph)
