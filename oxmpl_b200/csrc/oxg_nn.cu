@@ -843,6 +843,7 @@ __global__ void __launch_bounds__(NN_THREADS, DOT_MIN_CTAS) knn_rv_dot_kernel(co
 // kernel; per-CTA winners are merged by knn_merge_kernel.
 // ---------------------------------------------------------------------------------------
 constexpr int S1_THREADS = 256;
+constexpr int RS_MAXQ = 8;  // most queries a few-query (state-per-thread) kernel takes
 
 template <int D, int QN>
 __global__ void __launch_bounds__(S1_THREADS) nn1_stream_kernel(const ScanParams p) {
@@ -918,6 +919,147 @@ __global__ void __launch_bounds__(S1_THREADS) nn1_stream_kernel(const ScanParams
     // partial list layout of knn_merge_kernel with k = 1: [slice][Q]
     p.out_idx[(uint64_t)blockIdx.x * p.Q + a] = bx;
     p.out_dist[(uint64_t)blockIdx.x * p.Q + a] = bd;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Few-query k-NN (Q <= 8, 2 <= k <= 16): state-per-thread streaming like nn1_stream_kernel.
+// One pass over the CTA's slice per query (queries are few; the slice is re-read from L2 / HBM).
+// Every thread keeps a sorted k-list in shared memory (stride = threads); the CTA then extracts
+// its k best by k rounds of a block-wide (dist, idx) arg-min over the threads' list heads and
+// writes them as one partial list per (CTA, query); knn_select_kernel merges the partial lists
+// the same way.  Exactness as everywhere: admission by d2 <= U(kth), order by (sqrt(d2), idx).
+// ---------------------------------------------------------------------------------------
+struct ArgMin {
+  double d;
+  uint32_t i;
+  uint32_t who;
+};
+__device__ __forceinline__ ArgMin argmin_better(ArgMin a, ArgMin b) {
+  return (b.d < a.d || (b.d == a.d && b.i < a.i)) ? b : a;
+}
+// Block-wide arg-min of (d, i); result valid in every thread.  s_red: 3 x 32 words of scratch.
+__device__ __forceinline__ ArgMin block_argmin(ArgMin v, double* s_d, uint32_t* s_i, uint32_t* s_w) {
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMin u;
+    u.d = __shfl_xor_sync(0xFFFFFFFFu, v.d, o);
+    u.i = __shfl_xor_sync(0xFFFFFFFFu, v.i, o);
+    u.who = __shfl_xor_sync(0xFFFFFFFFu, v.who, o);
+    v = argmin_better(v, u);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();  // scratch free
+  if (lane == 0) {
+    s_d[warp] = v.d;
+    s_i[warp] = v.i;
+    s_w[warp] = v.who;
+  }
+  __syncthreads();
+  ArgMin r;
+  r.d = lane < nw ? s_d[lane] : __longlong_as_double(0x7FF0000000000000ll);
+  r.i = lane < nw ? s_i[lane] : OXG_INVALID_INDEX;
+  r.who = lane < nw ? s_w[lane] : 0xFFFFFFFFu;
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMin u;
+    u.d = __shfl_xor_sync(0xFFFFFFFFu, r.d, o);
+    u.i = __shfl_xor_sync(0xFFFFFFFFu, r.i, o);
+    u.who = __shfl_xor_sync(0xFFFFFFFFu, r.who, o);
+    r = argmin_better(r, u);
+  }
+  return r;
+}
+
+template <int D>
+__global__ void __launch_bounds__(S1_THREADS) knn_stream_kernel(const ScanParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int k = (int)p.k;
+  double* s_list = reinterpret_cast<double*>(smem_raw);                 // [k][S1_THREADS]
+  uint32_t* i_list = reinterpret_cast<uint32_t*>(s_list + (size_t)k * S1_THREADS);
+  __shared__ double s_q[RS_MAXQ][D];
+  __shared__ double s_rd[32];
+  __shared__ uint32_t s_ri[32], s_rw[32];
+  if (threadIdx.x < p.Q * D) {
+    const uint32_t a = threadIdx.x / D, d = threadIdx.x % D;
+    s_q[a][d] = p.q.p[(uint64_t)a * p.q.stride_i + (uint64_t)d * p.q.stride_d];
+  }
+  __syncthreads();
+  const uint32_t n0 = blockIdx.x * p.split_len;
+  const uint32_t n1 = min(p.n_db, n0 + p.split_len);
+  double* sl = s_list + threadIdx.x;
+  uint32_t* il = i_list + threadIdx.x;
+  for (uint32_t a = 0; a < p.Q; ++a) {
+    uint32_t excl = OXG_INVALID_INDEX;
+    if (p.exclude_mode == EXCL_ARRAY) excl = p.exclude[a];
+    if (p.exclude_mode == EXCL_SELF) excl = p.self_base + a;
+    int have = 0;
+    long long ub = 0x7FF0000000000000ll;
+    for (uint32_t i = n0 + threadIdx.x; i < n1; i += S1_THREADS) {
+      double s = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const double df = __dsub_rn(s_q[a][d], __ldcs(p.db + (uint64_t)d * p.pitch + i));  // (query, stored)
+        const double m = __dmul_rn(df, df);
+        s = (d == 0) ? m : __dadd_rn(s, m);
+      }
+      if (__double_as_longlong(s) <= ub && s == s && i != excl) {
+        if (list_insert(sl, il, S1_THREADS, k, have, sqrt(s), i) && have == k)
+          ub = __double_as_longlong(sqrt_le_upper_dev(sl[(k - 1) * S1_THREADS]));
+      }
+    }
+    // the CTA's k best: k rounds of arg-min over the list heads
+    int head = 0;
+    const uint64_t o = ((uint64_t)blockIdx.x * p.Q + a) * (uint64_t)k;
+    for (int e = 0; e < k; ++e) {
+      ArgMin v;
+      v.d = head < have ? sl[head * S1_THREADS] : __longlong_as_double(0x7FF0000000000000ll);
+      v.i = head < have ? il[head * S1_THREADS] : OXG_INVALID_INDEX;
+      v.who = threadIdx.x;
+      const ArgMin w = block_argmin(v, s_rd, s_ri, s_rw);
+      if (w.i != OXG_INVALID_INDEX && w.who == threadIdx.x) ++head;
+      if (threadIdx.x == 0) {
+        p.out_idx[o + e] = w.i;
+        p.out_dist[o + e] = w.i == OXG_INVALID_INDEX ? __longlong_as_double(0x7FF0000000000000ll) : w.d;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Merges nparts sorted partial k-lists per query ([part][Q][k]) by the same k rounds of
+// block-wide arg-min over list heads.  One CTA per query.
+__global__ void __launch_bounds__(1024) knn_select_kernel(const uint32_t* __restrict__ part_idx,
+                                                          const double* __restrict__ part_dist,
+                                                          uint32_t Q, uint32_t k, uint32_t nparts,
+                                                          uint32_t* __restrict__ out_idx,
+                                                          double* __restrict__ out_dist) {
+  __shared__ double s_rd[32];
+  __shared__ uint32_t s_ri[32], s_rw[32];
+  const uint32_t qi = blockIdx.x;
+  // thread t owns partial list t (the launcher keeps nparts <= blockDim)
+  const uint32_t t = threadIdx.x;
+  uint32_t part = t, head = 0;
+  auto cur = [&](double* d, uint32_t* i) {
+    if (part < nparts && head < k) {
+      const uint64_t o = ((uint64_t)part * Q + qi) * k + head;
+      *i = part_idx[o];
+      *d = part_dist[o];
+    } else {
+      *i = OXG_INVALID_INDEX;
+      *d = __longlong_as_double(0x7FF0000000000000ll);
+    }
+  };
+  for (uint32_t e = 0; e < k; ++e) {
+    ArgMin v;
+    cur(&v.d, &v.i);
+    if (v.i == OXG_INVALID_INDEX) v.d = __longlong_as_double(0x7FF0000000000000ll);
+    v.who = t;
+    const ArgMin w = block_argmin(v, s_rd, s_ri, s_rw);
+    if (w.i != OXG_INVALID_INDEX && w.who == t) ++head;
+    if (t == 0) {
+      out_idx[(uint64_t)qi * k + e] = w.i;
+      out_dist[(uint64_t)qi * k + e] =
+          w.i == OXG_INVALID_INDEX ? __longlong_as_double(0x7FF0000000000000ll) : w.d;
+    }
   }
 }
 
@@ -1392,7 +1534,6 @@ __global__ void __launch_bounds__(NN_THREADS) radius_rv_dot_kernel(const ScanPar
 // counts[q * nsplit + slice], the fill pass writes the hits of each slice in ascending index
 // order (ballot + block prefix per round of S1_THREADS states).  The store is streamed once per
 // pass for all queries of the batch: HBM / L2 bound.
-constexpr int RS_MAXQ = 8;
 
 template <int D, bool FILL>
 __global__ void __launch_bounds__(S1_THREADS) radius_stream_kernel(const ScanParams p) {
@@ -1611,6 +1752,15 @@ static int launch_knn_rv_f32(const ScanParams& p, dim3 grid, cudaStream_t st) {
 }
 
 template <int D>
+static int launch_knn_stream(const ScanParams& p, size_t smem, cudaStream_t st) {
+  OXG_CUDA_TRY(cudaFuncSetAttribute(knn_stream_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+  knn_stream_kernel<D><<<p.nsplit, S1_THREADS, smem, st>>>(p);
+  OXG_LAUNCH_CHECK();
+  return OXG_OK;
+}
+
+template <int D>
 static int launch_nn1_stream(ScanParams p, uint32_t blocks, cudaStream_t st) {
   if (p.Q <= 1) {
     nn1_stream_kernel<D, 1><<<blocks, S1_THREADS, 0, st>>>(p);
@@ -1800,6 +1950,25 @@ int nn_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclu
       OXG_LAUNCH_CHECK();
       return OXG_OK;
     }
+  }
+  if (fast && k >= 2 && k <= 16 && Q <= (uint64_t)RS_MAXQ && p.n_db >= 4096) {
+    // few queries: state-per-thread streaming, partial lists per CTA, parallel selection
+    uint32_t ns = std::min<uint32_t>(std::max<uint32_t>(1, (p.n_db + 2047) / 2048), 1024);
+    p.split_len = round_up_u32((p.n_db + ns - 1) / ns, S1_THREADS);
+    p.nsplit = (p.n_db + p.split_len - 1) / p.split_len;
+    size_t npart = (size_t)p.nsplit * Q * k;
+    OXG_TRY(s->buf[B_PIDX].ensure(npart * sizeof(uint32_t)));
+    OXG_TRY(s->buf[B_PDIST].ensure(npart * sizeof(double)));
+    p.out_idx = s->buf[B_PIDX].as<uint32_t>();
+    p.out_dist = s->buf[B_PDIST].as<double>();
+    const size_t smem = (size_t)k * S1_THREADS * (sizeof(double) + sizeof(uint32_t));
+    int r = OXG_E_INTERNAL;
+    OXG_DISPATCH_D(s->dim, r = (launch_knn_stream<DD>(p, smem, s->stream)));
+    OXG_TRY(r);
+    knn_select_kernel<<<(unsigned)Q, 1024, 0, s->stream>>>(p.out_idx, p.out_dist, (uint32_t)Q, k,
+                                                           p.nsplit, d_idx, d_dist);
+    OXG_LAUNCH_CHECK();
+    return OXG_OK;
   }
   const bool f32 = fast && use_f32_filter();
   // several queries per thread once there is enough work to fill the machine that way

@@ -381,3 +381,31 @@ def test_randomised_shapes_against_oracle(oxg, orc):
             np.testing.assert_array_equal(off, ooff, err_msg=msg)
             np.testing.assert_array_equal(ridx, oidx, err_msg=msg)
             np.testing.assert_array_equal(rdist.view(np.uint64), odist.view(np.uint64), err_msg=msg)
+
+
+@pytest.mark.parametrize("q_count,k", [(1, 10), (3, 2), (8, 16), (5, 7)])
+def test_few_query_stream_knn(oxg, orc, q_count, k):
+    """Q <= 8, 2 <= k <= 16 over >= 4096 states: state-per-thread k-NN with per-CTA partial lists
+    and the parallel (dist, idx) selection; ties, self-exclusion and k > (states per slice)."""
+    for d, n in ((2, 4096), (7, 70001), (14, 9000)):
+        rows = uniform_states(700 + d, n, [0.0] * d, [1.0] * d)
+        queries = np.vstack([uniform_states(800 + d, q_count, [0.0] * d, [1.0] * d)])
+        sp_o = orc.space(d)
+        with oxg.StateStore(oxg.Space.real_vector(d)) as st:
+            st.append(rows)
+            idx, dist = st.knn(queries, k)
+            oi, od = orc.knn(sp_o, rows, queries, k)
+            np.testing.assert_array_equal(idx, oi)
+            np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+            ex = np.arange(q_count, dtype=np.uint32) * 5
+            idx, dist = st.knn(rows[ex], k, exclude=ex)
+            oi, od = orc.knn(sp_o, rows, rows[ex], k, exclude=ex)
+            np.testing.assert_array_equal(idx, oi)
+            np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+    rows = np.vstack([_adversarial(8, 3000, 3), _adversarial(9, 3000, 3)])   # mass exact ties
+    with oxg.StateStore(oxg.Space.real_vector(3)) as st:
+        st.append(rows)
+        idx, dist = st.knn(rows[:q_count], k)
+        oi, od = orc.knn(orc.space(3), rows, rows[:q_count], k)
+        np.testing.assert_array_equal(idx, oi)
+        np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
