@@ -55,7 +55,6 @@ struct ScanParams {
   uint32_t k;
   int exclude_mode;
   const uint32_t* exclude;
-  uint32_t exclude_one;  // few-query stream kernel: one excluded index (or OXG_INVALID_INDEX)
   uint32_t self_base;
   uint32_t split_len;  // stored states per blockIdx.y slice (multiple of NN_TILE)
   uint32_t nsplit;
@@ -851,11 +850,14 @@ __global__ void __launch_bounds__(S1_THREADS) nn1_stream_kernel(const ScanParams
   __shared__ uint32_t s_i[QN][S1_THREADS / 32];
   double q[QN][D];
   double best[QN];
-  uint32_t bi[QN];
+  uint32_t bi[QN], excl1[QN];
   long long ub[QN];
 #pragma unroll
   for (int a = 0; a < QN; ++a) {
     const uint32_t qq = (uint32_t)a < p.Q ? a : 0u;
+    excl1[a] = OXG_INVALID_INDEX;
+    if (p.exclude_mode == EXCL_ARRAY) excl1[a] = p.exclude[qq];
+    if (p.exclude_mode == EXCL_SELF) excl1[a] = p.self_base + qq;
 #pragma unroll
     for (int d = 0; d < D; ++d) q[a][d] = p.q.p[(uint64_t)qq * p.q.stride_i + (uint64_t)d * p.q.stride_d];
     best[a] = __longlong_as_double(0x7FF0000000000000ll);
@@ -878,7 +880,7 @@ __global__ void __launch_bounds__(S1_THREADS) nn1_stream_kernel(const ScanParams
         const double m = __dmul_rn(df, df);
         s = (d == 0) ? m : __dadd_rn(s, m);
       }
-      if (__double_as_longlong(s) <= ub[a] && s == s && i != p.exclude_one) {
+      if (__double_as_longlong(s) <= ub[a] && s == s && i != excl1[a]) {
         const double r = sqrt(s);
         if (r < best[a] || (r == best[a] && i < bi[a])) {
           best[a] = r;
@@ -1930,44 +1932,52 @@ int nn_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclu
   p.db32 = s->d_data32;
   p.maxabs = s->d_maxabs;
   const bool fast = is_pure_rv(s->space) && s->dim <= (uint32_t)kMaxFastDim;
-  if (fast && k == 1 && Q <= 8 && exclude_mode != EXCL_ARRAY) {
-    // few queries: stream the f64 store once, state-per-thread (HBM / L2 bound)
-    const uint32_t blocks =
-        (uint32_t)std::min<uint64_t>(((uint64_t)p.n_db + S1_THREADS - 1) / S1_THREADS, 148ull * 4);
-    p.exclude_one = (exclude_mode == EXCL_SELF) ? (uint32_t)self_base : OXG_INVALID_INDEX;
-    if (exclude_mode == EXCL_SELF && Q != 1) p.exclude_one = OXG_INVALID_INDEX;
-    if (!(exclude_mode == EXCL_SELF && Q != 1)) {
-      size_t npart = (size_t)blocks * Q;
-      OXG_TRY(s->buf[B_PIDX].ensure(npart * sizeof(uint32_t)));
-      OXG_TRY(s->buf[B_PDIST].ensure(npart * sizeof(double)));
-      p.out_idx = s->buf[B_PIDX].as<uint32_t>();
-      p.out_dist = s->buf[B_PDIST].as<double>();
-      int r = OXG_E_INTERNAL;
-      OXG_DISPATCH_D(s->dim, r = (launch_nn1_stream<DD>(p, blocks, s->stream)));
-      OXG_TRY(r);
-      nn1_final_kernel<<<(unsigned)Q, 256, 0, s->stream>>>(p.out_idx, p.out_dist, (uint32_t)Q, blocks,
-                                                          d_idx, d_dist);
-      OXG_LAUNCH_CHECK();
-      return OXG_OK;
+  // Few to moderately many queries (the planners' per-iteration calls, small sweeps): the
+  // state-per-thread streaming kernels, RS_MAXQ queries per launch.  Beyond a few dozen queries
+  // the query-per-thread kernels below win.
+  // (measured crossovers at N = 1e6, D = 7: ~40 queries for k = 1, ~100 for k = 10)
+  const bool stream1 = fast && k == 1 && Q <= 32;
+  const bool streamk = fast && k >= 2 && k <= 16 && Q <= 64 && p.n_db >= 4096;
+  if (stream1 || streamk) {
+    uint32_t blocks = 0;
+    size_t smem = 0;
+    if (stream1) {
+      blocks = (uint32_t)std::min<uint64_t>(((uint64_t)p.n_db + S1_THREADS - 1) / S1_THREADS, 148ull * 4);
+    } else {
+      uint32_t ns = std::min<uint32_t>(std::max<uint32_t>(1, (p.n_db + 2047) / 2048), 1024);
+      p.split_len = round_up_u32((p.n_db + ns - 1) / ns, S1_THREADS);
+      p.nsplit = (p.n_db + p.split_len - 1) / p.split_len;
+      blocks = p.nsplit;
+      smem = (size_t)k * S1_THREADS * (sizeof(double) + sizeof(uint32_t));
     }
-  }
-  if (fast && k >= 2 && k <= 16 && Q <= (uint64_t)RS_MAXQ && p.n_db >= 4096) {
-    // few queries: state-per-thread streaming, partial lists per CTA, parallel selection
-    uint32_t ns = std::min<uint32_t>(std::max<uint32_t>(1, (p.n_db + 2047) / 2048), 1024);
-    p.split_len = round_up_u32((p.n_db + ns - 1) / ns, S1_THREADS);
-    p.nsplit = (p.n_db + p.split_len - 1) / p.split_len;
-    size_t npart = (size_t)p.nsplit * Q * k;
+    const size_t npart = (size_t)blocks * RS_MAXQ * k;
     OXG_TRY(s->buf[B_PIDX].ensure(npart * sizeof(uint32_t)));
     OXG_TRY(s->buf[B_PDIST].ensure(npart * sizeof(double)));
     p.out_idx = s->buf[B_PIDX].as<uint32_t>();
     p.out_dist = s->buf[B_PDIST].as<double>();
-    const size_t smem = (size_t)k * S1_THREADS * (sizeof(double) + sizeof(uint32_t));
-    int r = OXG_E_INTERNAL;
-    OXG_DISPATCH_D(s->dim, r = (launch_knn_stream<DD>(p, smem, s->stream)));
-    OXG_TRY(r);
-    knn_select_kernel<<<(unsigned)Q, 1024, 0, s->stream>>>(p.out_idx, p.out_dist, (uint32_t)Q, k,
-                                                           p.nsplit, d_idx, d_dist);
-    OXG_LAUNCH_CHECK();
+    for (uint64_t c0 = 0; c0 < Q; c0 += RS_MAXQ) {
+      const uint32_t qn = (uint32_t)std::min<uint64_t>(RS_MAXQ, Q - c0);
+      ScanParams pc = p;
+      pc.q.p = q.p + c0 * q.stride_i;
+      pc.Q = qn;
+      pc.exclude = d_exclude ? d_exclude + c0 : nullptr;
+      pc.self_base = (uint32_t)(self_base + c0);
+      int r = OXG_E_INTERNAL;
+      if (stream1) {
+        // the 1-NN kernel keeps its queries in registers and takes one excluded index per query
+        // through the exclusion array or the self rule
+        OXG_DISPATCH_D(s->dim, r = (launch_nn1_stream<DD>(pc, blocks, s->stream)));
+        OXG_TRY(r);
+        nn1_final_kernel<<<qn, 256, 0, s->stream>>>(pc.out_idx, pc.out_dist, qn, blocks,
+                                                   d_idx + c0, d_dist + c0);
+      } else {
+        OXG_DISPATCH_D(s->dim, r = (launch_knn_stream<DD>(pc, smem, s->stream)));
+        OXG_TRY(r);
+        knn_select_kernel<<<qn, (unsigned)round_up_u32(blocks, 32), 0, s->stream>>>(
+            pc.out_idx, pc.out_dist, qn, k, blocks, d_idx + c0 * k, d_dist + c0 * k);
+      }
+      OXG_LAUNCH_CHECK();
+    }
     return OXG_OK;
   }
   const bool f32 = fast && use_f32_filter();
@@ -2034,7 +2044,13 @@ int nn_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclu
     scan_generic_kernel<0><<<grid, NN_THREADS, smem, s->stream>>>(g);
     OXG_LAUNCH_CHECK();
   }
-  if (p.nsplit > 1) {
+  if (p.nsplit >= 16 && p.nsplit <= 1024) {
+    // many slices: merge each query's partial lists in parallel (k rounds of block arg-min)
+    const unsigned threads = (unsigned)round_up_u32(p.nsplit, 32);
+    knn_select_kernel<<<(unsigned)Q, threads, 0, s->stream>>>(part_idx, part_dist, (uint32_t)Q, k,
+                                                              p.nsplit, d_idx, d_dist);
+    OXG_LAUNCH_CHECK();
+  } else if (p.nsplit > 1) {
     int threads = 64;
     size_t smem = (size_t)k * threads * (sizeof(double) + sizeof(uint32_t));
     OXG_CUDA_TRY(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

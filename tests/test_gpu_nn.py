@@ -288,7 +288,7 @@ def test_store_clear_resets_filter_scale(oxg, orc):
         np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
 
 
-@pytest.mark.parametrize("q_count", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("q_count", [1, 2, 3, 5, 8, 9, 27])
 def test_few_query_stream_scan(oxg, orc, q_count):
     """Q <= 8 takes the state-per-thread streaming kernel (the planners' per-iteration query)."""
     for d, n in ((2, 1), (3, 300), (7, 70001), (14, 4097)):
@@ -383,7 +383,7 @@ def test_randomised_shapes_against_oracle(oxg, orc):
             np.testing.assert_array_equal(rdist.view(np.uint64), odist.view(np.uint64), err_msg=msg)
 
 
-@pytest.mark.parametrize("q_count,k", [(1, 10), (3, 2), (8, 16), (5, 7)])
+@pytest.mark.parametrize("q_count,k", [(1, 10), (3, 2), (8, 16), (5, 7), (19, 10), (64, 3)])
 def test_few_query_stream_knn(oxg, orc, q_count, k):
     """Q <= 8, 2 <= k <= 16 over >= 4096 states: state-per-thread k-NN with per-CTA partial lists
     and the parallel (dist, idx) selection; ties, self-exclusion and k > (states per slice)."""
