@@ -927,7 +927,7 @@ int choose_ctas(uint64_t max_nodes, uint32_t dim, uint64_t n_obstacles, int sm_c
   const int forced = env_int_pl("OXG_PLAN_CTAS", 0);
   if (forced > 0) return std::min(forced, sm_count);
   uint64_t by_tree = (max_nodes * dim + 32767) / 32768;
-  uint64_t by_world = (n_obstacles + 255) / 256;
+  uint64_t by_world = (n_obstacles + 63) / 64;
   uint64_t g = std::max<uint64_t>(by_tree, by_world);
   if (g < 1) g = 1;
   if (g > (uint64_t)sm_count) g = (uint64_t)sm_count;
