@@ -40,7 +40,7 @@ DIM = 7
 SEED = 4
 # dram__bytes_read.sum + dram__bytes_write.sum of one k-NN launch at this config, from the
 # `ncu --set full` capture summarised in profiles/ (None until captured for the current kernel)
-KNN_DRAM_BYTES_NCU = 2268194000  # profiles/r01_ncu_full_knn_rv_dot_7_2.csv (2.061 GB read + 0.207 GB written)
+KNN_DRAM_BYTES_NCU = 2249420000  # profiles/r01_ncu_full_knn_rv_dot_7_2.csv (2.046 GB read + 0.204 GB written)
 
 
 def parse_args():

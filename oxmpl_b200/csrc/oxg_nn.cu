@@ -1901,9 +1901,20 @@ static void choose_split(uint32_t n_db, uint64_t qtiles, uint32_t tile, uint32_t
 }
 
 // k-NN of Q device-resident queries against the store; results in device memory.
+static int nn_knn_device_impl(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclude_mode,
+                              const uint32_t* d_exclude, uint64_t self_base, bool stored_first,
+                              uint32_t* d_idx, double* d_dist, int force_qpt, uint32_t force_nsplit);
+
 int nn_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclude_mode,
                   const uint32_t* d_exclude, uint64_t self_base, bool stored_first, uint32_t* d_idx,
                   double* d_dist) {
+  return nn_knn_device_impl(s, q, Q, k, exclude_mode, d_exclude, self_base, stored_first, d_idx,
+                            d_dist, 0, 0);
+}
+
+static int nn_knn_device_impl(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclude_mode,
+                              const uint32_t* d_exclude, uint64_t self_base, bool stored_first,
+                              uint32_t* d_idx, double* d_dist, int force_qpt, uint32_t force_nsplit) {
   if (Q == 0) return OXG_OK;
   if (s->size == 0) {
     set_error("nearest-neighbour query against an empty store");
@@ -1988,9 +1999,36 @@ int nn_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclu
     qpt = forced_qpt() >= 2 ? 2 : 1;
     if (qpt == 2 && k > 32) qpt = 1;
   }
+  if (force_qpt > 0) qpt = force_qpt;
   const uint32_t nq_per_cta = NN_THREADS * qpt;
   const uint64_t qtiles = (Q + nq_per_cta - 1) / nq_per_cta;
-  choose_split(p.n_db, qtiles, f32 ? F_TILE : NN_TILE, &p.nsplit, &p.split_len);
+  // Wave quantisation.  The batched kernels keep 3 CTAs per SM resident; a batch of W.f waves
+  // with a small fraction f pays a whole extra wave for a few CTAs (the 8-GPU PRM shard is 1.1
+  // waves).  Run the whole waves as they are and give the tail queries the entire machine by
+  // splitting the store into slices for them only.
+  if (f32 && qpt == 2 && force_nsplit == 0 && force_qpt == 0 && forced_qpt() == 0) {
+    const uint64_t slots = 148ull * 3;
+    const uint64_t whole = qtiles / slots, tail = qtiles % slots;
+    if (whole == 1 && tail > 0 && tail * 3 < slots && p.n_db >= 65536) {
+      const uint64_t q_main = whole * slots * nq_per_cta;
+      uint32_t ns = (uint32_t)std::min<uint64_t>(slots / tail, 16);
+      OXG_TRY(nn_knn_device_impl(s, q, q_main, k, exclude_mode, d_exclude, self_base, stored_first,
+                                 d_idx, d_dist, 2, 1));
+      StateView qt = q;
+      qt.p = q.p + q_main * q.stride_i;
+      return nn_knn_device_impl(s, qt, Q - q_main, k, exclude_mode,
+                                d_exclude ? d_exclude + q_main : nullptr, self_base + q_main,
+                                stored_first, d_idx + q_main * k, d_dist + q_main * k, 2, ns);
+    }
+  }
+  if (force_nsplit > 0) {
+    p.nsplit = force_nsplit;
+    const uint32_t tile = f32 ? F_TILE : NN_TILE;
+    p.split_len = round_up_u32((p.n_db + p.nsplit - 1) / p.nsplit, tile);
+    p.nsplit = std::max<uint32_t>(1, (p.n_db + p.split_len - 1) / p.split_len);
+  } else {
+    choose_split(p.n_db, qtiles, f32 ? F_TILE : NN_TILE, &p.nsplit, &p.split_len);
+  }
 
   uint32_t* part_idx = d_idx;
   double* part_dist = d_dist;

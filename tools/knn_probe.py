@@ -22,6 +22,7 @@ def main():
     d = int(sys.argv[2]) if len(sys.argv) > 2 else 7
     k = int(sys.argv[3]) if len(sys.argv) > 3 else 10
     reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+    rows_q = int(sys.argv[5]) if len(sys.argv) > 5 else n   # query rows [0, rows_q) (a shard)
     rng = np.random.default_rng(0)
     rows = rng.random((n, d)) * 5.0 - 2.5
     dev = torch.device("cuda", 0)
@@ -35,15 +36,16 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(ext):
             e0.record(ext)
-            check(lib.oxg_knn_rows_dev(st.handle, 0, n, k, C.c_void_p(idx.data_ptr()),
+            check(lib.oxg_knn_rows_dev(st.handle, 0, rows_q, k, C.c_void_p(idx.data_ptr()),
                                        C.c_void_p(dist.data_ptr())))
             e1.record(ext)
         ext.synchronize()
         if it > 0:
             times.append(e0.elapsed_time(e1))
     ms = float(np.median(times))
-    chk = int(idx.to(torch.int64).sum().item())
-    print(json.dumps({"n": n, "d": d, "k": k, "ms": ms, "pairs_per_s": n * n / (ms * 1e-3),
+    chk = int(idx[:rows_q].to(torch.int64).sum().item())
+    print(json.dumps({"n": n, "d": d, "k": k, "rows": rows_q, "ms": ms,
+                      "pairs_per_s": n * rows_q / (ms * 1e-3),
                       "filter": os.environ.get("OXG_KNN_FILTER", "1"),
                       "qpt": os.environ.get("OXG_KNN_QPT", "auto"), "idx_checksum": chk}))
 
