@@ -62,3 +62,56 @@ def test_prm_knn_matches_oracle(oxg, orc, n, k):
         np.testing.assert_array_equal(idx2, oi[a:b])
         np.testing.assert_array_equal(valid2, ov[a:b])
     gw.close()
+
+
+@pytest.mark.parametrize("n,k,shards", [(3001, 10, 2), (2000, 6, 4)])
+def test_device_pointer_pipeline_sharded_on_one_gpu(oxg, orc, n, k, shards):
+    """The multi-GPU PRM path (oxg_knn_rows_dev -> all-gather -> oxg_prm_edges_dev -> all-gather
+    -> oxg_prm_resolve_dev, as bench.py drives it with NCCL) emulated on one GPU: every shard's
+    rows are computed by separate calls into shared [n, k] device buffers (what the all-gathers
+    produce), the result must equal the unsharded oracle roadmap, and every candidate edge must
+    be motion-checked exactly once across the shards."""
+    import ctypes as C
+
+    import torch
+
+    from oxmpl_b200 import sharding
+    from oxmpl_b200._lib import check, lib
+
+    sp, sp_o = oxg.Space.real_vector(7), orc.space(7)
+    gw, ow, keep, res = _panda_world(oxg, orc)
+    rows = uniform_states(45, n, worlds.PANDA_LO, worlds.PANDA_HI)
+    oi, od, ov = orc.prm_knn(ow, sp_o, rows, k, res)
+    dev = torch.device("cuda", 0)
+    with oxg.StateStore(sp) as st:
+        st.append(rows)
+        ext = torch.cuda.ExternalStream(st.stream(), device=dev)
+        with torch.cuda.stream(ext):
+            idx_all = torch.empty((n, k), dtype=torch.int32, device=dev)
+            dist_all = torch.empty((n, k), dtype=torch.float64, device=dev)
+            valid_all = torch.full((n, k), 7, dtype=torch.uint8, device=dev)
+            counters = torch.zeros(2, dtype=torch.int64, device=dev)
+        ext.synchronize()
+        for r in range(shards):
+            rb, re = sharding.row_range(n, r, shards)
+            check(lib.oxg_knn_rows_dev(st.handle, rb, re, k, C.c_void_p(idx_all[rb:re].data_ptr()),
+                                       C.c_void_p(dist_all[rb:re].data_ptr())))
+        checked = 0
+        for r in range(shards):
+            rb, re = sharding.row_range(n, r, shards)
+            check(lib.oxg_prm_edges_dev(gw.handle, st.handle, C.c_void_p(idx_all.data_ptr()), k,
+                                        float(res), rb, re, C.c_void_p(valid_all.data_ptr()),
+                                        C.c_void_p(counters.data_ptr())))
+            st.sync()
+            checked += int(counters.cpu()[0])
+            own = sharding.owned_slots(oi, rb, re)                 # host mirror of the ownership rule
+            assert int(counters.cpu()[0]) == int(own.sum())
+        check(lib.oxg_prm_resolve_dev(st.handle, C.c_void_p(idx_all.data_ptr()), k,
+                                      C.c_void_p(valid_all.data_ptr())))
+        st.sync()
+        np.testing.assert_array_equal(idx_all.cpu().numpy().view(np.uint32), oi)
+        np.testing.assert_array_equal(dist_all.cpu().numpy().view(np.uint64), od.view(np.uint64))
+        np.testing.assert_array_equal(valid_all.cpu().numpy(), ov)
+        pairs = {(min(i, int(j)), max(i, int(j))) for i in range(n) for j in oi[i] if j != 0xFFFFFFFF}
+        assert checked == len(pairs)
+    gw.close()
