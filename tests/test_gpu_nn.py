@@ -409,3 +409,38 @@ def test_few_query_stream_knn(oxg, orc, q_count, k):
         oi, od = orc.knn(orc.space(3), rows, rows[:q_count], k)
         np.testing.assert_array_equal(idx, oi)
         np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+
+
+@pytest.mark.parametrize("offset,delta", [(0.0, 1e-9), (10.0, 1e-7), (1000.0, 1e-6), (3.0, 1e-15)])
+@pytest.mark.parametrize("nq", [40, 1100], ids=["diff_form", "dot_form"])
+def test_prefilter_at_the_threshold(oxg, orc, offset, delta, nq):
+    """Every query sits at the centre of a thin shell of stored states whose distances differ by
+    relative `delta` (down to a few ulps), and k is chosen so that the k-th neighbour lies in
+    the middle of its shell: the admission threshold U cuts through a cloud of near-equal d2
+    values, which is where a filter that rejected too eagerly (or a compare-before-sqrt) would
+    pick different indices.  Offsets make the FP32 images of states and queries collide."""
+    d, per = 7, 48
+    rng = np.random.default_rng(int(offset) + nq)
+    centres = offset + rng.random((nq, d)) * 4.0
+    u = rng.normal(size=(nq, per, d))
+    u /= np.linalg.norm(u, axis=2, keepdims=True)
+    radii = 0.25 * (1.0 + (np.arange(per) - per // 2) * delta)
+    rows = (centres[:, None, :] + u * radii[None, :, None]).reshape(-1, d)
+    perm = rng.permutation(len(rows))
+    rows = np.ascontiguousarray(rows[perm])
+    sp_o = orc.space(d)
+    k = per // 2
+    with oxg.StateStore(oxg.Space.real_vector(d)) as st:
+        st.append(rows)
+        idx, dist = st.knn(centres, k)
+        oi, od = orc.knn(sp_o, rows, centres, k)
+        np.testing.assert_array_equal(idx, oi)
+        np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+        i1, d1 = st.nn1(centres)
+        o1, od1 = orc.nn1(sp_o, rows, centres)
+        np.testing.assert_array_equal(i1, o1)
+        np.testing.assert_array_equal(d1.view(np.uint64), od1.view(np.uint64))
+        off, ridx = st.radius(centres, 0.25)
+        ooff, oidx = orc.radius(sp_o, rows, centres, 0.25)
+        np.testing.assert_array_equal(off, ooff)
+        np.testing.assert_array_equal(ridx, oidx)
