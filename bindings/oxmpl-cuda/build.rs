@@ -20,7 +20,7 @@ fn main() {
         let obj = out.join(src.replace(".cu", ".o"));
         let status = Command::new(&nvcc)
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo"])
-            .args(["-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off"])
+            .args(["-fmad=false", "--split-compile=0", "-Xcompiler", "-fPIC,-ffp-contract=off"])
             .arg("-c")
             .arg(csrc.join(src))
             .arg("-o")
