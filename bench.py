@@ -483,9 +483,16 @@ def run_ours(args):
             "roofline": roof,
         }
         if world_size == 1 and not args.no_extras:
-            line["extras"] = extras(oxg, args)
+            try:
+                line["extras"] = extras(oxg, args)
+            except Exception as e:  # secondary figures never break the headline line
+                line["extras"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world_size == 1:
-            line["cpu_baseline"] = cpu_baseline(args, rows_np, caps, res)
+            try:
+                line["cpu_baseline"] = cpu_baseline(args, rows_np, caps, res)
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port",
+                                        "sample": "failed: " + repr(e)}
         print(json.dumps(line), flush=True)
     if world_size > 1:
         dist.barrier()
