@@ -1888,8 +1888,10 @@ static uint32_t round_up_u32(uint32_t v, uint32_t m) { return (v + m - 1) / m * 
 // Chooses how many slices of the store each query tile is split into, so that small query
 // batches still fill the GPU.
 static void choose_split(uint32_t n_db, uint64_t qtiles, uint32_t tile, uint32_t* nsplit,
-                         uint32_t* split_len) {
-  const uint64_t target_ctas = 148ull * 6;
+                         uint32_t* split_len, uint32_t k = 1) {
+  // six CTA waves of slices fill the machine best; with k > 1 and few query tiles every slice
+  // repeats the top-k warm-up, so three waves win there (measured at N = 1e6, D = 7)
+  const uint64_t target_ctas = 148ull * ((k >= 4 && qtiles <= 100) ? 3 : 6);
   uint64_t want = (target_ctas + qtiles - 1) / qtiles;
   uint64_t max_split = std::max<uint64_t>(1, n_db / (tile * 4));
   uint64_t ns = std::min<uint64_t>(std::min<uint64_t>(want, max_split), 2048);
@@ -2027,7 +2029,7 @@ static int nn_knn_device_impl(oxg_store_s* s, StateView q, uint64_t Q, uint32_t 
     p.split_len = round_up_u32((p.n_db + p.nsplit - 1) / p.nsplit, tile);
     p.nsplit = std::max<uint32_t>(1, (p.n_db + p.split_len - 1) / p.split_len);
   } else {
-    choose_split(p.n_db, qtiles, f32 ? F_TILE : NN_TILE, &p.nsplit, &p.split_len);
+    choose_split(p.n_db, qtiles, f32 ? F_TILE : NN_TILE, &p.nsplit, &p.split_len, k);
   }
 
   uint32_t* part_idx = d_idx;
