@@ -316,4 +316,70 @@ OXG_DEV bool capsule_maybe_hit32(const float* xf, const float* __restrict__ cap,
   return !(d2 > T);
 }
 
+// Variants reading the mirror row from shared memory (32-bit shared address, 16-byte loads):
+// the validity kernels stage the world's f32 mirrors once per CTA, which turns the per-obstacle
+// row reads from warp-uniform global loads into broadcast LDS.128.
+__device__ __forceinline__ float4 lds128_row(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+
+template <int DT>
+OXG_DEV bool sphere_maybe_hit32_s(const float* xf, uint32_t row, float a2, float ce) {
+  constexpr int DN = DT > 0 ? DT : 1;  // (never called with DT == 0; keeps the arrays non-empty)
+  constexpr int NV = (DN + 2 + 3) / 4;
+  float c[NV * 4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 t4 = lds128_row(row + 16u * v);
+    c[4 * v] = t4.x;
+    c[4 * v + 1] = t4.y;
+    c[4 * v + 2] = t4.z;
+    c[4 * v + 3] = t4.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < DT; ++i) {
+    const float d = xf[i] - c[i];
+    s = __fmaf_rn(d, d, s);
+  }
+  const float T = __fmaf_ru(a2, c[DT + 1], __fadd_ru(c[DT], ce));
+  return !(s > T);
+}
+
+template <int DT>
+OXG_DEV bool capsule_maybe_hit32_s(const float* xf, uint32_t row, float a2, float ce) {
+  constexpr int DN = DT > 0 ? DT : 1;
+  constexpr int NV = (2 * DN + 3 + 3) / 4;
+  float c[NV * 4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 t4 = lds128_row(row + 16u * v);
+    c[4 * v] = t4.x;
+    c[4 * v + 1] = t4.y;
+    c[4 * v + 2] = t4.z;
+    c[4 * v + 3] = t4.w;
+  }
+  float ap[DN];
+  float num = 0.f;
+#pragma unroll
+  for (int i = 0; i < DT; ++i) {
+    ap[i] = xf[i] - c[i];
+    num = __fmaf_rn(ap[i], c[DT + i], num);
+  }
+  float t = num * c[2 * DT];
+  t = fminf(fmaxf(t, 0.f), 1.f);
+  float d2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < DT; ++i) {
+    const float e = __fmaf_rn(-t, c[DT + i], ap[i]);
+    d2 = __fmaf_rn(e, e, d2);
+  }
+  const float T = __fmaf_ru(a2, c[2 * DT + 2], __fadd_ru(c[2 * DT + 1], ce));
+  return !(d2 > T);
+}
+
 }  // namespace oxg

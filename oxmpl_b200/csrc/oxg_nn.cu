@@ -583,16 +583,6 @@ __device__ __forceinline__ float2 fma2_bcast(float g, float2 pv, float2 acc) {
 
 // k-NN with the dot-form pre-filter and per-warp fallback to the difference form.
 // grid = (ceil(Q / (NN_THREADS*QPT)), nsplit)
-// 16-byte shared-memory load from a 32-bit shared address (no generic-address conversion in
-// the inner loop).
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(addr));
-  return v;
-}
-
 // One tile of the filtered k-NN scan: 8 stored states per step, DOT selects the dot form
 // (columns 0..D-1 = coordinates, column D = squared norms) or the difference form.  Returns
 // the number of candidates this thread deferred.

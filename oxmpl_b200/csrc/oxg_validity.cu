@@ -63,6 +63,45 @@ __device__ __forceinline__ bool state_valid_filtered_dev(const WorldView& w, con
   return true;
 }
 
+// Same, with the sphere / capsule mirrors staged in shared memory (sm_sph / sm_cap: 32-bit
+// shared addresses of the first rows; 0 = not staged, read the global mirror).
+template <int DT>
+__device__ __forceinline__ bool state_valid_staged_dev(const WorldView& w, const double* x,
+                                                       const float* xf, const EdgeTol& tol,
+                                                       uint32_t sm_sph, uint32_t sm_cap) {
+  for (uint32_t i = 0; i < w.n_spheres; ++i)
+    if (sphere_maybe_hit32_s<DT>(xf, sm_sph + i * w.sphere32_stride * 4u, tol.a2_s, tol.ce_s) &&
+        sphere_hit_dev<DT>(x, w.spheres + (size_t)i * w.sphere_stride, DT))
+      return false;
+  for (uint32_t i = 0; i < w.n_aabbs; ++i)
+    if (aabb_maybe_hit32<DT>(xf, w.aabbs32 + (size_t)i * w.aabb_stride, DT) &&
+        aabb_hit_dev<DT>(x, w.aabbs + (size_t)i * w.aabb_stride, DT))
+      return false;
+  for (uint32_t i = 0; i < w.n_capsules; ++i)
+    if (capsule_maybe_hit32_s<DT>(xf, sm_cap + i * w.capsule32_stride * 4u, tol.a2_c, tol.ce_c) &&
+        capsule_hit_dev<DT>(x, w.capsules + (size_t)i * w.capsule_stride, DT))
+      return false;
+  return true;
+}
+
+// Copies the sphere and capsule f32 mirrors into dynamic shared memory (whole CTA); returns
+// false when the kernel was launched without the staging area.
+__device__ __forceinline__ bool stage_world32(const WorldView& w, uint32_t smem_bytes,
+                                              unsigned char* smem, uint32_t* sm_sph, uint32_t* sm_cap) {
+  const uint32_t sph_bytes = w.n_spheres * w.sphere32_stride * 4u;
+  const uint32_t cap_bytes = w.n_capsules * w.capsule32_stride * 4u;
+  if (smem_bytes < sph_bytes + cap_bytes || sph_bytes + cap_bytes == 0) return false;
+  float4* dst = reinterpret_cast<float4*>(smem);
+  const float4* s1 = reinterpret_cast<const float4*>(w.spheres32);
+  const float4* s2 = reinterpret_cast<const float4*>(w.capsules32);
+  for (uint32_t i = threadIdx.x; i < sph_bytes / 16; i += blockDim.x) dst[i] = s1[i];
+  for (uint32_t i = threadIdx.x; i < cap_bytes / 16; i += blockDim.x) dst[sph_bytes / 16 + i] = s2[i];
+  __syncthreads();
+  *sm_sph = (uint32_t)__cvta_generic_to_shared(smem);
+  *sm_cap = *sm_sph + sph_bytes;
+  return true;
+}
+
 template <int DT>
 __global__ void __launch_bounds__(128) is_valid_kernel(const WorldView w, const SpaceP sp,
                                                        const StateView st, uint64_t Q,
@@ -103,11 +142,15 @@ struct MotionParams {
   double resolution;
   uint8_t* valid;
   uint32_t* first_invalid;  // nullable
+  uint32_t world_smem_bytes;  // dynamic shared memory available for the staged f32 mirrors
 };
 
 template <int DT, int L>
 __global__ void __launch_bounds__(128) motion_kernel(const MotionParams p) {
+  extern __shared__ __align__(16) unsigned char world_smem[];
   constexpr int XN = DT > 0 ? DT : kMaxDim;
+  uint32_t sm_sph = 0, sm_cap = 0;
+  const bool staged = DT > 0 && stage_world32(p.w, p.world_smem_bytes, world_smem, &sm_sph, &sm_cap);
   const int n_real = DimOf<DT>::get((int)p.sp.n_real);
   const int n_so2 = DT > 0 ? 0 : (int)p.sp.n_so2;
   const int dim = n_real + n_so2;
@@ -173,7 +216,8 @@ __global__ void __launch_bounds__(128) motion_kernel(const MotionParams p) {
             float xf[XN];
 #pragma unroll
             for (int d = 0; d < dim; ++d) xf[d] = __double2float_rn(x[d]);
-            bad = !state_valid_filtered_dev<DT>(p.w, x, xf, tol);
+            bad = staged ? !state_valid_staged_dev<DT>(p.w, x, xf, tol, sm_sph, sm_cap)
+                         : !state_valid_filtered_dev<DT>(p.w, x, xf, tol);
           } else {
             bad = !state_valid_dev<DT>(p.w, x, n_real);
           }
@@ -332,6 +376,7 @@ int is_valid_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t
     p.resolution = 1.0;
     p.valid = d_out;
     p.first_invalid = nullptr;
+    p.world_smem_bytes = 0;
     OXG_DISPATCH_DT(fast_dim(sp), (motion_small_kernel<DD><<<(unsigned)Q, 256, 0, stream>>>(p)));
     OXG_LAUNCH_CHECK();
     return OXG_OK;
@@ -382,10 +427,14 @@ int motion_check_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStre
   const bool wide = E < 148ull * 64;
   const int L = wide ? 32 : 4;
   unsigned blocks = (unsigned)std::min<uint64_t>((E * L + threads - 1) / threads, 148ull * 16);
+  // stage the sphere / capsule f32 mirrors in shared memory when they fit beside 5 CTAs per SM
+  size_t stage = (size_t)w->n_spheres * w->sphere32_stride * 4 + (size_t)w->n_capsules * w->capsule32_stride * 4;
+  if (stage > 40 * 1024 || fast_dim(sp) == 0) stage = 0;
+  p.world_smem_bytes = (uint32_t)stage;
   if (wide) {
-    OXG_DISPATCH_DT(fast_dim(sp), (motion_kernel<DD, 32><<<blocks, threads, 0, stream>>>(p)));
+    OXG_DISPATCH_DT(fast_dim(sp), (motion_kernel<DD, 32><<<blocks, threads, stage, stream>>>(p)));
   } else {
-    OXG_DISPATCH_DT(fast_dim(sp), (motion_kernel<DD, 4><<<blocks, threads, 0, stream>>>(p)));
+    OXG_DISPATCH_DT(fast_dim(sp), (motion_kernel<DD, 4><<<blocks, threads, stage, stream>>>(p)));
   }
   OXG_LAUNCH_CHECK();
   return OXG_OK;
