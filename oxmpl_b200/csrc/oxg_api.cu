@@ -546,12 +546,30 @@ int oxg_world_create(uint32_t dim, const double* spheres, uint64_t n_spheres, co
     dst[2 * dim + 1] = u1_of(src[2 * dim + 1]);
     dst[2 * dim + 2] = sq_of(src[2 * dim + 1]);
   }
+  // capsule pairs (c, c+1) with interleaved values; an odd tail pairs with a dummy whose
+  // threshold is -inf (never "maybe hit")
+  w->capsule32p_stride = (2 * (2 * dim + 3) + 3) & ~3u;
+  const uint64_t n_pairs = (n_capsules + 1) / 2;
+  std::vector<float> hc32p(n_pairs * w->capsule32p_stride, 0.0f);
+  for (uint64_t pr = 0; pr < n_pairs; ++pr) {
+    float* dst = hc32p.data() + pr * w->capsule32p_stride;
+    for (int h = 0; h < 2; ++h) {
+      const uint64_t c = 2 * pr + h;
+      for (uint32_t v = 0; v < 2 * dim + 3; ++v) {
+        float val = 0.0f;
+        if (c < n_capsules) val = hc32[c * w->capsule32_stride + v];
+        else if (v == 2 * dim + 1) val = -INFINITY;
+        dst[2 * v + h] = val;
+      }
+    }
+  }
   int r = upload(&w->d_spheres, hs, w->stream);
   if (r == OXG_OK) r = upload(&w->d_aabbs, ha, w->stream);
   if (r == OXG_OK) r = upload(&w->d_capsules, hc, w->stream);
   if (r == OXG_OK) r = upload32(&w->d_spheres32, hs32, w->stream);
   if (r == OXG_OK) r = upload32(&w->d_aabbs32, ha32, w->stream);
   if (r == OXG_OK) r = upload32(&w->d_capsules32, hc32, w->stream);
+  if (r == OXG_OK) r = upload32(&w->d_capsules32p, hc32p, w->stream);
   if (r == OXG_OK && cudaStreamSynchronize(w->stream) != cudaSuccess) {
     set_error("world upload failed");
     r = OXG_E_CUDA;
@@ -601,6 +619,7 @@ int oxg_world_destroy(oxg_world w) {
   if (w->d_spheres32) cudaFree(w->d_spheres32);
   if (w->d_aabbs32) cudaFree(w->d_aabbs32);
   if (w->d_capsules32) cudaFree(w->d_capsules32);
+  if (w->d_capsules32p) cudaFree(w->d_capsules32p);
   if (w->d_so2_comp) cudaFree(w->d_so2_comp);
   if (w->d_so2_lohi) cudaFree(w->d_so2_lohi);
   for (auto& b : w->buf) b.release();

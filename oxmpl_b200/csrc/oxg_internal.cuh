@@ -188,6 +188,8 @@ struct oxg_world_s {
   float* d_spheres32 = nullptr;
   float* d_aabbs32 = nullptr;
   float* d_capsules32 = nullptr;
+  float* d_capsules32p = nullptr;  // capsules in pairs, values interleaved (c, c+1): packed FP32 math
+  uint32_t capsule32p_stride = 0;  // floats per pair row (multiple of 4)
   uint32_t sphere32_stride = 0, capsule32_stride = 0;
   double wmax_spheres = 0.0;   // max |centre coordinate|
   double wmax_capsules = 0.0;  // max over |a_d|, |b_d|, |ab_d|
@@ -212,6 +214,8 @@ struct WorldView {
   const float* spheres32;
   const float* aabbs32;
   const float* capsules32;
+  const float* capsules32p;
+  uint32_t capsule32p_stride;
   uint32_t sphere32_stride, capsule32_stride;
   double wmax_spheres, wmax_capsules;
   const uint32_t* so2_comp;
@@ -228,6 +232,8 @@ inline WorldView world_view(const oxg_world_s* w) {
   v.spheres32 = w->d_spheres32;
   v.aabbs32 = w->d_aabbs32;
   v.capsules32 = w->d_capsules32;
+  v.capsules32p = w->d_capsules32p;
+  v.capsule32p_stride = w->capsule32p_stride;
   v.sphere32_stride = w->sphere32_stride;
   v.capsule32_stride = w->capsule32_stride;
   v.wmax_spheres = w->wmax_spheres;

@@ -382,4 +382,40 @@ OXG_DEV bool capsule_maybe_hit32_s(const float* xf, uint32_t row, float a2, floa
   return !(d2 > T);
 }
 
+// Two capsules per call with packed FP32 arithmetic (FADD2 / FFMA2 / FMUL2): `row` is the shared
+// address of a pair row of the interleaved mirror (oxg_world_s::d_capsules32p).  Returns bit 0 /
+// bit 1 = "maybe hit" for the first / second capsule of the pair.
+template <int DT>
+OXG_DEV unsigned capsule_pair_maybe_hit32_s(const float* xf, uint32_t row, float a2, float ce) {
+  constexpr int DN = DT > 0 ? DT : 1;
+  constexpr int NV = (2 * (2 * DN + 3) + 3) / 4;
+  float2 c[NV * 2];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 t4 = lds128_row(row + 16u * v);
+    c[2 * v] = make_float2(t4.x, t4.y);
+    c[2 * v + 1] = make_float2(t4.z, t4.w);
+  }
+  float2 ap[DN];
+  float2 num = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < DN; ++i) {
+    ap[i] = __fadd2_rn(make_float2(xf[i], xf[i]), make_float2(-c[i].x, -c[i].y));
+    num = __ffma2_rn(ap[i], c[DN + i], num);
+  }
+  float2 t = __fmul2_rn(num, c[2 * DN]);
+  t.x = fminf(fmaxf(t.x, 0.f), 1.f);  // NaN -> 0: any t in [0,1] keeps the bound valid
+  t.y = fminf(fmaxf(t.y, 0.f), 1.f);
+  const float2 nt = make_float2(-t.x, -t.y);
+  float2 d2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < DN; ++i) {
+    const float2 e = __ffma2_rn(nt, c[DN + i], ap[i]);
+    d2 = __ffma2_rn(e, e, d2);
+  }
+  const float T0 = __fmaf_ru(a2, c[2 * DN + 2].x, __fadd_ru(c[2 * DN + 1].x, ce));
+  const float T1 = __fmaf_ru(a2, c[2 * DN + 2].y, __fadd_ru(c[2 * DN + 1].y, ce));
+  return (!(d2.x > T0) ? 1u : 0u) | (!(d2.y > T1) ? 2u : 0u);
+}
+
 }  // namespace oxg

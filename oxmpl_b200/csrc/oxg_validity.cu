@@ -77,10 +77,16 @@ __device__ __forceinline__ bool state_valid_staged_dev(const WorldView& w, const
     if (aabb_maybe_hit32<DT>(xf, w.aabbs32 + (size_t)i * w.aabb_stride, DT) &&
         aabb_hit_dev<DT>(x, w.aabbs + (size_t)i * w.aabb_stride, DT))
       return false;
-  for (uint32_t i = 0; i < w.n_capsules; ++i)
-    if (capsule_maybe_hit32_s<DT>(xf, sm_cap + i * w.capsule32_stride * 4u, tol.a2_c, tol.ce_c) &&
-        capsule_hit_dev<DT>(x, w.capsules + (size_t)i * w.capsule_stride, DT))
-      return false;
+  for (uint32_t i = 0; i < w.n_capsules; i += 2) {
+    const unsigned mh = capsule_pair_maybe_hit32_s<DT>(xf, sm_cap + (i >> 1) * w.capsule32p_stride * 4u,
+                                                       tol.a2_c, tol.ce_c);
+    if (mh) {
+      if ((mh & 1u) && capsule_hit_dev<DT>(x, w.capsules + (size_t)i * w.capsule_stride, DT)) return false;
+      if ((mh & 2u) && i + 1 < w.n_capsules &&
+          capsule_hit_dev<DT>(x, w.capsules + (size_t)(i + 1) * w.capsule_stride, DT))
+        return false;
+    }
+  }
   return true;
 }
 
@@ -89,11 +95,11 @@ __device__ __forceinline__ bool state_valid_staged_dev(const WorldView& w, const
 __device__ __forceinline__ bool stage_world32(const WorldView& w, uint32_t smem_bytes,
                                               unsigned char* smem, uint32_t* sm_sph, uint32_t* sm_cap) {
   const uint32_t sph_bytes = w.n_spheres * w.sphere32_stride * 4u;
-  const uint32_t cap_bytes = w.n_capsules * w.capsule32_stride * 4u;
+  const uint32_t cap_bytes = ((w.n_capsules + 1) / 2) * w.capsule32p_stride * 4u;
   if (smem_bytes < sph_bytes + cap_bytes || sph_bytes + cap_bytes == 0) return false;
   float4* dst = reinterpret_cast<float4*>(smem);
   const float4* s1 = reinterpret_cast<const float4*>(w.spheres32);
-  const float4* s2 = reinterpret_cast<const float4*>(w.capsules32);
+  const float4* s2 = reinterpret_cast<const float4*>(w.capsules32p);
   for (uint32_t i = threadIdx.x; i < sph_bytes / 16; i += blockDim.x) dst[i] = s1[i];
   for (uint32_t i = threadIdx.x; i < cap_bytes / 16; i += blockDim.x) dst[sph_bytes / 16 + i] = s2[i];
   __syncthreads();
@@ -428,7 +434,8 @@ int motion_check_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStre
   const int L = wide ? 32 : 4;
   unsigned blocks = (unsigned)std::min<uint64_t>((E * L + threads - 1) / threads, 148ull * 16);
   // stage the sphere / capsule f32 mirrors in shared memory when they fit beside 5 CTAs per SM
-  size_t stage = (size_t)w->n_spheres * w->sphere32_stride * 4 + (size_t)w->n_capsules * w->capsule32_stride * 4;
+  size_t stage = (size_t)w->n_spheres * w->sphere32_stride * 4 +
+                 (size_t)((w->n_capsules + 1) / 2) * w->capsule32p_stride * 4;
   if (stage > 40 * 1024 || fast_dim(sp) == 0) stage = 0;
   p.world_smem_bytes = (uint32_t)stage;
   if (wide) {
