@@ -90,6 +90,12 @@ class Oracle:
             "orc_prm_radius": (u64, [w, sp, d, d, vp, u64, vp, vp, vp, u64, C.POINTER(u64),
                                      C.POINTER(u64)]),
             "orc_prm_knn": (None, [w, sp, vp, u64, u32, d, u64, u64, vp, vp, vp, cnt]),
+            "orc_so3_distance": (d, [vp, vp]),
+            "orc_so3_interpolate": (None, [vp, vp, d, vp]),
+            "orc_so3_nn1_batch": (None, [vp, u64, vp, u64, vp, vp]),
+            "orc_so3_radius": (u64, [vp, u64, vp, d, vp, vp, u64]),
+            "orc_so3_is_valid": (C.c_int, [vp, u64, vp]),
+            "orc_so3_check_motion": (C.c_int, [vp, u64, vp, vp, d, C.POINTER(u32)]),
             "orc_build_info": (C.c_int, []),
             "orc_probe_mul_add": (d, [d, d, d]),
         }
@@ -198,6 +204,62 @@ class Oracle:
         idx = np.concatenate(idxs) if idxs else np.empty(0, np.uint32)
         dist = np.concatenate(dists) if dists else np.empty(0, np.float64)
         return (offsets, idx, dist) if want_dist else (offsets, idx)
+
+    # -- SO(3) ----------------------------------------------------------------------
+    def so3_distance(self, a, b):
+        a, b = _f64(a), _f64(b)
+        return self.lib.orc_so3_distance(_p(a), _p(b))
+
+    def so3_interpolate(self, a, b, t):
+        a, b = _f64(a), _f64(b)
+        out = np.empty(4, dtype=np.float64)
+        self.lib.orc_so3_interpolate(_p(a), _p(b), float(t), _p(out))
+        return out
+
+    def so3_nn1(self, rows, queries):
+        rows, q = _f64(rows), _f64(np.atleast_2d(queries))
+        idx = np.empty(q.shape[0], dtype=np.uint32)
+        dist = np.empty(q.shape[0], dtype=np.float64)
+        self.lib.orc_so3_nn1_batch(_p(rows), rows.shape[0], _p(q), q.shape[0], _p(idx), _p(dist))
+        return idx, dist
+
+    def so3_radius(self, rows, queries, r):
+        rows, q = _f64(rows), _f64(np.atleast_2d(queries))
+        N = rows.shape[0]
+        offsets = np.zeros(q.shape[0] + 1, dtype=np.uint64)
+        idxs, dists = [], []
+        buf_i = np.empty(max(N, 1), dtype=np.uint32)
+        buf_d = np.empty(max(N, 1), dtype=np.float64)
+        for i in range(q.shape[0]):
+            qi = np.ascontiguousarray(q[i])
+            n = self.lib.orc_so3_radius(_p(rows), N, _p(qi), float(r), _p(buf_i), _p(buf_d), N)
+            idxs.append(buf_i[:n].copy())
+            dists.append(buf_d[:n].copy())
+            offsets[i + 1] = offsets[i] + n
+        idx = np.concatenate(idxs) if idxs else np.empty(0, np.uint32)
+        dist = np.concatenate(dists) if dists else np.empty(0, np.float64)
+        return offsets, idx, dist
+
+    def so3_is_valid(self, cones, states):
+        cones, st = _f64(np.reshape(cones, (-1, 5))), _f64(np.atleast_2d(states))
+        return np.array([self.lib.orc_so3_is_valid(_p(cones), cones.shape[0],
+                                                   _p(np.ascontiguousarray(st[i])))
+                         for i in range(st.shape[0])], dtype=np.uint8)
+
+    def so3_check_motion(self, cones, frm, to, resolution):
+        cones = _f64(np.reshape(cones, (-1, 5)))
+        frm, to = _f64(np.atleast_2d(frm)), _f64(np.atleast_2d(to))
+        valid = np.empty(frm.shape[0], dtype=np.uint8)
+        first = np.empty(frm.shape[0], dtype=np.uint32)
+        for e in range(frm.shape[0]):
+            fi = C.c_uint32(0)
+            v = self.lib.orc_so3_check_motion(_p(cones), cones.shape[0],
+                                              _p(np.ascontiguousarray(frm[e])),
+                                              _p(np.ascontiguousarray(to[e])), float(resolution),
+                                              C.byref(fi))
+            valid[e] = v == 1
+            first[e] = fi.value
+        return valid, first
 
     def prm_knn(self, w, sp, rows, k, resolution, row_begin=0, row_end=None, counters=None):
         rows = _f64(rows)

@@ -687,6 +687,112 @@ void orc_prm_knn(const orc_world* w, const orc_space* sp, const double* rows, ui
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// SO(3) — unit quaternions (x, y, z, w), rows of 4 doubles.  acos / sin are the platform libm's,
+// which is also what Rust's f64::acos / f64::sin call on linux-gnu, so on one machine these are
+// the reference's own bits.  No golden value exists in the reference for this path (its SO3
+// tests assert path properties only): parity is pinned by the source text restated here.
+// ---------------------------------------------------------------------------------------
+
+// SO3StateSpace::distance — oxmpl/src/base/spaces/so3_state_space.rs:102-112
+//   abs_dot = (s1.x*s2.x + s1.y*s2.y + s1.z*s2.z + s1.w*s2.w).abs()
+//   if abs_dot > 1.0 - 1e-9 { 0.0 } else { abs_dot.acos() }
+double orc_so3_distance(const double* s1, const double* s2) {
+  double abs_dot = std::fabs(s1[0] * s2[0] + s1[1] * s2[1] + s1[2] * s2[2] + s1[3] * s2[3]);
+  if (abs_dot > 1.0 - 1e-9) return 0.0;
+  return std::acos(abs_dot);
+}
+
+// SO3StateSpace::interpolate — so3_state_space.rs:114-159: LERP + renormalise when the
+// (sign-corrected) dot exceeds 0.9995, SLERP otherwise.
+void orc_so3_interpolate(const double* from, const double* to, double t, double* out) {
+  double dot = from[0] * to[0] + from[1] * to[1] + from[2] * to[2] + from[3] * to[3];
+  double sign = dot < 0.0 ? -1.0 : 1.0;
+  dot *= sign;
+  if (dot > 0.9995) {
+    double v[4];
+    for (int c = 0; c < 4; ++c) v[c] = from[c] + t * (to[c] * sign - from[c]);
+    double norm = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+    for (int c = 0; c < 4; ++c) out[c] = v[c] / norm;
+  } else {
+    double theta = std::acos(dot);
+    double sin_theta = std::sin(theta);
+    double s0 = std::sin((1.0 - t) * theta) / sin_theta;
+    double s1 = std::sin(t * theta) / sin_theta * sign;
+    for (int c = 0; c < 4; ++c) out[c] = from[c] * s0 + to[c] * s1;
+  }
+}
+
+// 1-NN loop of rrt.rs:187-196 with distance(tree[i], q)
+void orc_so3_nn1_batch(const double* rows, uint64_t N, const double* queries, uint64_t Q,
+                       uint32_t* idx, double* dist) {
+#pragma omp parallel for schedule(static)
+  for (int64_t q = 0; q < (int64_t)Q; ++q) {
+    const double* qq = queries + (uint64_t)q * 4;
+    uint32_t best = 0;
+    double mn = orc_so3_distance(rows, qq);
+    for (uint64_t i = 1; i < N; ++i) {
+      double d = orc_so3_distance(rows + i * 4, qq);
+      if (d < mn) {
+        mn = d;
+        best = (uint32_t)i;
+      }
+    }
+    idx[q] = best;
+    dist[q] = mn;
+  }
+}
+
+// radius loop of rrt_star.rs:121-131 with distance(q, store[i]) < r; returns the count, writes
+// at most cap entries (ascending index).
+uint64_t orc_so3_radius(const double* rows, uint64_t N, const double* q, double r, uint32_t* idx,
+                        double* dist, uint64_t cap) {
+  uint64_t n = 0;
+  for (uint64_t i = 0; i < N; ++i) {
+    double d = orc_so3_distance(q, rows + i * 4);
+    if (d < r) {
+      if (n < cap) {
+        if (idx) idx[n] = (uint32_t)i;
+        if (dist) dist[n] = d;
+      }
+      ++n;
+    }
+  }
+  return n;
+}
+
+// ForbiddenConeChecker — oxmpl/tests/rrt_so3ss_tests.rs:46-56, any number of cones:
+//   valid iff distance(centre, state) > angle for every cone.  cones: rows (x, y, z, w, angle)
+int orc_so3_is_valid(const double* cones, uint64_t n_cones, const double* state) {
+  for (uint64_t c = 0; c < n_cones; ++c)
+    if (!(orc_so3_distance(cones + c * 5, state) > cones[c * 5 + 4])) return 0;
+  return 1;
+}
+
+// check_motion (rrt.rs:90-116) over SO3
+int orc_so3_check_motion(const double* cones, uint64_t n_cones, const double* from, const double* to,
+                         double resolution, uint32_t* first_invalid) {
+  double dist = orc_so3_distance(from, to);
+  uint64_t num_steps = ceil_as_usize(dist / resolution);
+  if (first_invalid) *first_invalid = 0;
+  if (num_steps <= 1) {
+    int v = orc_so3_is_valid(cones, n_cones, to);
+    if (!v && first_invalid) *first_invalid = 1;
+    return v;
+  }
+  if (num_steps > (1ull << 32)) return -1;
+  double st[4];
+  for (uint64_t i = 1; i <= num_steps; ++i) {
+    double t = (double)i / (double)num_steps;
+    orc_so3_interpolate(from, to, t, st);
+    if (!orc_so3_is_valid(cones, n_cones, st)) {
+      if (first_invalid) *first_invalid = (uint32_t)i;
+      return 0;
+    }
+  }
+  return 1;
+}
+
 // Build identification, so tests can assert the flags the oracle was compiled with.
 int orc_build_info(void) {
   int v = 1;

@@ -6,6 +6,7 @@ there is no CPU fallback.
 """
 from .api import (  # noqa: F401
     INVALID_INDEX,
+    So3Cones,
     Space,
     StateStore,
     World,

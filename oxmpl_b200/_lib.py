@@ -104,7 +104,7 @@ _pu32 = C.c_void_p
 _pu64 = C.c_void_p
 _pu8 = C.c_void_p
 
-# name -> (restype, argtypes); every symbol include/oxg.h declares.
+# name -> (restype, argtypes); every symbol include/oxg.h and include/oxg_so3.h declare.
 SIGNATURES = {
     "oxg_version": (C.c_int, []),
     "oxg_last_error": (C.c_char_p, []),
@@ -156,6 +156,13 @@ SIGNATURES = {
     "oxg_fp64_peak": (C.c_int, [C.POINTER(_dbl), C.POINTER(_dbl)]),
     "oxg_fp32_peak": (C.c_int, [C.POINTER(_dbl), C.POINTER(_dbl)]),
     "oxg_kernel_launches": (_u64, [C.c_int]),
+    # include/oxg_so3.h
+    "oxg_so3_nn1": (C.c_int, [_vp, _pd, _u64, _pu32, _pd]),
+    "oxg_so3_radius": (C.c_int, [_vp, _pd, _u64, _dbl, _pu64, _pu32, _u64, _pd]),
+    "oxg_so3_cones_create": (C.c_int, [_pd, _u64, C.POINTER(_vp)]),
+    "oxg_so3_cones_destroy": (C.c_int, [_vp]),
+    "oxg_so3_is_valid": (C.c_int, [_vp, _pd, _u64, _pu8]),
+    "oxg_so3_check_motion": (C.c_int, [_vp, _pd, _pd, _u64, _dbl, _pu8, _pu32]),
 }
 
 

@@ -218,6 +218,78 @@ class StateStore:
         return offsets, idx[:n].copy()
 
 
+    # -- SO(3): stores of unit quaternions (x, y, z, w), include/oxg_so3.h --------------------
+    def so3_nn1(self, queries):
+        """1-NN under ``SO3StateSpace::distance`` (so3_state_space.rs:102-112): the reference's
+        winner (lowest index at the minimum distance) and its libm distance."""
+        q = _f64(np.atleast_2d(queries), 4)
+        idx = np.empty(q.shape[0], dtype=np.uint32)
+        dist = np.empty(q.shape[0], dtype=np.float64)
+        check(lib.oxg_so3_nn1(self._h, _ptr(q), q.shape[0], _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def so3_radius(self, queries, r: float, want_dist: bool = False):
+        """Radius scan ``distance(query, stored) < r`` over SO3 -> CSR (offsets, idx[, dist])."""
+        q = _f64(np.atleast_2d(queries), 4)
+        Q = q.shape[0]
+        offsets = np.zeros(Q + 1, dtype=np.uint64)
+        cap = max(1024, 64 * Q)
+        while True:
+            idx = np.empty(cap, dtype=np.uint32)
+            dist = np.empty(cap, dtype=np.float64) if want_dist else None
+            code = lib.oxg_so3_radius(self._h, _ptr(q), Q, float(r), _ptr(offsets), _ptr(idx), cap,
+                                      _ptr(dist))
+            if code == _lib.OXG_E_CAPACITY:
+                cap = int(offsets[Q])
+                continue
+            check(code)
+            break
+        n = int(offsets[Q])
+        if want_dist:
+            return offsets, idx[:n].copy(), dist[:n].copy()
+        return offsets, idx[:n].copy()
+
+
+class So3Cones:
+    """Forbidden cones over SO(3): a state is valid iff ``distance(centre, state) > angle`` for
+    every cone (the reference fixture ``ForbiddenConeChecker``, oxmpl/tests/rrt_so3ss_tests.rs:46-56).
+    ``cones``: (n, 5) rows ``[x, y, z, w, angle]``."""
+
+    def __init__(self, cones):
+        c = _f64(np.reshape(np.asarray(cones, dtype=np.float64), (-1, 5)), 5)
+        self._h = C.c_void_p()
+        check(lib.oxg_so3_cones_create(_ptr(c), c.shape[0], C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib.oxg_so3_cones_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def is_valid(self, states) -> np.ndarray:
+        st = _f64(np.atleast_2d(states), 4)
+        out = np.empty(st.shape[0], dtype=np.uint8)
+        check(lib.oxg_so3_is_valid(self._h, _ptr(st), st.shape[0], _ptr(out)))
+        return out
+
+    def check_motion(self, frm, to, resolution: float, want_first_invalid=False):
+        """``check_motion(from, to)`` (rrt.rs:90-116) with SO3 interpolation."""
+        a = _f64(np.atleast_2d(frm), 4)
+        b = _f64(np.atleast_2d(to), 4)
+        if a.shape != b.shape:
+            raise ValueError("from/to shape mismatch")
+        valid = np.empty(a.shape[0], dtype=np.uint8)
+        first = np.empty(a.shape[0], dtype=np.uint32) if want_first_invalid else None
+        check(lib.oxg_so3_check_motion(self._h, _ptr(a), _ptr(b), a.shape[0], float(resolution),
+                                       _ptr(valid), _ptr(first)))
+        return (valid, first) if want_first_invalid else valid
+
+
 class World:
     """Declarative obstacle set implementing ``StateValidityChecker::is_valid``.
 

@@ -1,0 +1,742 @@
+// oxg_so3.cu — SO(3) scans and cone validity (include/oxg_so3.h).
+//
+// Reference: SO3StateSpace::distance / interpolate, oxmpl/src/base/spaces/so3_state_space.rs:99-159.
+// The device works only on a = |q1 . q2| (exactly reproducible); everything that involves libm
+// (acos, sin) runs on the host with the caller's libm, and every distance comparison is turned into
+// an exact threshold on `a` by a monotone search over f64 bit patterns.  See the header.
+#include <cstdlib>
+#include <limits>
+#include <vector>
+
+#include "../../include/oxg_so3.h"
+#include "oxg_internal.cuh"
+
+using namespace oxg;
+
+struct oxg_so3_cones_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t n = 0;
+  double* d_cones = nullptr;  // n x 5: centre (x, y, z, w), a-threshold: invalid iff a >= thr
+  DevBuf states, flags;
+};
+
+namespace {
+
+constexpr int SO3_THREADS = 256;
+constexpr int SO3_WARPS = SO3_THREADS / 32;
+constexpr int SO3_QC = 8;  // queries per CTA (kept in shared memory; one store pass serves all)
+constexpr int MODE_BEST = 0, MODE_FIRST = 1;
+
+struct So3Params {
+  const double* col[4];  // store columns x, y, z, w
+  uint32_t n;
+  uint32_t split_len;  // states per split, multiple of SO3_THREADS
+  uint32_t nsplit;
+  const double* queries;  // device, row-major Q x 4
+  uint64_t Q;
+  const double* thr;  // MODE_FIRST: per-query threshold on a
+  double thr_all;     // radius kernels: one threshold
+  long long* part_key;  // [Q][nsplit] bits of the best a (MODE_BEST)
+  uint32_t* part_idx;   // [Q][nsplit]
+  uint32_t* counts;         // radius: [Q][nsplit]
+  const uint64_t* offsets;  // radius fill: [Q][nsplit] output position of each slice
+  uint32_t* out_idx;
+  double* out_a;
+};
+
+// |s . q| in the reference's order: ((sx*qx + sy*qy) + sz*qz) + sw*qw, every operation rounded.
+__device__ __forceinline__ double so3_absdot(const double s[4], const double* q) {
+  double d = __dmul_rn(s[0], q[0]);
+  d = __dadd_rn(d, __dmul_rn(s[1], q[1]));
+  d = __dadd_rn(d, __dmul_rn(s[2], q[2]));
+  d = __dadd_rn(d, __dmul_rn(s[3], q[3]));
+  return fabs(d);
+}
+
+__device__ __forceinline__ void so3_stage_queries(const So3Params& p, double (*s_q)[4], uint64_t q0,
+                                                  int qn) {
+  if (threadIdx.x < SO3_QC * 4) {
+    const int a = threadIdx.x >> 2, c = threadIdx.x & 3;
+    s_q[a][c] = a < qn ? p.queries[(q0 + a) * 4 + c] : 0.0;  // qn <= SO3_QC
+  }
+}
+
+// MODE_BEST : per (query, slice) the largest a, lowest index on ties.  Keys are the bit patterns
+//             of a (order-preserving for a >= 0; +inf and NaN sort above every finite value).  A
+//             NaN at index 0 wins like in the reference loop (min starts as distance(tree[0], q)
+//             and nothing is < NaN); a NaN elsewhere never wins.
+// MODE_FIRST: per (query, slice) the lowest index with a >= thr[query].
+// QN = queries evaluated per state (1, 2, 4 or SO3_QC): a batch of fewer than SO3_QC queries runs
+// the narrower instantiation so a single-query scan stays HBM-bound instead of FP64-bound.
+template <int MODE, int QN>
+__global__ void __launch_bounds__(SO3_THREADS) so3_scan_kernel(const So3Params p) {
+  __shared__ double s_q[SO3_QC][4];
+  __shared__ double s_thr[SO3_QC];
+  __shared__ long long s_k[SO3_QC][SO3_WARPS];
+  __shared__ uint32_t s_i[SO3_QC][SO3_WARPS];
+  const uint64_t q0 = (uint64_t)blockIdx.x * QN;
+  const int qn = (int)min((uint64_t)QN, p.Q - q0);
+  so3_stage_queries(p, s_q, q0, qn);
+  if (MODE == MODE_FIRST && threadIdx.x < SO3_QC)
+    s_thr[threadIdx.x] = (int)threadIdx.x < qn ? p.thr[q0 + threadIdx.x]
+                                               : __longlong_as_double(0x7FF8000000000000ll);
+  __syncthreads();
+
+  long long bk[QN];
+  uint32_t bi[QN];
+#pragma unroll
+  for (int a = 0; a < QN; ++a) {
+    bk[a] = -1;
+    bi[a] = OXG_INVALID_INDEX;
+  }
+  const uint32_t n0 = blockIdx.y * p.split_len;
+  const uint32_t n1 = min(p.n, n0 + p.split_len);
+#pragma unroll(QN <= 2 ? 4 : 2)
+  for (uint32_t i = n0 + threadIdx.x; i < n1; i += SO3_THREADS) {
+    double s[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s[c] = __ldg(p.col[c] + i);
+#pragma unroll
+    for (int a = 0; a < QN; ++a) {
+      const double v = so3_absdot(s, s_q[a]);
+      if (MODE == MODE_BEST) {
+        long long key = __double_as_longlong(v);
+        if (v != v && i != 0) key = -1;
+        if (key > bk[a]) {
+          bk[a] = key;
+          bi[a] = i;
+        }
+      } else {
+        if (v >= s_thr[a] && bi[a] == OXG_INVALID_INDEX) bi[a] = i;
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < QN; ++a) {
+    long long k = bk[a];
+    uint32_t ix = bi[a];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const long long ok = __shfl_xor_sync(0xFFFFFFFFu, k, off);
+      const uint32_t oi = __shfl_xor_sync(0xFFFFFFFFu, ix, off);
+      const bool take = MODE == MODE_BEST ? (ok > k || (ok == k && oi < ix)) : (oi < ix);
+      if (take) {
+        k = ok;
+        ix = oi;
+      }
+    }
+    if (lane == 0) {
+      s_k[a][warp] = k;
+      s_i[a][warp] = ix;
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < qn) {
+    const int a = threadIdx.x;
+    long long k = s_k[a][0];
+    uint32_t ix = s_i[a][0];
+    for (int wv = 1; wv < SO3_WARPS; ++wv) {
+      const long long ok = s_k[a][wv];
+      const uint32_t oi = s_i[a][wv];
+      const bool take = MODE == MODE_BEST ? (ok > k || (ok == k && oi < ix)) : (oi < ix);
+      if (take) {
+        k = ok;
+        ix = oi;
+      }
+    }
+    const size_t o = (size_t)(q0 + a) * p.nsplit + blockIdx.y;
+    if (MODE == MODE_BEST) p.part_key[o] = k;
+    p.part_idx[o] = ix;
+  }
+}
+
+// Merges the per-slice partials of one query (one warp per query).
+template <int MODE>
+__global__ void __launch_bounds__(128) so3_final_kernel(const So3Params p) {
+  const uint64_t q = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (q >= p.Q) return;
+  const int lane = threadIdx.x & 31;
+  long long k = -1;
+  uint32_t ix = OXG_INVALID_INDEX;
+  for (uint32_t s = lane; s < p.nsplit; s += 32) {
+    const size_t o = (size_t)q * p.nsplit + s;
+    const long long ok = MODE == MODE_BEST ? p.part_key[o] : 0;
+    const uint32_t oi = p.part_idx[o];
+    const bool take = MODE == MODE_BEST ? (ok > k || (ok == k && oi < ix)) : (oi < ix);
+    if (take) {
+      k = ok;
+      ix = oi;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const long long ok = __shfl_xor_sync(0xFFFFFFFFu, k, off);
+    const uint32_t oi = __shfl_xor_sync(0xFFFFFFFFu, ix, off);
+    const bool take = MODE == MODE_BEST ? (ok > k || (ok == k && oi < ix)) : (oi < ix);
+    if (take) {
+      k = ok;
+      ix = oi;
+    }
+  }
+  if (lane == 0) {
+    p.out_idx[q] = ix;
+    if (MODE == MODE_BEST) p.out_a[q] = __longlong_as_double(k);
+  }
+}
+
+// Radius scan on the threshold form a >= thr_all.  FILL = false counts the hits of every
+// (query, slice); FILL = true writes them in ascending index order at the slice's offset
+// (ballot + block prefix per round of SO3_THREADS states).
+template <bool FILL, int QN>
+__global__ void __launch_bounds__(SO3_THREADS) so3_radius_kernel(const So3Params p) {
+  __shared__ double s_q[SO3_QC][4];
+  __shared__ uint32_t s_w[SO3_QC][SO3_WARPS];
+  const uint64_t q0 = (uint64_t)blockIdx.x * QN;
+  const int qn = (int)min((uint64_t)QN, p.Q - q0);
+  so3_stage_queries(p, s_q, q0, qn);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n0 = blockIdx.y * p.split_len;
+  const uint32_t n1 = min(p.n, n0 + p.split_len);
+  uint32_t run[QN];  // hits so far (FILL: of the whole CTA; count pass: of this warp lane 0)
+#pragma unroll
+  for (int a = 0; a < QN; ++a) run[a] = 0;
+  for (uint32_t base = n0; base < n1; base += SO3_THREADS) {
+    const uint32_t i = base + threadIdx.x;
+    const bool live = i < n1;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[c] = __ldg(p.col[c] + i);
+    }
+    double v[QN];
+    uint32_t bal[QN];
+#pragma unroll
+    for (int a = 0; a < QN; ++a) {
+      v[a] = so3_absdot(s, s_q[a]);
+      bal[a] = __ballot_sync(0xFFFFFFFFu, live && a < qn && v[a] >= p.thr_all);
+    }
+    if (!FILL) {
+#pragma unroll
+      for (int a = 0; a < QN; ++a) run[a] += __popc(bal[a]);
+    } else {
+      if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < QN; ++a) s_w[a][warp] = __popc(bal[a]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int a = 0; a < QN; ++a) {
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int wv = 0; wv < SO3_WARPS; ++wv) {
+          const uint32_t c = s_w[a][wv];
+          before += wv < warp ? c : 0;
+          total += c;
+        }
+        if (bal[a] >> lane & 1u) {
+          const uint64_t o = p.offsets[(size_t)(q0 + a) * p.nsplit + blockIdx.y] + run[a] + before +
+                             __popc(bal[a] & ((1u << lane) - 1u));
+          p.out_idx[o] = i;
+          if (p.out_a) p.out_a[o] = v[a];
+        }
+        run[a] += total;
+      }
+      __syncthreads();
+    }
+  }
+  if (!FILL) {
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < QN; ++a) s_w[a][warp] = run[a];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < qn) {
+      uint32_t tot = 0;
+      for (int wv = 0; wv < SO3_WARPS; ++wv) tot += s_w[threadIdx.x][wv];
+      p.counts[(size_t)(q0 + threadIdx.x) * p.nsplit + blockIdx.y] = tot;
+    }
+  }
+}
+
+// valid iff a(centre_c, state) < thr_c for every cone c (NaN a => invalid, as "NaN > angle" is false).
+__global__ void __launch_bounds__(256) so3_cones_kernel(const double* __restrict__ cones, uint32_t n_cones,
+                                                        const double* __restrict__ states, uint64_t Q,
+                                                        uint8_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Q) return;
+  double s[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) s[c] = states[i * 4 + c];
+  bool ok = true;
+  for (uint32_t c = 0; c < n_cones && ok; ++c) {
+    const double* cn = cones + (size_t)c * 5;
+    // distance(centre, state): centre.x * state.x + ...  (products commute bit for bit)
+    const double ctr[4] = {__ldg(cn), __ldg(cn + 1), __ldg(cn + 2), __ldg(cn + 3)};
+    ok = so3_absdot(ctr, s) < __ldg(cn + 4);
+  }
+  out[i] = ok ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ host: libm side
+inline double from_bits(uint64_t b) {
+  double d;
+  std::memcpy(&d, &b, 8);
+  return d;
+}
+inline uint64_t to_bits(double d) {
+  uint64_t b;
+  std::memcpy(&b, &d, 8);
+  return b;
+}
+constexpr uint64_t kInfBits = 0x7FF0000000000000ull;
+
+// distance as a function of a = |dot| (so3_state_space.rs:105-111); acos is the platform libm's
+inline double so3_f(double a) { return a > 1.0 - 1e-9 ? 0.0 : std::acos(a); }
+
+// Smallest x in [+0, +inf] (by bit pattern) with pred(so3_f(x)); pred must be monotone (false
+// below, true above), which it is for "f(x) < r" and "f(x) <= r" because f is non-increasing.
+// NaN if no x qualifies ("a >= NaN" is then false for every a).
+template <class Pred>
+double so3_threshold(Pred pred) {
+  uint64_t lo = 0, hi = kInfBits;
+  if (!pred(so3_f(from_bits(hi)))) return std::numeric_limits<double>::quiet_NaN();
+  while (lo < hi) {
+    const uint64_t mid = lo + (hi - lo) / 2;
+    if (pred(so3_f(from_bits(mid))))
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  return from_bits(lo);
+}
+
+// Smallest x with f(x) == f(a) for a finite a >= 0: gallops down from a (plateaus are a few ulps
+// wide except next to 0), then bisects.
+double so3_plateau_low(double a) {
+  const double d = so3_f(a);
+  const uint64_t top = to_bits(a);
+  uint64_t step = 1, hi = top;  // f(hi) == d
+  uint64_t lo;
+  for (;;) {
+    if (hi == 0) return from_bits(0);
+    lo = hi > step ? hi - step : 0;
+    if (so3_f(from_bits(lo)) != d) break;  // f(lo) > d
+    hi = lo;
+    step *= 2;
+  }
+  while (hi - lo > 1) {
+    const uint64_t mid = lo + (hi - lo) / 2;
+    if (so3_f(from_bits(mid)) == d)
+      hi = mid;
+    else
+      lo = mid;
+  }
+  return from_bits(hi);
+}
+
+// SO3StateSpace::interpolate, so3_state_space.rs:114-159 (host: sin / acos are libm's).
+void so3_interpolate_host(const double* f, const double* g, double t, double* o) {
+  double dot = f[0] * g[0] + f[1] * g[1] + f[2] * g[2] + f[3] * g[3];
+  const double sign = dot < 0.0 ? -1.0 : 1.0;
+  dot *= sign;
+  if (dot > 0.9995) {
+    for (int c = 0; c < 4; ++c) o[c] = f[c] + t * (g[c] * sign - f[c]);
+    const double norm = std::sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3]);
+    for (int c = 0; c < 4; ++c) o[c] /= norm;
+  } else {
+    const double theta = std::acos(dot);
+    const double sin_theta = std::sin(theta);
+    const double s0 = std::sin((1.0 - t) * theta) / sin_theta;
+    const double s1 = std::sin(t * theta) / sin_theta * sign;
+    for (int c = 0; c < 4; ++c) o[c] = f[c] * s0 + g[c] * s1;
+  }
+}
+
+inline double so3_distance_host(const double* p, const double* q) {
+  const double dot = p[0] * q[0] + p[1] * q[1] + p[2] * q[2] + p[3] * q[3];
+  return so3_f(std::fabs(dot));
+}
+
+int so3_check_store(oxg_store s) {
+  if (!s) {
+    set_error("store is NULL");
+    return OXG_E_NULL;
+  }
+  if (s->space.n_real != 4 || s->space.n_so2 != 0) {
+    set_error("SO3 scans need a store of 4 real coordinates (x, y, z, w)");
+    return OXG_E_DIM;
+  }
+  return OXG_OK;
+}
+
+inline int so3_qn(uint64_t Q) { return Q >= 5 ? SO3_QC : Q >= 3 ? 4 : Q == 2 ? 2 : 1; }
+
+void so3_plan(const oxg_store_s* s, uint64_t Q, So3Params& p, int qc = SO3_QC) {
+  const uint64_t qchunks = (Q + qc - 1) / qc;
+  const uint32_t n = (uint32_t)s->size;
+  const uint32_t max_split = (n + SO3_THREADS - 1) / SO3_THREADS;
+  uint64_t want = (148ull * 4 + qchunks - 1) / qchunks;
+  if (want < 1) want = 1;
+  if (want > max_split) want = max_split;
+  if (want > 592) want = 592;
+  uint32_t len = (uint32_t)((n + want - 1) / want);
+  len = (len + SO3_THREADS - 1) / SO3_THREADS * SO3_THREADS;
+  p.split_len = len;
+  p.nsplit = (n + len - 1) / len;
+  p.n = n;
+  p.Q = Q;
+  for (int c = 0; c < 4; ++c) p.col[c] = s->d_data + (size_t)c * s->pitch;
+}
+
+// Runs one MODE over `Q` uploaded queries (device pointer), result in d_idx / d_a (device).
+template <int MODE>
+int so3_scan(oxg_store_s* s, So3Params p, uint32_t* d_idx, double* d_a) {
+  const size_t np = (size_t)p.Q * p.nsplit;
+  OXG_TRY(s->buf[B_PIDX].ensure(np * sizeof(uint32_t)));
+  OXG_TRY(s->buf[B_PDIST].ensure(np * sizeof(long long)));
+  p.part_idx = s->buf[B_PIDX].as<uint32_t>();
+  p.part_key = s->buf[B_PDIST].as<long long>();
+  p.out_idx = d_idx;
+  p.out_a = d_a;
+  // the grid's x dimension carries the query chunks (up to 2^31 - 1)
+  const int qn = so3_qn(p.Q);
+  const uint64_t qchunks = (p.Q + qn - 1) / qn;
+  dim3 grid((unsigned)qchunks, p.nsplit);
+  switch (qn) {
+    case 1: so3_scan_kernel<MODE, 1><<<grid, SO3_THREADS, 0, s->stream>>>(p); break;
+    case 2: so3_scan_kernel<MODE, 2><<<grid, SO3_THREADS, 0, s->stream>>>(p); break;
+    case 4: so3_scan_kernel<MODE, 4><<<grid, SO3_THREADS, 0, s->stream>>>(p); break;
+    default: so3_scan_kernel<MODE, SO3_QC><<<grid, SO3_THREADS, 0, s->stream>>>(p); break;
+  }
+  OXG_LAUNCH_CHECK();
+  so3_final_kernel<MODE><<<(unsigned)((p.Q + 3) / 4), 128, 0, s->stream>>>(p);
+  OXG_LAUNCH_CHECK();
+  return OXG_OK;
+}
+
+template <bool FILL>
+void launch_so3_radius(int qn, dim3 grid, cudaStream_t st, const So3Params& p) {
+  switch (qn) {
+    case 1: so3_radius_kernel<FILL, 1><<<grid, SO3_THREADS, 0, st>>>(p); break;
+    case 2: so3_radius_kernel<FILL, 2><<<grid, SO3_THREADS, 0, st>>>(p); break;
+    case 4: so3_radius_kernel<FILL, 4><<<grid, SO3_THREADS, 0, st>>>(p); break;
+    default: so3_radius_kernel<FILL, SO3_QC><<<grid, SO3_THREADS, 0, st>>>(p); break;
+  }
+}
+
+int so3_upload(oxg_store_s* s, StoreBuf which, const void* src, size_t bytes) {
+  OXG_TRY(s->buf[which].ensure(bytes));
+  OXG_CUDA_TRY(cudaMemcpyAsync(s->buf[which].p, src, bytes, cudaMemcpyHostToDevice, s->stream));
+  return OXG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int oxg_so3_nn1(oxg_store s, const double* queries, uint64_t Q, uint32_t* idx, double* dist) {
+  OXG_API_BEGIN
+  OXG_TRY(so3_check_store(s));
+  if ((Q > 0 && !queries) || !idx || !dist) {
+    set_error("NULL argument");
+    return OXG_E_NULL;
+  }
+  if (Q == 0) return OXG_OK;
+  if (s->size == 0) {
+    set_error("nearest-neighbour query against an empty store");
+    return OXG_E_EMPTY;
+  }
+  if (Q > 0x3FFFFFFFull) {
+    set_error("too many queries in one call");
+    return OXG_E_ARG;
+  }
+  OXG_CUDA_TRY(cudaSetDevice(s->device));
+  OXG_TRY(so3_upload(s, B_QUERY, queries, Q * 4 * sizeof(double)));
+  OXG_TRY(s->buf[B_OIDX].ensure(Q * sizeof(uint32_t)));
+  OXG_TRY(s->buf[B_ODIST].ensure(Q * sizeof(double)));
+  So3Params p{};
+  so3_plan(s, Q, p, so3_qn(Q));
+  p.queries = s->buf[B_QUERY].as<double>();
+  OXG_CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+  OXG_TRY(so3_scan<MODE_BEST>(s, p, s->buf[B_OIDX].as<uint32_t>(), s->buf[B_ODIST].as<double>()));
+  OXG_CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+  std::vector<double> a(Q);
+  OXG_CUDA_TRY(cudaMemcpyAsync(idx, s->buf[B_OIDX].p, Q * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                               s->stream));
+  OXG_CUDA_TRY(cudaMemcpyAsync(a.data(), s->buf[B_ODIST].p, Q * sizeof(double), cudaMemcpyDeviceToHost,
+                               s->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+
+  // Host: distances from libm, and the queries whose winner sits on an acos plateau that reaches
+  // below max a — a lower index with a slightly smaller a has the same distance and wins.
+  std::vector<uint64_t> redo;
+  std::vector<double> redo_q, redo_thr;
+  for (uint64_t q = 0; q < Q; ++q) {
+    const double av = a[q];
+    if (av != av) {  // NaN at index 0 (see the kernel)
+      dist[q] = av;
+      continue;
+    }
+    dist[q] = so3_f(av);
+    double lo;
+    if (av > 1.0 - 1e-9) {
+      lo = std::nextafter(1.0 - 1e-9, 2.0);  // the whole clamp region has distance 0
+    } else {
+      lo = so3_plateau_low(av);
+    }
+    if (lo < av) {
+      redo.push_back(q);
+      redo_thr.push_back(lo);
+      redo_q.insert(redo_q.end(), queries + q * 4, queries + q * 4 + 4);
+    }
+  }
+  if (!redo.empty()) {
+    const uint64_t R = redo.size();
+    OXG_TRY(so3_upload(s, B_QUERY, redo_q.data(), R * 4 * sizeof(double)));
+    OXG_TRY(so3_upload(s, B_AUX, redo_thr.data(), R * sizeof(double)));
+    So3Params p2{};
+    so3_plan(s, R, p2, so3_qn(R));
+    p2.queries = s->buf[B_QUERY].as<double>();
+    p2.thr = s->buf[B_AUX].as<double>();
+    OXG_TRY(so3_scan<MODE_FIRST>(s, p2, s->buf[B_OIDX].as<uint32_t>(), nullptr));
+    std::vector<uint32_t> first(R);
+    OXG_CUDA_TRY(cudaMemcpyAsync(first.data(), s->buf[B_OIDX].p, R * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, s->stream));
+    OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    for (uint64_t r = 0; r < R; ++r) {
+      if (first[r] == OXG_INVALID_INDEX) {
+        set_error("internal error: SO3 plateau pass found no state");
+        return OXG_E_INTERNAL;
+      }
+      idx[redo[r]] = first[r];
+    }
+  }
+  return OXG_OK;
+  OXG_API_END
+}
+
+int oxg_so3_radius(oxg_store s, const double* queries, uint64_t Q, double r, uint64_t* offsets,
+                   uint32_t* idx, uint64_t cap, double* dist) {
+  OXG_API_BEGIN
+  OXG_TRY(so3_check_store(s));
+  if (!offsets || (Q > 0 && !queries)) {
+    set_error("NULL argument");
+    return OXG_E_NULL;
+  }
+  offsets[0] = 0;
+  if (Q == 0) return OXG_OK;
+  if (Q > 0x3FFFFFFFull) {
+    set_error("too many queries in one call");
+    return OXG_E_ARG;
+  }
+  if (s->size == 0) {
+    for (uint64_t q = 0; q < Q; ++q) offsets[q + 1] = 0;
+    return OXG_OK;
+  }
+  OXG_CUDA_TRY(cudaSetDevice(s->device));
+  // distance(query, stored) < r  <=>  a >= thr   (NaN r or r <= 0: thr = NaN, nothing matches)
+  const double thr = so3_threshold([r](double d) { return d < r; });
+  OXG_TRY(so3_upload(s, B_QUERY, queries, Q * 4 * sizeof(double)));
+  So3Params p{};
+  const int qn = so3_qn(Q);
+  so3_plan(s, Q, p, qn);
+  p.queries = s->buf[B_QUERY].as<double>();
+  p.thr_all = thr;
+  const size_t np = (size_t)Q * p.nsplit;
+  OXG_TRY(s->buf[B_COUNTS].ensure(np * sizeof(uint32_t)));
+  OXG_TRY(s->buf[B_OFFSETS].ensure(np * sizeof(uint64_t)));
+  p.counts = s->buf[B_COUNTS].as<uint32_t>();
+  const uint64_t qchunks = (Q + qn - 1) / qn;
+  dim3 grid((unsigned)qchunks, p.nsplit);
+  OXG_CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+  launch_so3_radius<false>(qn, grid, s->stream, p);
+  OXG_LAUNCH_CHECK();
+  std::vector<uint32_t> counts(np);
+  OXG_CUDA_TRY(cudaMemcpyAsync(counts.data(), p.counts, np * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                               s->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  std::vector<uint64_t> slice_off(np);
+  uint64_t total = 0;
+  for (uint64_t q = 0; q < Q; ++q) {
+    for (uint32_t sl = 0; sl < p.nsplit; ++sl) {
+      slice_off[q * p.nsplit + sl] = total;
+      total += counts[q * p.nsplit + sl];
+    }
+    offsets[q + 1] = total;
+  }
+  if (total > cap || (total > 0 && !idx)) {
+    set_error("radius result needs %llu entries, capacity is %llu", (unsigned long long)total,
+              (unsigned long long)cap);
+    return OXG_E_CAPACITY;
+  }
+  if (total == 0) return OXG_OK;
+  OXG_CUDA_TRY(cudaMemcpyAsync(s->buf[B_OFFSETS].p, slice_off.data(), np * sizeof(uint64_t),
+                               cudaMemcpyHostToDevice, s->stream));
+  OXG_TRY(s->buf[B_PIDX].ensure(total * sizeof(uint32_t)));
+  if (dist) OXG_TRY(s->buf[B_PDIST].ensure(total * sizeof(double)));
+  p.offsets = s->buf[B_OFFSETS].as<uint64_t>();
+  p.out_idx = s->buf[B_PIDX].as<uint32_t>();
+  p.out_a = dist ? s->buf[B_PDIST].as<double>() : nullptr;
+  launch_so3_radius<true>(qn, grid, s->stream, p);
+  OXG_LAUNCH_CHECK();
+  OXG_CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+  OXG_CUDA_TRY(cudaMemcpyAsync(idx, p.out_idx, total * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                               s->stream));
+  if (dist)
+    OXG_CUDA_TRY(cudaMemcpyAsync(dist, p.out_a, total * sizeof(double), cudaMemcpyDeviceToHost,
+                                 s->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (dist)
+    for (uint64_t i = 0; i < total; ++i) dist[i] = so3_f(dist[i]);
+  return OXG_OK;
+  OXG_API_END
+}
+
+int oxg_so3_cones_create(const double* cones, uint64_t n, oxg_so3_cones* out) {
+  OXG_API_BEGIN
+  if (!out || (n > 0 && !cones)) {
+    set_error("NULL argument");
+    return OXG_E_NULL;
+  }
+  *out = nullptr;
+  if (n > 0x7FFFFFFFull) {
+    set_error("too many cones");
+    return OXG_E_ARG;
+  }
+  int dev = 0;
+  OXG_CUDA_TRY(cudaGetDevice(&dev));
+  oxg_so3_cones_s* c = new oxg_so3_cones_s();
+  c->device = dev;
+  c->n = n;
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    delete c;
+    return OXG_E_CUDA;
+  }
+  if (n > 0) {
+    // valid iff distance(centre, state) > angle  <=>  NOT (f(a) <= angle)  <=>  a < thr
+    std::vector<double> h(n * 5);
+    for (uint64_t i = 0; i < n; ++i) {
+      for (int k = 0; k < 4; ++k) h[i * 5 + k] = cones[i * 5 + k];
+      const double angle = cones[i * 5 + 4];
+      double thr = so3_threshold([angle](double d) { return d <= angle; });
+      // no a reaches the cone (angle < 0 or NaN): "a < +inf" keeps every non-NaN state valid
+      // only when the comparison "distance > angle" is true, i.e. angle is not NaN
+      if (thr != thr) thr = angle == angle ? std::numeric_limits<double>::infinity() : thr;
+      h[i * 5 + 4] = thr;
+    }
+    e = cudaMalloc(&c->d_cones, h.size() * sizeof(double));
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(c->d_cones, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice,
+                          c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+      set_error("cone upload failed: %s", cudaGetErrorString(e));
+      oxg_so3_cones_destroy(c);
+      return OXG_E_CUDA;
+    }
+  }
+  *out = c;
+  return OXG_OK;
+  OXG_API_END
+}
+
+int oxg_so3_cones_destroy(oxg_so3_cones c) {
+  if (!c) return OXG_OK;
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->d_cones) cudaFree(c->d_cones);
+  c->states.release();
+  c->flags.release();
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return OXG_OK;
+}
+
+static int so3_is_valid_impl(oxg_so3_cones c, const double* states, uint64_t Q, uint8_t* out) {
+  OXG_CUDA_TRY(cudaSetDevice(c->device));
+  OXG_TRY(c->states.ensure(Q * 4 * sizeof(double)));
+  OXG_TRY(c->flags.ensure(Q));
+  OXG_CUDA_TRY(cudaMemcpyAsync(c->states.p, states, Q * 4 * sizeof(double), cudaMemcpyHostToDevice,
+                               c->stream));
+  so3_cones_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, c->stream>>>(
+      c->d_cones, (uint32_t)c->n, c->states.as<double>(), Q, c->flags.as<uint8_t>());
+  OXG_LAUNCH_CHECK();
+  OXG_CUDA_TRY(cudaMemcpyAsync(out, c->flags.p, Q, cudaMemcpyDeviceToHost, c->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return OXG_OK;
+}
+
+int oxg_so3_is_valid(oxg_so3_cones c, const double* states, uint64_t Q, uint8_t* out) {
+  OXG_API_BEGIN
+  if (!c || (Q > 0 && (!states || !out))) {
+    set_error("NULL argument");
+    return OXG_E_NULL;
+  }
+  if (Q == 0) return OXG_OK;
+  if (Q > 0x7FFFFFFFull * 256) {
+    set_error("too many states in one call");
+    return OXG_E_ARG;
+  }
+  return so3_is_valid_impl(c, states, Q, out);
+  OXG_API_END
+}
+
+int oxg_so3_check_motion(oxg_so3_cones c, const double* from, const double* to, uint64_t E,
+                         double resolution, uint8_t* valid, uint32_t* first_invalid) {
+  OXG_API_BEGIN
+  if (!c || (E > 0 && (!from || !to || !valid))) {
+    set_error("NULL argument");
+    return OXG_E_NULL;
+  }
+  if (!(resolution > 0.0)) {
+    set_error("resolution must be > 0 (the reference loop would not terminate)");
+    return OXG_E_RESOLUTION;
+  }
+  if (E == 0) return OXG_OK;
+  // rrt.rs:90-116: n = ceil(distance / resolution) as usize; n <= 1 tests `to` only, else the
+  // states at t = i / n for i = 1..=n, stopping at the first invalid one.
+  std::vector<uint64_t> first(E + 1, 0);
+  std::vector<double> states;
+  for (uint64_t e = 0; e < E; ++e) {
+    const double* f = from + e * 4;
+    const double* g = to + e * 4;
+    const double steps = std::ceil(so3_distance_host(f, g) / resolution);
+    uint64_t n = 0;  // Rust `as usize`: NaN -> 0, saturating
+    if (steps == steps && steps > 0.0) n = steps >= 4294967296.0 ? 0xFFFFFFFFull : (uint64_t)steps;
+    if (n > (1ull << 24)) {
+      set_error("edge %llu needs %llu interpolation steps", (unsigned long long)e,
+                (unsigned long long)n);
+      return OXG_E_ARG;
+    }
+    if (n <= 1) {
+      states.insert(states.end(), g, g + 4);
+    } else {
+      const size_t at = states.size();
+      states.resize(at + n * 4);
+      for (uint64_t i = 1; i <= n; ++i)
+        so3_interpolate_host(f, g, (double)i / (double)n, states.data() + at + (i - 1) * 4);
+    }
+    first[e + 1] = states.size() / 4;
+  }
+  const uint64_t S = states.size() / 4;
+  std::vector<uint8_t> ok(S);
+  OXG_TRY(so3_is_valid_impl(c, states.data(), S, ok.data()));
+  for (uint64_t e = 0; e < E; ++e) {
+    uint32_t bad = 0;
+    for (uint64_t i = first[e]; i < first[e + 1]; ++i)
+      if (!ok[i]) {
+        bad = (uint32_t)(i - first[e] + 1);
+        break;
+      }
+    valid[e] = bad == 0;
+    if (first_invalid) first_invalid[e] = bad;
+  }
+  return OXG_OK;
+  OXG_API_END
+}
+
+}  // extern "C"

@@ -1,4 +1,4 @@
-"""The C-ABI library loads and exports every symbol include/oxg.h declares; without a CUDA
+"""The C-ABI library loads and exports every symbol include/*.h declare; without a CUDA
 device the compute entry points fail loudly (there is no CPU fallback)."""
 import ctypes as C
 import os
@@ -11,9 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_symbols():
-    src = open(os.path.join(ROOT, "include", "oxg.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(oxg_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for header in ("oxg.h", "oxg_so3.h"):
+        src = open(os.path.join(ROOT, "include", header)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(oxg_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_symbols_exported_and_bound():
@@ -23,7 +26,7 @@ def test_header_symbols_exported_and_bound():
     assert len(declared) >= 30
     raw = C.CDLL(_lib.LIB_PATH)
     for name in declared:
-        assert hasattr(raw, name), f"{name} declared in oxg.h but not exported by liboxg.so"
+        assert hasattr(raw, name), f"{name} declared in include/*.h but not exported by liboxg.so"
     # the Python binding covers the whole header, nothing more
     assert sorted(_lib.SIGNATURES) == declared
 
