@@ -85,6 +85,106 @@ class GpuValidityChecker:
         return self.world.is_valid(self._space, rows)
 
 
+class SO3State:
+    """oxmpl_py.base.SO3State(x, y, z, w) (oxmpl-py/src/base/so3_state.rs): a unit quaternion."""
+
+    __slots__ = ("x", "y", "z", "w")
+
+    def __init__(self, x: float, y: float, z: float, w: float):
+        self.x, self.y, self.z, self.w = float(x), float(y), float(z), float(w)
+
+    @staticmethod
+    def identity() -> "SO3State":
+        return SO3State(0.0, 0.0, 0.0, 1.0)
+
+    @property
+    def values(self):
+        return [self.x, self.y, self.z, self.w]
+
+    def __repr__(self):
+        return f"SO3State(x={self.x}, y={self.y}, z={self.z}, w={self.w})"
+
+
+class SO3StateSpace:
+    """oxmpl_py.base.SO3StateSpace(bounds=None); host arithmetic restates
+    oxmpl/src/base/spaces/so3_state_space.rs:26-60,99-159,196-232 in Python floats (IEEE f64, no
+    FMA; math.acos / math.sin are the libm calls Rust makes)."""
+
+    def __init__(self, bounds=None):
+        if bounds is None:
+            self.bounds = (SO3State.identity(), math.pi)
+        else:
+            centre, max_angle = bounds
+            if max_angle < 0.0:
+                raise ValueError("InvalidAngularDistance: the maximum angle must be non-negative")
+            self.bounds = (centre, min(float(max_angle), math.pi))
+        self._fraction = 0.05
+
+    def distance(self, state1: SO3State, state2: SO3State) -> float:
+        abs_dot = abs(state1.x * state2.x + state1.y * state2.y + state1.z * state2.z
+                      + state1.w * state2.w)
+        return 0.0 if abs_dot > 1.0 - 1e-9 else math.acos(abs_dot)
+
+    def interpolate(self, frm: SO3State, to: SO3State, t: float) -> SO3State:
+        dot = frm.x * to.x + frm.y * to.y + frm.z * to.z + frm.w * to.w
+        sign = -1.0 if dot < 0.0 else 1.0
+        dot *= sign
+        f, g = frm.values, to.values
+        if dot > 0.9995:
+            v = [f[c] + t * (g[c] * sign - f[c]) for c in range(4)]
+            norm = math.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3])
+            return SO3State(*[c / norm for c in v])
+        theta = math.acos(dot)
+        sin_theta = math.sin(theta)
+        s0 = math.sin((1.0 - t) * theta) / sin_theta
+        s1 = math.sin(t * theta) / sin_theta * sign
+        return SO3State(*[f[c] * s0 + g[c] * s1 for c in range(4)])
+
+    def get_maximum_extent(self) -> float:
+        return 0.5 * math.pi
+
+    def set_longest_valid_segment_fraction(self, fraction: float):
+        self._fraction = fraction if 0.0 < fraction <= 1.0 else (0.0 if fraction <= 0.0 else 1.0)
+
+    def get_longest_valid_segment_length(self) -> float:
+        return self.get_maximum_extent() * self._fraction
+
+    def satisfies_bounds(self, state: SO3State) -> bool:
+        return self.distance(self.bounds[0], state) <= self.bounds[1]
+
+    def sample_uniform(self, rng: random.Random) -> SO3State:
+        centre, max_angle = self.bounds
+        if max_angle < 1e-9:
+            return SO3State(*centre.values)
+        while True:     # rejection sampling inside the unit 4-ball, so3_state_space.rs:205-228
+            x, y, z, w = (rng.uniform(-1.0, 1.0) for _ in range(4))
+            norm_sq = x * x + y * y + z * z + w * w
+            if 1e-9 < norm_sq < 1.0:
+                norm = math.sqrt(norm_sq)
+                q = SO3State(x / norm, y / norm, z / norm, w / norm)
+                if self.distance(centre, q) <= max_angle:
+                    return q
+
+    def _space(self) -> api.Space:
+        return api.Space.real_vector(4)
+
+
+class GpuConeChecker:
+    """Declarative ``StateValidityChecker<SO3State>``: forbidden cones ``(centre, angle)``; a state
+    is valid iff ``distance(centre, state) > angle`` for all of them (the reference's SO3 fixture,
+    oxmpl/tests/rrt_so3ss_tests.rs:46-56 / oxmpl-py/tests/test_rrt_so3ss.py:38-44)."""
+
+    def __init__(self, cones):
+        rows = [list(c.values) + [float(a)] for c, a in cones]
+        self.cones = api.So3Cones(np.asarray(rows, dtype=np.float64).reshape(-1, 5))
+
+    def __call__(self, state: SO3State) -> bool:
+        return bool(self.cones.is_valid(np.asarray([state.values]))[0])
+
+    def is_valid_batch(self, rows) -> np.ndarray:
+        return self.cones.is_valid(rows)
+
+
 @dataclass
 class ProblemDefinition:
     """oxmpl_py.base.ProblemDefinition (oxmpl-py/src/base/problem_definition.rs:51-77)."""
@@ -98,6 +198,15 @@ class ProblemDefinition:
         for attr in ("target", "radius", "is_satisfied", "sample_goal"):
             if not hasattr(goal, attr):
                 raise TypeError(f"goal must provide `{attr}` (a ball goal: target + radius)")
+        return ProblemDefinition(space, start_state, goal)
+
+    @staticmethod
+    def from_so3(space, start_state, goal) -> "ProblemDefinition":
+        """oxmpl-py/src/base/problem_definition.rs:108-133: any goal object with
+        ``is_satisfied(state)`` and ``sample_goal()``."""
+        for attr in ("is_satisfied", "sample_goal"):
+            if not hasattr(goal, attr):
+                raise TypeError(f"goal must provide `{attr}`")
         return ProblemDefinition(space, start_state, goal)
 
 

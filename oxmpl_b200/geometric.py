@@ -14,7 +14,8 @@ from collections import deque
 import numpy as np
 
 from . import api
-from .base import GpuValidityChecker, Path, PlanningError, ProblemDefinition, RealVectorState
+from .base import (GpuConeChecker, GpuValidityChecker, Path, PlanningError, ProblemDefinition,
+                   RealVectorState, SO3State, SO3StateSpace)
 
 
 def _checker(validity) -> GpuValidityChecker:
@@ -63,11 +64,54 @@ class _TreePlanner:
 
 
 class RRT(_TreePlanner):
-    """oxmpl_py.geometric.RRT (oxmpl-py/src/geometric/rrt.rs) over oxg_rrt_solve."""
+    """oxmpl_py.geometric.RRT (oxmpl-py/src/geometric/rrt.rs) over oxg_rrt_solve.  Over an
+    :class:`SO3StateSpace` it runs the reference loop unfused: ``oxg_so3_nn1`` -> steer on the
+    host (SLERP needs libm) -> ``oxg_so3_check_motion`` -> append (include/oxg_so3.h)."""
+
+    def setup(self, validity):
+        if not isinstance(self.pd.space, SO3StateSpace):
+            return super().setup(validity)
+        if not isinstance(validity, GpuConeChecker):
+            raise TypeError("SO3 planning takes a declarative GpuConeChecker, not a Python "
+                            "callback (oxmpl_b200 has no CPU fallback)")
+        self.vc = validity
+        self.tree = api.StateStore(self.pd.space._space(), capacity=1024)
+        self.tree.append(np.asarray([self.pd.start_state.values]))
+        self.nodes = [self.pd.start_state]
+        self.parents = [-1]
+
+    def _solve_so3(self, timeout_secs: float) -> Path:
+        pd, space = self.pd, self.pd.space
+        res = self._resolution()
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 <= timeout_secs:          # rrt.rs:170-225
+            q_rand = pd.goal.sample_goal() if self.rng.random() < self.goal_bias \
+                else space.sample_uniform(self.rng)
+            idx, dist = self.tree.so3_nn1(np.asarray([q_rand.values]))
+            near, min_dist = int(idx[0]), float(dist[0])
+            q_near = self.nodes[near]
+            if min_dist > self.max_distance:
+                q_new = space.interpolate(q_near, q_rand, self.max_distance / min_dist)
+            else:
+                q_new = q_rand
+            if self.vc.cones.check_motion(np.asarray([q_near.values]), np.asarray([q_new.values]),
+                                          res)[0]:
+                self.tree.append(np.asarray([q_new.values]))
+                self.nodes.append(q_new)
+                self.parents.append(near)
+                if pd.goal.is_satisfied(q_new):
+                    out, node = [], len(self.nodes) - 1
+                    while node >= 0:
+                        out.append(self.nodes[node])
+                        node = self.parents[node]
+                    return Path(out[::-1])
+        raise PlanningError(PlanningError.TIMEOUT)
 
     def solve(self, timeout_secs: float) -> Path:
         if self.vc is None:
             raise PlanningError(PlanningError.UNINITIALISED)
+        if isinstance(self.pd.space, SO3StateSpace):
+            return self._solve_so3(timeout_secs)
         t0 = time.perf_counter()
         while True:
             left = timeout_secs - (time.perf_counter() - t0)

@@ -5,6 +5,7 @@ replaced by the declarative GpuValidityChecker and re-used here as the independe
 import math
 import random
 
+import numpy as np
 import pytest
 
 from oxmpl_b200.base import (GpuValidityChecker, PlanningError, ProblemDefinition, RealVectorState,
@@ -101,3 +102,97 @@ def test_python_callback_is_rejected_and_checker_matches_callback():
         assert vc(RealVectorState(xy)) == is_state_valid(RealVectorState(xy))
     with pytest.raises(PlanningError, match="uninitialised"):
         RRT(0.5, 0.05, pd).solve(1.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# SO(3): oxmpl-py/tests/test_rrt_so3ss.py against the mirror (unfused loop over include/oxg_so3.h)
+# ---------------------------------------------------------------------------------------------
+def _quat_axis_angle(axis, angle):
+    from oxmpl_b200.base import SO3State
+    s, c = math.sin(angle * 0.5), math.cos(angle * 0.5)
+    return SO3State(x=axis[0] * s, y=axis[1] * s, z=axis[2] * s, w=c)
+
+
+class _QuaternionGoalRegion:
+    def __init__(self, space, target, radius):
+        self.space, self.target, self.radius = space, target, radius
+        self.rng = random.Random(123)
+
+    def is_satisfied(self, state):
+        return self.space.distance(self.target, state) <= self.radius
+
+    def sample_goal(self):
+        from oxmpl_b200.base import SO3State
+        while True:
+            x, y, z, w = [self.rng.uniform(-1.0, 1.0) for _ in range(4)]
+            norm_sq = x * x + y * y + z * z + w * w
+            if 1e-9 < norm_sq < 1.0:
+                norm = math.sqrt(norm_sq)
+                q = SO3State(x / norm, y / norm, z / norm, w / norm)
+                if self.is_satisfied(q):
+                    return q
+
+
+def _so3_problem():
+    from oxmpl_b200.base import GpuConeChecker, ProblemDefinition, SO3State, SO3StateSpace
+    space = SO3StateSpace()
+    start = _quat_axis_angle((0.0, 1.0, 0.0), math.pi / 2.0)
+    goal = _QuaternionGoalRegion(space, _quat_axis_angle((0.0, 1.0, 0.0), -math.pi / 2.0),
+                                 math.radians(10.0))
+    checker = GpuConeChecker([(SO3State.identity(), math.radians(44.9))])
+    return space, start, goal, checker, ProblemDefinition.from_so3(space, start, goal)
+
+
+def test_rrt_finds_path_in_so3ss(oxg):
+    from oxmpl_b200.geometric import RRT
+    space, start, goal, checker, pd = _so3_problem()
+    assert checker(start) and checker(goal.target)
+    planner = RRT(max_distance=0.5, goal_bias=0.05, problem_definition=pd)
+    with pytest.raises(TypeError):
+        planner.setup(lambda s: True)
+    planner.setup(checker)
+    path = planner.solve(timeout_secs=20.0)
+    assert len(path.states) > 1
+    assert space.distance(path.states[0], start) < 1e-9
+    assert goal.is_satisfied(path.states[-1])
+    forbidden = math.radians(44.9)
+    ident = type(start).identity()
+    for a, b in zip(path.states[:-1], path.states[1:]):        # is_path_valid, rrt_so3ss_tests.rs:106-143
+        assert space.distance(ident, a) > forbidden and space.distance(ident, b) > forbidden
+        n = math.ceil(space.distance(a, b) / space.get_longest_valid_segment_length())
+        for j in range(1, n + 1 if n > 1 else 0):
+            assert space.distance(ident, space.interpolate(a, b, j / n)) > forbidden
+
+
+def test_so3_rrt_tree_identical_to_oracle_loop(oxg, orc):
+    """The unfused GPU loop and the same loop driven by the oracle grow the same tree, bit for bit."""
+    from oxmpl_b200.geometric import RRT
+    space, start, goal, checker, pd = _so3_problem()
+    planner = RRT(max_distance=0.5, goal_bias=0.05, problem_definition=pd, seed=7)
+    planner.setup(checker)
+    path = planner.solve(timeout_secs=20.0)
+    got = np.asarray([n.values for n in planner.nodes])
+    # replay with the oracle: same draws (seed 7 for the planner, 123 inside the goal)
+    space2, start2, goal2, _, _ = _so3_problem()
+    rng = random.Random(7)
+    cones = np.array([[0.0, 0.0, 0.0, 1.0, math.radians(44.9)]])
+    res = space2.get_longest_valid_segment_length() * 0.1
+    rows, parents = [np.asarray(start2.values)], [-1]
+    while True:
+        q = goal2.sample_goal() if rng.random() < 0.05 else space2.sample_uniform(rng)
+        q = np.asarray(q.values)
+        idx, dist = orc.so3_nn1(np.asarray(rows), q)
+        near, d = int(idx[0]), float(dist[0])
+        q_new = orc.so3_interpolate(rows[near], q, 0.5 / d) if d > 0.5 else q
+        valid, _ = orc.so3_check_motion(cones, rows[near], q_new, res)
+        if valid[0]:
+            rows.append(q_new)
+            parents.append(near)
+            if orc.so3_distance(goal2.target.values, q_new) <= goal2.radius:
+                break
+        assert len(rows) <= len(got)
+    want = np.asarray(rows)
+    assert got.shape == want.shape
+    np.testing.assert_array_equal(got.view(np.uint64), want.view(np.uint64))
+    assert planner.parents == parents
+    assert len(path.states) >= 2
