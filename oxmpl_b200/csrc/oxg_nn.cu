@@ -1792,6 +1792,15 @@ static bool use_f32_filter() {
   static const bool on = env_int("OXG_KNN_FILTER", 1) != 0;
   return on;
 }
+// Smallest batch the dot-form k-NN kernel takes (below it the difference-form filter runs).  Its
+// looser bound costs more exact re-tests while the lists warm up, which long slices amortise:
+// measured at D = 7 it wins from 128 queries up on a 1e7-state store, from ~1000 on 1e6 states.
+static uint64_t dot_min_q(uint32_t n_db) {
+  static const int v = env_int("OXG_KNN_DOT_MINQ", 0);
+  if (v > 0) return (uint64_t)v;
+  return n_db >= 4000000u ? 65 : 1024;
+}
+
 static bool use_dot_form() {
   static const bool on = [] {
     const char* v = getenv("OXG_KNN_FORM");
@@ -1985,8 +1994,14 @@ static int nn_knn_device_impl(oxg_store_s* s, StateView q, uint64_t Q, uint32_t 
   }
   const bool f32 = fast && use_f32_filter();
   // several queries per thread once there is enough work to fill the machine that way
+  // (two queries per thread halve the shared-memory reads per pair but also the number of
+  // query tiles, so the store is cut into more slices: it pays once every slice is long —
+  // measured at D = 7: from ~1e10 pairs for k = 1, ~1e11 pairs for k > 1, see tools/medq_probe.py)
   int qpt = 1;
   if (fast && Q >= 2ull * 148 * NN_THREADS * 2 && k <= 32) qpt = 2;
+  if (fast && use_f32_filter() && use_dot_form() && Q >= dot_min_q(p.n_db) && k <= 32 &&
+      (double)Q * (double)p.n_db >= (k == 1 ? 1e10 : 1e11))
+    qpt = 2;
   if (fast && forced_qpt() > 0) {
     qpt = forced_qpt() >= 2 ? 2 : 1;
     if (qpt == 2 && k > 32) qpt = 1;
@@ -2035,7 +2050,7 @@ static int nn_knn_device_impl(oxg_store_s* s, StateView q, uint64_t Q, uint32_t 
   p.out_dist = part_dist;
   dim3 grid((unsigned)qtiles, p.nsplit);
 
-  if (f32 && use_dot_form() && Q >= 1024) {
+  if (f32 && use_dot_form() && Q >= dot_min_q(p.n_db)) {
     int r = OXG_E_INTERNAL;
     if (qpt == 2) {
       OXG_DISPATCH_D(s->dim, r = (launch_knn_rv_dot<DD, 2>(p, grid, s->stream)));

@@ -444,3 +444,25 @@ def test_prefilter_at_the_threshold(oxg, orc, offset, delta, nq):
         ooff, oidx = orc.radius(sp_o, rows, centres, 0.25)
         np.testing.assert_array_equal(off, ooff)
         np.testing.assert_array_equal(ridx, oidx)
+
+
+@pytest.mark.parametrize("q_count,k", [(70, 1), (130, 1), (130, 4), (300, 10)])
+def test_medium_batches_on_a_large_store(oxg, orc, q_count, k):
+    """On stores of >= 4e6 states, batches of 65..1023 queries take the dot-form kernel (one query
+    per thread, the store cut into slices) instead of the difference-form one."""
+    d, n = 2, 4_200_000
+    rows = uniform_states(900, n, [0.0] * d, [1.0] * d)
+    rows[1_000_000] = rows[3]                                    # a far-apart duplicate pair
+    queries = uniform_states(901 + q_count, q_count, [0.0] * d, [1.0] * d)
+    queries[0] = rows[3]
+    with oxg.StateStore(oxg.Space.real_vector(d), capacity=n) as st:
+        st.append(rows)
+        idx, dist = st.knn(queries, k)
+        oi, od = orc.knn(orc.space(d), rows, queries, k)
+        np.testing.assert_array_equal(idx, oi)
+        np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+        if k == 1:
+            idx1, dist1 = st.nn1(queries)
+            o1, od1 = orc.nn1(orc.space(d), rows, queries)
+            np.testing.assert_array_equal(idx1, o1)
+            np.testing.assert_array_equal(dist1.view(np.uint64), od1.view(np.uint64))
