@@ -32,6 +32,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <chrono>
+
 #include "oxg_internal.cuh"
 #include "oxg_math.cuh"
 
@@ -58,7 +60,13 @@ struct TreeView {
   double* data;
   uint64_t pitch;
   long long* parent;
+  int cg;  // 1: several CTAs append to the tree, read it with ld.global.cg (L1 is not coherent
+           // across SMs); 0: a single CTA runs the loop and its own L1 serves the reads
 };
+template <class V>
+__device__ __forceinline__ V ld_tree(const TreeView& T, const V* p) {
+  return T.cg ? __ldcg(p) : *p;
+}
 
 struct PlanCtrl {
   unsigned long long n[2];
@@ -124,9 +132,9 @@ struct PlanShared {
 };
 
 // ------------------------------------------------------------------------------- arithmetic
-// Accessors: a state in shared memory, or a tree / goal state in global memory.  Global states
-// are read with ld.global.cg: other CTAs append to the tree during the kernel, and L1 is not
-// coherent across SMs.
+// Accessors: a state in shared memory, or a tree / goal state in global memory.  With several
+// CTAs global states are read with ld.global.cg: other CTAs append to the tree during the kernel,
+// and L1 is not coherent across SMs.
 struct SmState {
   const double* p;
   __device__ __forceinline__ double operator[](uint32_t d) const { return p[d]; }
@@ -134,11 +142,14 @@ struct SmState {
 struct GlState {
   const double* p;
   uint64_t stride;
-  __device__ __forceinline__ double operator[](uint32_t d) const { return __ldcg(p + d * stride); }
+  bool cg;
+  __device__ __forceinline__ double operator[](uint32_t d) const {
+    return cg ? __ldcg(p + d * stride) : p[d * stride];
+  }
 };
 __device__ __forceinline__ SmState sm(const double* p) { return SmState{p}; }
 __device__ __forceinline__ GlState node(const TreeView& T, uint32_t i) {
-  return GlState{T.data + i, T.pitch};
+  return GlState{T.data + i, T.pitch, T.cg != 0};
 }
 
 // distance(a, b) in the reference's operation and argument order (real_vector_state_space.rs:
@@ -364,7 +375,7 @@ __device__ void phase_steer(const PlanParams& P, PlanShared& sh, const TreeView&
   const double min_dist = sh.bc_d[0];
   if ((int)threadIdx.x < dim)
     sh.q_near[threadIdx.x] = (near == pend_idx) ? sh.pend[threadIdx.x]
-                                                : __ldcg(&T.data[(uint64_t)threadIdx.x * T.pitch + near]);
+                                                : ld_tree(T, &T.data[(uint64_t)threadIdx.x * T.pitch + near]);
   __syncthreads();
   const bool far = min_dist > P.max_distance;
   if ((int)threadIdx.x < dim) {
@@ -435,7 +446,7 @@ __device__ void motion_tasks(const PlanParams& P, PlanShared& sh, double* st_buf
       const uint32_t ns = e_nb ? steps[e_nb[e]] : steps[e];
       const uint32_t i = s_glob - pre[e] + 1;
       const double o = other_sm ? other_sm[d]
-                                : __ldcg(&T.data[(uint64_t)d * T.pitch + sh.nb_idx[e_nb[e]]]);
+                                : ld_tree(T, &T.data[(uint64_t)d * T.pitch + sh.nb_idx[e_nb[e]]]);
       const double f = fixed_is_to ? o : fixed[d];
       const double t = fixed_is_to ? fixed[d] : o;
       // `if num_steps <= 1 { return is_valid(to) }`; step i of n: t = i / n (rrt.rs:99-105)
@@ -660,7 +671,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
 
   auto goal_ok = [&]() -> bool {
     if (!P.goal || P.goal_radius < 0.0) return false;
-    return dist_ab(P, sm(sh.q_new), GlState{P.goal, 1}) <= P.goal_radius;
+    return dist_ab(P, sm(sh.q_new), GlState{P.goal, 1, false}) <= P.goal_radius;
   };
 
   for (;;) {
@@ -794,11 +805,11 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
       // ---- choose parent (rrt_star.rs:233-249)
       // cost(temp, nbr) = nbr.cost + distance(temp.state, nbr.state); the distance is the radius
       // scan's value (same argument order).
-      const double cost_near = __ldcg(&P.cost[near]);
+      const double cost_near = ld_tree(T, &P.cost[near]);
       const double min_cost0 = __dadd_rn(cost_near, dist_ab(P, sm(sh.q_new), sm(sh.q_near)));
       for (uint32_t u = tid; u < m; u += PL_THREADS) {
         const uint32_t j = sh.nb_idx[u];
-        sh.nb_c[u] = __dadd_rn(__ldcg(&P.cost[j]), sh.nb_dist[u]);
+        sh.nb_c[u] = __dadd_rn(ld_tree(T, &P.cost[j]), sh.nb_dist[u]);
         // check_motion(neighbour.state, q_new): dist = distance(from = nbr, to = new)
         const double dd = dist_ab(P, node(T, j), sm(sh.q_new));
         const unsigned long long ns64 = motion_steps(dd, P.resolution);
@@ -851,7 +862,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_kernel(const PlanParams
         const uint32_t j = sh.nb_idx[u];
         const double dn = dist_ab(P, node(T, j), sm(sh.q_new));
         const double c = __dadd_rn(min_cost, dn);
-        const bool cand = (j != best) && (c < __ldcg(&P.cost[j]));
+        const bool cand = (j != best) && (c < ld_tree(T, &P.cost[j]));
         sh.nb_c[u] = c;
         // check_motion(new, nbr): dist = distance(from = new, to = nbr)
         const double dd = dist_ab(P, sm(sh.q_new), node(T, j));
@@ -927,7 +938,9 @@ int choose_ctas(uint64_t max_nodes, uint32_t dim, uint64_t n_obstacles, int sm_c
   const int forced = env_int_pl("OXG_PLAN_CTAS", 0);
   if (forced > 0) return std::min(forced, sm_count);
   uint64_t by_tree = (max_nodes * dim + 32767) / 32768;
-  uint64_t by_world = (n_obstacles + 63) / 64;
+  // below ~2000 obstacles one CTA sweeps a motion in less time than two grid barriers cost
+  // (config 2, 1000 boxes: 7.0 us per iteration on 1 CTA, 8.7 on 16)
+  uint64_t by_world = n_obstacles >= 2048 ? (n_obstacles + 63) / 64 : 1;
   uint64_t g = std::max<uint64_t>(by_tree, by_world);
   if (g < 1) g = 1;
   if (g > (uint64_t)sm_count) g = (uint64_t)sm_count;
@@ -1014,11 +1027,13 @@ int check_plan_args(oxg_world w, oxg_store tree, const oxg_plan_params* p, const
   return OXG_OK;
 }
 
-// Shared driver of the three planners.
+// One launch of the planner kernel on G CTAs, growing the tree(s) up to stage_cap nodes
+// (<= prm->max_nodes, which sizes the allocations).
 template <int MODE>
-int plan_solve(oxg_world w, oxg_store t0, oxg_store t1, const oxg_plan_params* prm,
+int plan_stage(oxg_world w, oxg_store t0, oxg_store t1, const oxg_plan_params* prm,
                const double* goal_target, const double* samples, uint64_t n_samples,
-               int64_t* parents0, int64_t* parents1, double* costs, oxg_plan_result* out) {
+               int64_t* parents0, int64_t* parents1, double* costs, oxg_plan_result* out, int G,
+               uint64_t stage_cap) {
   OXG_TRY(check_plan_args(w, t0, prm, samples, n_samples, out));
   if (MODE == MODE_CONNECT) {
     if (!t1 || t1->size == 0) {
@@ -1048,14 +1063,8 @@ int plan_solve(oxg_world w, oxg_store t0, oxg_store t1, const oxg_plan_params* p
     OXG_CUDA_TRY(cudaStreamSynchronize(t1->stream));
   }
 
-  int dev = 0, sm_count = 148;
-  OXG_CUDA_TRY(cudaGetDevice(&dev));
-  OXG_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  const uint64_t n_obst = w->n_spheres + w->n_aabbs + w->n_capsules + w->n_so2;
-  const int G = choose_ctas(prm->max_nodes, dim, n_obst, sm_count);
-
   // scratch layout in B_PLAN
-  const uint32_t capc = (uint32_t)(((prm->max_nodes + G - 1) / G + 31) / 32 * 32 + 32);
+  const uint32_t capc = (uint32_t)(((stage_cap + G - 1) / G + 31) / 32 * 32 + 32);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -1091,14 +1100,14 @@ int plan_solve(oxg_world w, oxg_store t0, oxg_store t1, const oxg_plan_params* p
 
   PlanParams P;
   memset(&P, 0, sizeof(P));
-  P.tree[0] = TreeView{t0->d_data, t0->pitch, t0->buf[B_PARENT].as<long long>()};
+  P.tree[0] = TreeView{t0->d_data, t0->pitch, t0->buf[B_PARENT].as<long long>(), G > 1 ? 1 : 0};
   P.n_init[0] = (uint32_t)t0->size;
   if (MODE == MODE_CONNECT) {
-    P.tree[1] = TreeView{t1->d_data, t1->pitch, t1->buf[B_PARENT].as<long long>()};
+    P.tree[1] = TreeView{t1->d_data, t1->pitch, t1->buf[B_PARENT].as<long long>(), G > 1 ? 1 : 0};
     P.n_init[1] = (uint32_t)t1->size;
   }
   P.cost = t0->buf[B_COST].as<double>();
-  P.max_nodes = (uint32_t)prm->max_nodes;
+  P.max_nodes = (uint32_t)stage_cap;
   P.n_real = s->space.n_real;
   P.n_so2 = s->space.n_so2;
   P.w_real = s->space.w_real;
@@ -1180,6 +1189,83 @@ int plan_solve(oxg_world w, oxg_store t0, oxg_store t1, const oxg_plan_params* p
               MAX_STEPS, prm->resolution);
     return OXG_E_RESOLUTION;
   }
+  return OXG_OK;
+}
+
+// Shared driver of the three planners.  The grid grows with the tree: a run starts on the CTA
+// count that suits a tree of 4096 nodes and is relaunched (the kernels resume from the trees in
+// the stores) when a tree reaches 4096 / 32 768 / 262 144 / 2 097 152 nodes and a larger tree wants
+// more CTAs — a small tree on many CTAs only pays grid barriers.  Worlds of >= 2048 obstacles ask
+// for their CTAs from the start (choose_ctas), so those runs are a single launch.
+template <int MODE>
+int plan_solve(oxg_world w, oxg_store t0, oxg_store t1, const oxg_plan_params* prm,
+               const double* goal_target, const double* samples, uint64_t n_samples,
+               int64_t* parents0, int64_t* parents1, double* costs, oxg_plan_result* out) {
+  OXG_TRY(check_plan_args(w, t0, prm, samples, n_samples, out));
+  if (MODE == MODE_CONNECT && !t1) {
+    set_error("RRT-Connect needs a goal tree holding the goal state (rrt_connect.rs:201-216)");
+    return OXG_E_EMPTY;
+  }
+  int dev = 0, sm_count = 148;
+  OXG_CUDA_TRY(cudaGetDevice(&dev));
+  OXG_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  const uint64_t n_obst = w->n_spheres + w->n_aabbs + w->n_capsules + w->n_so2;
+  const uint32_t dim = t0->dim;
+  static const uint64_t kCaps[] = {4096ull, 32768ull, 262144ull, 2097152ull};
+  auto grid_for = [&](uint64_t cap) { return choose_ctas(cap, dim, n_obst, sm_count); };
+
+  oxg_plan_result acc;
+  memset(&acc, 0, sizeof(acc));
+  uint64_t consumed = 0;
+  const auto t_begin = std::chrono::steady_clock::now();
+  for (;;) {
+    uint64_t cur = t0->size;
+    if (MODE == MODE_CONNECT && t1->size > cur) cur = t1->size;
+    uint64_t cap = prm->max_nodes;
+    for (uint64_t c : kCaps)
+      if (c > cur && c < prm->max_nodes) {
+        cap = c;
+        break;
+      }
+    const int G = grid_for(cap);
+    for (uint64_t c : kCaps)  // later stages that want the same grid join this one
+      if (c > cap && c < prm->max_nodes && grid_for(c) == G) cap = c;
+    if (grid_for(prm->max_nodes) == G) {
+      bool last = true;
+      for (uint64_t c : kCaps)
+        if (c > cap && c < prm->max_nodes) last = false;
+      if (last) cap = prm->max_nodes;
+    }
+    oxg_plan_params sp = *prm;
+    if (prm->timeout_s > 0.0) {
+      const double used =
+          std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+      if (consumed > 0 && used >= prm->timeout_s) {
+        acc.status = ST_TIMEOUT;
+        break;
+      }
+      sp.timeout_s = std::max(prm->timeout_s - used, 1e-6);
+    }
+    oxg_plan_result r;
+    OXG_TRY((plan_stage<MODE>(w, t0, t1, &sp, goal_target, samples + consumed * dim,
+                              n_samples - consumed, parents0, parents1, costs, &r, G, cap)));
+    consumed += r.iters;
+    acc.iters += r.iters;
+    acc.motion_checks += r.motion_checks;
+    acc.motion_checks_executed += r.motion_checks_executed;
+    acc.device_ms += r.device_ms;
+    for (int i = 0; i < 8; ++i) acc.phase_ms[i] += r.phase_ms[i];
+    acc.n_nodes[0] = r.n_nodes[0];
+    acc.n_nodes[1] = r.n_nodes[1];
+    acc.goal_node[0] = r.goal_node[0];
+    acc.goal_node[1] = r.goal_node[1];
+    acc.solved = r.solved;
+    acc.status = r.status;
+    acc.ctas = r.ctas;
+    if (r.status == ST_FULL && cap < prm->max_nodes && consumed < n_samples) continue;
+    break;
+  }
+  *out = acc;
   return OXG_OK;
 }
 

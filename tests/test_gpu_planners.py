@@ -226,3 +226,60 @@ def test_planner_bounds_and_errors(oxg, orc):
         st.append(np.array([c["start"]]))
         _, r = oxg.rrt_solve(gw, st, np.tile(samples, (400, 1)), 1e-4, res, 10**6, timeout_s=0.05)
         assert r["status"] in ("timeout", "samples_exhausted")
+
+
+def test_grid_grows_with_the_tree(oxg, orc, monkeypatch):
+    """Without OXG_PLAN_CTAS a run starts on one CTA and is relaunched on a larger grid when a
+    tree passes 4096 nodes (the kernels resume from the stores): sample consumption, trees,
+    parents, costs and counters must be those of one uninterrupted run."""
+    monkeypatch.delenv("OXG_PLAN_CTAS", raising=False)
+    c = worlds.CONFIG1
+    sp, sp_o = oxg.Space.real_vector(2), orc.space(2)
+    res = _res(oxg, orc, c["lo"], c["hi"])
+    # RRT, no goal: 9000 samples grow ~8000 nodes; max_nodes = 40000 asks for 3 CTAs later on
+    samples = worlds.sample_stream(71, 9000, c["lo"], c["hi"], 0.0, c["goal"])
+    ow, keep = orc.world(2, spheres=c["spheres"])
+    t_o, p_o, solved_o, it_o = orc.rrt(ow, sp_o, c["start"], c["goal"], -1.0, c["max_distance"], res,
+                                       samples, 40000)
+    assert len(t_o) > 6000 and not solved_o
+    with oxg.World(2, spheres=c["spheres"]) as gw, oxg.StateStore(sp) as st:
+        st.append(np.array([c["start"]]))
+        parents, r = oxg.rrt_solve(gw, st, samples, c["max_distance"], res, 40000)
+        assert r["status"] == "samples_exhausted" and r["iters"] == it_o == 9000
+        assert r["ctas"] > 1                                           # the last stage's grid
+        np.testing.assert_array_equal(_bits(st.read()), _bits(t_o))
+        np.testing.assert_array_equal(parents, p_o)
+    # RRT*: choose-parent / rewire state (costs) must survive the relaunch
+    samples = worlds.sample_stream(72, 5200, c["lo"], c["hi"], 0.0, c["goal"])
+    o = orc.rrt_star(ow, sp_o, c["start"], c["goal"], -1.0, 0.5, 0.6, res, samples, 40000,
+                     stop_at_goal=False)
+    assert len(o["tree"]) > 4300
+    with oxg.World(2, spheres=c["spheres"]) as gw, oxg.StateStore(sp) as st:
+        st.append(np.array([c["start"]]))
+        parents, costs, r = oxg.rrt_star_solve(gw, st, samples, 0.5, 0.6, res, 40000,
+                                               stop_at_goal=False)
+        assert r["iters"] == o["iters"] and r["n_nodes"][0] == len(o["tree"])
+        np.testing.assert_array_equal(_bits(st.read()), _bits(o["tree"]))
+        np.testing.assert_array_equal(parents, o["parents"])
+        np.testing.assert_array_equal(_bits(costs), _bits(o["costs"]))
+        assert r["motion_checks"] == o["motion_checks"]
+    # RRT-Connect: both trees cross the threshold
+    lo, hi = [0.0, 0.0], [100.0, 100.0]
+    start, goal = [5.0, 5.0], [95.0, 95.0]
+    samples = np.random.default_rng(73).uniform(0.0, 100.0, size=(18000, 2))
+    res2 = _res(oxg, orc, lo, hi)
+    wall = np.array([[49.0, -1.0, 51.0, 101.0]])                        # keeps the trees apart
+    ow2, keep2 = orc.world(2, aabbs=wall)
+    o = orc.rrt_connect(ow2, sp_o, start, goal, goal, 0.5, 0.7, res2, samples, 40000)
+    assert min(len(o["start_tree"]), len(o["goal_tree"])) > 4300
+    with oxg.World(2, aabbs=wall) as gw, oxg.StateStore(sp) as ta, \
+            oxg.StateStore(sp) as tb:
+        ta.append(np.array([start]))
+        tb.append(np.array([goal]))
+        pa, pb, r = oxg.rrt_connect_solve(gw, ta, tb, samples, 0.7, res2, 40000,
+                                          goal_target=goal, goal_radius=0.5)
+        assert r["iters"] == o["iters"] and r["solved"] == o["solved"]
+        np.testing.assert_array_equal(_bits(ta.read()), _bits(o["start_tree"]))
+        np.testing.assert_array_equal(_bits(tb.read()), _bits(o["goal_tree"]))
+        np.testing.assert_array_equal(pa, o["start_parents"])
+        np.testing.assert_array_equal(pb, o["goal_parents"])

@@ -103,7 +103,8 @@ def config2(n_samples):
                       "solved": r["solved"], "nodes": r["n_nodes"], "gpu_ms": r["device_ms"],
                       "gpu_us_per_iter": r["device_ms"] * 1e3 / max(r["iters"], 1),
                       "cpu_s": cpu_s, "cpu_us_per_iter": cpu_s * 1e6 / max(o["iters"], 1),
-                      "bit_identical": bool(same), "ctas": r["ctas"]})
+                      "bit_identical": bool(same), "ctas": r["ctas"],
+                      "phase_us_per_iter": [round(v * 1e3 / max(r["iters"], 1), 3) for v in r["phase_ms"]]})
 
 
 if __name__ == "__main__":
