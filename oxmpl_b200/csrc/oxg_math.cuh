@@ -20,9 +20,31 @@ struct DimOf {
   OXG_DEV static int get(int rt) { return DT > 0 ? DT : rt; }
 };
 
+// fmod(x, c), bit for bit, without libdevice's long-division loop on the common path.  fmod is
+// an exact operation: r = x - q*c with q = trunc(x / c) is always representable, so one FMA from
+// the right q produces it without rounding.  q from the rounded quotient can be off by one; the
+// exact value is then r - c < 0 or r + c >= c, which survives the FMA's single rounding as such
+// and is repaired from the original x.  |x| < c (angles already in range) returns x itself.
+// Anything unusual (c <= 0, huge ratio, inf, NaN) takes libdevice's fmod.
+OXG_DEV double fmod_exact_dev(double x, double c) {
+  const double ax = fabs(x);
+  if (!(c > 0.0) || !(ax < __dmul_rn(c, 4503599627370496.0))) return fmod(x, c);
+  if (ax < c) return x;
+  double q = trunc(__ddiv_rn(ax, c));
+  double r = __fma_rn(-q, c, ax);
+  if (r < 0.0) {
+    q = __dsub_rn(q, 1.0);
+    r = __fma_rn(-q, c, ax);
+  } else if (r >= c) {
+    q = __dadd_rn(q, 1.0);
+    r = __fma_rn(-q, c, ax);
+  }
+  return copysign(r, x);
+}
+
 // f64::rem_euclid (Rust core): r = self % rhs; if r < 0.0 { r + rhs.abs() } else { r }
 OXG_DEV double rem_euclid_dev(double v, double rhs) {
-  double r = fmod(v, rhs);
+  double r = fmod_exact_dev(v, rhs);
   if (r < 0.0) r = __dadd_rn(r, fabs(rhs));
   return r;
 }

@@ -2278,6 +2278,28 @@ int nn_radius_offsets(oxg_store_s* s, uint64_t Q, uint64_t* d_out) {
 
 using namespace oxg;
 
+// The reference's 1-NN loop starts from min = distance(tree[0], q) and replaces it only when
+// d < min (rrt.rs:187-196).  If that first distance is NaN nothing ever replaces it and the
+// answer is (0, NaN), whatever the other states are; the scan kernels treat NaN as "never a
+// winner" for every index, so this fix-up restores the reference's answer for index 0.
+__global__ void nn1_first_nan_kernel(StateView db, StateView q, uint64_t Q, uint32_t n_real,
+                                     uint32_t n_so2, double w_real, double w_so2,
+                                     uint32_t* __restrict__ idx, double* __restrict__ dist) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Q) return;
+  double a[kMaxDim], b[kMaxDim];
+  const uint32_t dim = n_real + n_so2;
+  for (uint32_t d = 0; d < dim; ++d) {
+    a[d] = db.p[d * db.stride_d];
+    b[d] = q.p[i * q.stride_i + d * q.stride_d];
+  }
+  const double d0 = space_distance_dev(n_real, n_so2, w_real, w_so2, a, b);
+  if (d0 != d0) {
+    idx[i] = 0;
+    dist[i] = d0;
+  }
+}
+
 extern "C" {
 
 static int upload_queries(oxg_store s, const double* queries, uint64_t Q) {
@@ -2318,6 +2340,12 @@ static int knn_host(oxg_store s, const double* queries, uint64_t Q, uint32_t k,
   OXG_CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
   OXG_TRY(nn_knn_device(s, rows_view(s->buf[B_QUERY].as<double>(), s->dim), Q, k,
                         exclude_idx ? EXCL_ARRAY : EXCL_NONE, d_excl, 0, stored_first, d_idx, d_dist));
+  if (k == 1 && stored_first) {
+    nn1_first_nan_kernel<<<(unsigned)((Q + 127) / 128), 128, 0, s->stream>>>(
+        store_view(s), rows_view(s->buf[B_QUERY].as<double>(), s->dim), Q, s->space.n_real,
+        s->space.n_so2, s->space.w_real, s->space.w_so2, d_idx, d_dist);
+    OXG_LAUNCH_CHECK();
+  }
   OXG_CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
   OXG_CUDA_TRY(cudaMemcpyAsync(idx, d_idx, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
   OXG_CUDA_TRY(cudaMemcpyAsync(dist, d_dist, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));

@@ -1,4 +1,6 @@
 """GPU parity: nn1 / knn / radius through the C ABI vs the CPU oracle (bit-exact)."""
+import math
+
 import numpy as np
 import pytest
 
@@ -466,3 +468,85 @@ def test_medium_batches_on_a_large_store(oxg, orc, q_count, k):
             o1, od1 = orc.nn1(orc.space(d), rows, queries)
             np.testing.assert_array_equal(idx1, o1)
             np.testing.assert_array_equal(dist1.view(np.uint64), od1.view(np.uint64))
+
+
+def test_so2_remainder_is_exact_on_adversarial_angles(oxg, orc):
+    """The device computes `fmod` with one FMA from a corrected quotient (oxg_math.cuh
+    fmod_exact_dev) instead of libdevice's division loop: every pairwise SO2 distance — all k = N
+    neighbours of every query — must carry the oracle's bit pattern, for angles at and next to the
+    multiples of pi and 2*pi, huge, tiny, signed zeros and non-finite values."""
+    pi = math.pi
+    base = [0.0, -0.0, pi, -pi, 2 * pi, -2 * pi, 3 * pi, -3 * pi, 4 * pi, pi / 2, -pi / 2, 1e-300,
+            -1e-300, 5e-324, 1.0, -1.0, 100.0, -100.0, 1e6, -1e6, 1e15, -1e15, 2.0 ** 52 * 2 * pi,
+            2.0 ** 53 * 2 * pi, 1e300, -1e300, 710.0 * pi, 12345.678]
+    vals = []
+    for v in base:
+        vals.append(v)
+        up = down = v
+        for _ in range(3):
+            up, down = np.nextafter(up, np.inf), np.nextafter(down, -np.inf)
+            vals += [up, down]
+    rng = np.random.default_rng(3)
+    vals += list(rng.uniform(-50, 50, size=60)) + list(rng.uniform(-1e9, 1e9, size=40))
+    vals = np.array(vals, dtype=np.float64)
+    sp, sp_o = oxg.Space.so2(), orc.space(0, 1)
+    qs = np.concatenate([vals, [np.inf, -np.inf, np.nan]])[:, None]
+    for lo in range(0, len(vals), 64):
+        rows = vals[lo:lo + 64, None]
+        with oxg.StateStore(sp) as st:
+            st.append(rows)
+            k = len(rows)
+            idx, dist = st.knn(qs, k)
+            oi, od = orc.knn(sp_o, rows, qs, k)
+            np.testing.assert_array_equal(idx, oi)
+            np.testing.assert_array_equal(dist.view(np.uint64), od.view(np.uint64))
+            i1, d1 = st.nn1(qs)
+            o1, od1 = orc.nn1(sp_o, rows, qs)
+            np.testing.assert_array_equal(i1, o1)
+            nan = np.isnan(od1)                      # NaN payloads are not part of the contract
+            np.testing.assert_array_equal(np.isnan(d1), nan)
+            np.testing.assert_array_equal(d1[~nan].view(np.uint64), od1[~nan].view(np.uint64))
+    # interpolation / normalise through check_motion over SO2 with an interval obstacle
+    w_o, keep = orc.world(0, so2_intervals=[(0, 1.0, 1.3)])
+    frm = rng.uniform(-20, 20, size=(400, 1))
+    to = rng.uniform(-20, 20, size=(400, 1))
+    frm[:20, 0] = vals[:20]
+    to[:20, 0] = vals[20:40]
+    res = math.pi * 0.05 * 0.1
+    with oxg.World(0, so2_intervals=[(0, 1.0, 1.3)]) as gw:
+        valid, first = gw.check_motion(sp, frm, to, res, want_first_invalid=True)
+    ovalid, ofirst = orc.check_motion(w_o, sp_o, frm, to, res)
+    np.testing.assert_array_equal(valid, ovalid)
+    np.testing.assert_array_equal(first, ofirst)
+
+
+def test_nn1_nan_first_state_keeps_index_zero(oxg, orc):
+    """rrt.rs:187-196 starts from min = distance(tree[0], q): when that is NaN nothing is `<` it and
+    the reference answers (0, NaN) even if other states are finite; a NaN elsewhere never wins."""
+    for d in (1, 3, 7, 20):
+        sp, sp_o = oxg.Space.real_vector(d), orc.space(d)
+        rng = np.random.default_rng(d)
+        rows = rng.random((5000, d))
+        qs = rng.random((40, d))
+        rows[0, d - 1] = np.nan
+        rows[77, 0] = np.nan
+        with oxg.StateStore(sp) as st:
+            st.append(rows)
+            for q in (qs[:1], qs[:9], qs):
+                idx, dist = st.nn1(q)
+                oi, od = orc.nn1(sp_o, rows, q)
+                assert (oi == 0).all() and np.isnan(od).all()
+                np.testing.assert_array_equal(idx, oi)
+                assert np.isnan(dist).all()
+        rows[0] = rng.random(d)                       # only a later state is NaN now
+        qs[3, 0] = np.inf                              # inf - finite = inf: not NaN, a plain loser
+        qs[5, 0] = np.nan
+        with oxg.StateStore(sp) as st:
+            st.append(rows)
+            idx, dist = st.nn1(qs)
+            oi, od = orc.nn1(sp_o, rows, qs)
+            np.testing.assert_array_equal(idx, oi)
+            nan = np.isnan(od)
+            assert nan[5] and not nan[0]
+            np.testing.assert_array_equal(np.isnan(dist), nan)
+            np.testing.assert_array_equal(dist[~nan].view(np.uint64), od[~nan].view(np.uint64))
