@@ -106,4 +106,17 @@ extern "C" {
     pub fn oxg_rrt_star_solve(w: oxg_world, tree: oxg_store, params: *const oxg_plan_params,
                               goal_target: *const f64, samples: *const f64, n_samples: u64,
                               parents: *mut i64, costs: *mut f64, out: *mut oxg_plan_result) -> c_int;
+
+    // include/oxg_so3.h — SO(3) scans, cone validity, check_motion
+    pub fn oxg_so3_nn1(s: oxg_store, queries: *const f64, q: u64, idx: *mut u32, dist: *mut f64) -> c_int;
+    pub fn oxg_so3_radius(s: oxg_store, queries: *const f64, q: u64, r: f64, offsets: *mut u64,
+                          idx: *mut u32, cap: u64, dist: *mut f64) -> c_int;
+    pub fn oxg_so3_cones_create(cones: *const f64, n_cones: u64, out: *mut oxg_so3_cones) -> c_int;
+    pub fn oxg_so3_cones_destroy(cones: oxg_so3_cones) -> c_int;
+    pub fn oxg_so3_is_valid(cones: oxg_so3_cones, states: *const f64, q: u64, out: *mut u8) -> c_int;
+    pub fn oxg_so3_check_motion(cones: oxg_so3_cones, from: *const f64, to: *const f64, e: u64,
+                                resolution: f64, valid: *mut u8, first_invalid: *mut u32) -> c_int;
 }
+
+#[allow(non_camel_case_types)]
+pub type oxg_so3_cones = *mut std::os::raw::c_void;

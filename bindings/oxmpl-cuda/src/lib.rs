@@ -195,3 +195,44 @@ impl<G: BallGoal> Planner<RealVectorState, RealVectorStateSpace, G> for GpuRRT<G
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// SO(3): the forbidden-cone checker of oxmpl/tests/rrt_so3ss_tests.rs:46-56 on the GPU.
+// `SO3StateSpace::distance` needs libm's acos, which has no bit-identical device routine; the
+// library compares a = |q1 . q2| against thresholds found with this process's own libm, so the
+// booleans are the reference's (include/oxg_so3.h).
+// ------------------------------------------------------------------------------------------
+pub struct GpuConeChecker {
+    cones: ffi::oxg_so3_cones,
+}
+impl GpuConeChecker {
+    /// `cones`: (centre, angle) pairs; a state is valid iff `distance(centre, state) > angle` for all.
+    pub fn new(cones: &[(oxmpl::base::state::SO3State, f64)]) -> Self {
+        let rows: Vec<f64> = cones.iter().flat_map(|(c, a)| [c.x, c.y, c.z, c.w, *a]).collect();
+        let mut h = std::ptr::null_mut();
+        check(unsafe { ffi::oxg_so3_cones_create(rows.as_ptr(), cones.len() as u64, &mut h) });
+        Self { cones: h }
+    }
+    /// check_motion (rrt.rs:90-116) for one edge; `resolution` = lvsl * 0.1 computed by the caller.
+    pub fn check_motion(&self, from: &oxmpl::base::state::SO3State, to: &oxmpl::base::state::SO3State,
+                        resolution: f64) -> bool {
+        let (a, b) = ([from.x, from.y, from.z, from.w], [to.x, to.y, to.z, to.w]);
+        let mut ok = 0u8;
+        check(unsafe {
+            ffi::oxg_so3_check_motion(self.cones, a.as_ptr(), b.as_ptr(), 1, resolution, &mut ok,
+                                      std::ptr::null_mut())
+        });
+        ok != 0
+    }
+}
+impl Drop for GpuConeChecker {
+    fn drop(&mut self) { unsafe { ffi::oxg_so3_cones_destroy(self.cones); } }
+}
+impl StateValidityChecker<oxmpl::base::state::SO3State> for GpuConeChecker {
+    fn is_valid(&self, state: &oxmpl::base::state::SO3State) -> bool {
+        let v = [state.x, state.y, state.z, state.w];
+        let mut out = 0u8;
+        check(unsafe { ffi::oxg_so3_is_valid(self.cones, v.as_ptr(), 1, &mut out) });
+        out != 0
+    }
+}

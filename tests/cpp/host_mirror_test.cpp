@@ -14,6 +14,7 @@
 #include <memory>
 
 #include "../../include/oxmpl_cuda.hpp"
+#include "../../include/oxmpl_cuda_so3.hpp"
 
 using namespace oxmpl::cuda;
 
@@ -187,6 +188,63 @@ int main() {
       boxed.solve(0.3);
     } catch (const PlanningError& e) {
       threw = e.kind == PlanningError::Timeout;
+    }
+    EXPECT(threw);
+  }
+  // ---- SO(3): oxmpl/tests/rrt_so3ss_tests.rs:146-229 — rotate from +90 deg to -90 deg about y
+  // around a forbidden cone of 44.9 deg at the identity; goal region of 10 deg; RRT(0.5, 0.0).
+  std::printf("SO3 RRT(0.5, 0.0)\n");
+  {
+    const double kPi = 3.14159265358979323846;
+    auto axis_angle = [](double ax, double ay, double az, double angle) {
+      const double s = std::sin(angle * 0.5), c = std::cos(angle * 0.5);
+      return SO3State{ax * s, ay * s, az * s, c};
+    };
+    auto space = std::make_shared<SO3StateSpace>();
+    const SO3State start = axis_angle(0.0, 1.0, 0.0, kPi / 2.0);
+    const SO3State target = axis_angle(0.0, 1.0, 0.0, -kPi / 2.0);
+    const double goal_radius = 10.0 * kPi / 180.0, cone = 44.9 * kPi / 180.0;
+    auto pd = std::make_shared<SO3ProblemDefinition>();
+    pd->space = space;
+    pd->start_states = {start};
+    pd->goal_is_satisfied = [=](const SO3State& s) { return space->distance(s, target) <= goal_radius; };
+    pd->sample_goal = [=](std::mt19937_64& rng) {
+      SO3StateSpace around(target, goal_radius);
+      return around.sample_uniform(rng);
+    };
+    auto vc = std::make_shared<GpuConeChecker>(
+        std::vector<std::pair<SO3State, double>>{{SO3State::identity(), cone}});
+    auto host_valid = [&](const SO3State& s) { return space->distance(SO3State::identity(), s) > cone; };
+    EXPECT(vc->is_valid(start) && vc->is_valid(target) && !vc->is_valid(SO3State::identity()));
+    const SO3State rim = axis_angle(0.0, 1.0, 0.0, 2.0 * cone);         // on the rim of the cone
+    EXPECT(vc->is_valid(rim) == host_valid(rim));
+    SO3RRT planner(0.5, 0.0);
+    planner.setup(pd, vc);
+    try {
+      const SO3Path path = planner.solve(20.0);
+      EXPECT(path.size() > 1);
+      EXPECT(space->distance(path.front(), start) < 1e-9);
+      EXPECT(pd->goal_is_satisfied(path.back()));
+      bool ok = true;  // is_path_valid, rrt_so3ss_tests.rs:106-143
+      for (std::size_t i = 0; i + 1 < path.size(); ++i) {
+        ok = ok && host_valid(path[i]) && host_valid(path[i + 1]);
+        const double dist = space->distance(path[i], path[i + 1]);
+        const std::size_t n = (std::size_t)std::ceil(dist / space->get_longest_valid_segment_length());
+        for (std::size_t j = 1; n > 1 && j <= n; ++j)
+          ok = ok && host_valid(space->interpolate(path[i], path[i + 1], (double)j / (double)n));
+      }
+      EXPECT(ok);
+      std::printf("  so3_rrt: %zu states, tree %llu\n", path.size(), (unsigned long long)planner.tree_size());
+    } catch (const std::exception& e) {
+      std::printf("  FAILED: %s\n", e.what());
+      ++g_failures;
+    }
+    SO3RRT fresh(0.5, 0.0);
+    bool threw = false;
+    try {
+      fresh.solve(1.0);
+    } catch (const PlanningError& e) {
+      threw = e.kind == PlanningError::PlannerUninitialised;
     }
     EXPECT(threw);
   }
