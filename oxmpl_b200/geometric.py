@@ -201,7 +201,14 @@ class PRM:
         self.edges = []
 
     def setup(self, validity):
-        self.vc = _checker(validity)
+        self.so3 = isinstance(self.pd.space, SO3StateSpace)
+        if self.so3:
+            if not isinstance(validity, GpuConeChecker):
+                raise TypeError("SO3 planning takes a declarative GpuConeChecker, not a Python "
+                                "callback (oxmpl_b200 has no CPU fallback)")
+            self.vc = validity
+        else:
+            self.vc = _checker(validity)
         self.store = api.StateStore(self.pd.space._space(), capacity=1024)
         self.edges = []                                       # prm.rs:224
 
@@ -213,6 +220,8 @@ class PRM:
             raise PlanningError(PlanningError.UNINITIALISED)
         if self.edges:
             return                                            # prm.rs:106-113
+        if self.so3:
+            return self._construct_so3(max_samples)
         sp, res = self.pd.space, self.pd.space.get_longest_valid_segment_length() * 0.1
         t0, drawn = time.perf_counter(), 0
         while time.perf_counter() - t0 <= self.timeout and (max_samples is None or drawn < max_samples):
@@ -231,6 +240,33 @@ class PRM:
                     self.edges[first + i].append(int(j))                    # prm.rs:135
                     self.edges[int(j)].append(first + i)                    # prm.rs:143-145
 
+    def _construct_so3(self, max_samples):
+        """prm.rs:117-146 over SO3: node i joins every earlier node j with distance(q_i, q_j) <
+        connection_radius whose check_motion(q_i, q_j) holds — batched: one radius scan and one
+        motion-check call per batch of samples (include/oxg_so3.h)."""
+        sp, res = self.pd.space, self.pd.space.get_longest_valid_segment_length() * 0.1
+        t0, drawn = time.perf_counter(), 0
+        self.rows = np.empty((0, 4))
+        while time.perf_counter() - t0 <= self.timeout and (max_samples is None or drawn < max_samples):
+            nb = min(self.batch, 2048) if max_samples is None else min(self.batch, 2048, max_samples - drawn)
+            rows = np.array([sp.sample_uniform(self.rng).values for _ in range(nb)])
+            drawn += nb
+            keep = rows[self.vc.is_valid_batch(rows).astype(bool)]          # prm.rs:123
+            if not len(keep):
+                continue
+            first = self.store.append(keep)
+            self.rows = np.vstack([self.rows, keep])
+            off, idx = self.store.so3_radius(keep, self.connection_radius)
+            src = np.repeat(np.arange(first, first + len(keep)), np.diff(off).astype(np.int64))
+            lower = idx < src                                               # only j < i (prm.rs:131)
+            src, dst = src[lower], idx[lower].astype(np.int64)
+            ok = self.vc.cones.check_motion(self.rows[src], self.rows[dst], res).astype(bool) \
+                if len(src) else np.empty(0, bool)
+            self.edges.extend([] for _ in range(len(keep)))
+            for i, j in zip(src[ok], dst[ok]):
+                self.edges[int(i)].append(int(j))                           # prm.rs:135
+                self.edges[int(j)].append(int(i))                           # prm.rs:143-145
+
     def solve(self, timeout_secs: float) -> Path:
         if self.vc is None:
             raise PlanningError(PlanningError.UNINITIALISED)
@@ -242,11 +278,20 @@ class PRM:
         sp, res = self.pd.space, self.pd.space.get_longest_valid_segment_length() * 0.1
         rows = self.store.read()
         q = np.asarray([start.values])
+        mk = (lambda r: SO3State(*r)) if self.so3 else RealVectorState
+        if self.so3:
+            off, nb = self.store.so3_radius(q, self.connection_radius)      # prm.rs:249-256
+            ok = self.vc.cones.check_motion(np.repeat(q, len(nb), axis=0), rows[nb], res) \
+                if len(nb) else np.empty(0, np.uint8)
+            return self._search(start, rows, nb, ok, mk)
         off, nb = self.store.radius(q, self.connection_radius)              # prm.rs:249-256
         ok = self.vc.world.check_motion(sp._space(), np.repeat(q, len(nb), axis=0), rows[nb], res) \
             if len(nb) else np.empty(0, np.uint8)
+        return self._search(start, rows, nb, ok, mk)
+
+    def _search(self, start, rows, nb, ok, mk) -> Path:
         start_conn = [int(j) for j, v in zip(nb, ok) if v]
-        goal = [self.pd.goal.is_satisfied(RealVectorState(r)) for r in rows]   # prm.rs:259-264
+        goal = [self.pd.goal.is_satisfied(mk(r)) for r in rows]             # prm.rs:259-264
         if not start_conn or not any(goal):
             raise PlanningError(PlanningError.NO_SOLUTION)
         parent = {j: None for j in start_conn}
@@ -256,7 +301,7 @@ class PRM:
             if goal[cur]:
                 out = []
                 while cur is not None:
-                    out.append(RealVectorState(rows[cur]))
+                    out.append(mk(rows[cur]))
                     cur = parent[cur]
                 return Path([start] + out[::-1])
             for j in self.edges[cur]:

@@ -196,3 +196,41 @@ def test_so3_rrt_tree_identical_to_oracle_loop(oxg, orc):
     np.testing.assert_array_equal(got.view(np.uint64), want.view(np.uint64))
     assert planner.parents == parents
     assert len(path.states) >= 2
+
+
+def test_prm_finds_path_in_so3ss_and_roadmap_matches_oracle(oxg, orc):
+    """oxmpl-py/tests/test_prm_so3ss.py: PRM(timeout=5, connection_radius=0.5) around the forbidden
+    cone; the roadmap (prm.rs:117-146: lower-index neighbours inside the radius whose motion is
+    valid) is also rebuilt with the oracle and compared edge list by edge list."""
+    from oxmpl_b200.geometric import PRM
+    space, start, goal, checker, pd = _so3_problem()
+    planner = PRM(timeout=5.0, connection_radius=0.5, problem_definition=pd, seed=3)
+    with pytest.raises(PlanningError):
+        planner.solve(1.0)                                    # PlannerUninitialised
+    planner.setup(checker)
+    with pytest.raises(PlanningError):
+        planner.solve(1.0)                                    # UnsampledStateSpace
+    planner.construct_roadmap(max_samples=2500)
+    path = planner.solve(timeout_secs=5.0)
+    assert len(path.states) > 1
+    assert space.distance(path.states[0], start) < 1e-9
+    assert goal.is_satisfied(path.states[-1])
+    forbidden = math.radians(44.9)
+    ident = type(start).identity()
+    for s in path.states:
+        assert space.distance(ident, s) > forbidden
+    # oracle rebuild of the same roadmap from the same valid samples
+    rows = planner.rows
+    cones = np.array([[0.0, 0.0, 0.0, 1.0, forbidden]])
+    res = space.get_longest_valid_segment_length() * 0.1
+    assert len(rows) > 800 and orc.so3_is_valid(cones, rows).all()
+    edges = [[] for _ in range(len(rows))]
+    for i in range(1, len(rows)):
+        _, nb, _ = orc.so3_radius(rows[:i], rows[i], 0.5)
+        if len(nb):
+            ok, _ = orc.so3_check_motion(cones, np.repeat(rows[i:i + 1], len(nb), axis=0), rows[nb], res)
+            for j in nb[ok.astype(bool)]:
+                edges[i].append(int(j))
+                edges[int(j)].append(i)
+    assert planner.get_roadmap() == edges
+    assert sum(len(e) for e in edges) > 2 * len(rows)
