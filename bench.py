@@ -52,9 +52,9 @@ def parse_args():
     ap.add_argument("--nodes", type=int, default=1_000_000)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--capsules", type=int, default=256)
-    ap.add_argument("--cpu-queries", type=int, default=600,
+    ap.add_argument("--cpu-queries", type=int, default=2400,
                     help="k-NN queries in the single-thread cpu_baseline sample")
-    ap.add_argument("--cpu-edges", type=int, default=20000)
+    ap.add_argument("--cpu-edges", type=int, default=24000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--star-nodes", type=int, default=60000,
                     help="tree size of the RRT* (config 3) extra; the full config is 200000")
@@ -543,16 +543,22 @@ def extras(oxg, args):
                     "query upload, result download and launch latency of the synchronous C-ABI call",
         }
     torch.cuda.empty_cache()
-    # -- fused sequential planners (BASELINE configs 2 and 3), GPU vs the CPU oracle on the same
-    #    pre-drawn stream, trees compared bit for bit ------------------------------------------
+    # -- fused sequential planners (BASELINE configs 2 and 3): GPU only here; the CPU oracle on the
+    #    same pre-drawn streams (trees compared bit for bit) is timed in the cpu_baseline leg -----
     try:
-        from tools import planner_probe
-
-        out["rrt_connect_config2"] = planner_probe.config2(30000)
-        out["rrt_star_config3"] = planner_probe.config3(args.star_nodes, 10000, 2000)
+        planner_probe = _planner_probe()
+        out["rrt_connect_config2"] = planner_probe.config2(30000, cpu=False)
+        out["rrt_star_config3"] = planner_probe.config3(args.star_nodes, 10000, 0)
     except Exception as e:  # extras never break the headline line
         out["planners_error"] = repr(e)
     return out
+
+
+def _planner_probe():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "probes"))
+    import planner_probe
+
+    return planner_probe
 
 
 def _measured_hbm():
@@ -573,7 +579,24 @@ def cpu_baseline(args, rows, caps, res):
     t = cpu_sample(orc, ow, sp_o, rows, args, res, args.cpu_queries, args.cpu_edges, 1)
     edges_per_node = 0.75 * args.k
     s_node = t["s_per_query"] + edges_per_node * t["s_per_edge"]
+    planners = None
+    if not args.no_extras:  # the sequential planners' CPU side (configs 2 and 3), same streams
+        try:
+            pp = _planner_probe()
+            c2 = pp.config2(30000, cpu=True)
+            c3 = pp.config3(2000, 10000, 2000)
+            planners = {
+                "rrt_connect_config2": {k: c2.get(k) for k in ("iters", "cpu_us_per_iter",
+                                                               "gpu_us_per_iter", "bit_identical")},
+                "rrt_star_config3_first_2000_iters": {
+                    "cpu_iters_per_s": c3.get("prefix_cpu_iters_per_s"),
+                    "gpu_iters_per_s": c3.get("prefix_gpu_iters_per_s"),
+                    "bit_identical": c3.get("prefix_bit_identical")},
+            }
+        except Exception as e:
+            planners = {"error": repr(e)}
     return {
+        "planners": planners,
         "value": 1.0 / s_node, "unit": UNIT, "cores": 1, "kind": "port",
         "host_cores_available": os.cpu_count(),
         "knn_queries_per_s": 1.0 / t["s_per_query"], "edges_checked_per_s": 1.0 / t["s_per_edge"],

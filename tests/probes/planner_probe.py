@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """GPU probe for the fused planner kernels at BASELINE configs 2 and 3 scale: iterations/s on
-the GPU for the full run, and GPU vs the CPU oracle on a bounded prefix of the same stream
-(parity-checked).  Prints JSON lines.  (Measurement aid; the oracle is only the checker / CPU
-baseline here.)"""
+the GPU for the full run, and (cpu=True / cpu_prefix > 0) GPU vs the CPU oracle on the same
+stream, parity-checked.  Prints JSON lines.  Test infrastructure: the oracle is imported only when
+the CPU leg is requested (bench.py's extras run the GPU part; its cpu_baseline leg the CPU part)."""
 import json
 import math
 import os
@@ -11,11 +11,10 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import oxmpl_b200 as oxg  # noqa: E402
-from oracle import oracle  # noqa: E402
 from oxmpl_b200 import worlds  # noqa: E402
 
 
@@ -37,7 +36,6 @@ def config3(n_nodes, n_spheres, cpu_prefix):
     free = float(oxg.World(dim, spheres=sph).is_valid(sp, samples[:20000]).mean())
     vol = (2.0 ** dim) * free
     search_radius = (30.0 * vol / n_nodes / (math.pi ** 3 / 6.0)) ** (1.0 / dim)
-    orc = oracle.get()
     out = {"config": "3: RRT* 6-D", "spheres": n_spheres, "free_fraction": free,
            "search_radius": search_radius, "max_distance": max_distance, "resolution": res}
     with oxg.World(dim, spheres=sph) as gw, oxg.StateStore(sp) as st:
@@ -54,6 +52,9 @@ def config3(n_nodes, n_spheres, cpu_prefix):
                     "motion_checks_per_s": r["motion_checks"] / (r["device_ms"] * 1e-3),
                     "ctas": r["ctas"], "phase_ms": r["phase_ms"]})
     if cpu_prefix:
+        from oracle import oracle
+
+        orc = oracle.get()
         sp_o = orc.space(dim)
         ow, keep = orc.world(dim, spheres=sph)
         t0 = time.perf_counter()
@@ -76,7 +77,7 @@ def config3(n_nodes, n_spheres, cpu_prefix):
     return out
 
 
-def config2(n_samples):
+def config2(n_samples, cpu=True):
     lo, hi = [0.0, 0.0], [100.0, 100.0]
     start, goal = [5.0, 5.0, 0.0], [95.0, 95.0, 1.0]
     boxes = worlds.aabb_world(2, lo, hi, 1000, 1.0, 3.5, keep_clear=[start[:2], goal[:2]])
@@ -85,26 +86,31 @@ def config2(n_samples):
                                rng.uniform(-math.pi, math.pi, n_samples)])
     sp = oxg.Space.compound(2, 1, 1.0, 0.5)
     res = res_of(lo, hi)
-    orc = oracle.get()
-    sp_o = orc.space(2, 1, 1.0, 0.5)
-    ow, keep = orc.world(2, aabbs=boxes)
-    t0 = time.perf_counter()
-    o = orc.rrt_connect(ow, sp_o, start, goal, goal, 1.0, 2.0, res, samples, n_samples)
-    cpu_s = time.perf_counter() - t0
     with oxg.World(2, aabbs=boxes) as gw, oxg.StateStore(sp) as ta, oxg.StateStore(sp) as tb:
         ta.append(np.array([start]))
         tb.append(np.array([goal]))
         pa, pb, r = oxg.rrt_connect_solve(gw, ta, tb, samples, 2.0, res, n_samples,
                                           goal_target=goal, goal_radius=1.0)
-        same = (np.array_equal(ta.read().view(np.uint64), o["start_tree"].view(np.uint64))
-                and np.array_equal(tb.read().view(np.uint64), o["goal_tree"].view(np.uint64))
+        tree_a, tree_b = ta.read(), tb.read()
+    out = {"config": "2: RRT-Connect R2xSO2, 1000 AABBs", "iters": r["iters"],
+           "solved": r["solved"], "nodes": r["n_nodes"], "gpu_ms": r["device_ms"],
+           "gpu_us_per_iter": r["device_ms"] * 1e3 / max(r["iters"], 1), "ctas": r["ctas"],
+           "phase_us_per_iter": [round(v * 1e3 / max(r["iters"], 1), 3) for v in r["phase_ms"]]}
+    if cpu:
+        from oracle import oracle
+
+        orc = oracle.get()
+        sp_o = orc.space(2, 1, 1.0, 0.5)
+        ow, keep = orc.world(2, aabbs=boxes)
+        t0 = time.perf_counter()
+        o = orc.rrt_connect(ow, sp_o, start, goal, goal, 1.0, 2.0, res, samples, n_samples)
+        cpu_s = time.perf_counter() - t0
+        same = (np.array_equal(tree_a.view(np.uint64), o["start_tree"].view(np.uint64))
+                and np.array_equal(tree_b.view(np.uint64), o["goal_tree"].view(np.uint64))
                 and np.array_equal(pa, o["start_parents"]) and np.array_equal(pb, o["goal_parents"]))
-    return ({"config": "2: RRT-Connect R2xSO2, 1000 AABBs", "iters": r["iters"],
-                      "solved": r["solved"], "nodes": r["n_nodes"], "gpu_ms": r["device_ms"],
-                      "gpu_us_per_iter": r["device_ms"] * 1e3 / max(r["iters"], 1),
-                      "cpu_s": cpu_s, "cpu_us_per_iter": cpu_s * 1e6 / max(o["iters"], 1),
-                      "bit_identical": bool(same), "ctas": r["ctas"],
-                      "phase_us_per_iter": [round(v * 1e3 / max(r["iters"], 1), 3) for v in r["phase_ms"]]})
+        out.update({"cpu_s": cpu_s, "cpu_us_per_iter": cpu_s * 1e6 / max(o["iters"], 1),
+                    "bit_identical": bool(same)})
+    return out
 
 
 if __name__ == "__main__":

@@ -56,10 +56,15 @@ def test_no_cpu_fallback_without_device():
 
 
 def test_product_package_never_imports_the_oracle():
-    pkg = os.path.join(ROOT, "oxmpl_b200")
-    for dirpath, _, files in os.walk(pkg):
+    """The product (package, public headers, bindings) and the GPU-only tools never touch the
+    oracle: it is test infrastructure, loaded only from tests/, smoke() and bench.py's CPU legs."""
+    files_to_scan = []
+    for sub in ("oxmpl_b200", "include", "bindings", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            files_to_scan += [(dirpath, f) for f in files]
+    for dirpath, files in [(d, [f]) for d, f in files_to_scan]:
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".rs")):
                 text = open(os.path.join(dirpath, f)).read()
                 # comments may cite the oracle's definition; code may not include, import,
                 # link, dlopen or call it
