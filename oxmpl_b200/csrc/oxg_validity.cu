@@ -152,7 +152,7 @@ struct MotionParams {
 };
 
 template <int DT, int L>
-__global__ void __launch_bounds__(128) motion_kernel(const MotionParams p) {
+__global__ void __launch_bounds__(128, 6) motion_kernel(const MotionParams p) {
   extern __shared__ __align__(16) unsigned char world_smem[];
   constexpr int XN = DT > 0 ? DT : kMaxDim;
   uint32_t sm_sph = 0, sm_cap = 0;

@@ -115,3 +115,72 @@ def test_device_pointer_pipeline_sharded_on_one_gpu(oxg, orc, n, k, shards):
         pairs = {(min(i, int(j)), max(i, int(j))) for i in range(n) for j in oi[i] if j != 0xFFFFFFFF}
         assert checked == len(pairs)
     gw.close()
+
+
+def test_config4_full_size_roadmap_properties(oxg, orc):
+    """BASELINE config 4 at FULL size (1 000 000 valid 7-D samples, k = 10, 256 capsules — the
+    bench.py workload).  The oracle cannot rebuild 1e12 pairs, so the whole table is checked through
+    size-independent properties, and a random sample of rows / edges against the oracle:
+      * every listed distance equals the reference-order f64 distance recomputed from the rows;
+      * rows are sorted by (distance, index), exclude themselves, hold k distinct neighbours;
+      * mutual consistency: if j is listed for i at distance d and (d, i) beats j's k-th entry,
+        then i is listed for j — with the same distance bits (the metric is bitwise symmetric);
+      * an undirected edge gets the same motion verdict from both of its slots;
+      * idempotence: a second build returns the same bits."""
+    n, k, d = 1_000_000, 10, 7
+    lo, hi = worlds.PANDA_LO, worlds.PANDA_HI
+    caps = worlds.capsule_world(4, lo, hi, 256)
+    sp, sp_o = oxg.Space.real_vector(d), orc.space(d)
+    res = oxg.motion_resolution(oxg.real_vector_max_extent(list(zip(lo, hi))))
+    rng = np.random.default_rng(4)
+    with oxg.World(d, capsules=caps) as gw, oxg.StateStore(sp, capacity=n) as st:
+        rows = np.empty((0, d))
+        while len(rows) < n:
+            s = lo + (hi - lo) * rng.random((n // 2, d))
+            rows = np.vstack([rows, s[gw.is_valid(sp, s).astype(bool)]])
+        rows = np.ascontiguousarray(rows[:n])
+        st.append(rows)
+        idx, dist, valid, stats = oxg.prm_build_knn(gw, st, k, res)
+        idx2, dist2, valid2, _ = oxg.prm_build_knn(gw, st, k, res)
+    assert np.array_equal(idx, idx2) and np.array_equal(dist.view(np.uint64), dist2.view(np.uint64))
+    assert np.array_equal(valid, valid2)
+    own = np.arange(n, dtype=np.uint32)[:, None]
+    assert (idx != own).all() and (idx < n).all()
+    # distances: reference order s = 0; s = s + (a_d - b_d)^2 ...; sqrt(s)   (no reassociation)
+    a = rows[np.repeat(np.arange(n), k)]
+    b = rows[idx.reshape(-1)]
+    acc = np.zeros(n * k)
+    for c in range(d):
+        df = a[:, c] - b[:, c]
+        acc = acc + df * df
+    want = np.sqrt(acc).reshape(n, k)
+    del a, b, acc
+    assert np.array_equal(dist.view(np.uint64), want.view(np.uint64))
+    # sorted by (distance, index); k distinct neighbours
+    dd, ii = np.diff(dist, axis=1), np.diff(idx.astype(np.int64), axis=1)
+    assert ((dd > 0) | ((dd == 0) & (ii > 0))).all()
+    # mutual consistency against the neighbour's own k-th entry
+    src = np.repeat(np.arange(n, dtype=np.int64), k)
+    dst = idx.reshape(-1).astype(np.int64)
+    dflat = dist.reshape(-1)
+    kth_d, kth_i = dist[dst, k - 1], idx[dst, k - 1].astype(np.int64)
+    must = (dflat < kth_d) | ((dflat == kth_d) & (src <= kth_i))
+    listed = (idx[dst] == src[:, None].astype(np.uint32))
+    assert (listed.any(axis=1) >= must).all()
+    slot = listed.argmax(axis=1)
+    both = listed.any(axis=1)
+    assert np.array_equal(dist[dst[both], slot[both]].view(np.uint64), dflat[both].view(np.uint64))
+    # the two slots of a mutual pair describe the same undirected edge: same verdict
+    vflat = valid.reshape(-1)
+    assert np.array_equal(valid[dst[both], slot[both]], vflat[both])
+    assert 0.5 < vflat.mean() < 1.0 and stats["n_edges_checked"] > 5_000_000
+    # a sample of rows and of edges against the oracle
+    pick = np.sort(np.random.default_rng(1).choice(n, size=48, replace=False)).astype(np.uint32)
+    oi, od = orc.knn(sp_o, rows, rows[pick], k, exclude=pick)
+    assert np.array_equal(idx[pick], oi)
+    assert np.array_equal(dist[pick].view(np.uint64), od.view(np.uint64))
+    ow, keep = orc.world(d, capsules=caps)
+    e = np.random.default_rng(2).choice(n * k, size=4000, replace=False)
+    i_e, j_e = src[e], dst[e]
+    ov, _ = orc.check_motion(ow, sp_o, rows[np.maximum(i_e, j_e)], rows[np.minimum(i_e, j_e)], res)
+    assert np.array_equal(vflat[e], ov)
