@@ -283,3 +283,53 @@ def test_grid_grows_with_the_tree(oxg, orc, monkeypatch):
         np.testing.assert_array_equal(_bits(tb.read()), _bits(o["goal_tree"]))
         np.testing.assert_array_equal(pa, o["start_parents"])
         np.testing.assert_array_equal(pb, o["goal_parents"])
+
+
+def test_config3_full_size_tree_properties(oxg, orc, monkeypatch):
+    """BASELINE config 3 at FULL size: RRT* in 6-D among 10 000 spheres, run to 200 000 nodes.  The
+    oracle needs minutes for that, so the full tree is checked through properties — it is a tree
+    (rewiring may point a node to a later one, so: acyclic with a single root), every node is valid, costs are finite and positive, a sample of tree edges passes the oracle's
+    check_motion in the direction the planner checked them (parent -> child) — and the first
+    3 000 iterations are compared with the oracle bit for bit."""
+    monkeypatch.delenv("OXG_PLAN_CTAS", raising=False)
+    dim, n_nodes = 6, 200_000
+    lo, hi = [-1.0] * dim, [1.0] * dim
+    start, goal = [-0.9] * dim, [0.9] * dim
+    sph = worlds.sphere_world(3, lo, hi, 10000, 0.22, 0.32, keep_clear=[start, goal])
+    sp, sp_o = oxg.Space.real_vector(dim), orc.space(dim)
+    res = _res(oxg, orc, lo, hi)
+    samples = worlds.sample_stream(33, int(n_nodes * 1.6), lo, hi, 0.0, goal)
+    search_radius, max_distance = 0.41, 0.2
+    ow, keep = orc.world(dim, spheres=sph)
+    with oxg.World(dim, spheres=sph) as gw, oxg.StateStore(sp) as st:
+        st.append(np.array([start]))
+        parents, costs, r = oxg.rrt_star_solve(gw, st, samples, max_distance, search_radius, res,
+                                               n_nodes, stop_at_goal=False)
+        tree = st.read()
+        assert r["status"] == "tree_full" and len(tree) == n_nodes
+        assert gw.is_valid(sp, tree).all()
+    assert parents[0] == -1 and (parents[1:] >= 0).all() and (parents < n_nodes).all()
+    assert (parents[1:] != np.arange(1, n_nodes)).all()
+    # acyclic: pointer-jumping reaches the root from every node within log2(n) rounds of doubling
+    hop = np.where(parents < 0, 0, parents).astype(np.int64)
+    for _ in range(18):
+        hop = hop[hop]
+    assert (hop == 0).all()
+    assert costs[0] == 0.0 and np.isfinite(costs).all() and (costs[1:] > 0.0).all()
+    # every tree edge was accepted by check_motion(parent -> child): re-check a sample on the oracle
+    pick = np.random.default_rng(5).choice(np.arange(1, n_nodes), size=3000, replace=False)
+    ov, _ = orc.check_motion(ow, sp_o, tree[parents[pick]], tree[pick], res)
+    assert ov.all()
+    # edges never exceed the steering / rewiring reach
+    seg = np.sqrt(((tree[1:] - tree[parents[1:]]) ** 2).sum(axis=1))
+    assert (seg <= max(max_distance, search_radius) * (1 + 1e-12)).all()
+    # prefix parity with the sequential reference
+    o = orc.rrt_star(ow, sp_o, start, None, -1.0, max_distance, search_radius, res, samples[:3000],
+                     3001, stop_at_goal=False)
+    with oxg.World(dim, spheres=sph) as gw, oxg.StateStore(sp) as st:
+        st.append(np.array([start]))
+        p2, c2, r2 = oxg.rrt_star_solve(gw, st, samples[:3000], max_distance, search_radius, res,
+                                        3001, stop_at_goal=False)
+        np.testing.assert_array_equal(_bits(st.read()), _bits(o["tree"]))
+        np.testing.assert_array_equal(p2, o["parents"])
+        np.testing.assert_array_equal(_bits(c2), _bits(o["costs"]))
