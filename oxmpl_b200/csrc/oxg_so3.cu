@@ -62,10 +62,12 @@ __device__ __forceinline__ void so3_stage_queries(const So3Params& p, double (*s
   }
 }
 
-// MODE_BEST : per (query, slice) the largest a, lowest index on ties.  Keys are the bit patterns
-//             of a (order-preserving for a >= 0; +inf and NaN sort above every finite value).  A
-//             NaN at index 0 wins like in the reference loop (min starts as distance(tree[0], q)
-//             and nothing is < NaN); a NaN elsewhere never wins.
+// MODE_BEST : per (query, slice) the largest a, lowest index on ties.  The hot loop compares a as
+//             doubles (a NaN never wins there); a NaN at index 0 must win like in the reference
+//             loop (min starts as distance(tree[0], q) and nothing is < NaN), so the CTA that owns
+//             state 0 re-tests it once and publishes the NaN's bit pattern as its partial key —
+//             partial keys are compared as integers (order-preserving for a >= 0; +inf and NaN
+//             sort above every finite value; "nothing found" is negative).
 // MODE_FIRST: per (query, slice) the lowest index with a >= thr[query].
 // QN = queries evaluated per state (1, 2, 4 or SO3_QC): a batch of fewer than SO3_QC queries runs
 // the narrower instantiation so a single-query scan stays HBM-bound instead of FP64-bound.
@@ -73,53 +75,81 @@ template <int MODE, int QN>
 __global__ void __launch_bounds__(SO3_THREADS) so3_scan_kernel(const So3Params p) {
   __shared__ double s_q[SO3_QC][4];
   __shared__ double s_thr[SO3_QC];
-  __shared__ long long s_k[SO3_QC][SO3_WARPS];
+  __shared__ double s_k[SO3_QC][SO3_WARPS];
   __shared__ uint32_t s_i[SO3_QC][SO3_WARPS];
+  __shared__ uint32_t s_nan0;
   const uint64_t q0 = (uint64_t)blockIdx.x * QN;
   const int qn = (int)min((uint64_t)QN, p.Q - q0);
   so3_stage_queries(p, s_q, q0, qn);
   if (MODE == MODE_FIRST && threadIdx.x < SO3_QC)
     s_thr[threadIdx.x] = (int)threadIdx.x < qn ? p.thr[q0 + threadIdx.x]
                                                : __longlong_as_double(0x7FF8000000000000ll);
+  if (threadIdx.x == 0) s_nan0 = 0u;
   __syncthreads();
 
-  long long bk[QN];
+  double bk[QN];
   uint32_t bi[QN];
 #pragma unroll
   for (int a = 0; a < QN; ++a) {
-    bk[a] = -1;
+    bk[a] = -1.0;
     bi[a] = OXG_INVALID_INDEX;
   }
   const uint32_t n0 = blockIdx.y * p.split_len;
   const uint32_t n1 = min(p.n, n0 + p.split_len);
-#pragma unroll(QN <= 2 ? 4 : 2)
-  for (uint32_t i = n0 + threadIdx.x; i < n1; i += SO3_THREADS) {
-    double s[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) s[c] = __ldg(p.col[c] + i);
+  auto eval = [&](const double* s, uint32_t i) {
 #pragma unroll
     for (int a = 0; a < QN; ++a) {
-      const double v = so3_absdot(s, s_q[a]);
+      const double sv[4] = {s[0], s[1], s[2], s[3]};
+      const double v = so3_absdot(sv, s_q[a]);
       if (MODE == MODE_BEST) {
-        long long key = __double_as_longlong(v);
-        if (v != v && i != 0) key = -1;
-        if (key > bk[a]) {
-          bk[a] = key;
+        if (v > bk[a]) {  // ascending i per thread: strict > keeps the lowest index
+          bk[a] = v;
           bi[a] = i;
         }
       } else {
         if (v >= s_thr[a] && bi[a] == OXG_INVALID_INDEX) bi[a] = i;
       }
     }
+  };
+  // U states per trip, all of their loads issued before the first use (memory-level parallelism
+  // is what a single-query scan lives on)
+  constexpr int U = QN <= 2 ? 4 : 2;
+  uint32_t i = n0 + threadIdx.x;
+  for (; i + (U - 1) * SO3_THREADS < n1; i += U * SO3_THREADS) {
+    double s[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[u][c] = __ldg(p.col[c] + i + u * SO3_THREADS);
+#pragma unroll
+    for (int u = 0; u < U; ++u) eval(s[u], i + u * SO3_THREADS);
+  }
+  for (; i < n1; i += SO3_THREADS) {
+    double s[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s[c] = __ldg(p.col[c] + i);
+    eval(s, i);
+  }
+  if (MODE == MODE_BEST && n0 == 0 && threadIdx.x == 0) {
+    double s[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s[c] = __ldg(p.col[c]);
+    uint32_t m = 0;
+#pragma unroll
+    for (int a = 0; a < QN; ++a) {
+      const double v = so3_absdot(s, s_q[a]);
+      if (v != v) m |= 1u << a;
+    }
+    s_nan0 = m;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int a = 0; a < QN; ++a) {
-    long long k = bk[a];
+    double k = bk[a];
     uint32_t ix = bi[a];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-      const long long ok = __shfl_xor_sync(0xFFFFFFFFu, k, off);
+      const double ok = __shfl_xor_sync(0xFFFFFFFFu, k, off);
       const uint32_t oi = __shfl_xor_sync(0xFFFFFFFFu, ix, off);
       const bool take = MODE == MODE_BEST ? (ok > k || (ok == k && oi < ix)) : (oi < ix);
       if (take) {
@@ -135,10 +165,10 @@ __global__ void __launch_bounds__(SO3_THREADS) so3_scan_kernel(const So3Params p
   __syncthreads();
   if ((int)threadIdx.x < qn) {
     const int a = threadIdx.x;
-    long long k = s_k[a][0];
+    double k = s_k[a][0];
     uint32_t ix = s_i[a][0];
     for (int wv = 1; wv < SO3_WARPS; ++wv) {
-      const long long ok = s_k[a][wv];
+      const double ok = s_k[a][wv];
       const uint32_t oi = s_i[a][wv];
       const bool take = MODE == MODE_BEST ? (ok > k || (ok == k && oi < ix)) : (oi < ix);
       if (take) {
@@ -147,7 +177,14 @@ __global__ void __launch_bounds__(SO3_THREADS) so3_scan_kernel(const So3Params p
       }
     }
     const size_t o = (size_t)(q0 + a) * p.nsplit + blockIdx.y;
-    if (MODE == MODE_BEST) p.part_key[o] = k;
+    if (MODE == MODE_BEST) {
+      long long key = __double_as_longlong(k);  // -1.0 ("nothing") is negative as an integer
+      if (s_nan0 >> a & 1u) {                   // state 0 is NaN for this query: it wins
+        key = 0x7FF8000000000000ll;
+        ix = 0;
+      }
+      p.part_key[o] = key;
+    }
     p.part_idx[o] = ix;
   }
 }
