@@ -1055,12 +1055,36 @@ __global__ void __launch_bounds__(1024) knn_select_kernel(const uint32_t* __rest
   }
 }
 
+// The reference's 1-NN loop starts from min = distance(tree[0], q) and replaces it only when
+// d < min (rrt.rs:187-196).  If that first distance is NaN nothing ever replaces it and the
+// answer is (0, NaN), whatever the other states are; the scan kernels treat NaN as "never a
+// winner" for every index, so this fix-up restores the reference's answer for index 0.
+__global__ void nn1_first_nan_kernel(StateView db, StateView q, uint64_t Q, uint32_t n_real,
+                                     uint32_t n_so2, double w_real, double w_so2,
+                                     uint32_t* __restrict__ idx, double* __restrict__ dist) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Q) return;
+  double a[kMaxDim], b[kMaxDim];
+  const uint32_t dim = n_real + n_so2;
+  for (uint32_t d = 0; d < dim; ++d) {
+    a[d] = db.p[d * db.stride_d];
+    b[d] = q.p[i * q.stride_i + d * q.stride_d];
+  }
+  const double d0 = space_distance_dev(n_real, n_so2, w_real, w_so2, a, b);
+  if (d0 != d0) {
+    idx[i] = 0;
+    dist[i] = d0;
+  }
+}
+
 // Final reduction of the stream kernel's per-CTA winners: one CTA per query, (dist, idx) order.
 __global__ void __launch_bounds__(256) nn1_final_kernel(const uint32_t* __restrict__ part_idx,
                                                         const double* __restrict__ part_dist,
                                                         uint32_t Q, uint32_t nparts,
                                                         uint32_t* __restrict__ out_idx,
-                                                        double* __restrict__ out_dist) {
+                                                        double* __restrict__ out_dist,
+                                                        StateView db, StateView q, uint32_t dim,
+                                                        int nan_first) {
   __shared__ double s_d[8];
   __shared__ uint32_t s_i[8];
   const uint32_t qi = blockIdx.x;
@@ -1093,6 +1117,20 @@ __global__ void __launch_bounds__(256) nn1_final_kernel(const uint32_t* __restri
         bd = s_d[wv];
         bx = s_i[wv];
       }
+    if (nan_first) {
+      // rrt.rs:187-196 starts from min = distance(tree[0], q): a NaN there is never replaced
+      // (same rule as nn1_first_nan_kernel, fused here for the few-query path; RealVector only)
+      double acc = 0.0;
+      for (uint32_t d = 0; d < dim; ++d) {
+        const double df = __dsub_rn(db.p[d * db.stride_d], q.p[qi * q.stride_i + d * q.stride_d]);
+        const double m = __dmul_rn(df, df);
+        acc = d == 0 ? m : __dadd_rn(acc, m);
+      }
+      if (acc != acc) {
+        bx = 0;
+        bd = acc;
+      }
+    }
     out_idx[qi] = bx;
     out_dist[qi] = bd;
   }
@@ -1981,7 +2019,8 @@ static int nn_knn_device_impl(oxg_store_s* s, StateView q, uint64_t Q, uint32_t 
         OXG_DISPATCH_D(s->dim, r = (launch_nn1_stream<DD>(pc, blocks, s->stream)));
         OXG_TRY(r);
         nn1_final_kernel<<<qn, 256, 0, s->stream>>>(pc.out_idx, pc.out_dist, qn, blocks,
-                                                   d_idx + c0, d_dist + c0);
+                                                   d_idx + c0, d_dist + c0, store_view(s), pc.q, s->dim,
+                                                   stored_first && exclude_mode == EXCL_NONE);
       } else {
         OXG_DISPATCH_D(s->dim, r = (launch_knn_stream<DD>(pc, smem, s->stream)));
         OXG_TRY(r);
@@ -2102,6 +2141,12 @@ static int nn_knn_device_impl(oxg_store_s* s, StateView q, uint64_t Q, uint32_t 
                                       (int)smem));
     knn_merge_kernel<<<(unsigned)((Q + threads - 1) / threads), threads, smem, s->stream>>>(
         part_idx, part_dist, (uint32_t)Q, k, p.nsplit, d_idx, d_dist);
+    OXG_LAUNCH_CHECK();
+  }
+  if (k == 1 && stored_first && exclude_mode == EXCL_NONE) {
+    nn1_first_nan_kernel<<<(unsigned)((Q + 127) / 128), 128, 0, s->stream>>>(
+        store_view(s), q, Q, s->space.n_real, s->space.n_so2, s->space.w_real, s->space.w_so2, d_idx,
+        d_dist);
     OXG_LAUNCH_CHECK();
   }
   return OXG_OK;
@@ -2278,28 +2323,6 @@ int nn_radius_offsets(oxg_store_s* s, uint64_t Q, uint64_t* d_out) {
 
 using namespace oxg;
 
-// The reference's 1-NN loop starts from min = distance(tree[0], q) and replaces it only when
-// d < min (rrt.rs:187-196).  If that first distance is NaN nothing ever replaces it and the
-// answer is (0, NaN), whatever the other states are; the scan kernels treat NaN as "never a
-// winner" for every index, so this fix-up restores the reference's answer for index 0.
-__global__ void nn1_first_nan_kernel(StateView db, StateView q, uint64_t Q, uint32_t n_real,
-                                     uint32_t n_so2, double w_real, double w_so2,
-                                     uint32_t* __restrict__ idx, double* __restrict__ dist) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Q) return;
-  double a[kMaxDim], b[kMaxDim];
-  const uint32_t dim = n_real + n_so2;
-  for (uint32_t d = 0; d < dim; ++d) {
-    a[d] = db.p[d * db.stride_d];
-    b[d] = q.p[i * q.stride_i + d * q.stride_d];
-  }
-  const double d0 = space_distance_dev(n_real, n_so2, w_real, w_so2, a, b);
-  if (d0 != d0) {
-    idx[i] = 0;
-    dist[i] = d0;
-  }
-}
-
 extern "C" {
 
 static int upload_queries(oxg_store s, const double* queries, uint64_t Q) {
@@ -2340,12 +2363,6 @@ static int knn_host(oxg_store s, const double* queries, uint64_t Q, uint32_t k,
   OXG_CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
   OXG_TRY(nn_knn_device(s, rows_view(s->buf[B_QUERY].as<double>(), s->dim), Q, k,
                         exclude_idx ? EXCL_ARRAY : EXCL_NONE, d_excl, 0, stored_first, d_idx, d_dist));
-  if (k == 1 && stored_first) {
-    nn1_first_nan_kernel<<<(unsigned)((Q + 127) / 128), 128, 0, s->stream>>>(
-        store_view(s), rows_view(s->buf[B_QUERY].as<double>(), s->dim), Q, s->space.n_real,
-        s->space.n_so2, s->space.w_real, s->space.w_so2, d_idx, d_dist);
-    OXG_LAUNCH_CHECK();
-  }
   OXG_CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
   OXG_CUDA_TRY(cudaMemcpyAsync(idx, d_idx, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
   OXG_CUDA_TRY(cudaMemcpyAsync(dist, d_dist, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
