@@ -63,6 +63,53 @@ class _TreePlanner:
         return out[::-1]
 
 
+class _So3Tree:
+    """A tree of SO3 states: device store (for the scans) + host copies (for steering / paths)."""
+
+    def __init__(self, space, root: SO3State):
+        self.store = api.StateStore(space._space(), capacity=1024)
+        self.store.append(np.asarray([root.values]))
+        self.nodes, self.parents, self.costs = [root], [-1], [0.0]
+
+    def nearest(self, q: SO3State):
+        idx, dist = self.store.so3_nn1(np.asarray([q.values]))
+        return int(idx[0]), float(dist[0])
+
+    def push(self, q: SO3State, parent: int, cost: float = 0.0) -> int:
+        self.store.append(np.asarray([q.values]))
+        self.nodes.append(q)
+        self.parents.append(parent)
+        self.costs.append(cost)
+        return len(self.nodes) - 1
+
+    def path_to(self, node: int):
+        out = []
+        while node >= 0:
+            out.append(self.nodes[node])
+            node = self.parents[node]
+        return out[::-1]
+
+
+def _so3_checker(validity) -> GpuConeChecker:
+    if not isinstance(validity, GpuConeChecker):
+        raise TypeError("SO3 planning takes a declarative GpuConeChecker, not a Python "
+                        "callback (oxmpl_b200 has no CPU fallback)")
+    return validity
+
+
+def _so3_steer(space, q_near: SO3State, q_rand: SO3State, min_dist: float, max_distance: float):
+    """rrt.rs:200-208 — returns (q_new, reached)."""
+    if min_dist > max_distance:
+        return space.interpolate(q_near, q_rand, max_distance / min_dist), False
+    return q_rand, True
+
+
+def _so3_motion(vc: GpuConeChecker, frm, to, res) -> np.ndarray:
+    a = np.asarray([s.values for s in frm]).reshape(-1, 4)
+    b = np.asarray([s.values for s in to]).reshape(-1, 4)
+    return vc.cones.check_motion(a, b, res).astype(bool) if len(a) else np.empty(0, bool)
+
+
 class RRT(_TreePlanner):
     """oxmpl_py.geometric.RRT (oxmpl-py/src/geometric/rrt.rs) over oxg_rrt_solve.  Over an
     :class:`SO3StateSpace` it runs the reference loop unfused: ``oxg_so3_nn1`` -> steer on the
@@ -128,15 +175,61 @@ class RRT(_TreePlanner):
 
 
 class RRTStar(_TreePlanner):
-    """oxmpl_py.geometric.RRTStar(max_distance, goal_bias, search_radius, problem_definition)."""
+    """oxmpl_py.geometric.RRTStar(max_distance, goal_bias, search_radius, problem_definition).
+    Over an :class:`SO3StateSpace` the reference loop (rrt_star.rs:182-289) runs unfused on
+    ``oxg_so3_nn1`` / ``oxg_so3_radius`` / ``oxg_so3_check_motion``: the choose-parent and rewire
+    candidates are motion-checked in one batch each and the strict-`<` selection is replayed in
+    neighbour order on the host."""
 
     def __init__(self, max_distance, goal_bias, search_radius, problem_definition, seed: int = 0):
         super().__init__(max_distance, goal_bias, problem_definition, seed)
         self.search_radius = float(search_radius)
 
+    def setup(self, validity):
+        if not isinstance(self.pd.space, SO3StateSpace):
+            return super().setup(validity)
+        self.vc = _so3_checker(validity)
+        self.t = _So3Tree(self.pd.space, self.pd.start_state)
+
+    def _solve_so3(self, timeout_secs: float) -> Path:
+        pd, space, t, res = self.pd, self.pd.space, self.t, self._resolution()
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 <= timeout_secs:
+            q_rand = pd.goal.sample_goal() if self.rng.random() < self.goal_bias \
+                else space.sample_uniform(self.rng)
+            near, min_dist = t.nearest(q_rand)
+            q_new, _ = _so3_steer(space, t.nodes[near], q_rand, min_dist, self.max_distance)
+            if not _so3_motion(self.vc, [t.nodes[near]], [q_new], res)[0]:
+                continue
+            q = np.asarray([q_new.values])
+            _, nbrs, nd = t.store.so3_radius(q, self.search_radius, want_dist=True)  # find_neighbours
+            nbrs = [int(j) for j in nbrs]
+            # choose parent (rrt_star.rs:233-249); cost(new, nbr) = nbr.cost + distance(new, nbr)
+            best = near
+            min_cost = t.costs[near] + space.distance(q_new, t.nodes[near])
+            via = [t.costs[j] + float(d) for j, d in zip(nbrs, nd)]
+            cand = [u for u, c in enumerate(via) if c < min_cost]
+            ok = _so3_motion(self.vc, [t.nodes[nbrs[u]] for u in cand], [q_new] * len(cand), res)
+            for u, good in zip(cand, ok):
+                if via[u] < min_cost and good:
+                    min_cost, best = via[u], nbrs[u]
+            new = t.push(q_new, best, min_cost)
+            # rewire (rrt_star.rs:261-282); cost(nbr, new) = new.cost + distance(nbr, new)
+            thru = [min_cost + float(d) for d in nd]
+            cand = [u for u, j in enumerate(nbrs) if j != best and thru[u] < t.costs[j]]
+            ok = _so3_motion(self.vc, [q_new] * len(cand), [t.nodes[nbrs[u]] for u in cand], res)
+            for u, good in zip(cand, ok):
+                if good:
+                    t.parents[nbrs[u]], t.costs[nbrs[u]] = new, thru[u]
+            if pd.goal.is_satisfied(q_new):
+                return Path(t.path_to(new))
+        raise PlanningError(PlanningError.TIMEOUT)
+
     def solve(self, timeout_secs: float) -> Path:
         if self.vc is None:
             raise PlanningError(PlanningError.UNINITIALISED)
+        if isinstance(self.pd.space, SO3StateSpace):
+            return self._solve_so3(timeout_secs)
         t0 = time.perf_counter()
         while True:
             left = timeout_secs - (time.perf_counter() - t0)
@@ -154,9 +247,43 @@ class RRTStar(_TreePlanner):
 
 
 class RRTConnect(_TreePlanner):
-    """oxmpl_py.geometric.RRTConnect over oxg_rrt_connect_solve."""
+    """oxmpl_py.geometric.RRTConnect over oxg_rrt_connect_solve; over an :class:`SO3StateSpace` the
+    reference loop (rrt_connect.rs:121-159,241-308) runs unfused on the SO3 entry points."""
+
+    def _extend_so3(self, t: "_So3Tree", target: SO3State):
+        """RRTConnect::extend — (reached, new index) or None when the motion is invalid."""
+        near, min_dist = t.nearest(target)
+        q_new, reached = _so3_steer(self.pd.space, t.nodes[near], target, min_dist, self.max_distance)
+        if not _so3_motion(self.vc, [t.nodes[near]], [q_new], self._resolution())[0]:
+            return None
+        return reached, t.push(q_new, near)
+
+    def _solve_so3(self, timeout_secs: float) -> Path:
+        pd, space = self.pd, self.pd.space
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 <= timeout_secs:
+            grow_start = len(self.ta.nodes) <= len(self.tb.nodes)          # rrt_connect.rs:249-254
+            a, b = (self.ta, self.tb) if grow_start else (self.tb, self.ta)
+            q_rand = pd.goal.sample_goal() if self.rng.random() < self.goal_bias \
+                else space.sample_uniform(self.rng)
+            ext = self._extend_so3(a, q_rand)
+            if ext is None:
+                continue
+            q_new = a.nodes[ext[1]]
+            if grow_start and pd.goal.is_satisfied(q_new):
+                return Path(self.ta.path_to(ext[1]))
+            con = self._extend_so3(b, q_new)
+            if con is not None and con[0]:
+                s_idx, g_idx = (ext[1], con[1]) if grow_start else (con[1], ext[1])
+                return Path(self.ta.path_to(s_idx) + self.tb.path_to(g_idx)[::-1][1:])
+        raise PlanningError(PlanningError.TIMEOUT)
 
     def setup(self, validity):
+        if isinstance(self.pd.space, SO3StateSpace):
+            self.vc = _so3_checker(validity)
+            self.ta = _So3Tree(self.pd.space, self.pd.start_state)
+            self.tb = _So3Tree(self.pd.space, self.pd.goal.sample_goal())   # rrt_connect.rs:207-214
+            return
         super().setup(validity)
         self.goal_tree = api.StateStore(self.pd.space._space(), capacity=1024)
         self.goal_tree.append(np.asarray([self.pd.goal.sample_goal().values]))  # rrt_connect.rs:207-214
@@ -164,6 +291,8 @@ class RRTConnect(_TreePlanner):
     def solve(self, timeout_secs: float) -> Path:
         if self.vc is None:
             raise PlanningError(PlanningError.UNINITIALISED)
+        if isinstance(self.pd.space, SO3StateSpace):
+            return self._solve_so3(timeout_secs)
         t0 = time.perf_counter()
         while True:
             left = timeout_secs - (time.perf_counter() - t0)

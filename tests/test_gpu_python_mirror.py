@@ -114,9 +114,16 @@ def _quat_axis_angle(axis, angle):
 
 
 class _QuaternionGoalRegion:
-    def __init__(self, space, target, radius):
+    """oxmpl-py/tests/test_rrt_so3ss.py:14-33.  `valid_only` additionally rejects samples inside the
+    forbidden cone: the upstream goal region (10 deg around a rotation 45 deg from the identity)
+    lies mostly inside the 44.9 deg cone, so most draws are invalid states — harmless as RRT targets,
+    but RRTConnect::setup roots its goal tree at one draw (rrt_connect.rs:207-214) and an invalid
+    root can never be extended."""
+
+    def __init__(self, space, target, radius, valid_only=False):
         self.space, self.target, self.radius = space, target, radius
         self.rng = random.Random(123)
+        self.valid_only = valid_only
 
     def is_satisfied(self, state):
         return self.space.distance(self.target, state) <= self.radius
@@ -129,16 +136,18 @@ class _QuaternionGoalRegion:
             if 1e-9 < norm_sq < 1.0:
                 norm = math.sqrt(norm_sq)
                 q = SO3State(x / norm, y / norm, z / norm, w / norm)
-                if self.is_satisfied(q):
+                if self.is_satisfied(q) and not (
+                        self.valid_only
+                        and self.space.distance(SO3State.identity(), q) <= math.radians(44.9)):
                     return q
 
 
-def _so3_problem():
+def _so3_problem(valid_goal=False):
     from oxmpl_b200.base import GpuConeChecker, ProblemDefinition, SO3State, SO3StateSpace
     space = SO3StateSpace()
     start = _quat_axis_angle((0.0, 1.0, 0.0), math.pi / 2.0)
     goal = _QuaternionGoalRegion(space, _quat_axis_angle((0.0, 1.0, 0.0), -math.pi / 2.0),
-                                 math.radians(10.0))
+                                 math.radians(10.0), valid_only=valid_goal)
     checker = GpuConeChecker([(SO3State.identity(), math.radians(44.9))])
     return space, start, goal, checker, ProblemDefinition.from_so3(space, start, goal)
 
@@ -234,3 +243,119 @@ def test_prm_finds_path_in_so3ss_and_roadmap_matches_oracle(oxg, orc):
                 edges[int(j)].append(i)
     assert planner.get_roadmap() == edges
     assert sum(len(e) for e in edges) > 2 * len(rows)
+
+
+def _check_so3_path(space, start, goal, path):
+    forbidden = math.radians(44.9)
+    ident = type(start).identity()
+    assert len(path.states) > 1
+    assert space.distance(path.states[0], start) < 1e-9
+    assert goal.is_satisfied(path.states[-1])
+    for a, b in zip(path.states[:-1], path.states[1:]):
+        assert space.distance(ident, a) > forbidden and space.distance(ident, b) > forbidden
+        n = math.ceil(space.distance(a, b) / space.get_longest_valid_segment_length())
+        for j in range(1, n + 1 if n > 1 else 0):
+            assert space.distance(ident, space.interpolate(a, b, j / n)) > forbidden
+
+
+@pytest.mark.parametrize("max_distance", [1.0, 0.05])
+def test_rrt_connect_so3ss_and_trees_match_oracle_loop(oxg, orc, max_distance):
+    """oxmpl-py/tests/test_rrt_connect_so3ss.py (RRTConnect(1.0, 0.05); 0.05 grows longer trees) +
+    both trees rebuilt by the same loop on the oracle (rrt_connect.rs:121-159,241-308)."""
+    from oxmpl_b200.geometric import RRTConnect
+    space, start, goal, checker, pd = _so3_problem(valid_goal=True)
+    planner = RRTConnect(max_distance=max_distance, goal_bias=0.05, problem_definition=pd, seed=11)
+    planner.setup(checker)
+    path = planner.solve(timeout_secs=20.0)
+    _check_so3_path(space, start, goal, path)
+    # oracle replay: same draws (planner seed 11; the goal's own generator, first used at setup)
+    space2, start2, goal2, _, _ = _so3_problem(valid_goal=True)
+    rng = random.Random(11)
+    cones = np.array([[0.0, 0.0, 0.0, 1.0, math.radians(44.9)]])
+    res = space2.get_longest_valid_segment_length() * 0.1
+    trees = [[np.asarray(start2.values)], [np.asarray(goal2.sample_goal().values)]]
+    parents = [[-1], [-1]]
+
+    def extend(t, target):
+        idx, dist = orc.so3_nn1(np.asarray(trees[t]), target)
+        near, d = int(idx[0]), float(dist[0])
+        reached = not d > max_distance
+        q_new = target if reached else orc.so3_interpolate(trees[t][near], target, max_distance / d)
+        if not orc.so3_check_motion(cones, trees[t][near], q_new, res)[0][0]:
+            return None
+        trees[t].append(q_new)
+        parents[t].append(near)
+        return reached, len(trees[t]) - 1
+
+    for _ in range(100000):
+        a = 0 if len(trees[0]) <= len(trees[1]) else 1
+        q = goal2.sample_goal() if rng.random() < 0.05 else space2.sample_uniform(rng)
+        ext = extend(a, np.asarray(q.values))
+        if ext is None:
+            continue
+        q_new = trees[a][ext[1]]
+        if a == 0 and orc.so3_distance(goal2.target.values, q_new) <= goal2.radius:
+            break
+        con = extend(a ^ 1, q_new)
+        if con is not None and con[0]:
+            break
+    for t, tree in ((0, planner.ta), (1, planner.tb)):
+        got = np.asarray([n.values for n in tree.nodes])
+        want = np.asarray(trees[t])
+        assert got.shape == want.shape
+        np.testing.assert_array_equal(got.view(np.uint64), want.view(np.uint64))
+        assert tree.parents == parents[t]
+
+
+def test_rrt_star_so3ss_and_tree_matches_oracle_loop(oxg, orc):
+    """oxmpl-py/tests/test_rrt_star_so3ss.py (RRTStar(0.5, 0.05, 0.25)) + tree, parents and costs
+    rebuilt by the sequential reference loop on the oracle (rrt_star.rs:182-289)."""
+    from oxmpl_b200.geometric import RRTStar
+    space, start, goal, checker, pd = _so3_problem()
+    planner = RRTStar(max_distance=0.5, goal_bias=0.05, search_radius=0.25, problem_definition=pd,
+                      seed=5)
+    planner.setup(checker)
+    path = planner.solve(timeout_secs=30.0)
+    _check_so3_path(space, start, goal, path)
+    space2, start2, goal2, _, _ = _so3_problem()
+    rng = random.Random(5)
+    cones = np.array([[0.0, 0.0, 0.0, 1.0, math.radians(44.9)]])
+    res = space2.get_longest_valid_segment_length() * 0.1
+    rows, parents, costs = [np.asarray(start2.values)], [-1], [0.0]
+
+    def motion(a, b):
+        return bool(orc.so3_check_motion(cones, a, b, res)[0][0])
+
+    for _ in range(100000):
+        q = goal2.sample_goal() if rng.random() < 0.05 else space2.sample_uniform(rng)
+        q = np.asarray(q.values)
+        idx, dist = orc.so3_nn1(np.asarray(rows), q)
+        near, d = int(idx[0]), float(dist[0])
+        q_new = orc.so3_interpolate(rows[near], q, 0.5 / d) if d > 0.5 else q
+        if not motion(rows[near], q_new):
+            continue
+        _, nbrs, _ = orc.so3_radius(np.asarray(rows), q_new, 0.25)
+        best, min_cost = near, costs[near] + orc.so3_distance(q_new, rows[near])
+        for j in nbrs:                                        # sequential, lazy: the reference loop
+            c = costs[j] + orc.so3_distance(q_new, rows[j])
+            if c < min_cost and motion(rows[j], q_new):
+                min_cost, best = c, int(j)
+        rows.append(q_new)
+        parents.append(best)
+        costs.append(min_cost)
+        new = len(rows) - 1
+        for j in nbrs:
+            if parents[new] == j:
+                continue
+            c = costs[new] + orc.so3_distance(rows[j], q_new)
+            if c < costs[j] and motion(q_new, rows[j]):
+                parents[j], costs[j] = new, c
+        if orc.so3_distance(goal2.target.values, q_new) <= goal2.radius:
+            break
+    got = np.asarray([n.values for n in planner.t.nodes])
+    want = np.asarray(rows)
+    assert got.shape == want.shape
+    np.testing.assert_array_equal(got.view(np.uint64), want.view(np.uint64))
+    assert planner.t.parents == parents
+    np.testing.assert_array_equal(np.asarray(planner.t.costs).view(np.uint64),
+                                  np.asarray(costs).view(np.uint64))
