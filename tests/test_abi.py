@@ -53,6 +53,9 @@ def test_no_cpu_fallback_without_device():
     assert e.value.code == -4  # OXG_E_CUDA
     with pytest.raises(oxg.OxgError):
         oxg.World(2, spheres=np.array([[0.0, 0.0, 1.0]]))
+    with pytest.raises(oxg.OxgError) as e:
+        oxg.So3Cones(np.array([[0.0, 0.0, 0.0, 1.0, 0.5]]))
+    assert e.value.code == -4
 
 
 def test_product_package_never_imports_the_oracle():
