@@ -1939,6 +1939,30 @@ static void choose_split(uint32_t n_db, uint64_t qtiles, uint32_t tile, uint32_t
   *nsplit = std::max<uint32_t>(1, (n_db + len - 1) / len);
 }
 
+// A second stream per device for work that may overlap a store's own stream (lowest priority,
+// so the store's kernels get the SMs first).
+struct AuxStream {
+  cudaStream_t st = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static AuxStream* aux_stream_for(int device) {
+  static AuxStream table[64];
+  if (device < 0 || device >= 64) return nullptr;
+  AuxStream* a = &table[device];
+  if (!a->st) {
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) lo = 0;
+    if (cudaStreamCreateWithPriority(&a->st, cudaStreamNonBlocking, lo) != cudaSuccess ||
+        cudaEventCreateWithFlags(&a->fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&a->join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      a->st = nullptr;
+      return nullptr;
+    }
+  }
+  return a;
+}
+
 // k-NN of Q device-resident queries against the store; results in device memory.
 static int nn_knn_device_impl(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclude_mode,
                               const uint32_t* d_exclude, uint64_t self_base, bool stored_first,
@@ -2055,16 +2079,33 @@ static int nn_knn_device_impl(oxg_store_s* s, StateView q, uint64_t Q, uint32_t 
   if (f32 && qpt == 2 && force_nsplit == 0 && force_qpt == 0 && forced_qpt() == 0) {
     const uint64_t slots = 148ull * 3;
     const uint64_t whole = qtiles / slots, tail = qtiles % slots;
-    if (whole == 1 && tail > 0 && tail * 3 < slots && p.n_db >= 65536) {
+    // The tail runs on a second, lower-priority stream next to the whole waves: the block
+    // scheduler drains the main kernel's CTAs first and fills the slots its last wave frees with
+    // the tail's short CTAs, so neither part ends on an idle machine (main writes the outputs
+    // directly, the tail goes through the partial-list scratch: no shared buffer).
+    if (whole >= 1 && tail > 0 && tail * 2 <= slots && p.n_db >= 65536) {
       const uint64_t q_main = whole * slots * nq_per_cta;
       uint32_t ns = (uint32_t)std::min<uint64_t>(slots / tail, 16);
+      AuxStream* ax = env_int("OXG_KNN_TAIL_CONCURRENT", 1) != 0 ? aux_stream_for(s->device) : nullptr;
+      if (ax) {
+        OXG_CUDA_TRY(cudaEventRecord(ax->fork, s->stream));
+        OXG_CUDA_TRY(cudaStreamWaitEvent(ax->st, ax->fork, 0));
+      }
       OXG_TRY(nn_knn_device_impl(s, q, q_main, k, exclude_mode, d_exclude, self_base, stored_first,
                                  d_idx, d_dist, 2, 1));
       StateView qt = q;
       qt.p = q.p + q_main * q.stride_i;
-      return nn_knn_device_impl(s, qt, Q - q_main, k, exclude_mode,
-                                d_exclude ? d_exclude + q_main : nullptr, self_base + q_main,
-                                stored_first, d_idx + q_main * k, d_dist + q_main * k, 2, ns);
+      cudaStream_t own = s->stream;
+      if (ax) s->stream = ax->st;
+      const int rc = nn_knn_device_impl(s, qt, Q - q_main, k, exclude_mode,
+                                        d_exclude ? d_exclude + q_main : nullptr, self_base + q_main,
+                                        stored_first, d_idx + q_main * k, d_dist + q_main * k, 2, ns);
+      s->stream = own;
+      if (ax) {
+        OXG_CUDA_TRY(cudaEventRecord(ax->join, ax->st));
+        OXG_CUDA_TRY(cudaStreamWaitEvent(s->stream, ax->join, 0));
+      }
+      return rc;
     }
   }
   if (force_nsplit > 0) {

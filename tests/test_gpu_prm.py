@@ -184,3 +184,34 @@ def test_config4_full_size_roadmap_properties(oxg, orc):
     i_e, j_e = src[e], dst[e]
     ov, _ = orc.check_motion(ow, sp_o, rows[np.maximum(i_e, j_e)], rows[np.minimum(i_e, j_e)], res)
     assert np.array_equal(vflat[e], ov)
+
+
+@pytest.mark.parametrize("concurrent", ["1", "0"])
+def test_row_shards_of_the_full_build_equal_the_full_table(oxg, orc, concurrent, monkeypatch):
+    """The multi-GPU build gives each rank a contiguous block of query rows of the 1M-node store
+    (500 000 / 250 000 / 125 000 rows at 2 / 4 / 8 ranks).  Such a block is a few whole waves of CTAs
+    plus a tail; the tail runs with the store cut into slices, concurrently with the whole waves on a
+    second stream.  Every shard must reproduce the rows of the one-piece build bit for bit."""
+    monkeypatch.setenv("OXG_KNN_TAIL_CONCURRENT", concurrent)
+    n, k, d = 1_000_000, 10, 7
+    lo, hi = worlds.PANDA_LO, worlds.PANDA_HI
+    caps = worlds.capsule_world(4, lo, hi, 256)
+    sp = oxg.Space.real_vector(d)
+    res = oxg.motion_resolution(oxg.real_vector_max_extent(list(zip(lo, hi))))
+    rows = lo + (hi - lo) * np.random.default_rng(14).random((n, d))
+    with oxg.World(d, capsules=caps) as gw, oxg.StateStore(sp, capacity=n) as st:
+        st.append(rows)
+        idx, dist, valid, _ = oxg.prm_build_knn(gw, st, k, res)
+        for ranks in (2, 4, 8):
+            for r in ((0, ranks - 1) if ranks > 2 else (0, 1)):
+                rb, re = r * n // ranks, (r + 1) * n // ranks
+                for rep in range(2):
+                    i2, d2, v2, _ = oxg.prm_build_knn(gw, st, k, res, rb, re)
+                    assert np.array_equal(i2, idx[rb:re]), (ranks, r, rep)
+                    assert np.array_equal(d2.view(np.uint64), dist[rb:re].view(np.uint64))
+                    assert np.array_equal(v2, valid[rb:re])
+        # odd shard sizes around the wave boundaries (444 CTAs x 256 queries = 113 664 rows)
+        for rows_q in (113_664, 113_665, 113_664 + 256 * 221, 113_664 + 256 * 222 + 1, 227_328 + 17):
+            i2, d2, v2, _ = oxg.prm_build_knn(gw, st, k, res, 1000, 1000 + rows_q)
+            assert np.array_equal(i2, idx[1000:1000 + rows_q]), rows_q
+            assert np.array_equal(d2.view(np.uint64), dist[1000:1000 + rows_q].view(np.uint64))
