@@ -83,3 +83,48 @@ def test_host_resolution_helpers_match_config1():
     assert ext == 28.284271247461902
     assert oxg.motion_resolution(ext) == 0.14142135623730953
     assert oxg.real_vector_max_extent([(0.0, float("inf"))]) == 1.0
+
+
+def test_public_headers_are_plain_c():
+    """include/*.h is the drop-in boundary: it must be consumable by a C compiler (cgo / bindgen /
+    cffi read it as C), with no C++ or torch types in any signature."""
+    import subprocess
+
+    inc = os.path.join(ROOT, "include")
+    for header in ("oxg.h", "oxg_so3.h"):
+        r = subprocess.run(["gcc", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror",
+                            "-fsyntax-only", "-I", inc, os.path.join(inc, header)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        text = re.sub(r"/\*.*?\*/", "", open(os.path.join(inc, header)).read(), flags=re.S)
+        assert "torch" not in text and "std::" not in text and "at::" not in text
+
+
+def test_python_so3_mirror_matches_the_oracle(orc):
+    """oxmpl_b200.base.SO3StateSpace (host arithmetic of the Python mirror) against the oracle."""
+    from oxmpl_b200.base import SO3State, SO3StateSpace
+
+    rng = np.random.default_rng(17)
+    q = rng.normal(size=(300, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    q[200:] = q[100:200] + rng.normal(size=(100, 4)) * 0.01       # near pairs: the LERP branch
+    q[200:] /= np.linalg.norm(q[200:], axis=1, keepdims=True)
+    space = SO3StateSpace()
+    assert space.get_maximum_extent() == 0.5 * np.pi
+    assert space.get_longest_valid_segment_length() * 0.1 == 0.5 * np.pi * 0.05 * 0.1
+    for i in range(100):
+        for a, b in ((q[i], q[100 + i]), (q[100 + i], q[200 + i]), (q[i], -q[i])):
+            sa, sb = SO3State(*a), SO3State(*b)
+            d = space.distance(sa, sb)
+            assert np.float64(d).view(np.uint64) == np.float64(orc.so3_distance(a, b)).view(np.uint64)
+            for t in (0.0, 0.3, 1.0):
+                got = np.asarray(space.interpolate(sa, sb, t).values)
+                np.testing.assert_array_equal(got.view(np.uint64),
+                                              orc.so3_interpolate(a, b, t).view(np.uint64))
+    import random
+    s = space.sample_uniform(random.Random(0))
+    assert abs(sum(v * v for v in s.values) - 1.0) < 1e-12
+    bounded = SO3StateSpace((SO3State.identity(), 0.2))
+    assert all(bounded.satisfies_bounds(bounded.sample_uniform(random.Random(k))) for k in range(20))
+    with pytest.raises(ValueError):
+        SO3StateSpace((SO3State.identity(), -0.1))
