@@ -107,6 +107,24 @@ extern "C" {
                               goal_target: *const f64, samples: *const f64, n_samples: u64,
                               parents: *mut i64, costs: *mut f64, out: *mut oxg_plan_result) -> c_int;
 
+    // housekeeping, device-pointer pipeline of the multi-GPU PRM shard, measurement helpers
+    pub fn oxg_version() -> c_int;
+    pub fn oxg_store_reserve(s: oxg_store, capacity: u64) -> c_int;
+    pub fn oxg_store_sync(s: oxg_store) -> c_int;
+    pub fn oxg_store_stream(s: oxg_store, out_stream: *mut *mut c_void) -> c_int;
+    pub fn oxg_store_last_scan_ms(s: oxg_store, out_ms: *mut f64) -> c_int;
+    pub fn oxg_world_sync(w: oxg_world) -> c_int;
+    pub fn oxg_knn_rows_dev(s: oxg_store, row_begin: u64, row_end: u64, k: u32, d_idx: *mut u32,
+                            d_dist: *mut f64) -> c_int;
+    pub fn oxg_prm_edges_dev(w: oxg_world, s: oxg_store, d_idx_all: *const u32, k: u32,
+                             resolution: f64, row_begin: u64, row_end: u64, d_valid_all: *mut u8,
+                             d_counters: *mut u64) -> c_int;
+    pub fn oxg_prm_resolve_dev(s: oxg_store, d_idx_all: *const u32, k: u32,
+                               d_valid_all: *mut u8) -> c_int;
+    pub fn oxg_fp64_peak(out_ops_per_s: *mut f64, out_ms: *mut f64) -> c_int;
+    pub fn oxg_fp32_peak(out_ops_per_s: *mut f64, out_ms: *mut f64) -> c_int;
+    pub fn oxg_kernel_launches(reset: c_int) -> u64;
+
     // include/oxg_so3.h — SO(3) scans, cone validity, check_motion
     pub fn oxg_so3_nn1(s: oxg_store, queries: *const f64, q: u64, idx: *mut u32, dist: *mut f64) -> c_int;
     pub fn oxg_so3_radius(s: oxg_store, queries: *const f64, q: u64, r: f64, offsets: *mut u64,

@@ -128,3 +128,11 @@ def test_python_so3_mirror_matches_the_oracle(orc):
     assert all(bounded.satisfies_bounds(bounded.sample_uniform(random.Random(k))) for k in range(20))
     with pytest.raises(ValueError):
         SO3StateSpace((SO3State.identity(), -0.1))
+
+
+def test_rust_ffi_block_declares_every_header_symbol():
+    """bindings/oxmpl-cuda/src/ffi.rs (the reference-side binding; not compiled in this image) must
+    stay one-to-one with include/*.h."""
+    rs = open(os.path.join(ROOT, "bindings", "oxmpl-cuda", "src", "ffi.rs")).read()
+    declared = set(re.findall(r"pub fn (oxg_[a-z0-9_]+)\s*\(", rs))
+    assert sorted(declared) == _declared_symbols()
