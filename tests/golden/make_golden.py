@@ -98,5 +98,40 @@ def main():
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 
+def main_so3():
+    """SO(3): 1-NN / radius over unit quaternions, cone validity, check_motion (so3.npz).  acos / sin
+    come from this machine's libm (glibc), the one Rust's f64 methods call on linux-gnu."""
+    orc = oracle.get()
+    rng = np.random.default_rng(77)
+
+    def unit(n):
+        q = rng.normal(size=(n, 4))
+        return q / np.linalg.norm(q, axis=1, keepdims=True)
+
+    rows, queries = unit(900), unit(30)
+    rows[400] = rows[3]                                   # duplicate: lowest index wins
+    rows[401] = -rows[5]                                  # antipodal: the same rotation
+    queries[:4] = rows[[3, 5, 400, 17]]
+    i1, d1 = orc.so3_nn1(rows, queries)
+    off, ir, dr = orc.so3_radius(rows, queries, 0.4)
+    cones = np.hstack([unit(6), rng.uniform(0.1, 0.4, size=(6, 1))])
+    states = unit(500)
+    ok = orc.so3_is_valid(cones, states)
+    frm, to = unit(120), unit(120)
+    to[:40] = frm[:40] + rng.normal(size=(40, 4)) * 0.01
+    to[:40] /= np.linalg.norm(to[:40], axis=1, keepdims=True)
+    res = 0.5 * math.pi * 0.05 * 0.1
+    mv, mf = orc.so3_check_motion(cones, frm, to, res)
+    np.savez_compressed(os.path.join(HERE, "so3.npz"), rows=rows, queries=queries, nn1_idx=i1,
+                        nn1_dist=d1, rad_off=off, rad_idx=ir, rad_dist=dr, radius=0.4, cones=cones,
+                        states=states, valid=ok, frm=frm, to=to, resolution=res, motion_valid=mv,
+                        motion_first=mf)
+    print("so3.npz", os.path.getsize(os.path.join(HERE, "so3.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "so3":
+        main_so3()
+    else:
+        main()
+        main_so3()

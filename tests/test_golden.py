@@ -119,3 +119,47 @@ def test_gpu_matches_golden_validity_and_planners(oxg):
         np.testing.assert_array_equal(parents, p["star_parents"])
         np.testing.assert_array_equal(_bits(costs), _bits(p["star_costs"]))
         assert r["motion_checks"] == int(p["star_motion_checks"])
+
+
+# ------------------------------------------------------------------------------ SO(3)
+def _check_so3_against_golden(nn1, radius, is_valid, check_motion):
+    """Shared by the CPU (oracle) and GPU (liboxg) tests: callables with the oracle's shapes."""
+    g = _load("so3.npz")
+    idx, dist = nn1(g["rows"], g["queries"])
+    np.testing.assert_array_equal(idx, g["nn1_idx"])
+    np.testing.assert_array_equal(_bits(dist), _bits(g["nn1_dist"]))
+    off, ridx, rdist = radius(g["rows"], g["queries"], float(g["radius"]))
+    np.testing.assert_array_equal(off, g["rad_off"])
+    np.testing.assert_array_equal(ridx, g["rad_idx"])
+    np.testing.assert_array_equal(_bits(rdist), _bits(g["rad_dist"]))
+    np.testing.assert_array_equal(is_valid(g["cones"], g["states"]), g["valid"])
+    mv, mf = check_motion(g["cones"], g["frm"], g["to"], float(g["resolution"]))
+    np.testing.assert_array_equal(mv, g["motion_valid"])
+    np.testing.assert_array_equal(mf, g["motion_first"])
+    assert 0 < int(g["valid"].sum()) < len(g["valid"]) and 0 < int(g["motion_valid"].sum()) < 120
+    assert g["nn1_idx"][0] == 3 and g["nn1_idx"][2] == 3 and g["nn1_dist"][1] == 0.0
+
+
+def test_oracle_matches_golden_so3(orc):
+    _check_so3_against_golden(orc.so3_nn1, orc.so3_radius, orc.so3_is_valid, orc.so3_check_motion)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_golden_so3(oxg):
+    def nn1(rows, queries):
+        with oxg.StateStore(oxg.Space.real_vector(4)) as st:
+            st.append(rows)
+            return st.so3_nn1(queries)
+
+    def radius(rows, queries, r):
+        with oxg.StateStore(oxg.Space.real_vector(4)) as st:
+            st.append(rows)
+            return st.so3_radius(queries, r, want_dist=True)
+
+    def is_valid(cones, states):
+        return oxg.So3Cones(cones).is_valid(states)
+
+    def check_motion(cones, frm, to, res):
+        return oxg.So3Cones(cones).check_motion(frm, to, res, want_first_invalid=True)
+
+    _check_so3_against_golden(nn1, radius, is_valid, check_motion)
