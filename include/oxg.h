@@ -302,6 +302,11 @@ int oxg_fp64_peak(double* out_ops_per_s, double* out_ms);
  * the mix's flop rate is 1.5x this figure). */
 int oxg_fp32_peak(double* out_ops_per_s, double* out_ms);
 uint64_t oxg_kernel_launches(int reset);
+/* A/B switches for measurements; every setting runs hand-written sm_100a kernels and gives
+ * bit-identical results.  "knn_tree": 1 = always answer oxg_knn / oxg_prm_build_knn through the
+ * store's bounding-box hierarchy when the space allows it, 0 = always scan every pair,
+ * -1 = choose by batch and store size (default). */
+int oxg_tuning_set(const char* key, int64_t value);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,7 @@ from .api import (  # noqa: F401
     rrt_connect_solve,
     rrt_solve,
     rrt_star_solve,
+    tuning_set,
 )
 from ._lib import OxgError, PlanParams, PlanResult, PrmStats, SpaceDesc  # noqa: F401
 

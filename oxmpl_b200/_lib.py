@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboxg.so")
+LIB_PATH = os.environ.get("OXG_LIB_PATH") or os.path.join(_HERE, "liboxg.so")  # override: A/B builds
 
 OXG_OK = 0
 OXG_E_NULL = -1
@@ -156,6 +156,7 @@ SIGNATURES = {
     "oxg_fp64_peak": (C.c_int, [C.POINTER(_dbl), C.POINTER(_dbl)]),
     "oxg_fp32_peak": (C.c_int, [C.POINTER(_dbl), C.POINTER(_dbl)]),
     "oxg_kernel_launches": (_u64, [C.c_int]),
+    "oxg_tuning_set": (C.c_int, [C.c_char_p, C.c_int64]),
     # include/oxg_so3.h
     "oxg_so3_nn1": (C.c_int, [_vp, _pd, _u64, _pu32, _pd]),
     "oxg_so3_radius": (C.c_int, [_vp, _pd, _u64, _dbl, _pu64, _pu32, _u64, _pd]),

@@ -107,6 +107,12 @@ def kernel_launches(reset: bool = False) -> int:
     return int(lib.oxg_kernel_launches(1 if reset else 0))
 
 
+def tuning_set(key: str, value: int) -> None:
+    """A/B switch for measurements (``oxg_tuning_set``): e.g. ``tuning_set("knn_tree", 1)`` forces
+    the bounding-box hierarchy for every eligible k-NN, 0 the all-pairs scan, -1 automatic."""
+    check(lib.oxg_tuning_set(key.encode(), int(value)))
+
+
 class StateStore:
     """GPU-resident SoA f64 state store (replaces ``Vec<Node<S>>``)."""
 

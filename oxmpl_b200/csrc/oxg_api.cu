@@ -10,6 +10,7 @@ namespace oxg {
 
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_tune_knn_tree{-1};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -245,6 +246,19 @@ uint64_t oxg_kernel_launches(int reset) {
   return g_launches.load();
 }
 
+int oxg_tuning_set(const char* key, int64_t value) {
+  if (!key) {
+    set_error("key is NULL");
+    return OXG_E_NULL;
+  }
+  if (strcmp(key, "knn_tree") == 0) {
+    g_tune_knn_tree.store(value < 0 ? -1 : (value ? 1 : 0));
+    return OXG_OK;
+  }
+  set_error("unknown tuning key '%s'", key);
+  return OXG_E_ARG;
+}
+
 // ------------------------------------------------------------------ store
 int oxg_store_create(const oxg_space_desc* space, uint64_t capacity, oxg_store* out) {
   OXG_API_BEGIN
@@ -297,6 +311,7 @@ int oxg_store_destroy(oxg_store s) {
   if (s->d_data32) cudaFree(s->d_data32);
   if (s->d_maxabs) cudaFree(s->d_maxabs);
   for (auto& b : s->buf) b.release();
+  tree_release(s);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->ev2) cudaEventDestroy(s->ev2);
@@ -312,6 +327,7 @@ int oxg_store_clear(oxg_store s) {
   }
   s->size = 0;
   s->n_planned = 0;
+  s->epoch += 1;
   OXG_CUDA_TRY(cudaMemsetAsync(s->d_maxabs, 0, 2 * sizeof(unsigned long long), s->stream));
   return OXG_OK;
 }
@@ -357,6 +373,7 @@ int oxg_store_append(oxg_store s, const double* rows, uint64_t n, uint64_t* firs
   // the caller may reuse `rows` immediately
   OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
   s->size += n;
+  s->epoch += 1;
   return OXG_OK;
   OXG_API_END
 }

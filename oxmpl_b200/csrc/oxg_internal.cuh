@@ -167,6 +167,8 @@ struct oxg_store_s {
   uint64_t n_planned = 0;    // nodes whose B_PARENT / B_COST entries are valid
   oxg::DevBuf buf[oxg::B_COUNT];  // named scratch arenas, see enum StoreBuf
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  uint64_t epoch = 0;        // bumped whenever the contents change (append, clear, planner growth)
+  void* tree = nullptr;      // oxg::StoreTree, the bounding-box hierarchy of oxg_tree.cu (lazy)
 };
 
 struct oxg_world_s {
@@ -289,5 +291,16 @@ int nn_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double r, const ui
 int nn_radius_nsplit(const oxg_store_s* s, uint64_t Q);
 int store_refresh_mirror(oxg_store_s* s, uint64_t first, uint64_t n);
 int nn_radius_offsets(oxg_store_s* s, uint64_t Q, uint64_t* d_out);
+
+// oxg_tree.cu: exact k-NN through the store's bounding-box hierarchy
+void tree_release(oxg_store_s* s);
+bool tree_supported(const oxg_store_s* s, uint32_t k);
+bool tree_is_current(const oxg_store_s* s);
+int tree_build(oxg_store_s* s);
+int tree_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclude_mode,
+                    const uint32_t* d_exclude, uint64_t self_base, uint32_t* d_idx, double* d_dist,
+                    unsigned long long* d_stats);
+// runtime tuning switches (oxg_tuning_set): -1 = automatic
+extern std::atomic<int> g_tune_knn_tree;
 
 }  // namespace oxg

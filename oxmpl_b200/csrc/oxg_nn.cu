@@ -2006,6 +2006,26 @@ static int nn_knn_device_impl(oxg_store_s* s, StateView q, uint64_t Q, uint32_t 
   p.db32 = s->d_data32;
   p.maxabs = s->d_maxabs;
   const bool fast = is_pure_rv(s->space) && s->dim <= (uint32_t)kMaxFastDim;
+  // Exact spatial pruning (oxg_tree.cu): low-dimensional RealVector stores with enough pairs to
+  // pay for the hierarchy (or a hierarchy that is still current).  OXG_KNN_TREE=0/1 and
+  // oxg_tuning_set("knn_tree", 0/1) force the choice for A/B runs; results are bit-identical.
+  if (fast && force_qpt == 0 && force_nsplit == 0 && tree_supported(s, k)) {
+    int mode = g_tune_knn_tree.load();
+    if (mode < 0) mode = env_int("OXG_KNN_TREE", -1);
+    bool use = mode > 0;
+    if (mode < 0)
+      use = p.n_db >= 16384 && (tree_is_current(s) ? Q >= 64 : (double)Q * (double)p.n_db >= 4.0e9);
+    if (use) {
+      OXG_TRY(tree_knn_device(s, q, Q, k, exclude_mode, d_exclude, self_base, d_idx, d_dist, nullptr));
+      if (k == 1 && stored_first && exclude_mode == EXCL_NONE) {
+        nn1_first_nan_kernel<<<(unsigned)((Q + 127) / 128), 128, 0, s->stream>>>(
+            store_view(s), q, Q, s->space.n_real, s->space.n_so2, s->space.w_real, s->space.w_so2, d_idx,
+            d_dist);
+        OXG_LAUNCH_CHECK();
+      }
+      return OXG_OK;
+    }
+  }
   // Few to moderately many queries (the planners' per-iteration calls, small sweeps): the
   // state-per-thread streaming kernels, RS_MAXQ queries per launch.  Beyond a few dozen queries
   // the query-per-thread kernels below win.

@@ -1148,11 +1148,13 @@ int plan_stage(oxg_world w, oxg_store t0, oxg_store t1, const oxg_plan_params* p
   const uint64_t old0 = t0->size;
   t0->size = h.n[0];
   t0->n_planned = h.n[0];
+  t0->epoch += 1;
   OXG_TRY(store_refresh_mirror(t0, old0, h.n[0] - old0));
   if (MODE == MODE_CONNECT) {
     const uint64_t old1 = t1->size;
     t1->size = h.n[1];
     t1->n_planned = h.n[1];
+    t1->epoch += 1;
     // t1's columns were written on t0's stream; its own stream sees them after the sync above
     OXG_TRY(store_refresh_mirror(t1, old1, h.n[1] - old1));
     OXG_CUDA_TRY(cudaStreamSynchronize(t1->stream));

@@ -1,0 +1,858 @@
+// oxg_tree.cu — exact k-NN over the store through a 32-ary bounding-box hierarchy.
+//
+// The batched scans of oxg_nn.cu evaluate every (query, stored state) pair: N pairs per query
+// for lists whose members sit in a tiny ball around the query.  For the low-dimensional stores
+// the planners build (PRM roadmaps, rrt_star.rs:121-131 / prm.rs:131-138 neighbourhoods) almost
+// all of those pairs can be discarded without being evaluated, and the discard can be made
+// EXACT: a group of stored states is skipped only when a certified lower bound of every
+// reference-order distance in it exceeds the query's current k-th distance.  The answer is the
+// same list — the k smallest by (reference distance value, index), bit for bit — because the
+// list is ordered by (distance, index) and not by visiting order.
+//
+// Structure (rebuilt when the store changes; ~1 ms for 1e6 states):
+//   * states sorted by a 32-bit space-filling key: the bits of the quantised coordinates
+//     interleaved in the order a k-d tree would split (always the dimension whose cell is
+//     currently widest), computed on the device from the store's bounding box;
+//   * leaves of 32 consecutive sorted states, stored leaf-major SoA ([leaf][d][32] f64) so a warp
+//     reads a leaf with D coalesced 256-byte loads;
+//   * levels of 32-ary nodes above them, every node the exact (min, max) box of its children,
+//     stored [group][2D][32] so a warp tests the 32 children of a node with 2D coalesced loads.
+//
+// Query (one warp per query, queries themselves processed in key order so neighbouring warps
+// touch the same leaves and hit L1): depth-first, nearest child first.  Lane c evaluates the
+// box of child c; __ballot / __reduce_min pick the next child; at a leaf lane c evaluates
+// stored state c in the reference's operation order (real_vector_state_space.rs:148-153) and
+// the survivors of the admission test  d2 <= U  are merged into the warp's sorted list — one
+// (distance, index) entry per lane, insertion by ballot + shuffle, lowest index first on ties.
+//
+// Certified bound.  For a box B and query q let t_d = max(lo_d - q_d, q_d - hi_d, 0).  Every
+// state p in B has real squared distance >= sum t_d^2.  The f64 evaluation lb of that sum and
+// the reference-order evaluation d2 of the true sum each carry at most D+2 roundings of relative
+// size 2^-53, so  d2 >= lb (1 - 1e-13)  whenever lb is not in the underflow range; a node is
+// skipped only if  lb (1 - 1e-13) > U  where U >= max{x : sqrt(x) <= s_kth}.  NaN coordinates
+// never enter a box (fmin/fmax drop them) and never enter a list (d2 != d2), as in the scans.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "oxg_internal.cuh"
+#include "oxg_math.cuh"
+
+namespace oxg {
+
+constexpr int TREE_LEVELS = 5;       // 32^6 = 2^30 states at most (tree_supported checks)
+constexpr int TREE_KEY_BITS = 32;
+constexpr int TREE_MAX_DIM = 8;      // dimensions the tree kernels are instantiated for
+#ifndef OXG_TK_THREADS
+#define OXG_TK_THREADS 256
+#endif
+#ifndef OXG_TK_MIN_CTAS
+#define OXG_TK_MIN_CTAS 3
+#endif
+#ifndef OXG_TK_QPC
+#define OXG_TK_QPC 128
+#endif
+#ifndef OXG_TK_PERSISTENT
+#define OXG_TK_PERSISTENT 0
+#endif
+#ifndef OXG_TK_TWO_LEAVES
+#define OXG_TK_TWO_LEAVES 1
+#endif
+#ifndef OXG_TK_QBOX_SMEM
+#define OXG_TK_QBOX_SMEM 1
+#endif
+#ifndef OXG_TK_MERGE_INLINE
+#define OXG_TK_MERGE_INLINE 1
+#endif
+#ifndef OXG_TK_MERGE_AT
+#define OXG_TK_MERGE_AT 12
+#endif
+constexpr int TK_THREADS = OXG_TK_THREADS;  // query kernel: warps per CTA x 32
+constexpr int TK_QPC = OXG_TK_QPC;          // consecutive (key-ordered) queries per chunk
+
+struct TreePlan {  // device-resident quantisation plan, written by tree_plan_kernel
+  double lo[kMaxFastDim];
+  double scale[kMaxFastDim];  // cells per unit length
+  uint32_t bits[kMaxFastDim];
+  uint32_t seq[TREE_KEY_BITS];  // dimension that owns key bit b (most significant first)
+  uint32_t nbits;               // key bits in use
+  // "box space" of the certified f32 box tests: x' = (x - c_d) * sc with sc a power of two that
+  // brings the largest half-extent into [0.5, 1) (clamped to 2^+-100), so the tests are
+  // translation- and scale-invariant
+  double c[kMaxFastDim];
+  double sc, sc2;
+};
+
+struct TreeView {
+  const double* pts;     // [n_leaves][D][32]
+  const uint32_t* perm;  // [n_leaves*32] sorted position -> store index (pads: OXG_INVALID_INDEX)
+  const double* boxes[TREE_LEVELS];  // level l nodes in groups of 32: [groups][2D][32]
+  const float* boxes32[TREE_LEVELS]; // the same boxes in the plan's box space, rounded outward
+  uint32_t count[TREE_LEVELS];       // nodes per level (level 0 = leaves)
+  int top;                           // highest level; count[top] <= 32
+};
+
+struct StoreTree {
+  uint64_t epoch = ~0ull;
+  uint64_t size = 0;
+  DevBuf pts, perm, keys, keys2, vals, vals2, plan, bounds, qorder, tmp;
+  DevBuf boxes[TREE_LEVELS];
+  DevBuf boxes32[TREE_LEVELS];
+  TreeView view;
+};
+
+// ---- order-preserving u64 encoding of doubles (for atomicMin / atomicMax) ----------------
+__device__ __forceinline__ unsigned long long ord_encode(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ord_decode(unsigned long long e) {
+  unsigned long long b = (e & 0x8000000000000000ull) ? (e & 0x7FFFFFFFFFFFFFFFull) : ~e;
+  return __longlong_as_double((long long)b);
+}
+
+__global__ void tree_bounds_init_kernel(unsigned long long* bounds) {
+  const int t = threadIdx.x;
+  if (t < kMaxFastDim) {
+    bounds[t] = ~0ull;             // min slot
+    bounds[kMaxFastDim + t] = 0;   // max slot
+  }
+}
+
+// Per-dimension min / max over the finite coordinates of the store.
+__global__ void tree_bounds_kernel(const double* __restrict__ db, uint64_t pitch, uint32_t n, int dim,
+                                   unsigned long long* __restrict__ bounds) {
+  for (int d = 0; d < dim; ++d) {
+    double lo = __longlong_as_double(0x7FF0000000000000ll), hi = -lo;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const double v = db[(uint64_t)d * pitch + i];
+      if (fabs(v) < 1.0e300) {  // finite and not absurd; NaN fails
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+      atomicMin(&bounds[d], ord_encode(lo));
+      atomicMax(&bounds[kMaxFastDim + d], ord_encode(hi));
+    }
+  }
+}
+
+// Allots the key bits: bit after bit goes to the dimension whose cell is currently the widest
+// (what a k-d tree splitting the widest side at its midpoint would do on uniform data).
+__global__ void tree_plan_kernel(const unsigned long long* __restrict__ bounds, int dim, TreePlan* plan) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double cell[kMaxFastDim];
+  bool any = false;
+  for (int d = 0; d < dim; ++d) {
+    const double lo = ord_decode(bounds[d]), hi = ord_decode(bounds[kMaxFastDim + d]);
+    double ext = (lo <= hi) ? hi - lo : 0.0;
+    if (!(ext > 0.0) || !(ext < 1.0e300)) ext = 0.0;
+    plan->lo[d] = (lo <= hi) ? lo : 0.0;
+    plan->bits[d] = 0;
+    cell[d] = ext;
+    any = any || ext > 0.0;
+  }
+  uint32_t nb = 0;
+  if (any) {
+    for (int b = 0; b < TREE_KEY_BITS; ++b) {
+      int best = 0;
+      for (int d = 1; d < dim; ++d)
+        if (cell[d] > cell[best]) best = d;
+      plan->seq[b] = (uint32_t)best;
+      plan->bits[best] += 1;
+      cell[best] *= 0.5;
+      ++nb;
+    }
+  }
+  plan->nbits = nb;
+  {
+    double half = 0.0;
+    for (int d = 0; d < dim; ++d) {
+      const double lo = ord_decode(bounds[d]), hi = ord_decode(bounds[kMaxFastDim + d]);
+      const bool ok = lo <= hi;
+      plan->c[d] = ok ? 0.5 * lo + 0.5 * hi : 0.0;
+      if (ok) half = fmax(half, fmax(hi - plan->c[d], plan->c[d] - lo));
+    }
+    int e = 0;
+    if (half > 0.0 && half < 1.0e300) {
+      int ex = 0;
+      frexp(half, &ex);  // half = m 2^ex, m in [0.5, 1)
+      e = -ex;
+    }
+    e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    plan->sc = ldexp(1.0, e);
+    plan->sc2 = ldexp(1.0, 2 * e);
+  }
+  for (int d = 0; d < dim; ++d) {
+    const double lo = ord_decode(bounds[d]), hi = ord_decode(bounds[kMaxFastDim + d]);
+    const double ext = (lo <= hi) ? hi - lo : 0.0;
+    double sc = (plan->bits[d] > 0 && ext > 0.0) ? (double)(1ull << plan->bits[d]) / ext : 0.0;
+    if (!(sc < 1.0e300)) sc = 0.0;
+    plan->scale[d] = sc;
+  }
+}
+
+// Key of every state of `v` under the plan; vals[i] = i.
+__global__ void tree_keys_kernel(StateView v, uint32_t n, int dim, const TreePlan* __restrict__ plan,
+                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  __shared__ TreePlan sp;
+  for (int t = threadIdx.x; t < (int)(sizeof(TreePlan) / 4); t += blockDim.x)
+    reinterpret_cast<uint32_t*>(&sp)[t] = reinterpret_cast<const uint32_t*>(plan)[t];
+  __syncthreads();
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t cell[kMaxFastDim];
+    uint32_t rem[kMaxFastDim];
+    bool bad = false;
+    for (int d = 0; d < dim; ++d) {
+      const double x = v.p[(uint64_t)i * v.stride_i + (uint64_t)d * v.stride_d];
+      const uint32_t nb = sp.bits[d];
+      const double top = (double)((1ull << nb) - 1ull);
+      double c = floor((x - sp.lo[d]) * sp.scale[d]);
+      if (!(c == c)) {
+        bad = bad || !(x == x);  // NaN coordinates sort to the end
+        c = 0.0;
+      }
+      c = fmin(fmax(c, 0.0), top);
+      cell[d] = (uint32_t)c;
+      rem[d] = nb;
+    }
+    uint32_t key = 0;
+    for (uint32_t b = 0; b < sp.nbits; ++b) {
+      const uint32_t d = sp.seq[b];
+      rem[d] -= 1;
+      key = (key << 1) | ((cell[d] >> rem[d]) & 1u);
+    }
+    keys[i] = bad ? 0xFFFFFFFFu : key;
+    vals[i] = i;
+  }
+}
+
+// One warp per leaf slot: gathers the leaf's states into the leaf-major layout and writes the
+// leaf's box.  Slots past the last leaf (padding of the last group) get empty boxes.
+template <int D>
+__global__ void tree_leaves_kernel(const double* __restrict__ db, uint64_t pitch, uint32_t n,
+                                   const uint32_t* __restrict__ sorted, uint32_t n_leaves,
+                                   uint32_t n_slots, double* __restrict__ pts,
+                                   uint32_t* __restrict__ perm, double* __restrict__ boxes0) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (leaf >= n_slots) return;
+  const double inf = __longlong_as_double(0x7FF0000000000000ll);
+  double lo[D], hi[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    lo[d] = inf;
+    hi[d] = -inf;
+  }
+  if (leaf < n_leaves) {
+    const uint32_t pos = leaf * 32u + lane;
+    const uint32_t j = pos < n ? sorted[pos] : OXG_INVALID_INDEX;
+    perm[pos] = j;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double x = (j != OXG_INVALID_INDEX) ? db[(uint64_t)d * pitch + j]
+                                                : __longlong_as_double(0x7FF8000000000000ll);
+      pts[((uint64_t)leaf * D + d) * 32 + lane] = x;
+      lo[d] = fmin(lo[d], x);  // fmin / fmax drop NaN
+      hi[d] = fmax(hi[d], x);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fmin(lo[d], __shfl_xor_sync(0xFFFFFFFFu, lo[d], o));
+      hi[d] = fmax(hi[d], __shfl_xor_sync(0xFFFFFFFFu, hi[d], o));
+    }
+  if (lane == 0) {
+    double* g = boxes0 + (uint64_t)(leaf >> 5) * (2 * D * 32) + (leaf & 31u);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      g[d * 32] = lo[d];
+      g[(D + d) * 32] = hi[d];
+    }
+  }
+}
+
+// One warp per node slot of level l+1: the union of its 32 children (a group of level l).
+template <int D>
+__global__ void tree_level_kernel(const double* __restrict__ child_boxes, uint32_t n_children,
+                                  uint32_t n_nodes, uint32_t n_slots, double* __restrict__ boxes) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (node >= n_slots) return;
+  const double inf = __longlong_as_double(0x7FF0000000000000ll);
+  double lo[D], hi[D];
+  const bool have = node < n_nodes && node * 32u + lane < n_children;
+  const double* c = child_boxes + (uint64_t)node * (2 * D * 32) + lane;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    lo[d] = have ? c[d * 32] : inf;
+    hi[d] = have ? c[(D + d) * 32] : -inf;
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fmin(lo[d], __shfl_xor_sync(0xFFFFFFFFu, lo[d], o));
+      hi[d] = fmax(hi[d], __shfl_xor_sync(0xFFFFFFFFu, hi[d], o));
+    }
+  if (lane == 0) {
+    double* g = boxes + (uint64_t)(node >> 5) * (2 * D * 32) + (node & 31u);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      g[d * 32] = lo[d];
+      g[(D + d) * 32] = hi[d];
+    }
+  }
+}
+
+// f64 boxes of one level -> box space, rounded outward (directed rounding at every step, so
+// lo32 <= (lo - c) sc and hi32 >= (hi - c) sc hold exactly).
+__global__ void tree_boxes32_kernel(const double* __restrict__ boxes, uint64_t n_vals, int dim,
+                                    const TreePlan* __restrict__ plan, float* __restrict__ out) {
+  const double sc = plan->sc;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vals;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const int row = (int)((i >> 5) % (uint64_t)(2 * dim));
+    const double v = boxes[i];
+    if (row < dim)
+      out[i] = __double2float_rd(__dmul_rd(__dsub_rd(v, plan->c[row]), sc));
+    else
+      out[i] = __double2float_ru(__dmul_ru(__dsub_ru(v, plan->c[row - dim]), sc));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// query kernel
+// ---------------------------------------------------------------------------------------
+struct TreeKnnParams {
+  TreeView t;
+  const TreePlan* plan;
+  StateView q;
+  uint32_t Q;
+  const uint32_t* qorder;  // [Q] query ids in key order
+  uint32_t k;
+  int exclude_mode;
+  const uint32_t* exclude;
+  uint32_t self_base;
+  uint32_t* out_idx;   // [Q][k]
+  double* out_dist;
+  unsigned long long* stats;  // nullable: [0] leaves visited, [1] box groups tested, [2] candidates, [3] merges
+};
+
+constexpr int TK_MERGE_AT = OXG_TK_MERGE_AT;  // buffered candidates that trigger a merge into the list
+
+template <int D>
+struct WarpQuery {
+  double q[D];
+#if OXG_TK_QBOX_SMEM
+  const float* qbox;     // shared: the query in the box space, [0..D) rounded down, [D..2D) rounded up
+#else
+  float qbox[2 * D];     // the query in the box space, [0..D) rounded down, [D..2D) rounded up
+#endif
+  double my_s;           // this lane's list entry (lane e holds the e-th smallest)
+  uint32_t my_i;
+  int have;
+  int k;
+  unsigned long long ub;  // bits of U (admission: bits(d2) <= ub, unsigned: every NaN pattern is above)
+  float Uf;               // U in the box space, rounded up (pruning: lb32 > Uf)
+  int bc;                 // buffered candidates
+  double* b_d2;           // this warp's candidate buffer (shared memory)
+  uint32_t* b_j;
+  uint32_t excl;
+  int lane;
+  unsigned n_leaf, n_box, n_cand, n_merge;
+};
+
+// Upper bound of max{x : sqrt(x) <= sw}: any upper bound is correct here because admitted
+// candidates still go through the exact (sqrt, index) ordering of the merge.
+__device__ __forceinline__ double tree_sqrt_le_upper(double sw) {
+  const double u = __dmul_ru(sw, sw);
+  if (!(u > 1.0e-290)) return sqrt_le_threshold_dev(sw);
+  return __dadd_ru(u, __dmul_ru(u, 8.8817841970012523e-16));  // 2^-50
+}
+
+template <int D>
+__device__ __forceinline__ void set_bound(const TreeKnnParams& p, WarpQuery<D>& w, double sk) {
+  const double U = tree_sqrt_le_upper(sk);
+  w.ub = (unsigned long long)__double_as_longlong(U);
+  // box space: squared lengths scale by sc2 (a power of two); 1e-12 covers the roundings of the
+  // reference-order evaluation (d2 >= true (1 - (D+2) 2^-53))
+  w.Uf = __double2float_ru(__dmul_ru(__dmul_ru(U, __ldg(&p.plan->sc2)), 1.0 + 1.0e-12));
+}
+
+// (s, j) pairs: lexicographic "a before b".
+__device__ __forceinline__ bool pair_before(double sa, uint32_t ja, double sb, uint32_t jb) {
+  return (sa < sb) || (sa == sb && ja < jb);
+}
+
+// Merges the buffered candidates into the sorted list: bitonic sort of the buffer across the
+// lanes, min-exchange against the reversed list, bitonic merge.  Order is the exact
+// (sqrt(d2), index) one, so visiting order never shows in the result.
+template <int D>
+#if OXG_TK_MERGE_INLINE
+__device__ __forceinline__ void merge_buffer(
+#else
+__device__ __noinline__ void merge_buffer(
+#endif
+const TreeKnnParams& p, WarpQuery<D>& w) {
+  const double inf = __longlong_as_double(0x7FF0000000000000ll);
+  __syncwarp();
+  double s = inf;
+  uint32_t j = OXG_INVALID_INDEX;
+  if (w.lane < w.bc) {
+    j = w.b_j[w.lane];
+    s = sqrt(w.b_d2[w.lane]);
+    if (j == w.excl) {  // self-exclusion by index (oxg_knn contract)
+      s = inf;
+      j = OXG_INVALID_INDEX;
+    }
+  }
+  __syncwarp();
+  w.bc = 0;
+  ++w.n_merge;
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+      const double so = __shfl_xor_sync(0xFFFFFFFFu, s, j2);
+      const uint32_t jo = __shfl_xor_sync(0xFFFFFFFFu, j, j2);
+      const bool asc = (w.lane & k2) == 0;
+      const bool lower = (w.lane & j2) == 0;
+      const bool take_min = (lower == asc);
+      const bool other_first = pair_before(so, jo, s, j);
+      if (take_min == other_first) {
+        s = so;
+        j = jo;
+      }
+    }
+  }
+  // the 32 smallest of list + buffer, as a bitonic sequence
+  {
+    const double so = __shfl_sync(0xFFFFFFFFu, s, 31 - w.lane);
+    const uint32_t jo = __shfl_sync(0xFFFFFFFFu, j, 31 - w.lane);
+    if (pair_before(so, jo, w.my_s, w.my_i)) {
+      w.my_s = so;
+      w.my_i = jo;
+    }
+  }
+#pragma unroll
+  for (int j2 = 16; j2 > 0; j2 >>= 1) {
+    const double so = __shfl_xor_sync(0xFFFFFFFFu, w.my_s, j2);
+    const uint32_t jo = __shfl_xor_sync(0xFFFFFFFFu, w.my_i, j2);
+    const bool lower = (w.lane & j2) == 0;
+    const bool other_first = pair_before(so, jo, w.my_s, w.my_i);
+    if (lower == other_first) {
+      w.my_s = so;
+      w.my_i = jo;
+    }
+  }
+  if (w.lane >= w.k) {  // lanes past the list stay sentinels
+    w.my_s = inf;
+    w.my_i = OXG_INVALID_INDEX;
+  }
+  w.have = __popc(__ballot_sync(0xFFFFFFFFu, w.my_i != OXG_INVALID_INDEX));
+  if (w.have == w.k) set_bound<D>(p, w, __shfl_sync(0xFFFFFFFFu, w.my_s, w.k - 1));
+}
+
+// Reference-order squared distance of the query to state `lane` of a leaf
+// (real_vector_state_space.rs:148-153).
+template <int D>
+__device__ __forceinline__ double leaf_d2(const TreeKnnParams& p, const WarpQuery<D>& w, uint32_t leaf) {
+  const double* lp = p.t.pts + (uint64_t)leaf * (D * 32) + w.lane;
+  double pv[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) pv[d] = __ldg(lp + d * 32);
+  double d2 = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double df = __dsub_rn(w.q[d], pv[d]);
+    const double m = __dmul_rn(df, df);
+    d2 = (d == 0) ? m : __dadd_rn(d2, m);
+  }
+  return d2;
+}
+
+// Admission test of a leaf's 32 distances; the survivors go to the candidate buffer.
+template <int D>
+__device__ __forceinline__ void leaf_commit(const TreeKnnParams& p, WarpQuery<D>& w, uint32_t leaf,
+                                            double d2) {
+  // d2 >= +0 or NaN; every NaN pattern (pads included) compares above any ub as unsigned
+  bool pass = (unsigned long long)__double_as_longlong(d2) <= w.ub;
+  uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
+  ++w.n_leaf;
+  if (m == 0) return;
+  int n = __popc(m);
+  if (w.bc + n > 32) {
+    merge_buffer<D>(p, w);
+    pass = (unsigned long long)__double_as_longlong(d2) <= w.ub;  // the bound moved
+    m = __ballot_sync(0xFFFFFFFFu, pass);
+    n = __popc(m);
+  }
+  if (pass) {
+    const int slot = w.bc + __popc(m & ((1u << w.lane) - 1u));
+    w.b_d2[slot] = d2;
+    w.b_j[slot] = __ldg(p.t.perm + (uint64_t)leaf * 32 + w.lane);
+  }
+  w.bc += n;
+  w.n_cand += n;
+  if (w.bc >= TK_MERGE_AT || w.have < w.k) merge_buffer<D>(p, w);
+}
+
+// Tests the 32 children of `group` at level L and descends into the survivors, nearest first.
+template <int D, int L>
+struct Visit {
+  static __device__ __forceinline__ void run(const TreeKnnParams& p, WarpQuery<D>& w, uint32_t group) {
+    const uint32_t child0 = group * 32u;
+    const float* bp = p.t.boxes32[L] + (uint64_t)group * (2 * D * 32) + w.lane;
+    // certified lower bound in the box space: boxes rounded outward, the query bracketed, every
+    // operation rounded down
+    float blo[D], bhi[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      blo[d] = __ldg(bp + d * 32);
+      bhi[d] = __ldg(bp + (D + d) * 32);
+    }
+    float lb = 0.0f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float t = fmaxf(fmaxf(__fsub_rd(blo[d], w.qbox[D + d]), __fsub_rd(w.qbox[d], bhi[d])), 0.0f);
+      lb = __fadd_rd(lb, __fmul_rd(t, t));
+    }
+    ++w.n_box;
+    const uint32_t key = (__float_as_uint(lb) & 0xFFFFFFE0u) | (uint32_t)w.lane;
+    uint32_t cand = __ballot_sync(0xFFFFFFFFu, child0 + (uint32_t)w.lane < p.t.count[L]);
+    for (;;) {
+      const bool alive = ((cand >> w.lane) & 1u) && !(lb > w.Uf);
+      cand = __ballot_sync(0xFFFFFFFFu, alive);
+      if (!cand) break;
+      const uint32_t r = __reduce_min_sync(0xFFFFFFFFu, alive ? key : 0xFFFFFFFFu);
+      const uint32_t c = r & 31u;
+      cand &= ~(1u << c);
+      if constexpr (L == 0) {
+        // two leaves per round: both loads are in flight before either is consumed
+        const uint32_t r1 = OXG_TK_TWO_LEAVES
+                                ? __reduce_min_sync(0xFFFFFFFFu, (alive && (uint32_t)w.lane != c) ? key : 0xFFFFFFFFu)
+                                : 0xFFFFFFFFu;
+        if (OXG_TK_TWO_LEAVES && r1 != 0xFFFFFFFFu) {
+          const uint32_t c1 = r1 & 31u;
+          cand &= ~(1u << c1);
+          const double da = leaf_d2<D>(p, w, child0 + c);
+          const double db = leaf_d2<D>(p, w, child0 + c1);
+          leaf_commit<D>(p, w, child0 + c, da);
+          leaf_commit<D>(p, w, child0 + c1, db);
+        } else {
+          leaf_commit<D>(p, w, child0 + c, leaf_d2<D>(p, w, child0 + c));
+        }
+      } else {
+        Visit<D, L - 1>::run(p, w, child0 + c);
+      }
+    }
+  }
+};
+
+// Persistent CTAs: chunks of TK_QPC key-ordered queries are dealt round-robin to the CTAs, so all
+// warps of an SM work on neighbouring queries at the same time and share the leaves through L1.
+template <int D>
+__global__ void __launch_bounds__(TK_THREADS, OXG_TK_MIN_CTAS) tree_knn_kernel(const TreeKnnParams p) {
+  __shared__ double s_d2[TK_THREADS];
+  __shared__ uint32_t s_j[TK_THREADS];
+#if OXG_TK_QBOX_SMEM
+  __shared__ float s_qbox[TK_THREADS / 32][2 * D];
+#endif
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const double inf = __longlong_as_double(0x7FF0000000000000ll);
+  const double sc = p.plan->sc;
+  unsigned long long st_leaf = 0, st_box = 0, st_cand = 0, st_merge = 0;
+  const uint32_t n_chunks = (p.Q + TK_QPC - 1) / TK_QPC;
+  for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const uint32_t q_begin = chunk * (uint32_t)TK_QPC;
+    const uint32_t q_end = min(p.Q, q_begin + (uint32_t)TK_QPC);
+    for (uint32_t wq = q_begin + wid; wq < q_end; wq += TK_THREADS / 32) {
+      const uint32_t qi = p.qorder ? __ldg(p.qorder + wq) : wq;
+      WarpQuery<D> w;
+      bool qnan = false;
+      __syncwarp();
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        w.q[d] = p.q.p[(uint64_t)qi * p.q.stride_i + (uint64_t)d * p.q.stride_d];
+        qnan = qnan || !(w.q[d] == w.q[d]);
+        const double c = p.plan->c[d];
+#if OXG_TK_QBOX_SMEM
+        if (lane == 0) {
+          s_qbox[wid][d] = __double2float_rd(__dmul_rd(__dsub_rd(w.q[d], c), sc));
+          s_qbox[wid][D + d] = __double2float_ru(__dmul_ru(__dsub_ru(w.q[d], c), sc));
+        }
+#else
+        w.qbox[d] = __double2float_rd(__dmul_rd(__dsub_rd(w.q[d], c), sc));
+        w.qbox[D + d] = __double2float_ru(__dmul_ru(__dsub_ru(w.q[d], c), sc));
+#endif
+      }
+      __syncwarp();
+#if OXG_TK_QBOX_SMEM
+      w.qbox = s_qbox[wid];
+#endif
+      w.my_s = inf;
+      w.my_i = OXG_INVALID_INDEX;
+      w.have = 0;
+      w.k = (int)p.k;
+      w.ub = 0x7FF0000000000000ull;
+      w.Uf = __int_as_float(0x7F800000);
+      w.bc = 0;
+      w.b_d2 = s_d2 + wid * 32;
+      w.b_j = s_j + wid * 32;
+      w.lane = lane;
+      w.n_leaf = w.n_box = w.n_cand = w.n_merge = 0;
+      w.excl = OXG_INVALID_INDEX;
+      if (p.exclude_mode == 1) w.excl = __ldg(p.exclude + qi);
+      if (p.exclude_mode == 2) w.excl = p.self_base + qi;
+      if (!qnan) {  // a NaN query admits nothing (every distance is NaN)
+        switch (p.t.top) {
+          case 0: Visit<D, 0>::run(p, w, 0); break;
+          case 1: Visit<D, 1>::run(p, w, 0); break;
+          case 2: Visit<D, 2>::run(p, w, 0); break;
+          case 3: Visit<D, 3>::run(p, w, 0); break;
+          default: Visit<D, 4>::run(p, w, 0); break;
+        }
+        if (w.bc > 0) merge_buffer<D>(p, w);
+      }
+      if (lane < (int)p.k) {
+        const uint64_t o = (uint64_t)qi * p.k + lane;
+        p.out_idx[o] = w.my_i;
+        p.out_dist[o] = w.my_s;
+      }
+      st_leaf += w.n_leaf;
+      st_box += w.n_box;
+      st_cand += w.n_cand;
+      st_merge += w.n_merge;
+    }
+  }
+  if (p.stats && lane == 0) {
+    atomicAdd(&p.stats[0], st_leaf);
+    atomicAdd(&p.stats[1], st_box);
+    atomicAdd(&p.stats[2], st_cand);
+    atomicAdd(&p.stats[3], st_merge);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static unsigned grid_1d(uint64_t n, int threads, unsigned cap = 148u * 16u) {
+  return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + threads - 1) / threads, cap));
+}
+
+template <int D>
+static int tree_build_levels(oxg_store_s* s, StoreTree* t, const uint32_t* sorted) {
+  const uint32_t n = (uint32_t)s->size;
+  TreeView& v = t->view;
+  const uint32_t n_leaves = (n + 31u) / 32u;
+  uint32_t cnt = n_leaves;
+  int lvl = 0;
+  for (;;) {
+    v.count[lvl] = cnt;
+    const uint32_t groups = (cnt + 31u) / 32u;
+    OXG_TRY(t->boxes[lvl].ensure((size_t)groups * 2 * D * 32 * sizeof(double)));
+    OXG_TRY(t->boxes32[lvl].ensure((size_t)groups * 2 * D * 32 * sizeof(float)));
+    v.boxes[lvl] = t->boxes[lvl].as<double>();
+    v.boxes32[lvl] = t->boxes32[lvl].as<float>();
+    if (cnt <= 32u || lvl == TREE_LEVELS - 1) break;
+    cnt = groups;
+    ++lvl;
+  }
+  v.top = lvl;
+  for (int l = lvl + 1; l < TREE_LEVELS; ++l) {
+    v.count[l] = 0;
+    v.boxes[l] = nullptr;
+    v.boxes32[l] = nullptr;
+  }
+  OXG_TRY(t->pts.ensure((size_t)n_leaves * D * 32 * sizeof(double)));
+  OXG_TRY(t->perm.ensure((size_t)n_leaves * 32 * sizeof(uint32_t)));
+  v.pts = t->pts.as<double>();
+  v.perm = t->perm.as<uint32_t>();
+  {
+    const uint32_t slots = ((n_leaves + 31u) / 32u) * 32u;
+    tree_leaves_kernel<D><<<(slots * 32u + 255u) / 256u, 256, 0, s->stream>>>(
+        s->d_data, s->pitch, n, sorted, n_leaves, slots, t->pts.as<double>(), t->perm.as<uint32_t>(),
+        t->boxes[0].as<double>());
+    OXG_LAUNCH_CHECK();
+  }
+  for (int l = 1; l <= lvl; ++l) {
+    const uint32_t nodes = v.count[l];
+    const uint32_t slots = ((nodes + 31u) / 32u) * 32u;
+    tree_level_kernel<D><<<(slots * 32u + 255u) / 256u, 256, 0, s->stream>>>(
+        t->boxes[l - 1].as<double>(), v.count[l - 1], nodes, slots, t->boxes[l].as<double>());
+    OXG_LAUNCH_CHECK();
+  }
+  for (int l = 0; l <= lvl; ++l) {
+    const uint64_t n_vals = (uint64_t)((v.count[l] + 31u) / 32u) * 2 * D * 32;
+    tree_boxes32_kernel<<<grid_1d(n_vals, 256), 256, 0, s->stream>>>(
+        t->boxes[l].as<double>(), n_vals, D, t->plan.as<TreePlan>(), t->boxes32[l].as<float>());
+    OXG_LAUNCH_CHECK();
+  }
+  return OXG_OK;
+}
+
+static int sort_pairs(oxg_store_s* s, StoreTree* t, const uint32_t* k_in, uint32_t* k_out,
+                      const uint32_t* v_in, uint32_t* v_out, uint32_t n) {
+  size_t bytes = 0;
+  OXG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k_in, k_out, v_in, v_out, (int)n, 0,
+                                               TREE_KEY_BITS, s->stream));
+  OXG_TRY(t->tmp.ensure(bytes));
+  OXG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(t->tmp.p, bytes, k_in, k_out, v_in, v_out, (int)n, 0,
+                                               TREE_KEY_BITS, s->stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return OXG_OK;
+}
+
+static StoreTree* tree_of(oxg_store_s* s) {
+  if (!s->tree) s->tree = new StoreTree();
+  return static_cast<StoreTree*>(s->tree);
+}
+
+void tree_release(oxg_store_s* s) {
+  if (!s->tree) return;
+  StoreTree* t = static_cast<StoreTree*>(s->tree);
+  t->pts.release();
+  t->perm.release();
+  t->keys.release();
+  t->keys2.release();
+  t->vals.release();
+  t->vals2.release();
+  t->plan.release();
+  t->bounds.release();
+  t->qorder.release();
+  t->tmp.release();
+  for (auto& b : t->boxes) b.release();
+  for (auto& b : t->boxes32) b.release();
+  delete t;
+  s->tree = nullptr;
+}
+
+bool tree_supported(const oxg_store_s* s, uint32_t k) {
+  return is_pure_rv(s->space) && s->dim >= 1 && s->dim <= (uint32_t)TREE_MAX_DIM && k >= 1 && k <= 32 &&
+         s->size >= 1 && s->size <= (1ull << 30);
+}
+
+bool tree_is_current(const oxg_store_s* s) {
+  const StoreTree* t = static_cast<const StoreTree*>(s->tree);
+  return t && t->epoch == s->epoch && t->size == s->size;
+}
+
+#define OXG_TREE_DISPATCH_D(D_RT, CALL)              \
+  switch (D_RT) {                                    \
+    case 1: { constexpr int DD = 1; CALL; } break;   \
+    case 2: { constexpr int DD = 2; CALL; } break;   \
+    case 3: { constexpr int DD = 3; CALL; } break;   \
+    case 4: { constexpr int DD = 4; CALL; } break;   \
+    case 5: { constexpr int DD = 5; CALL; } break;   \
+    case 6: { constexpr int DD = 6; CALL; } break;   \
+    case 7: { constexpr int DD = 7; CALL; } break;   \
+    case 8: { constexpr int DD = 8; CALL; } break;   \
+    default: break;                                  \
+  }
+
+// (Re)builds the hierarchy of the store's current contents on the store's stream.
+int tree_build(oxg_store_s* s) {
+  StoreTree* t = tree_of(s);
+  if (tree_is_current(s)) return OXG_OK;
+  const uint32_t n = (uint32_t)s->size;
+  OXG_TRY(t->bounds.ensure((2 * kMaxFastDim + 4) * sizeof(unsigned long long)));
+  OXG_TRY(t->plan.ensure(sizeof(TreePlan)));
+  OXG_TRY(t->keys.ensure((size_t)n * sizeof(uint32_t)));
+  OXG_TRY(t->keys2.ensure((size_t)n * sizeof(uint32_t)));
+  OXG_TRY(t->vals.ensure((size_t)n * sizeof(uint32_t)));
+  OXG_TRY(t->vals2.ensure((size_t)n * sizeof(uint32_t)));
+  unsigned long long* bounds = t->bounds.as<unsigned long long>();
+  tree_bounds_init_kernel<<<1, 32, 0, s->stream>>>(bounds);
+  OXG_LAUNCH_CHECK();
+  tree_bounds_kernel<<<grid_1d(n, 256, 148u * 4u), 256, 0, s->stream>>>(s->d_data, s->pitch, n,
+                                                                       (int)s->dim, bounds);
+  OXG_LAUNCH_CHECK();
+  tree_plan_kernel<<<1, 32, 0, s->stream>>>(bounds, (int)s->dim, t->plan.as<TreePlan>());
+  OXG_LAUNCH_CHECK();
+  tree_keys_kernel<<<grid_1d(n, 256), 256, 0, s->stream>>>(store_view(s), n, (int)s->dim,
+                                                           t->plan.as<TreePlan>(), t->keys.as<uint32_t>(),
+                                                           t->vals.as<uint32_t>());
+  OXG_LAUNCH_CHECK();
+  OXG_TRY(sort_pairs(s, t, t->keys.as<uint32_t>(), t->keys2.as<uint32_t>(), t->vals.as<uint32_t>(),
+                     t->vals2.as<uint32_t>(), n));
+  int r = OXG_E_INTERNAL;
+  OXG_TREE_DISPATCH_D(s->dim, r = (tree_build_levels<DD>(s, t, t->vals2.as<uint32_t>())));
+  OXG_TRY(r);
+  t->epoch = s->epoch;
+  t->size = s->size;
+  return OXG_OK;
+}
+
+template <int D>
+static int launch_tree_knn(const TreeKnnParams& p, cudaStream_t st) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned chunks = (p.Q + TK_QPC - 1) / TK_QPC;
+  const unsigned grid = OXG_TK_PERSISTENT ? std::max(1u, std::min(chunks, (unsigned)sms * OXG_TK_MIN_CTAS)) : chunks;
+  tree_knn_kernel<D><<<grid, TK_THREADS, 0, st>>>(p);
+  OXG_LAUNCH_CHECK();
+  return OXG_OK;
+}
+
+// k-NN of Q device-resident queries through the hierarchy (same contract as nn_knn_device).
+int tree_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclude_mode,
+                    const uint32_t* d_exclude, uint64_t self_base, uint32_t* d_idx, double* d_dist,
+                    unsigned long long* d_stats) {
+  OXG_TRY(tree_build(s));
+  StoreTree* t = tree_of(s);
+  // queries in key order: neighbouring warps walk the same part of the hierarchy
+  OXG_TRY(t->qorder.ensure((size_t)Q * 4 * sizeof(uint32_t)));
+  uint32_t* qk = t->qorder.as<uint32_t>();
+  uint32_t* qk2 = qk + Q;
+  uint32_t* qv = qk + 2 * Q;
+  uint32_t* qv2 = qk + 3 * Q;
+  tree_keys_kernel<<<grid_1d(Q, 256), 256, 0, s->stream>>>(q, (uint32_t)Q, (int)s->dim,
+                                                           t->plan.as<TreePlan>(), qk, qv);
+  OXG_LAUNCH_CHECK();
+  OXG_TRY(sort_pairs(s, t, qk, qk2, qv, qv2, (uint32_t)Q));
+  TreeKnnParams p;
+  p.t = t->view;
+  p.plan = t->plan.as<TreePlan>();
+  p.q = q;
+  p.Q = (uint32_t)Q;
+  p.qorder = qv2;
+  p.k = k;
+  p.exclude_mode = exclude_mode;
+  p.exclude = d_exclude;
+  p.self_base = (uint32_t)self_base;
+  p.out_idx = d_idx;
+  p.out_dist = d_dist;
+  p.stats = d_stats;
+  // OXG_TREE_STATS=1 (diagnostics): count visited leaves / tested groups / insertions and print them
+  static const bool want_stats = [] {
+    const char* v = getenv("OXG_TREE_STATS");
+    return v && *v && *v != '0';
+  }();
+  if (want_stats && !d_stats) {
+    OXG_TRY(t->bounds.ensure((2 * kMaxFastDim + 4) * sizeof(unsigned long long)));
+    p.stats = t->bounds.as<unsigned long long>() + 2 * kMaxFastDim;
+    OXG_CUDA_TRY(cudaMemsetAsync(p.stats, 0, 4 * sizeof(unsigned long long), s->stream));
+  }
+  int r = OXG_E_INTERNAL;
+  OXG_TREE_DISPATCH_D(s->dim, r = (launch_tree_knn<DD>(p, s->stream)));
+  if (want_stats && !d_stats && r == OXG_OK) {
+    unsigned long long h[4] = {0, 0, 0, 0};
+    OXG_CUDA_TRY(cudaMemcpyAsync(h, p.stats, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    fprintf(stderr, "[oxg tree] Q=%llu n=%llu levels=%d: leaves/query %.1f, box groups/query %.1f, candidates/query %.1f, merges/query %.1f\n",
+            (unsigned long long)Q, (unsigned long long)s->size, t->view.top + 1, (double)h[0] / (double)Q,
+            (double)h[1] / (double)Q, (double)h[2] / (double)Q, (double)h[3] / (double)Q);
+  }
+  return r;
+}
+
+}  // namespace oxg

@@ -1,0 +1,150 @@
+"""GPU parity of the bounding-box-hierarchy k-NN (csrc/oxg_tree.cu) against the CPU oracle and
+against the all-pairs scan kernels: same lists bit for bit, whatever the visiting order."""
+import numpy as np
+import pytest
+
+from conftest import uniform_states
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def tree_on(oxg):
+    oxg.tuning_set("knn_tree", 1)
+    yield
+    oxg.tuning_set("knn_tree", -1)
+
+
+def _same(a, b):
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1].view(np.uint64), b[1].view(np.uint64))
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 6, 7, 8])
+@pytest.mark.parametrize("n", [1, 5, 31, 32, 33, 1000, 1024, 1025, 33000])
+def test_tree_knn_uniform(oxg, orc, tree_on, d, n):
+    rows = uniform_states(300 + d, n, [-1.0] * d, [2.0] * d)
+    queries = np.vstack([uniform_states(400 + d, 61, [-1.5] * d, [2.5] * d), rows[: min(n, 20)]])
+    sp_o = orc.space(d)
+    with oxg.StateStore(oxg.Space.real_vector(d)) as st:
+        st.append(rows)
+        for k in (1, 3, 10, 32):
+            _same(st.knn(queries, k), orc.knn(sp_o, rows, queries, k))
+        _same(st.nn1(queries), orc.nn1(sp_o, rows, queries))
+        ex = np.arange(min(n, 20), dtype=np.uint32)
+        _same(st.knn(rows[: min(n, 20)], 4, exclude=ex), orc.knn(sp_o, rows, rows[: min(n, 20)], 4, exclude=ex))
+
+
+@pytest.mark.parametrize("d", [2, 3, 7])
+def test_tree_adversarial_ties(oxg, orc, tree_on, d):
+    """Integer lattice + duplicates: every list is full of exact ties, the lowest index must win
+    although the hierarchy visits the states in key order."""
+    rng = np.random.default_rng(11 + d)
+    base = rng.integers(0, 4, size=(6000, d)).astype(np.float64)
+    near = base[:1500] + 0.0
+    near[:, 0] = np.nextafter(near[:, 0] + 0.5, np.inf)
+    rows = np.ascontiguousarray(np.vstack([base, base[rng.integers(0, 6000, 1500)], near]))
+    rng.shuffle(rows)
+    queries = np.vstack([rows[:300], rng.integers(0, 4, size=(100, d)).astype(np.float64) + 0.5])
+    sp_o = orc.space(d)
+    with oxg.StateStore(oxg.Space.real_vector(d)) as st:
+        st.append(rows)
+        for k in (1, 10, 32):
+            _same(st.knn(queries, k), orc.knn(sp_o, rows, queries, k))
+        ex = np.arange(300, dtype=np.uint32)
+        _same(st.knn(rows[:300], 7, exclude=ex), orc.knn(sp_o, rows, rows[:300], 7, exclude=ex))
+
+
+def test_tree_sqrt_collapse_and_special_values(oxg, orc, tree_on):
+    rng = np.random.default_rng(5)
+    rows = rng.random((5000, 3))
+    rows[17] = [np.nan, 0.5, 0.5]          # NaN states never enter a list
+    rows[40] = [np.inf, 0.5, 0.5]          # inf is an ordinary (last) distance
+    rows[41] = [-np.inf, 0.1, 0.2]
+    rows[100:132] = rows[99]               # a whole leaf of duplicates
+    queries = np.vstack([rng.random((50, 3)), [[np.nan, 0.1, 0.1]], [[np.inf, 0.0, 0.0]], rows[99:100]])
+    sp_o = orc.space(3)
+    with oxg.StateStore(oxg.Space.real_vector(3)) as st:
+        st.append(rows)
+        for k in (1, 5, 32):
+            _same(st.knn(queries, k), orc.knn(sp_o, rows, queries, k))
+    # fewer than k admissible states: padded rows
+    few = rng.random((7, 2))
+    with oxg.StateStore(oxg.Space.real_vector(2)) as st:
+        st.append(few)
+        q9 = np.random.default_rng(6).random((9, 2))
+        _same(st.knn(q9, 10), orc.knn(orc.space(2), few, q9, 10))
+
+
+@pytest.mark.parametrize("scale,offset", [(1.0, 1e7), (1.0, 1e15), (1e-30, 0.0), (1e-160, 0.0),
+                                          (1e153, 0.0), (1e200, 0.0)])
+def test_tree_extreme_scales(oxg, orc, tree_on, scale, offset):
+    """The box bound must stay a lower bound when squares overflow, underflow or cancel."""
+    rng = np.random.default_rng(21)
+    rows = (rng.random((4000, 3)) + offset) * scale
+    queries = np.vstack([(rng.random((40, 3)) + offset) * scale, rows[:40]])
+    sp_o = orc.space(3)
+    with oxg.StateStore(oxg.Space.real_vector(3)) as st:
+        st.append(rows)
+        for k in (1, 10):
+            _same(st.knn(queries, k), orc.knn(sp_o, rows, queries, k))
+
+
+def test_tree_clustered_and_degenerate_boxes(oxg, orc, tree_on):
+    """Clusters, a constant coordinate (zero extent) and a line: skewed keys, same lists."""
+    rng = np.random.default_rng(31)
+    centres = rng.random((12, 4)) * 100.0
+    rows = np.vstack([c + rng.normal(size=(1500, 4)) * 0.01 for c in centres])
+    rows[:, 2] = 7.25                              # zero-extent dimension
+    line = np.zeros((2000, 4))
+    line[:, 0] = np.linspace(0.0, 1.0, 2000)
+    rows = np.ascontiguousarray(np.vstack([rows, line]))
+    rng.shuffle(rows)
+    queries = np.vstack([rows[:200], rng.random((100, 4)) * 100.0])
+    sp_o = orc.space(4)
+    with oxg.StateStore(oxg.Space.real_vector(4)) as st:
+        st.append(rows)
+        _same(st.knn(queries, 10), orc.knn(sp_o, rows, queries, 10))
+
+
+def test_tree_follows_the_store(oxg, orc, tree_on):
+    """append / clear invalidate the hierarchy (it is rebuilt for the next batch)."""
+    rng = np.random.default_rng(41)
+    a, b = rng.random((3000, 5)), rng.random((2000, 5)) * 0.5
+    q = rng.random((64, 5))
+    sp_o = orc.space(5)
+    with oxg.StateStore(oxg.Space.real_vector(5)) as st:
+        st.append(a)
+        _same(st.knn(q, 6), orc.knn(sp_o, a, q, 6))
+        st.append(b)
+        ab = np.vstack([a, b])
+        _same(st.knn(q, 6), orc.knn(sp_o, ab, q, 6))
+        st.clear()
+        st.append(b)
+        _same(st.knn(q, 6), orc.knn(sp_o, b, q, 6))
+
+
+def test_tree_equals_all_pairs_scan_on_a_prm_table(oxg, orc):
+    """200 000 x 200 000, D = 7, k = 10: the hierarchy and the all-pairs scan kernels give the
+    same table; a sample of rows is compared with the oracle."""
+    from oxmpl_b200 import worlds
+
+    n = 200_000
+    rows = uniform_states(4, n, worlds.PANDA_LO, worlds.PANDA_HI)
+    with oxg.StateStore(oxg.Space.real_vector(7)) as st:
+        st.append(rows)
+        oxg.tuning_set("knn_tree", 1)
+        try:
+            ti, td = st.knn(rows, 10, exclude=np.arange(n, dtype=np.uint32))
+        finally:
+            oxg.tuning_set("knn_tree", 0)
+        try:
+            bi, bd = st.knn(rows, 10, exclude=np.arange(n, dtype=np.uint32))
+        finally:
+            oxg.tuning_set("knn_tree", -1)
+    np.testing.assert_array_equal(ti, bi)
+    np.testing.assert_array_equal(td.view(np.uint64), bd.view(np.uint64))
+    pick = np.random.default_rng(1).choice(n, 512, replace=False)
+    oi, od = orc.knn(orc.space(7), rows, rows[pick], 10, exclude=pick.astype(np.uint32))
+    np.testing.assert_array_equal(ti[pick], oi)
+    np.testing.assert_array_equal(td[pick].view(np.uint64), od.view(np.uint64))
