@@ -440,4 +440,123 @@ OXG_DEV unsigned capsule_pair_maybe_hit32_s(const float* xf, uint32_t row, float
   return (!(d2.x > T0) ? 1u : 0u) | (!(d2.y > T1) ? 2u : 0u);
 }
 
+// ----------------------------------------------------------------- whole-edge culling
+// "Could ANY state within rho of the point m hit this obstacle?"  Every interpolated state of
+// check_motion(from, to) lies within half the edge length of the midpoint, so one such test per
+// (edge, obstacle) replaces one test per (step, obstacle) for the obstacles it rules out.  Same
+// certified bound as the per-state filters with the obstacle grown by rho: a state x with
+// |x - m| <= rho' (rho' the exact half length plus the interpolation roundings; rho >= rho'
+// (1 + 1e-5) + 1e-6 M) can only hit if the exact sum at m is <= (sqrt(U) + rho')^2 =: S_fat, and
+// then d2_32(m) <= [S_fat + 2a sqrt(D S_fat) + 2 D a^2](1 + D 2^-22) <= T_fat below, where
+// rr >= sqrt(U1) + rho is taken from the mirror's sq >= sqrt(D U1).
+struct FatTol {
+  float rho;        // ball radius around the midpoint, rounded up
+  float sqrt_d;     // >= sqrt(D)
+  float inv_sqrt_d; // >= 1 / sqrt(D)
+};
+
+OXG_DEV float fat_threshold(float sq, float a2, float ce, const FatTol& f) {
+  const float rr = __fmaf_ru(sq, f.inv_sqrt_d, f.rho);
+  return __fmaf_ru(rr, rr, __fmaf_ru(a2, __fmul_ru(f.sqrt_d, rr), ce));
+}
+
+template <int DT>
+OXG_DEV bool sphere_fat_maybe_hit32_s(const float* mf, uint32_t row, float a2, float ce, const FatTol& f) {
+  constexpr int DN = DT > 0 ? DT : 1;
+  constexpr int NV = (DN + 2 + 3) / 4;
+  float c[NV * 4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 t4 = lds128_row(row + 16u * v);
+    c[4 * v] = t4.x;
+    c[4 * v + 1] = t4.y;
+    c[4 * v + 2] = t4.z;
+    c[4 * v + 3] = t4.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < DT; ++i) {
+    const float d = mf[i] - c[i];
+    s = __fmaf_rn(d, d, s);
+  }
+  return !(s > fat_threshold(c[DT + 1], a2, ce, f));
+}
+
+// AABB mirror row in global memory: [lo.. rounded down, hi.. rounded up].
+template <int DT>
+OXG_DEV bool aabb_fat_maybe_hit32(const float* mf, const float* __restrict__ box, const FatTol& f) {
+  bool near = true;
+#pragma unroll
+  for (int i = 0; i < DT; ++i)
+    near = near && !(mf[i] < __fsub_rd(__ldg(box + i), f.rho)) && !(mf[i] > __fadd_ru(__ldg(box + DT + i), f.rho));
+  return near;
+}
+
+// Pair row of the interleaved capsule mirror (see capsule_pair_maybe_hit32_s): bit 0 / bit 1.
+template <int DT>
+OXG_DEV unsigned capsule_pair_fat_maybe_hit32_s(const float* mf, uint32_t row, float a2, float ce,
+                                                const FatTol& f) {
+  constexpr int DN = DT > 0 ? DT : 1;
+  constexpr int NV = (2 * (2 * DN + 3) + 3) / 4;
+  float2 c[NV * 2];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 t4 = lds128_row(row + 16u * v);
+    c[2 * v] = make_float2(t4.x, t4.y);
+    c[2 * v + 1] = make_float2(t4.z, t4.w);
+  }
+  float2 ap[DN];
+  float2 num = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < DN; ++i) {
+    ap[i] = __fadd2_rn(make_float2(mf[i], mf[i]), make_float2(-c[i].x, -c[i].y));
+    num = __ffma2_rn(ap[i], c[DN + i], num);
+  }
+  float2 t = __fmul2_rn(num, c[2 * DN]);
+  t.x = fminf(fmaxf(t.x, 0.f), 1.f);  // NaN -> 0: any t in [0,1] keeps the bound valid
+  t.y = fminf(fmaxf(t.y, 0.f), 1.f);
+  const float2 nt = make_float2(-t.x, -t.y);
+  float2 d2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < DN; ++i) {
+    const float2 e = __ffma2_rn(nt, c[DN + i], ap[i]);
+    d2 = __ffma2_rn(e, e, d2);
+  }
+  const float T0 = fat_threshold(c[2 * DN + 2].x, a2, ce, f);
+  const float T1 = fat_threshold(c[2 * DN + 2].y, a2, ce, f);
+  return (!(d2.x > T0) ? 1u : 0u) | (!(d2.y > T1) ? 2u : 0u);
+}
+
+// One capsule of a pair row (half = 0 / 1): the per-state filter for the few capsules that
+// survive the edge cull.
+template <int DT>
+OXG_DEV bool capsule_half_maybe_hit32_s(const float* xf, uint32_t row, unsigned half, float a2, float ce) {
+  constexpr int DN = DT > 0 ? DT : 1;
+  constexpr int NV = (2 * (2 * DN + 3) + 3) / 4;
+  float c[NV * 2];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 t4 = lds128_row(row + 16u * v);
+    c[2 * v] = half ? t4.y : t4.x;
+    c[2 * v + 1] = half ? t4.w : t4.z;
+  }
+  float ap[DN];
+  float num = 0.f;
+#pragma unroll
+  for (int i = 0; i < DN; ++i) {
+    ap[i] = xf[i] - c[i];
+    num = __fmaf_rn(ap[i], c[DN + i], num);
+  }
+  float t = num * c[2 * DN];
+  t = fminf(fmaxf(t, 0.f), 1.f);
+  float d2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < DN; ++i) {
+    const float e = __fmaf_rn(-t, c[DN + i], ap[i]);
+    d2 = __fmaf_rn(e, e, d2);
+  }
+  const float T = __fmaf_ru(a2, c[2 * DN + 2], __fadd_ru(c[2 * DN + 1], ce));
+  return !(d2 > T);
+}
+
 }  // namespace oxg

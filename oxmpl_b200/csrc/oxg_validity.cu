@@ -13,6 +13,7 @@
 // served by L1/L2) and the FP64 pipe is the bound.  The boolean result does not depend on the
 // evaluation order, so it is bit-identical to the sequential reference loop.
 #include <algorithm>
+#include <cstdlib>
 
 #include "oxg_internal.cuh"
 #include "oxg_math.cuh"
@@ -243,6 +244,167 @@ __global__ void __launch_bounds__(128, 6) motion_kernel(const MotionParams p) {
   }
 }
 
+// check_motion with a whole-edge cull in front of the per-step tests (RealVector fast paths,
+// world mirrors staged in shared memory).  Phase 1: the L lanes of an edge share out the
+// obstacles and test each ONCE against the ball around the edge's midpoint that contains every
+// interpolated state (certified, *_fat_maybe_hit32*): an obstacle that fails it cannot
+// invalidate any step.  Phase 2: the reference's step loop (rrt.rs:104-109), lanes over steps
+// as in motion_kernel, against the few survivors only — per-state FP32 filter, then the exact
+// FP64 predicate.  Results (validity, first invalid step) are those of the sequential loop.
+constexpr int CULL_CAP = 40;  // survivors kept per edge; more than that falls back to the full walk
+
+template <int DT, int L>
+__global__ void __launch_bounds__(128, 6) motion_cull_kernel(const MotionParams p) {
+  extern __shared__ __align__(16) unsigned char world_smem[];
+  __shared__ uint16_t s_list[128 / L][CULL_CAP];
+  uint32_t sm_sph = 0, sm_cap = 0;
+  stage_world32(p.w, p.world_smem_bytes, world_smem, &sm_sph, &sm_cap);  // the launcher guarantees it fits
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lane_g = lane % L;
+  const unsigned group_shift = lane - lane_g;
+  const unsigned group_mask = (L == 32) ? 0xFFFFFFFFu : (((1u << L) - 1u) << group_shift);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const uint64_t gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) / L;
+  uint16_t* my_list = s_list[threadIdx.x / L];
+  const WorldView& w = p.w;
+  const uint32_t n_sph = w.n_spheres, n_box = w.n_aabbs, n_cap = w.n_capsules;
+  FatTol ft;
+  ft.sqrt_d = __double2float_ru(sqrt((double)DT) * 1.000001);
+  ft.inv_sqrt_d = __double2float_ru(1.000001 / sqrt((double)DT));
+
+  const uint64_t E = p.E_dev ? *p.E_dev : p.E;
+  const uint64_t e_rounds = (E + ngroups - 1) / ngroups;
+  for (uint64_t round = 0; round < e_rounds; ++round) {
+    const uint64_t e = gid + round * ngroups;
+    if (e >= E) continue;  // whole groups leave together: group-scoped ballots below stay matched
+    const uint64_t fi = p.from_idx ? p.from_idx[e] : e;
+    const uint64_t ti = p.to_idx ? p.to_idx[e] : e;
+    double from[DT], to[DT], x[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+      from[d] = p.from.p[fi * p.from.stride_i + (uint64_t)d * p.from.stride_d];
+      to[d] = p.to.p[ti * p.to.stride_i + (uint64_t)d * p.to.stride_d];
+    }
+    const double dist = sqrt(rv_sumsq_dev<DT>(from, to, DT));
+    const unsigned long long n = ceil_as_usize_dev(__ddiv_rn(dist, p.resolution));
+    unsigned long long first_bad = 0;
+    double ms = 0.0;
+    float mf[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+      ms = fmax(ms, fmax(fabs(from[d]), fabs(to[d])));
+      if (!(from[d] == from[d]) || !(to[d] == to[d])) ms = __longlong_as_double(0x7FF8000000000000ll);
+      mf[d] = __double2float_rn(0.5 * from[d] + 0.5 * to[d]);
+    }
+    const EdgeTol tol = edge_tol_dev(ms * 1.0000001, w.wmax_spheres, w.wmax_capsules, DT);
+    // every state of the edge lies within dist/2 (+ roundings) of the midpoint; NaN / inf make
+    // rho NaN / inf and then nothing is culled
+    ft.rho = __double2float_ru(0.5 * dist * 1.00001 + ms * 1.0e-6 + 1e-37);
+
+    // ---- phase 1: cull
+    unsigned cnt = 0;
+    for (uint32_t i0 = 0; i0 < n_sph; i0 += L) {
+      const uint32_t i = i0 + lane_g;
+      const bool keep = i < n_sph && sphere_fat_maybe_hit32_s<DT>(mf, sm_sph + i * w.sphere32_stride * 4u,
+                                                                  tol.a2_s, tol.ce_s, ft);
+      const unsigned b = __ballot_sync(group_mask, keep) & group_mask;
+      if (keep) {
+        const unsigned pos = cnt + __popc(b & lt_mask);
+        if (pos < CULL_CAP) my_list[pos] = (uint16_t)i;
+      }
+      cnt += __popc(b);
+    }
+    for (uint32_t i0 = 0; i0 < n_box; i0 += L) {
+      const uint32_t i = i0 + lane_g;
+      const bool keep = i < n_box && aabb_fat_maybe_hit32<DT>(mf, w.aabbs32 + (size_t)i * w.aabb_stride, ft);
+      const unsigned b = __ballot_sync(group_mask, keep) & group_mask;
+      if (keep) {
+        const unsigned pos = cnt + __popc(b & lt_mask);
+        if (pos < CULL_CAP) my_list[pos] = (uint16_t)(n_sph + i);
+      }
+      cnt += __popc(b);
+    }
+    for (uint32_t i0 = 0; i0 < n_cap; i0 += 2 * L) {
+      const uint32_t i = i0 + 2 * lane_g;
+      unsigned mh = 0;
+      if (i < n_cap)
+        mh = capsule_pair_fat_maybe_hit32_s<DT>(mf, sm_cap + (i >> 1) * w.capsule32p_stride * 4u, tol.a2_c,
+                                                tol.ce_c, ft);
+      if (i + 1 >= n_cap) mh &= 1u;
+      const unsigned b0 = __ballot_sync(group_mask, (mh & 1u) != 0) & group_mask;
+      const unsigned b1 = __ballot_sync(group_mask, (mh & 2u) != 0) & group_mask;
+      if (mh & 1u) {
+        const unsigned pos = cnt + __popc(b0 & lt_mask);
+        if (pos < CULL_CAP) my_list[pos] = (uint16_t)(n_sph + n_box + i);
+      }
+      cnt += __popc(b0);
+      if (mh & 2u) {
+        const unsigned pos = cnt + __popc(b1 & lt_mask);
+        if (pos < CULL_CAP) my_list[pos] = (uint16_t)(n_sph + n_box + i + 1);
+      }
+      cnt += __popc(b1);
+    }
+    __syncwarp(group_mask);
+    const bool full_walk = cnt > CULL_CAP;
+
+    // ---- phase 2: the step loop over the survivors
+    if (n > (1ull << 32)) {
+      first_bad = 0xFFFFFFFFull;  // the reference loop would not terminate in practice
+    } else if (cnt > 0) {
+      const bool single = n <= 1;   // `if num_steps <= 1 { return vc.is_valid(to); }` (rrt.rs:99-101)
+      const unsigned long long nn = single ? 1ull : n;
+      const double nf = (double)n;
+      for (unsigned long long base = 0; base < nn; base += L) {
+        const unsigned long long i = base + lane_g + 1;
+        bool bad = false;
+        if (i <= nn) {
+          if (single) {
+#pragma unroll
+            for (int d = 0; d < DT; ++d) x[d] = to[d];
+          } else {
+            const double t = __ddiv_rn((double)i, nf);  // `i as f64 / num_steps as f64` (rrt.rs:105)
+#pragma unroll
+            for (int d = 0; d < DT; ++d) x[d] = __dadd_rn(from[d], __dmul_rn(__dsub_rn(to[d], from[d]), t));
+          }
+          float xf[DT];
+#pragma unroll
+          for (int d = 0; d < DT; ++d) xf[d] = __double2float_rn(x[d]);
+          if (full_walk) {
+            bad = !state_valid_staged_dev<DT>(w, x, xf, tol, sm_sph, sm_cap);
+          } else {
+            for (unsigned sidx = 0; sidx < cnt && !bad; ++sidx) {
+              uint32_t o = my_list[sidx];
+              if (o < n_sph) {
+                bad = sphere_maybe_hit32_s<DT>(xf, sm_sph + o * w.sphere32_stride * 4u, tol.a2_s, tol.ce_s) &&
+                      sphere_hit_dev<DT>(x, w.spheres + (size_t)o * w.sphere_stride, DT);
+              } else if ((o -= n_sph) < n_box) {
+                bad = aabb_hit_dev<DT>(x, w.aabbs + (size_t)o * w.aabb_stride, DT);
+              } else {
+                o -= n_box;
+                bad = capsule_half_maybe_hit32_s<DT>(xf, sm_cap + (o >> 1) * w.capsule32p_stride * 4u, o & 1u,
+                                                     tol.a2_c, tol.ce_c) &&
+                      capsule_hit_dev<DT>(x, w.capsules + (size_t)o * w.capsule_stride, DT);
+              }
+            }
+          }
+        }
+        const unsigned b = (__ballot_sync(group_mask, bad) & group_mask) >> group_shift;
+        if (b) {
+          first_bad = base + (unsigned long long)(__ffs(b) - 1) + 1ull;
+          break;
+        }
+      }
+    }
+    __syncwarp(group_mask);  // the list is reused by the group's next edge
+    if (lane_g == 0) {
+      p.valid[e] = first_bad == 0 ? 1 : 0;
+      if (p.first_invalid)
+        p.first_invalid[e] = first_bad > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)first_bad;
+    }
+  }
+}
+
 // Few edges against a large world: one CTA per edge, threads spread over (step, obstacle) pairs
 // so that a single check_motion / is_valid call (the trait path, or an unfused planner
 // iteration) is not one thread walking thousands of obstacles.  first_invalid = the smallest
@@ -343,6 +505,27 @@ __global__ void __launch_bounds__(256) motion_small_kernel(const MotionParams p)
     default: { constexpr int DD = 0; CALL; } break;     \
   }
 
+#define OXG_DISPATCH_FAST_DT(D_RT, CALL)                \
+  switch (D_RT) {                                       \
+    case 1: { constexpr int DD = 1; CALL; } break;      \
+    case 2: { constexpr int DD = 2; CALL; } break;      \
+    case 3: { constexpr int DD = 3; CALL; } break;      \
+    case 4: { constexpr int DD = 4; CALL; } break;      \
+    case 5: { constexpr int DD = 5; CALL; } break;      \
+    case 6: { constexpr int DD = 6; CALL; } break;      \
+    case 7: { constexpr int DD = 7; CALL; } break;      \
+    case 8: { constexpr int DD = 8; CALL; } break;      \
+    case 9: { constexpr int DD = 9; CALL; } break;      \
+    case 10: { constexpr int DD = 10; CALL; } break;    \
+    case 11: { constexpr int DD = 11; CALL; } break;    \
+    case 12: { constexpr int DD = 12; CALL; } break;    \
+    case 13: { constexpr int DD = 13; CALL; } break;    \
+    case 14: { constexpr int DD = 14; CALL; } break;    \
+    case 15: { constexpr int DD = 15; CALL; } break;    \
+    case 16: { constexpr int DD = 16; CALL; } break;    \
+    default: break;                                     \
+  }
+
 static int check_world_space(const oxg_world_s* w, const oxg_space_desc& sp) {
   const bool has_rn = w->n_spheres || w->n_aabbs || w->n_capsules;
   if (has_rn && w->dim != sp.n_real) {
@@ -438,6 +621,17 @@ int motion_check_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStre
                  (size_t)((w->n_capsules + 1) / 2) * w->capsule32p_stride * 4;
   if (stage > 40 * 1024 || fast_dim(sp) == 0) stage = 0;
   p.world_smem_bytes = (uint32_t)stage;
+  // Whole-edge cull (motion_cull_kernel): staged RealVector worlds with enough obstacles for
+  // the cull pass to pay.  OXG_MOTION_CULL=0 runs the plain per-step walk for A/B measurements.
+  static const bool cull_on = [] {
+    const char* v = getenv("OXG_MOTION_CULL");
+    return !(v && v[0] == '0');
+  }();
+  if (cull_on && stage > 0 && !wide && w->n_so2 == 0 && n_obst >= 16 && n_obst <= 60000) {
+    OXG_DISPATCH_FAST_DT(fast_dim(sp), (motion_cull_kernel<DD, 4><<<blocks, threads, stage, stream>>>(p)));
+    OXG_LAUNCH_CHECK();
+    return OXG_OK;
+  }
   if (wide) {
     OXG_DISPATCH_DT(fast_dim(sp), (motion_kernel<DD, 32><<<blocks, threads, stage, stream>>>(p)));
   } else {

@@ -210,3 +210,60 @@ def test_few_states_large_world(oxg, orc, dim):
     np.testing.assert_array_equal(v, ov)
     np.testing.assert_array_equal(first, ofirst)
     gw2.close()
+
+
+@pytest.mark.parametrize("dim,scale,offset", [(2, 1.0, 0.0), (3, 1.0, 0.0), (7, 1.0, 0.0), (7, 1.0, 1e6),
+                                              (6, 1e-20, 0.0), (7, 1e150, 0.0), (14, 1.0, 0.0)])
+def test_whole_edge_cull_never_changes_results(oxg, orc, dim, scale, offset):
+    """Many edges take motion_cull_kernel: an obstacle is dropped for a whole edge only when the
+    ball around the midpoint provably clears it.  Validity AND the first invalid step must be the
+    sequential loop's (rrt.rs:90-116), for short, long, grazing, zero-length and NaN edges."""
+    spheres, aabbs, capsules = worlds.calibrated_obstacles(3 * dim, dim, 30, 20, 40, p_each=0.01)
+
+    def tr(a, radius_col=None):
+        a = a.copy()
+        if radius_col is None:
+            return a * scale + offset
+        a[:, :radius_col] = a[:, :radius_col] * scale + offset
+        a[:, radius_col] = a[:, radius_col] * scale
+        return a
+
+    S, B, C = tr(spheres, dim), tr(aabbs), tr(capsules, 2 * dim)
+    sp, sp_o = oxg.Space.real_vector(dim), orc.space(dim)
+    gw, ow, keep = _world_pair(oxg, orc, dim, S, B, C)
+    rng = np.random.default_rng(700 + dim)
+    n = 16000
+    frm = rng.uniform(-1.0, 1.0, size=(n, dim))
+    to = frm + rng.normal(scale=0.2, size=frm.shape) * rng.random((n, 1))
+    to[:2000] = rng.uniform(-1.0, 1.0, size=(2000, dim))            # long edges across the world
+    to[2000:2100] = frm[2000:2100]                                  # zero length
+    # grazing: start on a sphere's surface and leave tangentially / radially
+    k = min(len(spheres), 200)
+    c, r = spheres[:k, :dim], spheres[:k, dim]
+    u = rng.normal(size=(k, dim))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    frm[3000:3000 + k] = c + u * r[:, None]
+    to[3000:3000 + k] = frm[3000:3000 + k] + u * 0.05
+    v = rng.normal(size=(k, dim))
+    v -= (v * u).sum(1, keepdims=True) * u
+    frm[4000:4000 + k] = c + u * (r[:, None] * (1 + 1e-12))
+    to[4000:4000 + k] = frm[4000:4000 + k] + v * 0.1
+    frm, to = frm * scale + offset, to * scale + offset
+    frm[5000, 0] = np.nan
+    to[5001, dim - 1] = np.inf
+    res = 0.02 * scale
+    got_v, got_f = gw.check_motion(sp, frm, to, res, want_first_invalid=True)
+    want_v, want_f = orc.check_motion(ow, sp_o, frm, to, res)
+    np.testing.assert_array_equal(got_v, want_v)
+    # an infinitely long edge: the reference loop would never end; the library reports
+    # "invalid, step 0xFFFFFFFF" (include/oxg.h), the oracle wrapper "invalid, step 0"
+    assert got_v[5001] == 0 and got_f[5001] == 0xFFFFFFFF
+    got_f[5001] = want_f[5001]
+    np.testing.assert_array_equal(got_f, want_f)
+    if offset == 0.0:
+        assert 0 < want_v.sum() < want_v.size
+    with oxg.StateStore(sp) as st:
+        st.append(np.vstack([frm, to]))
+        fi = np.arange(n, dtype=np.uint32)
+        np.testing.assert_array_equal(gw.check_edges(st, fi, fi + n, res), want_v)
+    gw.close()
