@@ -121,6 +121,22 @@ extern "C" {
                              d_counters: *mut u64) -> c_int;
     pub fn oxg_prm_resolve_dev(s: oxg_store, d_idx_all: *const u32, k: u32,
                                d_valid_all: *mut u8) -> c_int;
+    // multi-GPU PRM build (NCCL inside the library; the id travels by the host's rendezvous)
+    pub fn oxg_dist_unique_id(out_id_128: *mut c_void) -> c_int;
+    pub fn oxg_dist_create(unique_id_128: *const c_void, rank: c_int, world_size: c_int,
+                           out: *mut oxg_dist) -> c_int;
+    pub fn oxg_dist_destroy(d: oxg_dist) -> c_int;
+    pub fn oxg_dist_row_range(n: u64, rank: c_int, world_size: c_int, radius_mode: c_int,
+                              row_begin: *mut u64, row_end: *mut u64) -> c_int;
+    pub fn oxg_prm_build_knn_dist(d: oxg_dist, w: oxg_world, s: oxg_store, k: u32, resolution: f64,
+                                  idx: *mut u32, dist: *mut f64, valid: *mut u8,
+                                  stats: *mut oxg_prm_stats) -> c_int;
+    pub fn oxg_prm_build_knn_dist_dev(d: oxg_dist, w: oxg_world, s: oxg_store, k: u32,
+                                      resolution: f64, d_idx_all: *mut u32, d_dist_all: *mut f64,
+                                      d_valid_all: *mut u8, d_counters: *mut u64) -> c_int;
+    pub fn oxg_prm_build_radius_dist(d: oxg_dist, w: oxg_world, s: oxg_store,
+                                     connection_radius: f64, resolution: f64, offsets: *mut u64,
+                                     idx: *mut u32, cap: u64, stats: *mut oxg_prm_stats) -> c_int;
     pub fn oxg_fp64_peak(out_ops_per_s: *mut f64, out_ms: *mut f64) -> c_int;
     pub fn oxg_fp32_peak(out_ops_per_s: *mut f64, out_ms: *mut f64) -> c_int;
     pub fn oxg_kernel_launches(reset: c_int) -> u64;
@@ -139,3 +155,5 @@ extern "C" {
 
 #[allow(non_camel_case_types)]
 pub type oxg_so3_cones = *mut std::os::raw::c_void;
+#[allow(non_camel_case_types)]
+pub type oxg_dist = *mut std::os::raw::c_void;

@@ -49,6 +49,7 @@ extern "C" {
 #define OXG_E_EMPTY (-7)      /* query against an empty store                   */
 #define OXG_E_ALLOC (-8)      /* host/device allocation failed                  */
 #define OXG_E_INTERNAL (-9)   /* unexpected C++ exception caught at the boundary */
+#define OXG_E_NCCL (-10)      /* NCCL unavailable in this process, or a NCCL call failed */
 
 #define OXG_INVALID_INDEX 0xFFFFFFFFu
 
@@ -286,6 +287,53 @@ int oxg_prm_resolve_dev(oxg_store s, const uint32_t* d_idx_all, uint32_t k,
 /* The CUDA stream of a store (cudaStream_t as void*), so callers can order their
  * own work (NCCL collectives, torch ops) after the library's. */
 int oxg_store_stream(oxg_store s, void** out_stream);
+
+/* ---- multi-GPU PRM build (one process per GPU, NCCL over NVLink) -----------------
+ * The sharded form of PRM::construct_roadmap's body (prm.rs:117-146): every rank holds
+ * the same store and world (each appended the same samples), owns a slice of the query
+ * rows and of the candidate edges, and the per-node rows are exchanged with NCCL
+ * all-gathers inside the library, on the store's stream.  Every rank returns the
+ * complete roadmap, identical to what the single-GPU entry point returns.
+ *
+ *  oxg_dist_unique_id : ncclGetUniqueId (128 bytes).  Rank 0 calls it and hands the bytes
+ *                       to the other ranks by whatever rendezvous the host has (MPI,
+ *                       torch.distributed, a file).
+ *  oxg_dist_create    : ncclCommInitRank on the calling thread's current CUDA device;
+ *                       collective over all ranks.  world_size 1 needs no id and no NCCL.
+ *  oxg_dist_row_range : the query rows rank owns.  k-NN mode: [rank n / world,
+ *                       (rank+1) n / world) (uniform work per row).  Radius mode:
+ *                       [n sqrt(rank/world), n sqrt((rank+1)/world)) — node i scans the i
+ *                       earlier nodes (prm.rs:131), so equal areas of the triangle balance it.
+ *  oxg_prm_build_knn_dist      : oxg_prm_build_knn over all rows; idx/dist/valid are
+ *                       [N][k] host arrays (each nullable: a rank that does not want the
+ *                       roadmap on the host passes NULL).  Exchanges: one grouped
+ *                       all-gather of the idx and dist rows, one of the validity rows.
+ *                       stats->knn_ms is the device time of the whole sharded build on
+ *                       this rank; n_edges_checked / n_edges_valid count this rank's shard.
+ *  oxg_prm_build_knn_dist_dev  : the same with device outputs ([N][k]; d_counters: 2 x u64
+ *                       = motion checks executed / valid on this rank), enqueued on the
+ *                       store's stream without synchronising.
+ *  oxg_prm_build_radius_dist   : oxg_prm_build_radius over all rows (reference-faithful
+ *                       mode); the ragged lower-index adjacency lists are exchanged with one
+ *                       broadcast per rank inside a group call.  offsets has N+1 entries;
+ *                       fails with OXG_E_CAPACITY (offsets filled) on every rank alike.
+ * NCCL is looked up at run time (the libnccl.so.2 already loaded in the process, else the
+ * system one); without it, world sizes above 1 fail with OXG_E_NCCL.
+ */
+typedef struct oxg_dist_s* oxg_dist;
+int oxg_dist_unique_id(void* out_id_128);
+int oxg_dist_create(const void* unique_id_128, int rank, int world_size, oxg_dist* out);
+int oxg_dist_destroy(oxg_dist d);
+int oxg_dist_row_range(uint64_t n, int rank, int world_size, int radius_mode,
+                       uint64_t* row_begin, uint64_t* row_end);
+int oxg_prm_build_knn_dist(oxg_dist d, oxg_world w, oxg_store s, uint32_t k, double resolution,
+                           uint32_t* idx, double* dist, uint8_t* valid, oxg_prm_stats* stats);
+int oxg_prm_build_knn_dist_dev(oxg_dist d, oxg_world w, oxg_store s, uint32_t k,
+                               double resolution, uint32_t* d_idx_all, double* d_dist_all,
+                               uint8_t* d_valid_all, uint64_t* d_counters);
+int oxg_prm_build_radius_dist(oxg_dist d, oxg_world w, oxg_store s, double connection_radius,
+                              double resolution, uint64_t* offsets, uint32_t* idx, uint64_t cap,
+                              oxg_prm_stats* stats);
 
 /* ---- measurement helpers ----------------------------------------------------------
  * oxg_fp64_peak: measures this GPU's unfused FP64 issue rate (independent DADD/DMUL

@@ -23,6 +23,7 @@ OXG_E_ARG = -6
 OXG_E_EMPTY = -7
 OXG_E_ALLOC = -8
 OXG_E_INTERNAL = -9
+OXG_E_NCCL = -10
 OXG_INVALID_INDEX = 0xFFFFFFFF
 
 ERROR_NAMES = {
@@ -35,6 +36,7 @@ ERROR_NAMES = {
     OXG_E_EMPTY: "OXG_E_EMPTY",
     OXG_E_ALLOC: "OXG_E_ALLOC",
     OXG_E_INTERNAL: "OXG_E_INTERNAL",
+    OXG_E_NCCL: "OXG_E_NCCL",
 }
 
 
@@ -152,6 +154,14 @@ SIGNATURES = {
     "oxg_knn_rows_dev": (C.c_int, [_vp, _u64, _u64, _u32, _pu32, _pd]),
     "oxg_prm_edges_dev": (C.c_int, [_vp, _vp, _pu32, _u32, _dbl, _u64, _u64, _pu8, _pu64]),
     "oxg_prm_resolve_dev": (C.c_int, [_vp, _pu32, _u32, _pu8]),
+    "oxg_dist_unique_id": (C.c_int, [_vp]),
+    "oxg_dist_create": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "oxg_dist_destroy": (C.c_int, [_vp]),
+    "oxg_dist_row_range": (C.c_int, [_u64, C.c_int, C.c_int, C.c_int, C.POINTER(_u64), C.POINTER(_u64)]),
+    "oxg_prm_build_knn_dist": (C.c_int, [_vp, _vp, _vp, _u32, _dbl, _pu32, _pd, _pu8, C.POINTER(PrmStats)]),
+    "oxg_prm_build_knn_dist_dev": (C.c_int, [_vp, _vp, _vp, _u32, _dbl, _pu32, _pd, _pu8, _pu64]),
+    "oxg_prm_build_radius_dist": (
+        C.c_int, [_vp, _vp, _vp, _dbl, _dbl, _pu64, _pu32, _u64, C.POINTER(PrmStats)]),
     "oxg_store_last_scan_ms": (C.c_int, [_vp, C.POINTER(_dbl)]),
     "oxg_fp64_peak": (C.c_int, [C.POINTER(_dbl), C.POINTER(_dbl)]),
     "oxg_fp32_peak": (C.c_int, [C.POINTER(_dbl), C.POINTER(_dbl)]),

@@ -1,12 +1,127 @@
-"""Host-side sharding of the PRM build over ranks: one process per GPU, the store
-and the world replicated, query rows partitioned, results exchanged with all-gathers.
+"""Sharding of the PRM build over ranks: one process per GPU, the store and the
+world replicated, query rows partitioned, results exchanged with all-gathers.
 
-Works on any torch.distributed backend: NCCL on the GPU box (bench.py), gloo in the CPU tests
-(tests/test_sharding_gloo.py).  No data-path collective other than the all-gathers of the
-fixed-width per-node rows exists."""
+``Dist`` is the product path: the library's own multi-GPU entry points (include/oxg.h,
+``oxg_prm_build_knn_dist`` / ``oxg_prm_build_radius_dist``), NCCL inside liboxg, the host only
+carries the 128-byte NCCL id between the ranks (``Dist.from_torch`` uses torch.distributed for
+that rendezvous and nothing else).
+
+The numpy helpers below restate the partitioning rules (row ranges, edge ownership) for the CPU
+tests (tests/test_sharding_gloo.py, world_size-2 gloo) and ``all_gather_rows`` is the
+torch.distributed form of the exchange they exercise."""
 from __future__ import annotations
 
+import ctypes as C
+import math
+
 import numpy as np
+
+
+def radius_row_range(n: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Rows of `rank` in radius mode: node i scans the i earlier nodes (prm.rs:131), so the cuts
+    sit at n*sqrt(g/G) (equal areas of the triangle).  Mirrors oxg_dist_row_range(radius_mode=1)."""
+    def cut(g):
+        if g <= 0:
+            return 0
+        if g >= world_size:
+            return n
+        return min(n, int(math.floor(float(n) * math.sqrt(float(g) / float(world_size)))))
+    return cut(rank), cut(rank + 1)
+
+
+class Dist:
+    """``oxg_dist``: this rank's handle on the library's NCCL communicator."""
+
+    def __init__(self, rank: int, world_size: int, unique_id: bytes | None = None):
+        from ._lib import check, lib
+
+        self.rank, self.world_size = rank, world_size
+        self._h = C.c_void_p()
+        buf = None
+        if world_size > 1:
+            if unique_id is None or len(unique_id) != 128:
+                raise ValueError("a 128-byte NCCL unique id is required for world_size > 1")
+            buf = C.create_string_buffer(bytes(unique_id), 128)
+        check(lib.oxg_dist_create(buf, rank, world_size, C.byref(self._h)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        from ._lib import check, lib
+
+        buf = C.create_string_buffer(128)
+        check(lib.oxg_dist_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def from_torch(cls, dist, rank: int, world_size: int) -> "Dist":
+        """Rendezvous through an initialised torch.distributed group: rank 0 draws the NCCL id
+        and broadcasts the 128 bytes; everything after that is the library's."""
+        if world_size == 1:
+            return cls(0, 1)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(rank, world_size, box[0])
+
+    @property
+    def handle(self):
+        return self._h
+
+    def row_range(self, n: int, radius_mode: bool = False) -> tuple[int, int]:
+        from ._lib import check, lib
+
+        rb, re = C.c_uint64(0), C.c_uint64(0)
+        check(lib.oxg_dist_row_range(n, self.rank, self.world_size, 1 if radius_mode else 0,
+                                     C.byref(rb), C.byref(re)))
+        return rb.value, re.value
+
+    def prm_build_knn(self, world, store, k: int, resolution: float, want_host: bool = True):
+        """The sharded k-NN build -> the complete (idx[N,k], dist[N,k], valid[N,k], stats)."""
+        from ._lib import PrmStats, check, lib
+
+        n = len(store)
+        idx = np.empty((n, k), dtype=np.uint32) if want_host else None
+        dst = np.empty((n, k), dtype=np.float64) if want_host else None
+        valid = np.empty((n, k), dtype=np.uint8) if want_host else None
+        st = PrmStats()
+        p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)  # noqa: E731
+        check(lib.oxg_prm_build_knn_dist(self._h, world.handle, store.handle, k, float(resolution),
+                                         p(idx), p(dst), p(valid), C.byref(st)))
+        return idx, dst, valid, {name: getattr(st, name) for name, _ in PrmStats._fields_}
+
+    def prm_build_radius(self, world, store, connection_radius: float, resolution: float):
+        """The sharded radius build -> CSR (offsets[N+1], idx) of every node's lower-index edges."""
+        from . import _lib
+        from ._lib import PrmStats, check, lib
+
+        n = len(store)
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        cap = max(1024, 32 * n)
+        st = PrmStats()
+        while True:
+            idx = np.empty(cap, dtype=np.uint32)
+            code = lib.oxg_prm_build_radius_dist(self._h, world.handle, store.handle,
+                                                 float(connection_radius), float(resolution),
+                                                 C.c_void_p(offsets.ctypes.data),
+                                                 C.c_void_p(idx.ctypes.data), cap, C.byref(st))
+            if code == _lib.OXG_E_CAPACITY:
+                cap = int(offsets[n])
+                continue
+            check(code)
+            break
+        return offsets, idx[: int(offsets[n])].copy()
+
+    def close(self):
+        from ._lib import lib
+
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.oxg_dist_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def row_range(n: int, rank: int, world_size: int) -> tuple[int, int]:

@@ -124,3 +124,59 @@ def test_row_ranges_cover_and_owner_rule():
     o = sharding.edge_owner(i, j)
     np.testing.assert_array_equal(o, sharding.edge_owner(j, i))     # symmetric
     np.testing.assert_array_equal(o, [3, 4, 10, 11])  # 3^8 odd->lo 3; 4^9 odd->lo 4; 10^2 even->hi; 11^5 even->hi
+
+
+def _range_worker(rank, world_size, port, n, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        import ctypes as C
+
+        from oxmpl_b200 import sharding
+        from oxmpl_b200._lib import lib
+
+        got = []
+        for radius_mode in (0, 1):
+            rb, re = C.c_uint64(0), C.c_uint64(0)
+            assert lib.oxg_dist_row_range(n, rank, world_size, radius_mode, C.byref(rb), C.byref(re)) == 0
+            got += [rb.value, re.value]
+        assert tuple(got[:2]) == sharding.row_range(n, rank, world_size)
+        assert tuple(got[2:]) == sharding.radius_row_range(n, rank, world_size)
+        t = torch.tensor(got, dtype=torch.int64)
+        allr = [torch.zeros(4, dtype=torch.int64) for _ in range(world_size)]
+        dist.all_gather(allr, t)
+        np.save(os.path.join(out_dir, f"ranges{rank}.npy"), torch.stack(allr).numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [601, 1_000_000])
+def test_library_row_ranges_partition_the_rows(tmp_path, n):
+    """The library's own partition (oxg_dist_row_range, used by oxg_prm_build_knn_dist /
+    oxg_prm_build_radius_dist) seen from two ranks: both modes tile [0, n) without gaps, and the
+    radius-mode cut balances the triangular work (node i scans i earlier nodes)."""
+    world_size = 2
+    mp.spawn(_range_worker, args=(world_size, _free_port(), n, str(tmp_path)), nprocs=world_size, join=True)
+    a = np.load(tmp_path / "ranges0.npy")
+    np.testing.assert_array_equal(a, np.load(tmp_path / "ranges1.npy"))
+    for c in (0, 2):
+        assert a[0, c] == 0 and a[-1, c + 1] == n and a[0, c + 1] == a[1, c]
+    work = [(a[r, 3] ** 2 - a[r, 2] ** 2) / 2 for r in range(world_size)]
+    assert abs(work[0] - work[1]) <= 0.01 * sum(work) + 2 * n
+
+
+def test_dist_entry_points_fail_loudly_without_a_device():
+    """No CPU fallback: without a GPU the communicator cannot be created; bad arguments are
+    rejected before anything else."""
+    import ctypes as C
+
+    import oxmpl_b200 as oxg
+    from oxmpl_b200._lib import OXG_E_ARG, OXG_E_CUDA, OXG_E_NULL, lib
+
+    h = C.c_void_p()
+    assert lib.oxg_dist_create(None, 2, 2, C.byref(h)) == OXG_E_ARG
+    assert lib.oxg_dist_create(None, 0, 2, C.byref(h)) == OXG_E_NULL       # world > 1 needs the id
+    assert lib.oxg_dist_row_range(10, 0, 1, 0, None, None) == OXG_E_NULL
+    if oxg.device_count() == 0:
+        assert lib.oxg_dist_create(None, 0, 1, C.byref(h)) == OXG_E_CUDA
