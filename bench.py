@@ -5,17 +5,23 @@ k = 10, capsule-obstacle world (BASELINE.json config 4), at 1/2/4/8 B200.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A *step* is one complete roadmap build over the resident store: the k-NN phase (every node
-against all nodes) and the motion check of every candidate edge.  At N > 1 the query rows and
-the candidate edges are sharded over the ranks against a replicated store (strong scaling:
-the 1M-node job is fixed) and the results are exchanged with two NCCL all-gathers.
+A *step* is one complete roadmap build over the resident store through the library's sharded
+entry point (oxg_prm_build_knn_dist_dev): the bounding-box hierarchy of the store (rebuilt every
+step: "tree_cache" is switched off), the k-NN of every node, the motion check of every candidate
+edge and — at N > 1, where the query rows and the candidate edges are sharded over the ranks
+against a replicated store (strong scaling: the 1M-node job is fixed) — the NCCL all-gathers the
+library issues itself.  Every rank ends with the complete roadmap.
 
-One JSON line is printed by rank 0 (see the task contract): `value` is nodes/s with the
-store resident in HBM, `e2e` is the same build through the host-buffer C ABI with the H2D
-upload of the samples and the D2H read of the roadmap inside the timed region, `roofline`
-is the k-NN kernel's algorithmic FP64 rate against the unfused-FP64 issue peak measured in
-the same run, `cpu_baseline` is the CPU oracle (single thread, as the reference is) on a
-bounded sample.  `--impl reference` times the CPU oracle with all host threads instead.
+One JSON line is printed by rank 0 (see the task contract): `value` is nodes/s with the store
+resident in HBM; `e2e` is the same build through the host-buffer entry point
+(oxg_prm_build_knn_dist) with the H2D upload of the samples and the D2H read of the complete
+roadmap inside the timed region; `roofline` describes the dominant kernel on EXECUTED work
+(tree_knn_kernel: FP64 lane-operations it issued / its own time, against the unfused FP64 issue
+peak measured in the same run), `roofline_all_pairs` the all-pairs scan kernel it replaced
+(executed FMA lane-instructions against the measured FP32 lane rate), `roofline_edges` the edge
+phase (the sequential reference's algorithmic operation count, from the oracle's counters);
+`cpu_baseline` is the CPU oracle (single thread, as the reference is) on a bounded sample.
+`--impl reference` times the CPU oracle with all host threads instead and never loads liboxg.
 """
 from __future__ import annotations
 
@@ -38,9 +44,10 @@ METRIC = "PRM edges checked/sec + k-NN queries/sec (7-D, 1M nodes) at 1/2/4/8 B2
 UNIT = "nodes/s (one k-NN query + the motion checks of its candidate edges per node)"
 DIM = 7
 SEED = 4
-# dram__bytes_read.sum + dram__bytes_write.sum of one k-NN launch at this config, from the
-# `ncu --set full` capture summarised in profiles/ (None until captured for the current kernel)
-KNN_DRAM_BYTES_NCU = 2249420000  # profiles/r01_ncu_full_knn_rv_dot_7_2.csv (2.046 GB read + 0.204 GB written)
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch at this config, from the `ncu --set
+# full` captures summarised in profiles/ (None until captured for the current kernel)
+TREE_DRAM_BYTES_NCU = None
+ALLPAIRS_DRAM_BYTES_NCU = 2249420000  # profiles/r01_ncu_full_knn_rv_dot_7_2.csv (2.046 GB read + 0.204 GB written)
 
 
 def parse_args():
@@ -63,7 +70,8 @@ def parse_args():
     return ap.parse_args()
 
 
-def config_dict(args, world_size):
+def config_dict(args):
+    """The same dict on both arms and at every N (the driver compares them)."""
     return {
         "workload": "config 4: PRM roadmap build, 7-D Panda-like joint box, %d valid uniform "
                     "samples (seed %d), k=%d, %d capsules (worlds.capsule_world seed %d, len<=3, "
@@ -72,8 +80,6 @@ def config_dict(args, world_size):
         "k": args.k,
         "dim": DIM,
         "capsules": args.capsules,
-        "sharding": "rows and candidate edges over %d rank(s), replicated store, 2 all-gathers"
-                    % world_size,
         "l2": "store (56 MB) is L2-resident by design; a 256 MiB memset flushes L2 between "
               "steps inside the timed region (<0.1% of a step)",
     }
@@ -83,18 +89,41 @@ def config_dict(args, world_size):
 # workload generation (host; the validity filter that discards invalid samples runs on the GPU
 # for the product arm and in the oracle for the reference arm — outside every timed region)
 # ------------------------------------------------------------------------------------------
-def raw_samples(n, seed):
-    from oxmpl_b200 import worlds
+_WORLDS = None
 
+
+def load_worlds():
+    """oxmpl_b200/worlds.py loaded by path: the generators are plain numpy, and importing the
+    package would map liboxg.so into the process — which the reference arm must not do."""
+    global _WORLDS
+    if _WORLDS is None:
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("oxg_bench_worlds",
+                                                      os.path.join(ROOT, "oxmpl_b200", "worlds.py"))
+        _WORLDS = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_WORLDS)
+    return _WORLDS
+
+
+def raw_samples(n, seed):
+    worlds = load_worlds()
     rng = np.random.default_rng(seed)
     return worlds.PANDA_LO + (worlds.PANDA_HI - worlds.PANDA_LO) * rng.random((n, DIM))
 
 
 def resolution():
-    from oxmpl_b200 import worlds
-    from oxmpl_b200.api import motion_resolution, real_vector_max_extent
+    """space.get_longest_valid_segment_length() * 0.1 (real_vector_state_space.rs:103-118,251-253,
+    rrt.rs:97) for the config-4 box; Python floats are IEEE binary64, math.sqrt is correctly
+    rounded (tests/test_abi.py pins the same arithmetic against the config-1 constants)."""
+    import math
 
-    return motion_resolution(real_vector_max_extent(list(zip(worlds.PANDA_LO, worlds.PANDA_HI))))
+    worlds = load_worlds()
+    s = 0.0
+    for lo, hi in zip(worlds.PANDA_LO, worlds.PANDA_HI):
+        d = float(hi) - float(lo)
+        s = s + d * d
+    return math.sqrt(s) * 0.05 * 0.1
 
 
 def valid_samples(n, is_valid_fn):
@@ -173,17 +202,20 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # reference arm: the CPU oracle (the Rust reference cannot be built here), all host threads
 # ------------------------------------------------------------------------------------------
-def cpu_sample(orc, ow, sp_o, rows, args, res, n_queries, n_edges, threads):
+def _set_omp_threads(threads):
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(threads))
+    except OSError:
+        pass
+
+
+def cpu_sample(orc, ow, sp_o, rows, args, res, n_queries, n_edges, threads, counters=None):
     """Times the oracle on a bounded sample of the same workload.  Returns a dict with the
     per-unit times and the extrapolated whole-build nodes/s."""
     n = rows.shape[0]
     k = args.k
-    os.environ["OMP_NUM_THREADS"] = str(threads)
-    try:
-        lib_omp = C.CDLL("libgomp.so.1")
-        lib_omp.omp_set_num_threads(int(threads))
-    except OSError:
-        pass
+    _set_omp_threads(threads)
     rng = np.random.default_rng(123)
     q_rows = np.sort(rng.choice(n, size=min(n_queries, n), replace=False)).astype(np.uint32)
     t0 = time.perf_counter()
@@ -209,7 +241,7 @@ def cpu_sample(orc, ow, sp_o, rows, args, res, n_queries, n_edges, threads):
         [t.start() for t in ts]
         [t.join() for t in ts]
     else:
-        orc.check_motion(ow, sp_o, frm, to, res)
+        orc.check_motion(ow, sp_o, frm, to, res, counters=counters)
     t_edge = time.perf_counter() - t0
     s_per_query = t_knn / len(q_rows)
     s_per_edge = t_edge / max(len(i), 1)
@@ -217,13 +249,36 @@ def cpu_sample(orc, ow, sp_o, rows, args, res, n_queries, n_edges, threads):
             "n_edges": int(len(i)), "t_knn": t_knn, "t_edge": t_edge}
 
 
+def edges_per_node_cpu(orc, sp_o, rows, k, n_probe=24):
+    """Distinct candidate edges per node of the k-NN build = k minus half of the mutual slots,
+    measured with the oracle: the k-NN rows of a few nodes and of all their neighbours."""
+    n = rows.shape[0]
+    _set_omp_threads(os.cpu_count() or 1)
+    rng = np.random.default_rng(321)
+    probe = np.sort(rng.choice(n, size=min(n_probe, n), replace=False)).astype(np.uint32)
+    idx, _ = orc.knn(sp_o, rows, rows[probe], k, exclude=probe)
+    nb = np.unique(idx[idx != 0xFFFFFFFF]).astype(np.uint32)
+    nidx, _ = orc.knn(sp_o, rows, rows[nb], k, exclude=nb)
+    row_of = {int(v): t for t, v in enumerate(nb)}
+    slots = mutual = 0
+    for r, i in enumerate(probe):
+        for j in idx[r]:
+            if j == 0xFFFFFFFF:
+                continue
+            slots += 1
+            mutual += int(i in nidx[row_of[int(j)]])
+    if slots == 0:
+        return float(k)
+    return (slots - 0.5 * mutual) / len(probe)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import oracle
-    from oxmpl_b200 import worlds
+    from oracle import oracle  # the only native library this arm loads
 
+    worlds = load_worlds()
     orc = oracle.get()
     threads = os.cpu_count() or 1
     caps = worlds.capsule_world(SEED, worlds.PANDA_LO, worlds.PANDA_HI, args.capsules)
@@ -231,36 +286,37 @@ def run_reference(args):
     ow, keep = orc.world(DIM, capsules=caps)
     res = resolution()
     rows = valid_samples(args.nodes, lambda s: orc.is_valid(ow, sp_o, s))
-    # edges per node of the full build ~ k minus half of the mutual pairs; measured on the sample
+    edges_per_node = edges_per_node_cpu(orc, sp_o, rows, args.k)
     n_q = max(threads * 24, 64)
     n_e = max(threads * 1500, 4000)
     times = []
-    per_step = None
     for it in range(args.warmup + args.steps):
         per_step = cpu_sample(orc, ow, sp_o, rows, args, res, n_q, n_e, threads)
         if it >= args.warmup:
             times.append(per_step)
     s_q = float(np.mean([t["s_per_query"] for t in times]))
     s_e = float(np.mean([t["s_per_edge"] for t in times]))
-    edges_per_node = 0.75 * args.k  # unique candidate edges per node (mutual pairs counted once)
     s_node = s_q + edges_per_node * s_e
     value = 1.0 / s_node
     ms_per_step = 1e3 * float(np.mean([t["t_knn"] + t["t_edge"] for t in times]))
     sample = ("per step: %d k-NN queries x %d nodes + %d motion checks, OpenMP/threads=%d; nodes/s "
-              "extrapolated as 1/(s_per_query + %.2f*s_per_edge)" % (n_q, args.nodes, n_e, threads,
-                                                                     edges_per_node))
+              "extrapolated as 1/(s_per_query + %.3f*s_per_edge), %.3f = distinct candidate edges per "
+              "node measured with the oracle" % (n_q, args.nodes, n_e, threads, edges_per_node,
+                                                 edges_per_node))
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, 1),
+        "config": config_dict(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "knn_queries_per_s": 1.0 / s_q, "edges_checked_per_s": 1.0 / s_e,
+        "edges_per_node": edges_per_node,
         "note": "CPU oracle (C++ restatement of the Rust reference, which cannot be built in this "
                 "image: no cargo/rustc); extrapolated from a bounded sample",
+        "liboxg_mapped": any("liboxg.so" in ln for ln in open("/proc/self/maps")),
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -274,9 +330,10 @@ def run_ours(args):
     import torch.distributed as dist
 
     import oxmpl_b200 as oxg
-    from oxmpl_b200 import worlds
+    from oxmpl_b200 import sharding
     from oxmpl_b200._lib import PrmStats, check, lib
 
+    worlds = load_worlds()
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -289,7 +346,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world_size > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)   # rendezvous only (carries the NCCL id)
+    dctx = sharding.Dist.from_torch(dist, rank, world_size)
 
     n, k = args.nodes, args.k
     sp = oxg.Space.real_vector(DIM)
@@ -302,13 +360,8 @@ def run_ours(args):
     st = oxg.StateStore(sp, capacity=n)
     st.append_ptr(rows_pinned.data_ptr(), n)
     ext = torch.cuda.ExternalStream(st.stream(), device=dev)
-
-    # shard: contiguous query rows (uniform work per query in k-NN-all mode)
-    from oxmpl_b200 import sharding
-
-    rb, re = sharding.row_range(n, rank, world_size)
-    rows_max = sharding.rows_max(n, world_size)
-    even = n % world_size == 0
+    rb, re = dctx.row_range(n)
+    oxg.tuning_set("tree_cache", 0)   # every build pays for its own hierarchy
 
     with torch.cuda.stream(ext):
         d_idx_all = torch.empty((n, k), dtype=torch.int32, device=dev)       # u32 bit patterns
@@ -316,38 +369,15 @@ def run_ours(args):
         d_valid_all = torch.empty((n, k), dtype=torch.uint8, device=dev)
         d_counters = torch.zeros(2, dtype=torch.int64, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        if not even:
-            pad_idx = torch.empty((world_size, rows_max, k), dtype=torch.int32, device=dev)
-            pad_dist = torch.empty((world_size, rows_max, k), dtype=torch.float64, device=dev)
-            pad_valid = torch.empty((world_size, rows_max, k), dtype=torch.uint8, device=dev)
     ext.synchronize()
+    P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
-    def gather(all_t, pad_t):
-        """all-gather of the row shards, in place on the [n, k] tensor."""
-        sharding.all_gather_rows(dist, all_t, rank, world_size, pad_t)
-
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-
-    def step(timed_events=None):
+    def step():
+        """One sharded roadmap build, device-resident, all exchanges inside the library."""
         with torch.cuda.stream(ext):
             flush.zero_()
-            if timed_events:
-                timed_events[0].record(ext)
-            check(lib.oxg_knn_rows_dev(st.handle, rb, re, k,
-                                       C.c_void_p(d_idx_all[rb:re].data_ptr()),
-                                       C.c_void_p(d_dist_all[rb:re].data_ptr())))
-            if timed_events:
-                timed_events[1].record(ext)
-            gather(d_idx_all, None if even else pad_idx)
-            gather(d_dist_all, None if even else pad_dist)
-            check(lib.oxg_prm_edges_dev(gw.handle, st.handle, C.c_void_p(d_idx_all.data_ptr()), k,
-                                        float(res), rb, re, C.c_void_p(d_valid_all.data_ptr()),
-                                        C.c_void_p(d_counters.data_ptr())))
-            gather(d_valid_all, None if even else pad_valid)
-            check(lib.oxg_prm_resolve_dev(st.handle, C.c_void_p(d_idx_all.data_ptr()), k,
-                                          C.c_void_p(d_valid_all.data_ptr())))
-            if timed_events:
-                timed_events[2].record(ext)
+        check(lib.oxg_prm_build_knn_dist_dev(dctx.handle, gw.handle, st.handle, k, float(res),
+                                             P(d_idx_all), P(d_dist_all), P(d_valid_all), P(d_counters)))
 
     def barrier():
         ext.synchronize()
@@ -364,50 +394,87 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     oxg.kernel_launches(reset=True)
-    knn_ms, total_ms = [], []
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record(ext)
-    step_events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    for s_i in range(args.steps):
-        step(step_events[s_i])
+    for _ in range(args.steps):
+        step()
     stop.record(ext)
     barrier()
     launches = oxg.kernel_launches()
     elapsed_ms = start.elapsed_time(stop)
-    for e in step_events:
-        knn_ms.append(e[0].elapsed_time(e[1]))
-        total_ms.append(e[0].elapsed_time(e[2]))
     counters = d_counters.cpu().numpy()
-    n_checked_local, n_valid_local = int(counters[0]), int(counters[1])
+    n_checked_local = int(counters[0])
 
-    # ---- end-to-end through the host-buffer C ABI ---------------------------------------------
-    rows_local = re - rb
-    h_idx = torch.empty((rows_local, k), dtype=torch.int32).pin_memory()
-    h_dist = torch.empty((rows_local, k), dtype=torch.float64).pin_memory()
-    h_valid = torch.empty((rows_local, k), dtype=torch.uint8).pin_memory()
+    # ---- phase attribution (untimed for the headline): this rank's k-NN rows, then its edges ----
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    knn_ms, edge_ms = [], []
+    oxg.tuning_set("tree_stats", 1)
+    for _ in range(3):
+        with torch.cuda.stream(ext):
+            flush.zero_()
+            ev[0].record(ext)
+        check(lib.oxg_knn_rows_dev(st.handle, rb, re, k, P(d_idx_all[rb:re]), P(d_dist_all[rb:re])))
+        ev[1].record(ext)
+        ext.synchronize()
+        tstats = st.tree_stats()
+        if world_size == 1:
+            check(lib.oxg_prm_edges_dev(gw.handle, st.handle, P(d_idx_all), k, float(res), rb, re,
+                                        P(d_valid_all), P(d_counters)))
+            ev[2].record(ext)
+            ext.synchronize()
+            edge_ms.append(ev[1].elapsed_time(ev[2]))
+        knn_ms.append(ev[0].elapsed_time(ev[1]))
+    oxg.tuning_set("tree_stats", 0)
+    knn_phase_ms = float(np.median(knn_ms))
+    edge_phase_ms = float(np.median(edge_ms)) if edge_ms else None
+
+    # ---- the all-pairs scan kernel this round's hierarchy replaces: one full wave, N = 1 only ----
+    allpairs = None
+    if world_size == 1 and n >= 200_000:
+        oxg.tuning_set("knn_tree", 0)
+        wave_rows = min(n, 148 * 3 * 256)
+        t_ms = []
+        for it in range(4):
+            with torch.cuda.stream(ext):
+                flush.zero_()
+                ev[0].record(ext)
+            check(lib.oxg_knn_rows_dev(st.handle, 0, wave_rows, k, P(d_idx_all[:wave_rows]),
+                                       P(d_dist_all[:wave_rows])))
+            ev[1].record(ext)
+            ext.synchronize()
+            if it:
+                t_ms.append(ev[0].elapsed_time(ev[1]))
+        oxg.tuning_set("knn_tree", -1)
+        allpairs = {"rows": wave_rows, "ms": float(np.median(t_ms))}
+
+    # ---- end-to-end through the host-buffer entry point -----------------------------------------
+    h_idx = torch.empty((n, k), dtype=torch.int32).pin_memory()
+    h_dist = torch.empty((n, k), dtype=torch.float64).pin_memory()
+    h_valid = torch.empty((n, k), dtype=torch.uint8).pin_memory()
     stats = PrmStats()
 
     def e2e_step():
         st.clear()
         st.append_ptr(rows_pinned.data_ptr(), n)                       # H2D: the samples
-        check(lib.oxg_prm_build_knn(gw.handle, st.handle, k, float(res), rb, re,
-                                    C.c_void_p(h_idx.data_ptr()), C.c_void_p(h_dist.data_ptr()),
-                                    C.c_void_p(h_valid.data_ptr()), C.byref(stats)))  # D2H: roadmap
+        check(lib.oxg_prm_build_knn_dist(dctx.handle, gw.handle, st.handle, k, float(res),
+                                         P(h_idx), P(h_dist), P(h_valid), C.byref(stats)))  # D2H: roadmap
 
     e2e_step()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 5))
     for _ in range(e2e_steps):
         e2e_step()
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     clocks = sampler.stop() if rank == 0 else None
+    # the roadmap the e2e path delivered must be the one the resident path holds
+    same = bool(torch.equal(h_idx, d_idx_all.cpu())) if world_size > 1 else None
 
     # ---- max over ranks ---------------------------------------------------------------------
-    vals = torch.tensor([elapsed_ms, e2e_s, float(np.mean(knn_ms)), float(np.mean(total_ms)),
-                         float(n_checked_local)], dtype=torch.float64, device=dev)
+    vals = torch.tensor([elapsed_ms, e2e_s, knn_phase_ms, float(n_checked_local)], dtype=torch.float64,
+                        device=dev)
     if world_size > 1:
         mx = vals.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -415,73 +482,82 @@ def run_ours(args):
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
     else:
         mx, sm = vals, vals
-    elapsed_ms_max, e2e_s_max, knn_ms_max, total_ms_max = (float(mx[0]), float(mx[1]), float(mx[2]),
-                                                           float(mx[3]))
-    edges_checked_total = float(sm[4])
+    elapsed_ms_max, e2e_s_max, knn_ms_max = float(mx[0]), float(mx[1]), float(mx[2])
+    edges_checked_total = float(sm[3])
 
     if rank == 0:
         ms_per_step = elapsed_ms_max / args.steps
         value = n / (ms_per_step * 1e-3)
         peak64_ops, _ = oxg.fp64_peak()
         peak32_ops, _ = oxg.fp32_peak()
-        # algorithmic work of the dominant kernel: 3*D flop per (query, stored) pair
         rows_rank0 = re - rb
-        flops_per_launch = 3.0 * DIM * float(rows_rank0) * float(n)
-        achieved = flops_per_launch / (knn_ms_max * 1e-3)
-        filtered = os.environ.get("OXG_KNN_FILTER", "1") != "0"
-        if filtered:
-            # The kernel evaluates every pair with the certified FP32 pre-filter (dot form: D
-            # packed FP32 FMAs per pair, FFMA2) and recomputes the ~1e-4 survivors in FP64 in
-            # the reference's order; the FP32 FMA pipe bounds it.  achieved = the algorithmic
-            # 3*D flop per pair of SURVEY §8(d) / time; peak = the measured FP32 FMA rate
-            # (lane-instruction rate x 2 flop).
-            peak = peak32_ops * 2.0
-            executed = 1.0 * DIM * float(rows_rank0) * float(n)   # FMA lane-instructions issued
-            roof = {
-                "kernel": "oxg::knn_rv_dot_kernel<7,2>", "bound": "fp32",
-                "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": KNN_DRAM_BYTES_NCU,
-                "algorithmic_flops_per_launch": flops_per_launch, "launch_ms": knn_ms_max,
-                "fma_pipe_utilisation": executed / (knn_ms_max * 1e-3) / peak32_ops,
-                "peak_source": "oxg_fp32_peak(): packed FP32 (FADD2/FFMA2) lane-instruction rate "
-                               "measured in this run x 2 flop per FMA (MEASURED_PEAKS.json holds HBM "
-                               "and bf16-tensor figures only; the path is neither: the store is "
-                               "L2-resident and separately-rounded f64 sums have no tensor-core form)",
-                "vs_unfused_fp64_peak": {
-                    "peak_tflops": peak64_ops / 1e12, "frac": achieved / peak64_ops,
-                    "note": "an all-FP64 evaluation (3*D DADD/DMUL per pair, no FMA) cannot exceed "
-                            "1.0 here; the certified FP32 pre-filter is how the kernel does"},
-                "hbm_peak_gbs_measured": _measured_hbm(),
-            }
-        else:
-            roof = {
-                "kernel": "oxg::knn_rv_kernel<7,2>", "bound": "fp64",
-                "achieved": achieved / 1e12, "peak": peak64_ops / 1e12, "unit": "TFLOP/s",
-                "frac": achieved / peak64_ops, "traffic": 313393408,
-                "algorithmic_flops_per_launch": flops_per_launch, "launch_ms": knn_ms_max,
-                "peak_source": "oxg_fp64_peak(): unfused DADD/DMUL issue rate measured in this run",
-                "hbm_peak_gbs_measured": _measured_hbm(),
-            }
-        edge_ms = total_ms_max - knn_ms_max
+        # dominant kernel: tree_knn_kernel.  Executed work = the reference-order distance
+        # evaluations it actually issued: visited leaves x 32 lanes x (3D - 1) separately rounded
+        # f64 operations (D sub, D mul, D-1 add; SURVEY §8d counts 3D).  The box tests are FP32
+        # and the list merges are shuffles: not counted.
+        kern_ms = tstats["query_kernel_ms"]
+        exec_flops = tstats["leaves_visited"] * 32.0 * (3.0 * DIM - 1.0)
+        achieved = exec_flops / (kern_ms * 1e-3)
+        roof = {
+            "kernel": "oxg::tree_knn_kernel<7>", "bound": "fp64",
+            "achieved": achieved / 1e12, "peak": peak64_ops / 1e12, "unit": "TFLOP/s (unfused f64 add|mul)",
+            "frac": achieved / peak64_ops, "traffic": TREE_DRAM_BYTES_NCU,
+            "launch_ms": kern_ms, "executed_flops_per_launch": exec_flops,
+            "leaves_visited_per_query": tstats["leaves_visited"] / max(tstats["queries"], 1.0),
+            "box_groups_per_query": tstats["box_groups_tested"] / max(tstats["queries"], 1.0),
+            "pairs_evaluated_fraction_of_all_pairs":
+                tstats["leaves_visited"] * 32.0 / (max(tstats["queries"], 1.0) * n),
+            "all_pairs_equivalent_tflops": 3.0 * DIM * float(rows_rank0) * float(n) / (kern_ms * 1e-3) / 1e12,
+            "hierarchy_build_ms": tstats["build_ms"],
+            "peak_source": "oxg_fp64_peak(): unfused DADD/DMUL issue rate measured in this run "
+                           "(MEASURED_PEAKS.json holds HBM and bf16-tensor figures only; the store is "
+                           "L2-resident and separately rounded f64 sums have no tensor-core form)",
+            "note": "an irregular, latency-bound traversal: the fraction is of the FP64 pipe on the "
+                    "work actually executed (about 1% of the all-pairs pair count); ncu stall "
+                    "attribution in profiles/",
+            "hbm_peak_gbs_measured": _measured_hbm(),
+        }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config_dict(args, world_size),
-            "knn_queries_per_s": n / (knn_ms_max * 1e-3),
-            "edges_checked_per_s": edges_checked_total / (max(edge_ms, 1e-6) * 1e-3),
+            "data": "synthetic", "config": config_dict(args),
+            "sharding": "rows and candidate edges over %d rank(s), replicated store; NCCL inside "
+                        "liboxg: one grouped all-gather (idx + dist rows), one all-gather (validity "
+                        "rows)" % world_size,
+            "knn_queries_per_s": float(rows_rank0) / (knn_ms_max * 1e-3) * world_size,
             "edges_checked_per_step": edges_checked_total,
-            "phase_ms": {"knn": knn_ms_max, "gather_edges_resolve": edge_ms},
+            "phase_ms": {"hierarchy_build": tstats["build_ms"], "knn_incl_build": knn_ms_max,
+                         "edges": edge_phase_ms,
+                         "rest_of_step": ms_per_step - knn_ms_max - (edge_phase_ms or 0.0)},
             "e2e": {"value": n / e2e_s_max, "unit": UNIT,
                     "h2d_bytes_per_step": int(n * DIM * 8),
-                    "d2h_bytes_per_step": int(rows_local * k * (4 + 8 + 1)),
+                    "d2h_bytes_per_step": int(n * k * (4 + 8 + 1)),
                     "ms_per_step": e2e_s_max * 1e3,
-                    "path": "oxg_store_clear + oxg_store_append(pinned host rows) + "
-                            "oxg_prm_build_knn(host outputs); wall clock around synchronous calls"},
+                    "path": "per rank: oxg_store_clear + oxg_store_append(pinned host rows) + "
+                            "oxg_prm_build_knn_dist(host outputs: the complete roadmap); wall clock "
+                            "around synchronous calls, max over ranks",
+                    "roadmap_equals_resident_run": same},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
         }
+        if edge_phase_ms:
+            line["edges_checked_per_s"] = edges_checked_total / (edge_phase_ms * 1e-3)
+        if allpairs:
+            executed = 1.0 * DIM * float(allpairs["rows"]) * float(n)   # FMA lane-instructions issued
+            line["roofline_all_pairs"] = {
+                "kernel": "oxg::knn_rv_dot_kernel<7,2>", "bound": "fp32",
+                "what": "the all-pairs scan (oxg_tuning_set knn_tree=0) on one full wave of %d query "
+                        "rows x %d states; not on the headline path any more" % (allpairs["rows"], n),
+                "launch_ms": allpairs["ms"],
+                "achieved": executed / (allpairs["ms"] * 1e-3) / 1e12, "peak": peak32_ops / 1e12,
+                "unit": "T FMA lane-instructions/s", "frac": executed / (allpairs["ms"] * 1e-3) / peak32_ops,
+                "traffic": ALLPAIRS_DRAM_BYTES_NCU,
+                "algorithmic_3D_flop_rate_tflops": 3.0 * executed / (allpairs["ms"] * 1e-3) / 1e12,
+                "full_table_ms_at_this_rate": allpairs["ms"] * n / allpairs["rows"],
+                "peak_source": "oxg_fp32_peak(): packed FP32 lane-instruction rate measured in this run",
+            }
         if world_size == 1 and not args.no_extras:
             try:
                 line["extras"] = extras(oxg, args)
@@ -493,10 +569,27 @@ def run_ours(args):
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port",
                                         "sample": "failed: " + repr(e)}
+            fl = (line.get("cpu_baseline") or {}).get("algorithmic_flops_per_edge")
+            if fl and edge_phase_ms:
+                alg = fl * edges_checked_total
+                line["roofline_edges"] = {
+                    "kernel": "oxg::motion_cull_kernel<7,4> (+ mark / scatter)", "bound": "fp64",
+                    "launch_ms": edge_phase_ms,
+                    "algorithmic_flops_per_edge": fl,
+                    "achieved": alg / (edge_phase_ms * 1e-3) / 1e12, "peak": peak64_ops / 1e12,
+                    "unit": "TFLOP/s (algorithmic: the sequential reference's operation count)",
+                    "frac": alg / (edge_phase_ms * 1e-3) / peak64_ops, "traffic": None,
+                    "note": "SURVEY §8(d) motion-check cost model counted by the oracle on the "
+                            "cpu_baseline edge sample (states x obstacles the sequential loop evaluates "
+                            "before its first hit).  The kernel executes far less: one certified FP32 "
+                            "midpoint-ball test per (edge, obstacle) rules out ~99% of the obstacles "
+                            "for all steps at once, so the algorithmic rate can exceed the FP64 peak",
+                }
         print(json.dumps(line), flush=True)
     if world_size > 1:
         dist.barrier()
         dist.destroy_process_group()
+    dctx.close()
     st.close()
     gw.close()
     return 0
@@ -572,12 +665,14 @@ def _measured_hbm():
 def cpu_baseline(args, rows, caps, res):
     """The CPU oracle, one thread (the reference is single-threaded), bounded sample."""
     from oracle import oracle
+    from oracle.oracle import OrcCounters
 
     orc = oracle.get()
     sp_o = orc.space(DIM)
     ow, keep = orc.world(DIM, capsules=caps)
-    t = cpu_sample(orc, ow, sp_o, rows, args, res, args.cpu_queries, args.cpu_edges, 1)
-    edges_per_node = 0.75 * args.k
+    cnt = OrcCounters()
+    t = cpu_sample(orc, ow, sp_o, rows, args, res, args.cpu_queries, args.cpu_edges, 1, counters=cnt)
+    edges_per_node = edges_per_node_cpu(orc, sp_o, rows, args.k)
     s_node = t["s_per_query"] + edges_per_node * t["s_per_edge"]
     planners = None
     if not args.no_extras:  # the sequential planners' CPU side (configs 2 and 3), same streams
@@ -600,8 +695,11 @@ def cpu_baseline(args, rows, caps, res):
         "value": 1.0 / s_node, "unit": UNIT, "cores": 1, "kind": "port",
         "host_cores_available": os.cpu_count(),
         "knn_queries_per_s": 1.0 / t["s_per_query"], "edges_checked_per_s": 1.0 / t["s_per_edge"],
+        "edges_per_node": edges_per_node,
+        "algorithmic_flops_per_edge": float(cnt.flops) / max(t["n_edges"], 1),
+        "states_per_edge": float(cnt.states) / max(t["n_edges"], 1),
         "sample": "%d k-NN queries x %d nodes (%.1f s) + %d motion checks (%.1f s), single thread; "
-                  "nodes/s extrapolated as 1/(s_per_query + %.2f*s_per_edge)"
+                  "nodes/s extrapolated as 1/(s_per_query + %.3f*s_per_edge)"
                   % (t["n_queries"], rows.shape[0], t["t_knn"], t["n_edges"], t["t_edge"],
                      edges_per_node),
     }

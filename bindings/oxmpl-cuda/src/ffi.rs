@@ -141,6 +141,7 @@ extern "C" {
     pub fn oxg_fp32_peak(out_ops_per_s: *mut f64, out_ms: *mut f64) -> c_int;
     pub fn oxg_kernel_launches(reset: c_int) -> u64;
     pub fn oxg_tuning_set(key: *const std::os::raw::c_char, value: i64) -> c_int;
+    pub fn oxg_store_tree_stats(s: oxg_store, out8: *mut f64) -> c_int;
 
     // include/oxg_so3.h — SO(3) scans, cone validity, check_motion
     pub fn oxg_so3_nn1(s: oxg_store, queries: *const f64, q: u64, idx: *mut u32, dist: *mut f64) -> c_int;

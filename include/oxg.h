@@ -353,8 +353,17 @@ uint64_t oxg_kernel_launches(int reset);
 /* A/B switches for measurements; every setting runs hand-written sm_100a kernels and gives
  * bit-identical results.  "knn_tree": 1 = always answer oxg_knn / oxg_prm_build_knn through the
  * store's bounding-box hierarchy when the space allows it, 0 = always scan every pair,
- * -1 = choose by batch and store size (default). */
+ * -1 = choose by batch and store size (default).  "tree_cache": 0 = rebuild the hierarchy for
+ * every batch instead of reusing it while the store is unchanged (benchmarks that must pay the
+ * build inside the timed step), 1 = reuse (default).  "tree_kind": 0 = order the states by a space-filling key (cheapest build),
+ * 1 = balanced partition order (a few ms per 1e6 states, about half the leaf visits per query),
+ * -1 = by batch size (default).  "tree_stats": 1 = count the visited
+ * leaves and time the query kernel for oxg_store_tree_stats (costs a few percent). */
 int oxg_tuning_set(const char* key, int64_t value);
+/* Counters of the most recent k-NN answered through the hierarchy with "tree_stats" on:
+ * out8 = { build ms, query-kernel ms, leaves visited, 32-child box groups tested, candidates
+ * admitted, list merges, stored states, queries }. */
+int oxg_store_tree_stats(oxg_store s, double* out8);
 
 #ifdef __cplusplus
 }

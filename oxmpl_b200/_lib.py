@@ -167,6 +167,7 @@ SIGNATURES = {
     "oxg_fp32_peak": (C.c_int, [C.POINTER(_dbl), C.POINTER(_dbl)]),
     "oxg_kernel_launches": (_u64, [C.c_int]),
     "oxg_tuning_set": (C.c_int, [C.c_char_p, C.c_int64]),
+    "oxg_store_tree_stats": (C.c_int, [_vp, C.POINTER(_dbl)]),
     # include/oxg_so3.h
     "oxg_so3_nn1": (C.c_int, [_vp, _pd, _u64, _pu32, _pd]),
     "oxg_so3_radius": (C.c_int, [_vp, _pd, _u64, _dbl, _pu64, _pu32, _u64, _pd]),

@@ -178,6 +178,15 @@ class StateStore:
         check(lib.oxg_store_last_scan_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def tree_stats(self) -> dict:
+        """Counters of the last k-NN answered through the bounding-box hierarchy (needs
+        ``tuning_set("tree_stats", 1)`` before the call)."""
+        out = (C.c_double * 8)()
+        check(lib.oxg_store_tree_stats(self._h, out))
+        names = ("build_ms", "query_kernel_ms", "leaves_visited", "box_groups_tested", "candidates",
+                 "merges", "stored_states", "queries")
+        return dict(zip(names, [float(v) for v in out]))
+
     def stream(self) -> int:
         s = C.c_void_p()
         check(lib.oxg_store_stream(self._h, C.byref(s)))

@@ -11,6 +11,9 @@ namespace oxg {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_tune_knn_tree{-1};
+std::atomic<int> g_tune_tree_cache{1};
+std::atomic<int> g_tune_tree_stats{0};
+std::atomic<int> g_tune_tree_kind{-1};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -253,6 +256,18 @@ int oxg_tuning_set(const char* key, int64_t value) {
   }
   if (strcmp(key, "knn_tree") == 0) {
     g_tune_knn_tree.store(value < 0 ? -1 : (value ? 1 : 0));
+    return OXG_OK;
+  }
+  if (strcmp(key, "tree_cache") == 0) {
+    g_tune_tree_cache.store(value ? 1 : 0);
+    return OXG_OK;
+  }
+  if (strcmp(key, "tree_kind") == 0) {
+    g_tune_tree_kind.store(value < 0 ? -1 : (value ? 1 : 0));
+    return OXG_OK;
+  }
+  if (strcmp(key, "tree_stats") == 0) {
+    g_tune_tree_stats.store(value ? 1 : 0);
     return OXG_OK;
   }
   set_error("unknown tuning key '%s'", key);

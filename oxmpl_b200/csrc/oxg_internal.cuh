@@ -296,11 +296,14 @@ int nn_radius_offsets(oxg_store_s* s, uint64_t Q, uint64_t* d_out);
 void tree_release(oxg_store_s* s);
 bool tree_supported(const oxg_store_s* s, uint32_t k);
 bool tree_is_current(const oxg_store_s* s);
-int tree_build(oxg_store_s* s);
+int tree_build(oxg_store_s* s, bool want_kd);
 int tree_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclude_mode,
                     const uint32_t* d_exclude, uint64_t self_base, uint32_t* d_idx, double* d_dist,
                     unsigned long long* d_stats);
 // runtime tuning switches (oxg_tuning_set): -1 = automatic
 extern std::atomic<int> g_tune_knn_tree;
+extern std::atomic<int> g_tune_tree_cache;  // 0 = rebuild the hierarchy for every batch
+extern std::atomic<int> g_tune_tree_kind;   // -1 auto, 0 space-filling key order, 1 balanced partition
+extern std::atomic<int> g_tune_tree_stats;  // 1 = count visits and time the query kernel
 
 }  // namespace oxg

@@ -35,6 +35,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "oxg_internal.cuh"
 #include "oxg_math.cuh"
@@ -93,12 +94,21 @@ struct TreeView {
   int top;                           // highest level; count[top] <= 32
 };
 
+struct KdTables;
+
 struct StoreTree {
   uint64_t epoch = ~0ull;
   uint64_t size = 0;
+  // measurement (oxg_tuning_set("tree_stats", 1) + oxg_store_tree_stats)
+  cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr, ev_q0 = nullptr, ev_q1 = nullptr;
+  bool have_build_ev = false, have_query_ev = false;
+  uint64_t last_Q = 0;
   DevBuf pts, perm, keys, keys2, vals, vals2, plan, bounds, qorder, tmp;
   DevBuf boxes[TREE_LEVELS];
   DevBuf boxes32[TREE_LEVELS];
+  DevBuf kd_tables, kd_cell_a, kd_cell_b, kd_dim, kd_keys_a, kd_keys_b;
+  KdTables* kd_host = nullptr;
+  int kind = 0;  // 0 = space-filling key order, 1 = balanced partition order
   TreeView view;
 };
 
@@ -307,6 +317,166 @@ __global__ void tree_level_kernel(const double* __restrict__ child_boxes, uint32
     for (int d = 0; d < D; ++d) {
       g[d * 32] = lo[d];
       g[(D + d) * 32] = hi[d];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Balanced partition order ("k-d order").  The space-filling key above is cheap but its leaves
+// are arbitrary runs of 32 along the curve: where the curve jumps, a leaf's box spans two distant
+// cells (measured on the config-4 store: the leaf boxes add up to 5.6x the volume of the domain
+// and a query's k-th-distance ball meets 129 of them; with the partition below 0.67x and 63).
+// Here every node of the 32-ary hierarchy is cut into its (up to) 32 children by three rounds of
+// splits — 4 ways, 4 ways, 2 ways — each along the widest side of the part's cell, at equal
+// counts of children, so children are compact cells and sibling groups never straddle a jump.
+// One round = one radix sort of (segment id, quantised coordinate) over all states; the segment
+// tables depend on N only and are made on the host.  3 rounds per hierarchy level (9 for 1e6).
+// ---------------------------------------------------------------------------------------
+struct KdRound {           // device-resident tables of one round (segmentation before the round)
+  uint32_t n_seg;          // segments before the round
+  uint32_t n_child;        // segments after it
+  const uint32_t* begin;   // [n_seg + 1] first position (in points) of every segment
+  const uint8_t* parts;    // [n_seg] parts this round cuts the segment into (1 = untouched)
+  const uint32_t* c_begin; // [n_child + 1] positions of the segments after the round
+  const uint32_t* c_parent;// [n_child]
+  const uint8_t* c_part;   // [n_child] which part of its parent
+};
+
+// The dimension every splitting segment is cut along: the widest side of its cell.
+__global__ void kd_choose_dim_kernel(KdRound r, int dim, const double* __restrict__ cell,
+                                     uint8_t* __restrict__ seg_dim) {
+  for (uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x; sidx < r.n_seg; sidx += gridDim.x * blockDim.x) {
+    const double* c = cell + (size_t)sidx * 2 * dim;
+    int best = 0;
+    double w = -1.0;
+    for (int d = 0; d < dim; ++d) {
+      const double e = c[dim + d] - c[d];
+      if (e > w) {  // NaN / empty extents never win
+        w = e;
+        best = d;
+      }
+    }
+    seg_dim[sidx] = (uint8_t)best;
+  }
+}
+
+// key = (segment << 32) | order-preserving 32-bit image of the split coordinate within the cell
+// (untouched segments keep their order: the position inside the segment).
+__global__ void kd_keys_kernel(KdRound r, int dim, const double* __restrict__ db, uint64_t pitch, uint32_t n,
+                               const uint32_t* __restrict__ order, const double* __restrict__ cell,
+                               const uint8_t* __restrict__ seg_dim, unsigned long long* __restrict__ keys) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t lo = 0, hi = r.n_seg;  // last segment with begin <= i
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(r.begin + mid) <= i) lo = mid; else hi = mid;
+    }
+    uint32_t sub = i - __ldg(r.begin + lo);
+    if (__ldg(r.parts + lo) > 1) {
+      const int d = seg_dim[lo];
+      const double c0 = cell[(size_t)lo * 2 * dim + d], c1 = cell[(size_t)lo * 2 * dim + dim + d];
+      const double x = db[(uint64_t)d * pitch + order[i]];
+      double t = (x - c0) / (c1 - c0);  // NaN (x NaN, or a zero-width cell) sorts last / together
+      t = fmin(fmax(t, 0.0), 1.0) * 4294967295.0;
+      sub = (t == t) ? (uint32_t)t : 0xFFFFFFFFu;
+      if (!(x == x)) sub = 0xFFFFFFFFu;
+    }
+    keys[i] = ((unsigned long long)lo << 32) | sub;
+  }
+}
+
+// Cells after the round: the parent's cell with the split side narrowed to the part's own
+// first / last coordinate (the states are sorted along it).
+__global__ void kd_cells_kernel(KdRound r, int dim, const double* __restrict__ db, uint64_t pitch, uint32_t n,
+                                const uint32_t* __restrict__ order, const double* __restrict__ cell,
+                                const uint8_t* __restrict__ seg_dim, double* __restrict__ cell_out) {
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < r.n_child; c += gridDim.x * blockDim.x) {
+    const uint32_t par = r.c_parent[c];
+    const double* pc = cell + (size_t)par * 2 * dim;
+    double* oc = cell_out + (size_t)c * 2 * dim;
+    for (int d = 0; d < 2 * dim; ++d) oc[d] = pc[d];
+    const uint32_t parts = r.parts[par];
+    if (parts > 1) {
+      const int d = seg_dim[par];
+      const uint32_t b = r.c_begin[c], e = r.c_begin[c + 1];
+      if (e > b) {
+        const uint32_t part = r.c_part[c];
+        const double first = db[(uint64_t)d * pitch + order[b]];
+        const double last = db[(uint64_t)d * pitch + order[e - 1]];
+        if (part > 0 && first == first) oc[d] = first;
+        if (part + 1 < parts && last == last) oc[dim + d] = last;
+      }
+    }
+  }
+}
+
+__global__ void kd_iota_kernel(uint32_t* __restrict__ v, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = i;
+}
+
+__global__ void kd_root_cell_kernel(const unsigned long long* __restrict__ bounds, int dim, double* cell) {
+  const int d = threadIdx.x;
+  if (d < dim) {
+    const double lo = ord_decode(bounds[d]), hi = ord_decode(bounds[kMaxFastDim + d]);
+    cell[d] = (lo <= hi) ? lo : 0.0;
+    cell[dim + d] = (lo <= hi) ? hi : 0.0;
+  }
+}
+
+// Host tables of all rounds for n states (they depend on n alone).
+struct KdTables {
+  uint64_t n = 0;
+  struct Round {
+    std::vector<uint32_t> begin, c_begin, c_parent;
+    std::vector<uint8_t> parts, c_part;
+  };
+  std::vector<Round> rounds;
+  std::vector<KdRound> dev_rounds;  // device views of the uploaded tables
+  uint32_t max_seg = 1;
+  bool uploaded = false;
+};
+
+static void kd_make_tables(uint64_t n, KdTables* out) {
+  out->n = n;
+  out->rounds.clear();
+  out->uploaded = false;
+  const uint64_t n_leaves = (n + 31) / 32;
+  // hierarchy levels above the leaves: a node of level l spans 32^l leaves
+  int top = 0;
+  for (uint64_t c = n_leaves; c > 32; c = (c + 31) / 32) ++top;
+  struct Seg { uint64_t a, b; };  // in leaves
+  std::vector<Seg> segs{{0, n_leaves}};
+  static const int kArity[3] = {4, 4, 2};
+  for (int lvl = top + 1; lvl >= 1; --lvl) {
+    uint64_t unit = 1;
+    for (int i = 1; i < lvl; ++i) unit *= 32;  // leaves per child of a level-`lvl` node
+    for (int sub = 0; sub < 3; ++sub) {
+      KdTables::Round rd;
+      std::vector<Seg> next;
+      bool any = false;
+      for (size_t si = 0; si < segs.size(); ++si) {
+        const Seg sg = segs[si];
+        const uint64_t nch = (sg.b - sg.a + unit - 1) / unit;
+        const uint64_t parts = std::min<uint64_t>((uint64_t)kArity[sub], std::max<uint64_t>(nch, 1));
+        rd.begin.push_back((uint32_t)std::min<uint64_t>(sg.a * 32, n));
+        rd.parts.push_back((uint8_t)parts);
+        any = any || parts > 1;
+        const uint64_t base = nch / parts, extra = nch % parts;
+        uint64_t a = sg.a;
+        for (uint64_t pt = 0; pt < parts; ++pt) {
+          const uint64_t c = base + (pt < extra ? 1 : 0);
+          const uint64_t b = parts == 1 ? sg.b : std::min<uint64_t>(a + c * unit, sg.b);
+          rd.c_begin.push_back((uint32_t)std::min<uint64_t>(a * 32, n));
+          rd.c_parent.push_back((uint32_t)si);
+          rd.c_part.push_back((uint8_t)pt);
+          next.push_back({a, b});
+          a = b;
+        }
+      }
+      rd.begin.push_back((uint32_t)n);
+      rd.c_begin.push_back((uint32_t)n);
+      segs.swap(next);
+      if (any) out->rounds.push_back(std::move(rd));
     }
   }
 }
@@ -731,6 +901,17 @@ void tree_release(oxg_store_s* s) {
   t->tmp.release();
   for (auto& b : t->boxes) b.release();
   for (auto& b : t->boxes32) b.release();
+  t->kd_tables.release();
+  t->kd_cell_a.release();
+  t->kd_cell_b.release();
+  t->kd_dim.release();
+  t->kd_keys_a.release();
+  t->kd_keys_b.release();
+  delete t->kd_host;
+  if (t->ev_b0) cudaEventDestroy(t->ev_b0);
+  if (t->ev_b1) cudaEventDestroy(t->ev_b1);
+  if (t->ev_q0) cudaEventDestroy(t->ev_q0);
+  if (t->ev_q1) cudaEventDestroy(t->ev_q1);
   delete t;
   s->tree = nullptr;
 }
@@ -742,7 +923,25 @@ bool tree_supported(const oxg_store_s* s, uint32_t k) {
 
 bool tree_is_current(const oxg_store_s* s) {
   const StoreTree* t = static_cast<const StoreTree*>(s->tree);
-  return t && t->epoch == s->epoch && t->size == s->size;
+  return t && g_tune_tree_cache.load() != 0 && t->epoch == s->epoch && t->size == s->size;
+}
+
+static bool tree_stats_on() {
+  if (g_tune_tree_stats.load() > 0) return true;
+  static const bool env_on = [] {
+    const char* v = getenv("OXG_TREE_STATS");
+    return v && *v && *v != '0';
+  }();
+  return env_on;
+}
+
+static int tree_events(StoreTree* t) {
+  if (t->ev_b0) return OXG_OK;
+  OXG_CUDA_TRY(cudaEventCreate(&t->ev_b0));
+  OXG_CUDA_TRY(cudaEventCreate(&t->ev_b1));
+  OXG_CUDA_TRY(cudaEventCreate(&t->ev_q0));
+  OXG_CUDA_TRY(cudaEventCreate(&t->ev_q1));
+  return OXG_OK;
 }
 
 #define OXG_TREE_DISPATCH_D(D_RT, CALL)              \
@@ -758,10 +957,99 @@ bool tree_is_current(const oxg_store_s* s) {
     default: break;                                  \
   }
 
-// (Re)builds the hierarchy of the store's current contents on the store's stream.
-int tree_build(oxg_store_s* s) {
+// The balanced partition order of the store's states -> `order` (device, n entries).
+static int kd_order(oxg_store_s* s, StoreTree* t, const unsigned long long* bounds, uint32_t** order_out) {
+  const uint32_t n = (uint32_t)s->size;
+  const int dim = (int)s->dim;
+  if (!t->kd_host) t->kd_host = new KdTables();
+  KdTables& T = *t->kd_host;
+  if (T.n != n || !T.uploaded) {
+    // one upload of every round's tables (kept until the store's size changes)
+    kd_make_tables(n, &T);
+    size_t bytes = 0;
+    T.max_seg = 1;
+    for (const auto& rd : T.rounds) {
+      bytes += (rd.begin.size() + rd.c_begin.size() + rd.c_parent.size()) * sizeof(uint32_t);
+      bytes += ((rd.parts.size() + 3) & ~size_t(3)) + ((rd.c_part.size() + 3) & ~size_t(3));
+      T.max_seg = std::max<uint32_t>(T.max_seg, (uint32_t)rd.c_parent.size());
+    }
+    std::vector<unsigned char> blob(bytes);
+    OXG_TRY(t->kd_tables.ensure(bytes + 16));
+    unsigned char* dbase = t->kd_tables.as<unsigned char>();
+    T.dev_rounds.clear();
+    size_t off = 0;
+    auto put = [&](const void* src, size_t nbytes) {
+      memcpy(blob.data() + off, src, nbytes);
+      const size_t at = off;
+      off += (nbytes + 3) & ~size_t(3);
+      return at;
+    };
+    for (const auto& rd : T.rounds) {
+      KdRound r;
+      r.n_seg = (uint32_t)rd.parts.size();
+      r.n_child = (uint32_t)rd.c_parent.size();
+      r.begin = reinterpret_cast<const uint32_t*>(dbase + put(rd.begin.data(), rd.begin.size() * 4));
+      r.c_begin = reinterpret_cast<const uint32_t*>(dbase + put(rd.c_begin.data(), rd.c_begin.size() * 4));
+      r.c_parent = reinterpret_cast<const uint32_t*>(dbase + put(rd.c_parent.data(), rd.c_parent.size() * 4));
+      r.parts = dbase + put(rd.parts.data(), rd.parts.size());
+      r.c_part = dbase + put(rd.c_part.data(), rd.c_part.size());
+      T.dev_rounds.push_back(r);
+    }
+    if (bytes) {
+      OXG_CUDA_TRY(cudaMemcpyAsync(dbase, blob.data(), bytes, cudaMemcpyHostToDevice, s->stream));
+      OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));  // `blob` is pageable host memory
+    }
+    T.uploaded = true;
+  }
+  const uint32_t max_seg = T.max_seg;
+  const std::vector<KdRound>& dev_rounds = T.dev_rounds;
+  OXG_TRY(t->kd_cell_a.ensure((size_t)max_seg * 2 * dim * sizeof(double)));
+  OXG_TRY(t->kd_cell_b.ensure((size_t)max_seg * 2 * dim * sizeof(double)));
+  OXG_TRY(t->kd_dim.ensure(max_seg));
+  OXG_TRY(t->kd_keys_a.ensure((size_t)n * sizeof(unsigned long long)));
+  OXG_TRY(t->kd_keys_b.ensure((size_t)n * sizeof(unsigned long long)));
+  double* cell = t->kd_cell_a.as<double>();
+  double* cell_next = t->kd_cell_b.as<double>();
+  uint32_t* ord = t->vals.as<uint32_t>();
+  uint32_t* ord_next = t->vals2.as<uint32_t>();
+  unsigned long long* keys = t->kd_keys_a.as<unsigned long long>();
+  unsigned long long* keys2 = t->kd_keys_b.as<unsigned long long>();
+  kd_iota_kernel<<<grid_1d(n, 256), 256, 0, s->stream>>>(ord, n);
+  OXG_LAUNCH_CHECK();
+  kd_root_cell_kernel<<<1, 32, 0, s->stream>>>(bounds, dim, cell);
+  OXG_LAUNCH_CHECK();
+  for (const KdRound& r : dev_rounds) {
+    kd_choose_dim_kernel<<<grid_1d(r.n_seg, 128), 128, 0, s->stream>>>(r, dim, cell, t->kd_dim.as<uint8_t>());
+    OXG_LAUNCH_CHECK();
+    kd_keys_kernel<<<grid_1d(n, 256), 256, 0, s->stream>>>(r, dim, s->d_data, s->pitch, n, ord, cell,
+                                                          t->kd_dim.as<uint8_t>(), keys);
+    OXG_LAUNCH_CHECK();
+    int seg_bits = 1;
+    while ((1u << seg_bits) < r.n_seg && seg_bits < 31) ++seg_bits;
+    size_t tmp_bytes = 0;
+    OXG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, ord, ord_next, (int)n, 0,
+                                                 32 + seg_bits, s->stream));
+    OXG_TRY(t->tmp.ensure(tmp_bytes));
+    OXG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(t->tmp.p, tmp_bytes, keys, keys2, ord, ord_next, (int)n, 0,
+                                                 32 + seg_bits, s->stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    std::swap(ord, ord_next);
+    kd_cells_kernel<<<grid_1d(r.n_child, 128), 128, 0, s->stream>>>(r, dim, s->d_data, s->pitch, n, ord, cell,
+                                                                   t->kd_dim.as<uint8_t>(), cell_next);
+    OXG_LAUNCH_CHECK();
+    std::swap(cell, cell_next);
+  }
+  *order_out = ord;
+  return OXG_OK;
+}
+
+// (Re)builds the hierarchy of the store's current contents on the store's stream.  want_kd: the
+// balanced partition order (a few ms for 1e6 states, about half the leaf visits per query);
+// otherwise the space-filling key order (a fraction of a ms).  A current hierarchy of the other
+// kind is reused when the cheaper one was asked for.
+int tree_build(oxg_store_s* s, bool want_kd) {
   StoreTree* t = tree_of(s);
-  if (tree_is_current(s)) return OXG_OK;
+  if (tree_is_current(s) && (t->kind == 1 || !want_kd)) return OXG_OK;
   const uint32_t n = (uint32_t)s->size;
   OXG_TRY(t->bounds.ensure((2 * kMaxFastDim + 4) * sizeof(unsigned long long)));
   OXG_TRY(t->plan.ensure(sizeof(TreePlan)));
@@ -770,6 +1058,11 @@ int tree_build(oxg_store_s* s) {
   OXG_TRY(t->vals.ensure((size_t)n * sizeof(uint32_t)));
   OXG_TRY(t->vals2.ensure((size_t)n * sizeof(uint32_t)));
   unsigned long long* bounds = t->bounds.as<unsigned long long>();
+  const bool stats = tree_stats_on();
+  if (stats) {
+    OXG_TRY(tree_events(t));
+    OXG_CUDA_TRY(cudaEventRecord(t->ev_b0, s->stream));
+  }
   tree_bounds_init_kernel<<<1, 32, 0, s->stream>>>(bounds);
   OXG_LAUNCH_CHECK();
   tree_bounds_kernel<<<grid_1d(n, 256, 148u * 4u), 256, 0, s->stream>>>(s->d_data, s->pitch, n,
@@ -777,15 +1070,27 @@ int tree_build(oxg_store_s* s) {
   OXG_LAUNCH_CHECK();
   tree_plan_kernel<<<1, 32, 0, s->stream>>>(bounds, (int)s->dim, t->plan.as<TreePlan>());
   OXG_LAUNCH_CHECK();
-  tree_keys_kernel<<<grid_1d(n, 256), 256, 0, s->stream>>>(store_view(s), n, (int)s->dim,
-                                                           t->plan.as<TreePlan>(), t->keys.as<uint32_t>(),
-                                                           t->vals.as<uint32_t>());
-  OXG_LAUNCH_CHECK();
-  OXG_TRY(sort_pairs(s, t, t->keys.as<uint32_t>(), t->keys2.as<uint32_t>(), t->vals.as<uint32_t>(),
-                     t->vals2.as<uint32_t>(), n));
+  if (!want_kd) {
+    tree_keys_kernel<<<grid_1d(n, 256), 256, 0, s->stream>>>(store_view(s), n, (int)s->dim,
+                                                             t->plan.as<TreePlan>(), t->keys.as<uint32_t>(),
+                                                             t->vals.as<uint32_t>());
+    OXG_LAUNCH_CHECK();
+  }
+  uint32_t* order = t->vals2.as<uint32_t>();
+  if (want_kd) {
+    OXG_TRY(kd_order(s, t, bounds, &order));
+  } else {
+    OXG_TRY(sort_pairs(s, t, t->keys.as<uint32_t>(), t->keys2.as<uint32_t>(), t->vals.as<uint32_t>(),
+                       t->vals2.as<uint32_t>(), n));
+  }
+  t->kind = want_kd ? 1 : 0;
   int r = OXG_E_INTERNAL;
-  OXG_TREE_DISPATCH_D(s->dim, r = (tree_build_levels<DD>(s, t, t->vals2.as<uint32_t>())));
+  OXG_TREE_DISPATCH_D(s->dim, r = (tree_build_levels<DD>(s, t, order)));
   OXG_TRY(r);
+  if (stats) {
+    OXG_CUDA_TRY(cudaEventRecord(t->ev_b1, s->stream));
+    t->have_build_ev = true;
+  }
   t->epoch = s->epoch;
   t->size = s->size;
   return OXG_OK;
@@ -807,7 +1112,9 @@ static int launch_tree_knn(const TreeKnnParams& p, cudaStream_t st) {
 int tree_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclude_mode,
                     const uint32_t* d_exclude, uint64_t self_base, uint32_t* d_idx, double* d_dist,
                     unsigned long long* d_stats) {
-  OXG_TRY(tree_build(s));
+  int kind = g_tune_tree_kind.load();
+  if (kind < 0) kind = (Q >= 32768 && s->size >= 65536) ? 1 : 0;
+  OXG_TRY(tree_build(s, kind == 1));
   StoreTree* t = tree_of(s);
   // queries in key order: neighbouring warps walk the same part of the hierarchy
   OXG_TRY(t->qorder.ensure((size_t)Q * 4 * sizeof(uint32_t)));
@@ -832,27 +1139,51 @@ int tree_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exc
   p.out_idx = d_idx;
   p.out_dist = d_dist;
   p.stats = d_stats;
-  // OXG_TREE_STATS=1 (diagnostics): count visited leaves / tested groups / insertions and print them
-  static const bool want_stats = [] {
-    const char* v = getenv("OXG_TREE_STATS");
-    return v && *v && *v != '0';
-  }();
-  if (want_stats && !d_stats) {
-    OXG_TRY(t->bounds.ensure((2 * kMaxFastDim + 4) * sizeof(unsigned long long)));
+  // counters + kernel time for oxg_store_tree_stats (measurement runs only: the counting costs
+  // a few instructions per visited leaf)
+  const bool stats = tree_stats_on();
+  if (stats && !d_stats) {
+    OXG_TRY(tree_events(t));
     p.stats = t->bounds.as<unsigned long long>() + 2 * kMaxFastDim;
     OXG_CUDA_TRY(cudaMemsetAsync(p.stats, 0, 4 * sizeof(unsigned long long), s->stream));
+    OXG_CUDA_TRY(cudaEventRecord(t->ev_q0, s->stream));
   }
   int r = OXG_E_INTERNAL;
   OXG_TREE_DISPATCH_D(s->dim, r = (launch_tree_knn<DD>(p, s->stream)));
-  if (want_stats && !d_stats && r == OXG_OK) {
-    unsigned long long h[4] = {0, 0, 0, 0};
-    OXG_CUDA_TRY(cudaMemcpyAsync(h, p.stats, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
-    OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
-    fprintf(stderr, "[oxg tree] Q=%llu n=%llu levels=%d: leaves/query %.1f, box groups/query %.1f, candidates/query %.1f, merges/query %.1f\n",
-            (unsigned long long)Q, (unsigned long long)s->size, t->view.top + 1, (double)h[0] / (double)Q,
-            (double)h[1] / (double)Q, (double)h[2] / (double)Q, (double)h[3] / (double)Q);
+  if (stats && !d_stats && r == OXG_OK) {
+    OXG_CUDA_TRY(cudaEventRecord(t->ev_q1, s->stream));
+    t->have_query_ev = true;
+    t->last_Q = Q;
   }
   return r;
 }
 
 }  // namespace oxg
+
+extern "C" int oxg_store_tree_stats(oxg_store s, double* out8) {
+  using namespace oxg;
+  OXG_API_BEGIN
+  if (!s || !out8) {
+    set_error("NULL argument");
+    return OXG_E_NULL;
+  }
+  for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+  StoreTree* t = static_cast<StoreTree*>(s->tree);
+  if (!t || !t->have_query_ev) {
+    set_error("no k-NN has run through the hierarchy with \"tree_stats\" switched on");
+    return OXG_E_ARG;
+  }
+  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  float ms = 0.f;
+  if (t->have_build_ev && cudaEventElapsedTime(&ms, t->ev_b0, t->ev_b1) == cudaSuccess) out8[0] = ms;
+  OXG_CUDA_TRY(cudaEventElapsedTime(&ms, t->ev_q0, t->ev_q1));
+  out8[1] = ms;
+  unsigned long long h[4] = {0, 0, 0, 0};
+  OXG_CUDA_TRY(cudaMemcpy(h, t->bounds.as<unsigned long long>() + 2 * kMaxFastDim, sizeof(h),
+                          cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; ++i) out8[2 + i] = (double)h[i];
+  out8[6] = (double)t->size;
+  out8[7] = (double)t->last_Q;
+  return OXG_OK;
+  OXG_API_END
+}

@@ -8,11 +8,15 @@ from conftest import uniform_states
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture()
-def tree_on(oxg):
+@pytest.fixture(params=[0, 1], ids=["key-order", "partition-order"])
+def tree_on(oxg, request):
+    """Forces the hierarchy for every eligible k-NN, in both state orders: the space-filling key
+    order and the balanced partition order (the 4-4-2 splits of csrc/oxg_tree.cu)."""
     oxg.tuning_set("knn_tree", 1)
+    oxg.tuning_set("tree_kind", request.param)
     yield
     oxg.tuning_set("knn_tree", -1)
+    oxg.tuning_set("tree_kind", -1)
 
 
 def _same(a, b):
@@ -135,8 +139,12 @@ def test_tree_equals_all_pairs_scan_on_a_prm_table(oxg, orc):
         st.append(rows)
         oxg.tuning_set("knn_tree", 1)
         try:
+            oxg.tuning_set("tree_kind", 0)
+            ki, kd = st.knn(rows, 10, exclude=np.arange(n, dtype=np.uint32))
+            oxg.tuning_set("tree_kind", 1)
             ti, td = st.knn(rows, 10, exclude=np.arange(n, dtype=np.uint32))
         finally:
+            oxg.tuning_set("tree_kind", -1)
             oxg.tuning_set("knn_tree", 0)
         try:
             bi, bd = st.knn(rows, 10, exclude=np.arange(n, dtype=np.uint32))
@@ -144,6 +152,8 @@ def test_tree_equals_all_pairs_scan_on_a_prm_table(oxg, orc):
             oxg.tuning_set("knn_tree", -1)
     np.testing.assert_array_equal(ti, bi)
     np.testing.assert_array_equal(td.view(np.uint64), bd.view(np.uint64))
+    np.testing.assert_array_equal(ki, bi)
+    np.testing.assert_array_equal(kd.view(np.uint64), bd.view(np.uint64))
     pick = np.random.default_rng(1).choice(n, 512, replace=False)
     oi, od = orc.knn(orc.space(7), rows, rows[pick], 10, exclude=pick.astype(np.uint32))
     np.testing.assert_array_equal(ti[pick], oi)
