@@ -259,11 +259,15 @@ __global__ void __launch_bounds__(128, 6) motion_cull_kernel(const MotionParams 
   __shared__ uint16_t s_list[128 / L][CULL_CAP];
   uint32_t sm_sph = 0, sm_cap = 0;
   stage_world32(p.w, p.world_smem_bytes, world_smem, &sm_sph, &sm_cap);  // the launcher guarantees it fits
+  // Control flow is kept warp-uniform so that every vote is a plain full-warp ballot (a vote
+  // over a 4-lane mask is emulated by one pass per group): edges past the end and finished
+  // step loops ride along predicated off.
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  constexpr unsigned GMASK = (L == 32) ? 0xFFFFFFFFu : ((1u << L) - 1u);
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lane_g = lane % L;
   const unsigned group_shift = lane - lane_g;
-  const unsigned group_mask = (L == 32) ? 0xFFFFFFFFu : (((1u << L) - 1u) << group_shift);
-  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned below = (1u << lane_g) - 1u;  // lanes of my group before me
   const uint64_t gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
   const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) / L;
   uint16_t* my_list = s_list[threadIdx.x / L];
@@ -277,14 +281,14 @@ __global__ void __launch_bounds__(128, 6) motion_cull_kernel(const MotionParams 
   const uint64_t e_rounds = (E + ngroups - 1) / ngroups;
   for (uint64_t round = 0; round < e_rounds; ++round) {
     const uint64_t e = gid + round * ngroups;
-    if (e >= E) continue;  // whole groups leave together: group-scoped ballots below stay matched
-    const uint64_t fi = p.from_idx ? p.from_idx[e] : e;
-    const uint64_t ti = p.to_idx ? p.to_idx[e] : e;
+    const bool live = e < E;
+    const uint64_t fi = live ? (p.from_idx ? p.from_idx[e] : e) : 0;
+    const uint64_t ti = live ? (p.to_idx ? p.to_idx[e] : e) : 0;
     double from[DT], to[DT], x[DT];
 #pragma unroll
     for (int d = 0; d < DT; ++d) {
-      from[d] = p.from.p[fi * p.from.stride_i + (uint64_t)d * p.from.stride_d];
-      to[d] = p.to.p[ti * p.to.stride_i + (uint64_t)d * p.to.stride_d];
+      from[d] = live ? p.from.p[fi * p.from.stride_i + (uint64_t)d * p.from.stride_d] : 0.0;
+      to[d] = live ? p.to.p[ti * p.to.stride_i + (uint64_t)d * p.to.stride_d] : 0.0;
     }
     const double dist = sqrt(rv_sumsq_dev<DT>(from, to, DT));
     const unsigned long long n = ceil_as_usize_dev(__ddiv_rn(dist, p.resolution));
@@ -306,21 +310,21 @@ __global__ void __launch_bounds__(128, 6) motion_cull_kernel(const MotionParams 
     unsigned cnt = 0;
     for (uint32_t i0 = 0; i0 < n_sph; i0 += L) {
       const uint32_t i = i0 + lane_g;
-      const bool keep = i < n_sph && sphere_fat_maybe_hit32_s<DT>(mf, sm_sph + i * w.sphere32_stride * 4u,
-                                                                  tol.a2_s, tol.ce_s, ft);
-      const unsigned b = __ballot_sync(group_mask, keep) & group_mask;
+      const bool keep = live && i < n_sph &&
+                        sphere_fat_maybe_hit32_s<DT>(mf, sm_sph + i * w.sphere32_stride * 4u, tol.a2_s, tol.ce_s, ft);
+      const unsigned b = (__ballot_sync(FULL, keep) >> group_shift) & GMASK;
       if (keep) {
-        const unsigned pos = cnt + __popc(b & lt_mask);
+        const unsigned pos = cnt + __popc(b & below);
         if (pos < CULL_CAP) my_list[pos] = (uint16_t)i;
       }
       cnt += __popc(b);
     }
     for (uint32_t i0 = 0; i0 < n_box; i0 += L) {
       const uint32_t i = i0 + lane_g;
-      const bool keep = i < n_box && aabb_fat_maybe_hit32<DT>(mf, w.aabbs32 + (size_t)i * w.aabb_stride, ft);
-      const unsigned b = __ballot_sync(group_mask, keep) & group_mask;
+      const bool keep = live && i < n_box && aabb_fat_maybe_hit32<DT>(mf, w.aabbs32 + (size_t)i * w.aabb_stride, ft);
+      const unsigned b = (__ballot_sync(FULL, keep) >> group_shift) & GMASK;
       if (keep) {
-        const unsigned pos = cnt + __popc(b & lt_mask);
+        const unsigned pos = cnt + __popc(b & below);
         if (pos < CULL_CAP) my_list[pos] = (uint16_t)(n_sph + i);
       }
       cnt += __popc(b);
@@ -328,76 +332,78 @@ __global__ void __launch_bounds__(128, 6) motion_cull_kernel(const MotionParams 
     for (uint32_t i0 = 0; i0 < n_cap; i0 += 2 * L) {
       const uint32_t i = i0 + 2 * lane_g;
       unsigned mh = 0;
-      if (i < n_cap)
+      if (live && i < n_cap)
         mh = capsule_pair_fat_maybe_hit32_s<DT>(mf, sm_cap + (i >> 1) * w.capsule32p_stride * 4u, tol.a2_c,
                                                 tol.ce_c, ft);
       if (i + 1 >= n_cap) mh &= 1u;
-      const unsigned b0 = __ballot_sync(group_mask, (mh & 1u) != 0) & group_mask;
-      const unsigned b1 = __ballot_sync(group_mask, (mh & 2u) != 0) & group_mask;
+      const unsigned b0 = (__ballot_sync(FULL, (mh & 1u) != 0) >> group_shift) & GMASK;
+      const unsigned b1 = (__ballot_sync(FULL, (mh & 2u) != 0) >> group_shift) & GMASK;
+      // list order inside a pair block: all first halves, then all second halves (any order is
+      // fine: the step loop takes the earliest step with ANY hit)
       if (mh & 1u) {
-        const unsigned pos = cnt + __popc(b0 & lt_mask);
+        const unsigned pos = cnt + __popc(b0 & below);
         if (pos < CULL_CAP) my_list[pos] = (uint16_t)(n_sph + n_box + i);
       }
       cnt += __popc(b0);
       if (mh & 2u) {
-        const unsigned pos = cnt + __popc(b1 & lt_mask);
+        const unsigned pos = cnt + __popc(b1 & below);
         if (pos < CULL_CAP) my_list[pos] = (uint16_t)(n_sph + n_box + i + 1);
       }
       cnt += __popc(b1);
     }
-    __syncwarp(group_mask);
+    __syncwarp();
     const bool full_walk = cnt > CULL_CAP;
 
     // ---- phase 2: the step loop over the survivors
-    if (n > (1ull << 32)) {
-      first_bad = 0xFFFFFFFFull;  // the reference loop would not terminate in practice
-    } else if (cnt > 0) {
-      const bool single = n <= 1;   // `if num_steps <= 1 { return vc.is_valid(to); }` (rrt.rs:99-101)
-      const unsigned long long nn = single ? 1ull : n;
-      const double nf = (double)n;
-      for (unsigned long long base = 0; base < nn; base += L) {
-        const unsigned long long i = base + lane_g + 1;
-        bool bad = false;
-        if (i <= nn) {
-          if (single) {
+    const bool endless = n > (1ull << 32);  // the reference loop would not terminate in practice
+    if (endless) first_bad = 0xFFFFFFFFull;
+    const bool single = n <= 1;   // `if num_steps <= 1 { return vc.is_valid(to); }` (rrt.rs:99-101)
+    const unsigned long long nn = single ? 1ull : n;
+    const double nf = (double)n;
+    bool running = live && !endless && cnt > 0;
+    for (unsigned long long base = 0; __ballot_sync(FULL, running && base < nn) != 0u; base += L) {
+      const unsigned long long i = base + lane_g + 1;
+      bool bad = false;
+      if (running && i <= nn) {
+        if (single) {
 #pragma unroll
-            for (int d = 0; d < DT; ++d) x[d] = to[d];
-          } else {
-            const double t = __ddiv_rn((double)i, nf);  // `i as f64 / num_steps as f64` (rrt.rs:105)
+          for (int d = 0; d < DT; ++d) x[d] = to[d];
+        } else {
+          const double t = __ddiv_rn((double)i, nf);  // `i as f64 / num_steps as f64` (rrt.rs:105)
 #pragma unroll
-            for (int d = 0; d < DT; ++d) x[d] = __dadd_rn(from[d], __dmul_rn(__dsub_rn(to[d], from[d]), t));
-          }
-          float xf[DT];
+          for (int d = 0; d < DT; ++d) x[d] = __dadd_rn(from[d], __dmul_rn(__dsub_rn(to[d], from[d]), t));
+        }
+        float xf[DT];
 #pragma unroll
-          for (int d = 0; d < DT; ++d) xf[d] = __double2float_rn(x[d]);
-          if (full_walk) {
-            bad = !state_valid_staged_dev<DT>(w, x, xf, tol, sm_sph, sm_cap);
-          } else {
-            for (unsigned sidx = 0; sidx < cnt && !bad; ++sidx) {
-              uint32_t o = my_list[sidx];
-              if (o < n_sph) {
-                bad = sphere_maybe_hit32_s<DT>(xf, sm_sph + o * w.sphere32_stride * 4u, tol.a2_s, tol.ce_s) &&
-                      sphere_hit_dev<DT>(x, w.spheres + (size_t)o * w.sphere_stride, DT);
-              } else if ((o -= n_sph) < n_box) {
-                bad = aabb_hit_dev<DT>(x, w.aabbs + (size_t)o * w.aabb_stride, DT);
-              } else {
-                o -= n_box;
-                bad = capsule_half_maybe_hit32_s<DT>(xf, sm_cap + (o >> 1) * w.capsule32p_stride * 4u, o & 1u,
-                                                     tol.a2_c, tol.ce_c) &&
-                      capsule_hit_dev<DT>(x, w.capsules + (size_t)o * w.capsule_stride, DT);
-              }
+        for (int d = 0; d < DT; ++d) xf[d] = __double2float_rn(x[d]);
+        if (full_walk) {
+          bad = !state_valid_staged_dev<DT>(w, x, xf, tol, sm_sph, sm_cap);
+        } else {
+          for (unsigned sidx = 0; sidx < cnt && !bad; ++sidx) {
+            uint32_t o = my_list[sidx];
+            if (o < n_sph) {
+              bad = sphere_maybe_hit32_s<DT>(xf, sm_sph + o * w.sphere32_stride * 4u, tol.a2_s, tol.ce_s) &&
+                    sphere_hit_dev<DT>(x, w.spheres + (size_t)o * w.sphere_stride, DT);
+            } else if ((o -= n_sph) < n_box) {
+              bad = aabb_hit_dev<DT>(x, w.aabbs + (size_t)o * w.aabb_stride, DT);
+            } else {
+              o -= n_box;
+              bad = capsule_half_maybe_hit32_s<DT>(xf, sm_cap + (o >> 1) * w.capsule32p_stride * 4u, o & 1u,
+                                                   tol.a2_c, tol.ce_c) &&
+                    capsule_hit_dev<DT>(x, w.capsules + (size_t)o * w.capsule_stride, DT);
             }
           }
         }
-        const unsigned b = (__ballot_sync(group_mask, bad) & group_mask) >> group_shift;
-        if (b) {
-          first_bad = base + (unsigned long long)(__ffs(b) - 1) + 1ull;
-          break;
-        }
       }
+      const unsigned b = (__ballot_sync(FULL, bad) >> group_shift) & GMASK;
+      if (running && b) {
+        first_bad = base + (unsigned long long)(__ffs(b) - 1) + 1ull;
+        running = false;
+      }
+      if (base + L >= nn) running = false;
     }
-    __syncwarp(group_mask);  // the list is reused by the group's next edge
-    if (lane_g == 0) {
+    __syncwarp();  // the list is reused by the group's next edge
+    if (live && lane_g == 0) {
       p.valid[e] = first_bad == 0 ? 1 : 0;
       if (p.first_invalid)
         p.first_invalid[e] = first_bad > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)first_bad;
