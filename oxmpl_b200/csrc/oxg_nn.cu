@@ -318,7 +318,10 @@ __device__ __forceinline__ double sqrt_le_upper_dev(double sw) {
 constexpr int CAND_CAP = 16;  // deferred candidates per query (u32 indices, shared memory)
 constexpr int DRAIN_EVERY = 16;  // tiles between scheduled warp-wide drains
 constexpr int DOT_STAGES = 4;   // tile ring of the dot kernel (full/empty mbarrier pairs)
-constexpr int DOT_MIN_CTAS = 3; // CTAs per SM the dot kernel is compiled for (caps registers)
+#ifndef OXG_DOT_MIN_CTAS
+#define OXG_DOT_MIN_CTAS 3
+#endif
+constexpr int DOT_MIN_CTAS = OXG_DOT_MIN_CTAS; // CTAs per SM the dot kernel is compiled for (caps registers)
 
 // Dot-product form of the pre-filter.  With g_d = -2 fl32(q_d), pn = fl32(|p|^2) and the FP32
 // FMA chain  A = fma(g_D, p_D, ... fma(g_1, p_1, pn)),  A approximates |p|^2 - 2 q.p = d2 - |q|^2

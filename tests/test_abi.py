@@ -136,3 +136,23 @@ def test_rust_ffi_block_declares_every_header_symbol():
     rs = open(os.path.join(ROOT, "bindings", "oxmpl-cuda", "src", "ffi.rs")).read()
     declared = set(re.findall(r"pub fn (oxg_[a-z0-9_]+)\s*\(", rs))
     assert sorted(declared) == _declared_symbols()
+
+
+def test_build_is_deterministic_for_the_scan_kernels():
+    """Every object is one plain nvcc invocation (csrc/Makefile): the all-pairs scan kernel gets the
+    same register allocation in every clean build (round 1 kept the best of several
+    --split-compile builds, which made the measured kernel irreproducible from source)."""
+    import shutil
+    import subprocess
+
+    mk = open(os.path.join(ROOT, "oxmpl_b200", "csrc", "Makefile")).read()
+    assert "--split-compile" not in re.sub(r"#.*", "", mk)
+    assert not os.path.exists(os.path.join(ROOT, "oxmpl_b200", "csrc", "build_nn.sh"))
+    obj = os.path.join(ROOT, "oxmpl_b200", "csrc", "oxg_nn.o")
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not (os.path.exists(obj) and os.path.exists(tool)):
+        pytest.skip("oxg_nn.o or cuobjdump not available")
+    out = subprocess.run([tool, "-res-usage", obj], capture_output=True, text=True).stdout
+    m = re.search(r"knn_rv_dot_kernelILi7ELi2E\w*:\s*\n\s*REG:(\d+)", out)
+    assert m, "knn_rv_dot_kernel<7,2> not found in oxg_nn.o"
+    assert int(m.group(1)) == 168
