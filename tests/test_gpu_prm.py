@@ -142,8 +142,17 @@ def test_config4_full_size_roadmap_properties(oxg, orc):
         st.append(rows)
         idx, dist, valid, stats = oxg.prm_build_knn(gw, st, k, res)
         idx2, dist2, valid2, _ = oxg.prm_build_knn(gw, st, k, res)
+        # the same table from the other neighbour algorithm: all 1e12 pairs scanned instead of
+        # the bounding-box hierarchy (two independent kernels, one answer)
+        oxg.tuning_set("knn_tree", 0)
+        try:
+            idx3, dist3, valid3, _ = oxg.prm_build_knn(gw, st, k, res)
+        finally:
+            oxg.tuning_set("knn_tree", -1)
     assert np.array_equal(idx, idx2) and np.array_equal(dist.view(np.uint64), dist2.view(np.uint64))
     assert np.array_equal(valid, valid2)
+    assert np.array_equal(idx, idx3) and np.array_equal(dist.view(np.uint64), dist3.view(np.uint64))
+    assert np.array_equal(valid, valid3)
     own = np.arange(n, dtype=np.uint32)[:, None]
     assert (idx != own).all() and (idx < n).all()
     # distances: reference order s = 0; s = s + (a_d - b_d)^2 ...; sqrt(s)   (no reassociation)
@@ -174,13 +183,30 @@ def test_config4_full_size_roadmap_properties(oxg, orc):
     vflat = valid.reshape(-1)
     assert np.array_equal(valid[dst[both], slot[both]], vflat[both])
     assert 0.5 < vflat.mean() < 1.0 and stats["n_edges_checked"] > 5_000_000
+    # no missed neighbour, mutual or not: for random pairs (i, j), whenever (d(i,j), j) sorts before
+    # i's k-th entry, j must be listed for i
+    pr = np.random.default_rng(3)
+    pi = pr.integers(0, n, size=400_000)
+    near = idx[pi, pr.integers(0, k, size=pi.size)].astype(np.int64)       # neighbours of neighbours:
+    pj = idx[near, pr.integers(0, k, size=pi.size)].astype(np.int64)       # pairs that are close
+    pj = np.where(pr.random(pi.size) < 0.25, pr.integers(0, n, size=pi.size), pj)
+    keep_p = pi != pj
+    pi, pj = pi[keep_p], pj[keep_p]
+    acc = np.zeros(pi.size)
+    for c in range(d):
+        df = rows[pi, c] - rows[pj, c]
+        acc = acc + df * df
+    dij = np.sqrt(acc)
+    beats = (dij < dist[pi, k - 1]) | ((dij == dist[pi, k - 1]) & (pj <= idx[pi, k - 1].astype(np.int64)))
+    assert beats.sum() > 50_000
+    assert (idx[pi[beats]] == pj[beats, None].astype(np.uint32)).any(axis=1).all()
     # a sample of rows and of edges against the oracle
-    pick = np.sort(np.random.default_rng(1).choice(n, size=48, replace=False)).astype(np.uint32)
+    pick = np.sort(np.random.default_rng(1).choice(n, size=4096, replace=False)).astype(np.uint32)
     oi, od = orc.knn(sp_o, rows, rows[pick], k, exclude=pick)
     assert np.array_equal(idx[pick], oi)
     assert np.array_equal(dist[pick].view(np.uint64), od.view(np.uint64))
     ow, keep = orc.world(d, capsules=caps)
-    e = np.random.default_rng(2).choice(n * k, size=4000, replace=False)
+    e = np.random.default_rng(2).choice(n * k, size=50_000, replace=False)
     i_e, j_e = src[e], dst[e]
     ov, _ = orc.check_motion(ow, sp_o, rows[np.maximum(i_e, j_e)], rows[np.minimum(i_e, j_e)], res)
     assert np.array_equal(vflat[e], ov)
