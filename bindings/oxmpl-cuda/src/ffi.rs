@@ -121,6 +121,15 @@ extern "C" {
                              d_counters: *mut u64) -> c_int;
     pub fn oxg_prm_resolve_dev(s: oxg_store, d_idx_all: *const u32, k: u32,
                                d_valid_all: *mut u8) -> c_int;
+    // PRM query phase (PRM::solve, prm.rs:227-307)
+    pub fn oxg_prm_solve(w: oxg_world, s: oxg_store, lower_offsets: *const u64, lower_idx: *const u32,
+                         connection_radius: f64, resolution: f64, start: *const f64,
+                         goal_target: *const f64, goal_radius: f64, path: *mut u32, path_cap: u32,
+                         out: *mut oxg_prm_query_result) -> c_int;
+    pub fn oxg_prm_solve_knn(w: oxg_world, s: oxg_store, idx: *const u32, valid: *const u8, k: u32,
+                             connection_radius: f64, resolution: f64, start: *const f64,
+                             goal_target: *const f64, goal_radius: f64, path: *mut u32,
+                             path_cap: u32, out: *mut oxg_prm_query_result) -> c_int;
     // multi-GPU PRM build (NCCL inside the library; the id travels by the host's rendezvous)
     pub fn oxg_dist_unique_id(out_id_128: *mut c_void) -> c_int;
     pub fn oxg_dist_create(unique_id_128: *const c_void, rank: c_int, world_size: c_int,
@@ -158,3 +167,19 @@ extern "C" {
 pub type oxg_so3_cones = *mut std::os::raw::c_void;
 #[allow(non_camel_case_types)]
 pub type oxg_dist = *mut std::os::raw::c_void;
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+#[allow(non_camel_case_types)]
+pub struct oxg_prm_query_result {
+    pub status: i32,
+    pub path_len: u32,
+    pub goal_node: u32,
+    pub n_start_connections: u32,
+    pub n_goal_nodes: u32,
+    pub bfs_levels: u32,
+    pub n_visited: u32,
+    pub reserved: u32,
+    pub n_adjacency: u64,
+    pub device_ms: f64,
+}

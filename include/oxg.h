@@ -203,6 +203,44 @@ int oxg_prm_build_knn(oxg_world w, oxg_store s, uint32_t k, double resolution,
                       uint64_t row_begin, uint64_t row_end, uint32_t* idx, double* dist,
                       uint8_t* valid, oxg_prm_stats* stats);
 
+/* ---- PRM query phase -----------------------------------------------------------------
+ * PRM::solve (prm.rs:227-307) on a roadmap the library built, all on the device: is_valid(start)
+ * (:244), start connection = radius scan + check_motion(start, roadmap[i]) (:249-256), goal scan
+ * over all nodes (:259-264; the goal is the ball distance(state, goal_target) <= goal_radius of
+ * the reference's tests), and the breadth-first search over roadmap[i].edges (:271-301) in the
+ * reference's queue order — the same parents, hence the same path, not merely a shortest one.
+ * The adjacency is symmetrised on the device (prm.rs:143-145), rows ascending, which is the
+ * order the reference's edge lists grow in.
+ *  oxg_prm_solve     : roadmap = the lower-index CSR oxg_prm_build_radius(_dist) returns for all
+ *                      N rows (offsets[N+1], idx).
+ *  oxg_prm_solve_knn : roadmap = idx / valid [N][k] of oxg_prm_build_knn(_dist); an edge exists
+ *                      where valid = 1 (no reference form: the reference has no k-NN PRM).
+ * path receives the roadmap indices from the start connection to the goal node (the reference's
+ * Path is the start state followed by these nodes' states, prm.rs:189-208).
+ * out->status: 0 = Ok(path), 1 = NoSolutionFound, 2 = InvalidStartState, 3 = UnsampledStateSpace.
+ */
+typedef struct oxg_prm_query_result {
+  int32_t status;
+  uint32_t path_len;            /* roadmap nodes on the path                        */
+  uint32_t goal_node;           /* OXG_INVALID_INDEX when no path                   */
+  uint32_t n_start_connections; /* start_connections.len()                          */
+  uint32_t n_goal_nodes;        /* goal_indices.len()                               */
+  uint32_t bfs_levels;
+  uint32_t n_visited;           /* nodes that entered the queue                     */
+  uint32_t reserved;
+  uint64_t n_adjacency;         /* directed adjacency entries after symmetrising    */
+  double device_ms;
+} oxg_prm_query_result;
+
+int oxg_prm_solve(oxg_world w, oxg_store s, const uint64_t* lower_offsets, const uint32_t* lower_idx,
+                  double connection_radius, double resolution, const double* start,
+                  const double* goal_target, double goal_radius, uint32_t* path, uint32_t path_cap,
+                  oxg_prm_query_result* out);
+int oxg_prm_solve_knn(oxg_world w, oxg_store s, const uint32_t* idx, const uint8_t* valid, uint32_t k,
+                      double connection_radius, double resolution, const double* start,
+                      const double* goal_target, double goal_radius, uint32_t* path,
+                      uint32_t path_cap, oxg_prm_query_result* out);
+
 /* ---- fused sequential planners ---------------------------------------------------------
  * The bodies of RRT::solve (rrt.rs:158-227), RRTConnect::solve (rrt_connect.rs:227-309 with
  * extend :121-159) and RRTStar::solve (rrt_star.rs:171-290) as ONE persistent kernel each:

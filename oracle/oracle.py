@@ -294,6 +294,23 @@ class Oracle:
         return (nodes[:n].copy(), offsets[: n + 1].copy(), idx[: int(offsets[n])].copy(),
                 pairs.value, mcs.value)
 
+    def prm_solve(self, w, sp, rows, lower_off, lower_idx, connection_radius, resolution, start,
+                  goal_target, goal_radius):
+        """PRM::solve (prm.rs:227-307) -> (status, path node indices)."""
+        rows = _f64(rows)
+        off = np.ascontiguousarray(lower_off, dtype=np.uint64)
+        idx = np.ascontiguousarray(lower_idx, dtype=np.uint32)
+        st, tg = _f64(start), _f64(goal_target)
+        g = OrcGoal(C.c_void_p(tg.ctypes.data), float(goal_radius))
+        path = np.empty(max(rows.shape[0], 1), dtype=np.uint32)
+        plen = C.c_uint32(0)
+        self.lib.orc_prm_solve.restype = C.c_int
+        status = self.lib.orc_prm_solve(C.byref(w), C.byref(sp), _p(rows), C.c_uint64(rows.shape[0]),
+                                        _p(off), _p(idx), C.c_double(connection_radius),
+                                        C.c_double(resolution), _p(st), C.byref(g), _p(path),
+                                        C.c_uint32(path.shape[0]), C.byref(plen))
+        return int(status), path[: plen.value].copy()
+
     def rrt(self, w, sp, start, goal_target, goal_radius, max_distance, resolution, samples,
             max_nodes):
         s = _f64(np.atleast_2d(samples))

@@ -793,6 +793,74 @@ int orc_so3_check_motion(const double* cones, uint64_t n_cones, const double* fr
   return 1;
 }
 
+// PRM::solve — prm.rs:227-307, on a roadmap given as each node's `new_node.edges` at push time
+// (the lower-index adjacency, CSR, what orc_prm_radius / the library's radius build emit).
+// The roadmap's edge lists are rebuilt the way construct_roadmap grows them: node i takes its
+// lower neighbours in ascending order (prm.rs:135) and is appended to each of them afterwards
+// (prm.rs:143-145).  Goal = ball (CircularGoalRegion).  Writes the roadmap indices of the path
+// (the reference's Path is the start state followed by these nodes' states, prm.rs:189-208).
+// Returns 0 = Ok(path), 1 = NoSolutionFound, 2 = InvalidStartState, 3 = UnsampledStateSpace.
+int orc_prm_solve(const orc_world* w, const orc_space* sp, const double* rows, uint64_t N,
+                  const uint64_t* lower_off, const uint32_t* lower_idx, double connection_radius,
+                  double resolution, const double* start, const orc_goal* goal, uint32_t* path,
+                  uint32_t cap, uint32_t* path_len) {
+  uint32_t dim = sp->n_real + sp->n_so2;
+  *path_len = 0;
+  if (N == 0) return 3;                                   // prm.rs:239-241
+  if (!orc_is_valid(w, sp, start, nullptr)) return 2;     // prm.rs:243-246
+  std::vector<std::vector<uint32_t>> edges(N);
+  for (uint64_t i = 0; i < N; ++i) {
+    for (uint64_t t = lower_off[i]; t < lower_off[i + 1]; ++t) edges[i].push_back(lower_idx[t]);
+    for (uint64_t t = lower_off[i]; t < lower_off[i + 1]; ++t) edges[lower_idx[t]].push_back((uint32_t)i);
+  }
+  // start connection — prm.rs:249-256
+  std::vector<uint32_t> start_connections;
+  for (uint64_t i = 0; i < N; ++i)
+    if (orc_distance(sp, start, rows + i * dim) < connection_radius &&
+        orc_check_motion(w, sp, start, rows + i * dim, resolution, nullptr, nullptr) == 1)
+      start_connections.push_back((uint32_t)i);
+  // goal nodes — prm.rs:259-264
+  std::vector<uint8_t> is_goal(N, 0);
+  bool any_goal = false;
+  for (uint64_t i = 0; i < N; ++i)
+    if (goal_satisfied(sp, goal, rows + i * dim)) is_goal[i] = 1, any_goal = true;
+  if (start_connections.empty() || !any_goal) return 1;   // prm.rs:266-268
+  // BFS — prm.rs:271-301.  The reference seeds the queue with the start connections AND pushes
+  // each of them again while filling parent_map; the duplicates are restated (they pop after the
+  // first copies and find every neighbour visited).
+  const uint32_t NONE = 0xFFFFFFFFu;
+  std::vector<uint32_t> queue(start_connections.begin(), start_connections.end());
+  std::vector<uint32_t> parent(N, NONE);
+  std::vector<uint8_t> visited(N, 0);
+  for (uint32_t idx : start_connections) {
+    queue.push_back(idx);
+    parent[idx] = NONE;
+    visited[idx] = 1;
+  }
+  int64_t goal_reached = -1;
+  for (size_t head = 0; head < queue.size(); ++head) {
+    uint32_t cur = queue[head];
+    if (is_goal[cur]) {
+      goal_reached = cur;
+      break;
+    }
+    for (uint32_t nb : edges[cur])
+      if (!visited[nb]) {
+        visited[nb] = 1;
+        parent[nb] = cur;
+        queue.push_back(nb);
+      }
+  }
+  if (goal_reached < 0) return 1;                          // prm.rs:304
+  // reconstruct_path — prm.rs:189-208
+  std::vector<uint32_t> chain;
+  for (uint32_t v = (uint32_t)goal_reached; v != NONE; v = parent[v]) chain.push_back(v);
+  std::reverse(chain.begin(), chain.end());
+  *path_len = (uint32_t)chain.size();
+  for (size_t i = 0; i < chain.size() && i < cap; ++i) path[i] = chain[i];
+  return 0;
+}
+
 // Build identification, so tests can assert the flags the oracle was compiled with.
 int orc_build_info(void) {
   int v = 1;

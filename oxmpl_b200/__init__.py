@@ -17,12 +17,14 @@ from .api import (  # noqa: F401
     motion_resolution,
     prm_build_knn,
     prm_build_radius,
+    prm_solve,
+    prm_solve_knn,
     real_vector_max_extent,
     rrt_connect_solve,
     rrt_solve,
     rrt_star_solve,
     tuning_set,
 )
-from ._lib import OxgError, PlanParams, PlanResult, PrmStats, SpaceDesc  # noqa: F401
+from ._lib import OxgError, PlanParams, PlanResult, PrmQueryResult, PrmStats, SpaceDesc  # noqa: F401
 
 __version__ = "0.1.0"

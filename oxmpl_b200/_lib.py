@@ -64,6 +64,23 @@ class PrmStats(C.Structure):
     ]
 
 
+class PrmQueryResult(C.Structure):
+    """struct oxg_prm_query_result."""
+
+    _fields_ = [
+        ("status", C.c_int32),
+        ("path_len", C.c_uint32),
+        ("goal_node", C.c_uint32),
+        ("n_start_connections", C.c_uint32),
+        ("n_goal_nodes", C.c_uint32),
+        ("bfs_levels", C.c_uint32),
+        ("n_visited", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("n_adjacency", C.c_uint64),
+        ("device_ms", C.c_double),
+    ]
+
+
 class PlanParams(C.Structure):
     """struct oxg_plan_params."""
 
@@ -138,6 +155,14 @@ SIGNATURES = {
     "oxg_prm_build_knn": (
         C.c_int,
         [_vp, _vp, _u32, _dbl, _u64, _u64, _pu32, _pd, _pu8, C.POINTER(PrmStats)],
+    ),
+    "oxg_prm_solve": (
+        C.c_int,
+        [_vp, _vp, _pu64, _pu32, _dbl, _dbl, _pd, _pd, _dbl, _pu32, _u32, C.POINTER(PrmQueryResult)],
+    ),
+    "oxg_prm_solve_knn": (
+        C.c_int,
+        [_vp, _vp, _pu32, _pu8, _u32, _dbl, _dbl, _pd, _pd, _dbl, _pu32, _u32, C.POINTER(PrmQueryResult)],
     ),
     "oxg_rrt_solve": (
         C.c_int,

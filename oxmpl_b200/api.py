@@ -405,6 +405,34 @@ def prm_build_knn(world: World, store: StateStore, k: int, resolution: float, ro
     return idx, dist, valid, _stats_dict(st)
 
 
+def prm_solve(world: World, store: StateStore, lower_offsets, lower_idx, connection_radius: float,
+              resolution: float, start, goal_target, goal_radius: float):
+    """PRM::solve (prm.rs:227-307) on the device -> (status, path node indices, result dict)."""
+    off = np.ascontiguousarray(lower_offsets, dtype=np.uint64)
+    idx = np.ascontiguousarray(lower_idx, dtype=np.uint32)
+    st, tg = _f64(start), _f64(goal_target)
+    path = np.empty(max(len(store), 1), dtype=np.uint32)
+    r = _lib.PrmQueryResult()
+    check(lib.oxg_prm_solve(world.handle, store.handle, _ptr(off), _ptr(idx), float(connection_radius),
+                            float(resolution), _ptr(st), _ptr(tg), float(goal_radius), _ptr(path),
+                            path.shape[0], C.byref(r)))
+    return int(r.status), path[: r.path_len].copy(), {n: getattr(r, n) for n, _ in r._fields_}
+
+
+def prm_solve_knn(world: World, store: StateStore, idx, valid, connection_radius: float,
+                  resolution: float, start, goal_target, goal_radius: float):
+    """The same query on a k-NN roadmap (idx / valid [N][k] of prm_build_knn)."""
+    idx = np.ascontiguousarray(idx, dtype=np.uint32)
+    valid = np.ascontiguousarray(valid, dtype=np.uint8)
+    st, tg = _f64(start), _f64(goal_target)
+    path = np.empty(max(len(store), 1), dtype=np.uint32)
+    r = _lib.PrmQueryResult()
+    check(lib.oxg_prm_solve_knn(world.handle, store.handle, _ptr(idx), _ptr(valid), idx.shape[1],
+                                float(connection_radius), float(resolution), _ptr(st), _ptr(tg),
+                                float(goal_radius), _ptr(path), path.shape[0], C.byref(r)))
+    return int(r.status), path[: r.path_len].copy(), {n: getattr(r, n) for n, _ in r._fields_}
+
+
 def prm_build_radius(world: World, store: StateStore, connection_radius: float, resolution: float,
                      row_begin: int = 0, row_end: int | None = None):
     """Reference-faithful radius PRM rows -> CSR (offsets, idx) of ``new_node.edges``

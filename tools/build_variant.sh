@@ -10,7 +10,7 @@ OBJ="$ROOT/tools/bin/${SRC%.cu}_$NAME.o"
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false \
   -Xcompiler -fPIC,-ffp-contract=off,-Wall -ccbin /usr/bin/g++ "$@" -c -o "$OBJ" "$SRC"
 OBJS=""
-for f in oxg_api oxg_nn oxg_validity oxg_prm oxg_planner oxg_peak oxg_so3 oxg_tree oxg_dist; do
+for f in oxg_api oxg_nn oxg_validity oxg_prm oxg_planner oxg_peak oxg_so3 oxg_tree oxg_dist oxg_query; do
   [ -f "$f.cu" ] || continue
   if [ "$f.cu" = "$SRC" ]; then OBJS="$OBJS $OBJ"; else OBJS="$OBJS $f.o"; fi
 done
