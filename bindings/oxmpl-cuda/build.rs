@@ -12,15 +12,25 @@ fn main() {
         .unwrap_or_else(|_| root.join("../../oxmpl_b200/csrc"));
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
+    // every translation unit of oxmpl_b200/csrc/Makefile (tests/test_abi.py keeps the two lists equal)
     let sources = [
         "oxg_api.cu", "oxg_nn.cu", "oxg_validity.cu", "oxg_prm.cu", "oxg_planner.cu", "oxg_peak.cu",
+        "oxg_so3.cu", "oxg_tree.cu", "oxg_dist.cu", "oxg_query.cu",
     ];
+    for hdr in ["oxg_internal.cuh", "oxg_math.cuh", "oxg_tma.cuh"] {
+        println!("cargo:rerun-if-changed={}", csrc.join(hdr).display());
+    }
+    for hdr in ["oxg.h", "oxg_so3.h"] {
+        println!("cargo:rerun-if-changed={}", csrc.join("../../include").join(hdr).display());
+    }
     let mut objects = Vec::new();
     for src in sources {
         let obj = out.join(src.replace(".cu", ".o"));
         let status = Command::new(&nvcc)
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo"])
-            .args(["-fmad=false", "--split-compile=0", "-Xcompiler", "-fPIC,-ffp-contract=off"])
+            // one plain nvcc invocation per file: --split-compile makes ptxas's register allocation
+            // of the scan kernels vary from build to build
+            .args(["-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off"])
             .arg("-c")
             .arg(csrc.join(src))
             .arg("-o")
@@ -40,4 +50,5 @@ fn main() {
     println!("cargo:rustc-link-search=native={cuda}/lib64");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
+    println!("cargo:rustc-link-lib=dylib=dl"); // oxg_dist.cu resolves NCCL with dlopen at run time
 }

@@ -57,6 +57,7 @@ pub type oxg_world = *mut c_void;
 
 pub const OXG_OK: c_int = 0;
 pub const OXG_E_CAPACITY: c_int = -3;
+pub const OXG_E_NCCL: c_int = -10;
 
 extern "C" {
     pub fn oxg_last_error() -> *const c_char;

@@ -3,11 +3,20 @@
 //! * [`GpuValidityChecker`] implements `oxmpl::base::validity::StateValidityChecker` for
 //!   `RealVectorState` (declarative spheres / AABBs / capsules), so it drops into
 //!   `Planner::setup(problem_def, Arc::new(checker))` of the stock planners unchanged.
-//! * [`GpuRRT`] implements `oxmpl::base::planner::Planner` with the same constructor and
-//!   `setup` / `solve(timeout)` contract as `oxmpl::geometric::RRT`, but keeps its tree in a
-//!   GPU-resident store and runs the loop as one persistent kernel per chunk of pre-drawn
-//!   samples (`oxg_rrt_solve`).  `GpuRRTConnect`, `GpuRRTStar` and `GpuPRM` follow the same
-//!   pattern over `oxg_rrt_connect_solve`, `oxg_rrt_star_solve`, `oxg_prm_build_radius`.
+//! * [`GpuRRT`], [`GpuRRTConnect`] and [`GpuRRTStar`] implement `oxmpl::base::planner::Planner`
+//!   with the constructors and the `setup` / `solve(timeout)` contract of
+//!   `oxmpl::geometric::{RRT, RRTConnect, RRTStar}` (rrt.rs:75, rrt_connect.rs:86, rrt_star.rs:65),
+//!   but keep their trees in GPU-resident stores and run the loop as one persistent kernel per
+//!   chunk of pre-drawn samples (`oxg_rrt_solve`, `oxg_rrt_connect_solve`, `oxg_rrt_star_solve`).
+//! * [`GpuPRM`] is `oxmpl::geometric::PRM` (prm.rs:70-154, 227-307): `construct_roadmap` batches
+//!   the incremental radius build through `oxg_prm_build_radius`, `solve` runs the start
+//!   connection, the goal scan and the reference-order BFS on the device (`oxg_prm_solve`).
+//!
+//! `Planner::setup` receives `Arc<dyn StateValidityChecker<S>>` like every reference planner.
+//! The GPU planners need the checker's device handle, and a trait object cannot be downcast, so
+//! [`GpuValidityChecker::into_arc`] records the address of the `Arc`'s payload in a process-wide
+//! registry; `setup` looks the incoming trait object up by that address and panics — loudly, like
+//! the reference's `assert_eq!`s — if it is some other checker (there is no CPU fallback).
 //!
 //! Sampling stays in Rust and uses exactly the reference's call sequence
 //! (`rng.random_bool(goal_bias)` then `goal.sample_goal` or `space.sample_uniform`,
@@ -15,7 +24,12 @@
 //! nothing the planner can observe.
 pub mod ffi;
 
-use std::{ffi::CStr, sync::Arc, time::{Duration, Instant}};
+use std::{
+    collections::HashMap,
+    ffi::CStr,
+    sync::{Arc, Mutex, OnceLock},
+    time::{Duration, Instant},
+};
 
 use oxmpl::base::{
     error::PlanningError,
@@ -60,9 +74,35 @@ impl GpuValidityChecker {
         ffi::oxg_space_desc { n_real: self.dim, n_so2: 0, w_real: 1.0, w_so2: 1.0 }
     }
     pub(crate) fn handle(&self) -> ffi::oxg_world { self.world }
+
+    /// Wraps the checker for `Planner::setup` and registers it so the GPU planners can recover the
+    /// device handle from the `Arc<dyn StateValidityChecker<_>>` the reference's signature passes.
+    pub fn into_arc(self) -> Arc<Self> {
+        let arc = Arc::new(self);
+        registry().lock().unwrap().insert(Arc::as_ptr(&arc) as *const u8 as usize, arc.world as usize);
+        arc
+    }
+}
+fn registry() -> &'static Mutex<HashMap<usize, usize>> {
+    static R: OnceLock<Mutex<HashMap<usize, usize>>> = OnceLock::new();
+    R.get_or_init(|| Mutex::new(HashMap::new()))
+}
+/// The device handle behind a trait object handed to `setup`, or a panic naming the problem.
+fn gpu_world_of(vc: &Arc<dyn StateValidityChecker<RealVectorState>>) -> ffi::oxg_world {
+    let key = Arc::as_ptr(vc) as *const u8 as usize;
+    match registry().lock().unwrap().get(&key) {
+        Some(w) => *w as ffi::oxg_world,
+        None => panic!(
+            "oxmpl-cuda planners need a GpuValidityChecker created with into_arc(): the checker \
+             passed to setup() is not a registered declarative GPU checker (no CPU fallback)"
+        ),
+    }
 }
 impl Drop for GpuValidityChecker {
-    fn drop(&mut self) { unsafe { ffi::oxg_world_destroy(self.world); } }
+    fn drop(&mut self) {
+        registry().lock().unwrap().retain(|_, w| *w != self.world as usize);
+        unsafe { ffi::oxg_world_destroy(self.world); }
+    }
 }
 impl StateValidityChecker<RealVectorState> for GpuValidityChecker {
     /// validity.rs:47 — one state per call (correct but slow: the GPU planners below use the
@@ -114,7 +154,7 @@ pub struct GpuRRT<G: BallGoal> {
     /// tree capacity (the reference is bounded by the timeout only)
     pub max_nodes: usize,
     problem_def: Option<Arc<ProblemDefinition<RealVectorState, RealVectorStateSpace, G>>>,
-    checker: Option<Arc<GpuValidityChecker>>,
+    checker: Option<(Arc<dyn StateValidityChecker<RealVectorState>>, ffi::oxg_world)>,
     tree: Option<Store>,
 }
 
@@ -123,18 +163,46 @@ impl<G: BallGoal> GpuRRT<G> {
         Self { max_distance, goal_bias, chunk: 1 << 14, max_nodes: 1 << 20, problem_def: None,
                checker: None, tree: None }
     }
-    /// The GPU path needs the concrete checker (its device handle); `Planner::setup` below takes
-    /// the trait object the reference's signature demands and this records the concrete one.
-    pub fn set_gpu_checker(&mut self, checker: Arc<GpuValidityChecker>) { self.checker = Some(checker); }
+}
+
+/// `chunk` iterations of the reference's per-iteration draw (rrt.rs:177-184), row-major.
+fn draw_stream<G: BallGoal>(
+    pd: &ProblemDefinition<RealVectorState, RealVectorStateSpace, G>, goal_bias: f64, chunk: usize,
+    rng: &mut impl Rng,
+) -> Vec<f64> {
+    let mut stream = Vec::with_capacity(chunk * pd.space.dimension);
+    for _ in 0..chunk {
+        let q = if rng.random_bool(goal_bias) {
+            pd.goal.sample_goal(rng).unwrap()
+        } else {
+            pd.space.sample_uniform(rng).unwrap()
+        };
+        stream.extend_from_slice(&q.values);
+    }
+    stream
+}
+
+/// reconstruct_path (rrt.rs:118-128): walk the parents from `last` to the root, reversed.
+fn chain(tree: &Store, parents: &[i64], last: i64) -> Vec<RealVectorState> {
+    let mut states = Vec::new();
+    let mut i = last;
+    while i >= 0 {
+        states.push(tree.get(i as usize));
+        i = parents[i as usize];
+    }
+    states.reverse();
+    states
 }
 
 impl<G: BallGoal> Planner<RealVectorState, RealVectorStateSpace, G> for GpuRRT<G> {
     fn setup(
         &mut self,
         problem_def: Arc<ProblemDefinition<RealVectorState, RealVectorStateSpace, G>>,
-        _validity_checker: Arc<dyn StateValidityChecker<RealVectorState>>,
+        validity_checker: Arc<dyn StateValidityChecker<RealVectorState>>,
     ) {
-        // rrt.rs:139-156: clear the tree, push the start state
+        // rrt.rs:139-156: remember the problem and the checker, clear the tree, push the start state
+        let world = gpu_world_of(&validity_checker);
+        self.checker = Some((validity_checker, world));
         let tree = Store::new(problem_def.space.dimension);
         tree.push(&problem_def.start_states[0]);
         self.tree = Some(tree);
@@ -143,9 +211,8 @@ impl<G: BallGoal> Planner<RealVectorState, RealVectorStateSpace, G> for GpuRRT<G
 
     fn solve(&mut self, timeout: Duration) -> Result<Path<RealVectorState>, PlanningError> {
         let pd = self.problem_def.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
-        let vc = self.checker.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
+        let world = self.checker.as_ref().ok_or(PlanningError::PlannerUninitialised)?.1;
         let tree = self.tree.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
-        let dim = pd.space.dimension;
         let start_time = Instant::now();
         let mut rng = rand::rng();
         let mut parents = vec![-1i64; self.max_nodes];
@@ -164,34 +231,335 @@ impl<G: BallGoal> Planner<RealVectorState, RealVectorStateSpace, G> for GpuRRT<G
             }
             prm.timeout_s = (timeout - elapsed).as_secs_f64();
             // the reference's per-iteration draw (rrt.rs:177-184), `chunk` iterations ahead
-            let mut stream = Vec::with_capacity(self.chunk * dim);
-            for _ in 0..self.chunk {
-                let q = if rng.random_bool(self.goal_bias) {
-                    pd.goal.sample_goal(&mut rng).unwrap()
-                } else {
-                    pd.space.sample_uniform(&mut rng).unwrap()
-                };
-                stream.extend_from_slice(&q.values);
-            }
+            let stream = draw_stream(pd, self.goal_bias, self.chunk, &mut rng);
             let mut r = ffi::oxg_plan_result::default();
             check(unsafe {
-                ffi::oxg_rrt_solve(vc.handle(), tree.0, &prm, pd.goal.target().values.as_ptr(),
+                ffi::oxg_rrt_solve(world, tree.0, &prm, pd.goal.target().values.as_ptr(),
                                    stream.as_ptr(), self.chunk as u64, parents.as_mut_ptr(), &mut r)
             });
             if r.solved != 0 {
-                // reconstruct_path (rrt.rs:118-128)
-                let mut states = Vec::new();
-                let mut i = r.goal_node[0];
-                while i >= 0 {
-                    states.push(tree.get(i as usize));
-                    i = parents[i as usize];
-                }
-                states.reverse();
-                return Ok(Path(states));
+                return Ok(Path(chain(tree, &parents, r.goal_node[0])));
             }
             if r.status == 3 || r.status == 2 {
                 return Err(PlanningError::Timeout);
             }
+        }
+    }
+}
+
+/// `oxmpl::geometric::RRTConnect` (rrt_connect.rs:63-310) with both trees on the GPU.
+pub struct GpuRRTConnect<G: BallGoal> {
+    pub max_distance: f64,
+    pub goal_bias: f64,
+    pub chunk: usize,
+    pub max_nodes: usize,
+    problem_def: Option<Arc<ProblemDefinition<RealVectorState, RealVectorStateSpace, G>>>,
+    checker: Option<(Arc<dyn StateValidityChecker<RealVectorState>>, ffi::oxg_world)>,
+    start_tree: Option<Store>,
+    goal_tree: Option<Store>,
+}
+
+impl<G: BallGoal> GpuRRTConnect<G> {
+    /// rrt_connect.rs:86
+    pub fn new(max_distance: f64, goal_bias: f64) -> Self {
+        Self { max_distance, goal_bias, chunk: 1 << 14, max_nodes: 1 << 20, problem_def: None,
+               checker: None, start_tree: None, goal_tree: None }
+    }
+}
+
+impl<G: BallGoal> Planner<RealVectorState, RealVectorStateSpace, G> for GpuRRTConnect<G> {
+    fn setup(
+        &mut self,
+        problem_def: Arc<ProblemDefinition<RealVectorState, RealVectorStateSpace, G>>,
+        validity_checker: Arc<dyn StateValidityChecker<RealVectorState>>,
+    ) {
+        // rrt_connect.rs:199-225: the start tree holds the start state, the goal tree one sampled goal
+        let world = gpu_world_of(&validity_checker);
+        self.checker = Some((validity_checker, world));
+        let dim = problem_def.space.dimension;
+        let (a, b) = (Store::new(dim), Store::new(dim));
+        a.push(&problem_def.start_states[0]);
+        let mut rng = rand::rng();
+        b.push(&problem_def.goal.sample_goal(&mut rng).unwrap());
+        self.start_tree = Some(a);
+        self.goal_tree = Some(b);
+        self.problem_def = Some(problem_def);
+    }
+
+    fn solve(&mut self, timeout: Duration) -> Result<Path<RealVectorState>, PlanningError> {
+        let pd = self.problem_def.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
+        let world = self.checker.as_ref().ok_or(PlanningError::PlannerUninitialised)?.1;
+        let (ta, tb) = (self.start_tree.as_ref().unwrap(), self.goal_tree.as_ref().unwrap());
+        let start_time = Instant::now();
+        let mut rng = rand::rng();
+        let (mut pa, mut pb) = (vec![-1i64; self.max_nodes], vec![-1i64; self.max_nodes]);
+        let mut prm = ffi::oxg_plan_params {
+            max_distance: self.max_distance,
+            resolution: pd.space.get_longest_valid_segment_length() * 0.1, // rrt_connect.rs:173
+            goal_radius: pd.goal.radius(),
+            max_nodes: self.max_nodes as u64,
+            stop_at_goal: 1,
+            ..Default::default()
+        };
+        loop {
+            let elapsed = start_time.elapsed();
+            if elapsed > timeout {
+                return Err(PlanningError::Timeout); // rrt_connect.rs:243-245
+            }
+            prm.timeout_s = (timeout - elapsed).as_secs_f64();
+            let stream = draw_stream(pd, self.goal_bias, self.chunk, &mut rng); // rrt_connect.rs:258-262
+            let mut r = ffi::oxg_plan_result::default();
+            check(unsafe {
+                ffi::oxg_rrt_connect_solve(world, ta.0, tb.0, &prm, pd.goal.target().values.as_ptr(),
+                                           stream.as_ptr(), self.chunk as u64, pa.as_mut_ptr(),
+                                           pb.as_mut_ptr(), &mut r)
+            });
+            if r.solved != 0 {
+                // rrt_connect.rs:271-304: the start tree reached the goal itself, or the trees met
+                let mut path = chain(ta, &pa, r.goal_node[0]);
+                if r.goal_node[1] >= 0 {
+                    let mut goal_side = chain(tb, &pb, r.goal_node[1]);
+                    goal_side.reverse();
+                    path.extend(goal_side.into_iter().skip(1)); // skip the duplicate connection point
+                }
+                return Ok(Path(path));
+            }
+            if r.status == 3 || r.status == 2 {
+                return Err(PlanningError::Timeout);
+            }
+        }
+    }
+}
+
+/// `oxmpl::geometric::RRTStar` (rrt_star.rs:40-291): radius neighbours, choose-parent, rewire.
+pub struct GpuRRTStar<G: BallGoal> {
+    pub max_distance: f64,
+    pub goal_bias: f64,
+    pub search_radius: f64,
+    pub chunk: usize,
+    pub max_nodes: usize,
+    problem_def: Option<Arc<ProblemDefinition<RealVectorState, RealVectorStateSpace, G>>>,
+    checker: Option<(Arc<dyn StateValidityChecker<RealVectorState>>, ffi::oxg_world)>,
+    tree: Option<Store>,
+}
+
+impl<G: BallGoal> GpuRRTStar<G> {
+    /// rrt_star.rs:65
+    pub fn new(max_distance: f64, goal_bias: f64, search_radius: f64) -> Self {
+        Self { max_distance, goal_bias, search_radius, chunk: 1 << 14, max_nodes: 1 << 20,
+               problem_def: None, checker: None, tree: None }
+    }
+}
+
+impl<G: BallGoal> Planner<RealVectorState, RealVectorStateSpace, G> for GpuRRTStar<G> {
+    fn setup(
+        &mut self,
+        problem_def: Arc<ProblemDefinition<RealVectorState, RealVectorStateSpace, G>>,
+        validity_checker: Arc<dyn StateValidityChecker<RealVectorState>>,
+    ) {
+        // rrt_star.rs:152-170: the tree holds the start state at cost 0
+        let world = gpu_world_of(&validity_checker);
+        self.checker = Some((validity_checker, world));
+        let tree = Store::new(problem_def.space.dimension);
+        tree.push(&problem_def.start_states[0]);
+        self.tree = Some(tree);
+        self.problem_def = Some(problem_def);
+    }
+
+    fn solve(&mut self, timeout: Duration) -> Result<Path<RealVectorState>, PlanningError> {
+        let pd = self.problem_def.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
+        let world = self.checker.as_ref().ok_or(PlanningError::PlannerUninitialised)?.1;
+        let tree = self.tree.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
+        let start_time = Instant::now();
+        let mut rng = rand::rng();
+        let mut parents = vec![-1i64; self.max_nodes];
+        let mut costs = vec![0.0f64; self.max_nodes];
+        let mut prm = ffi::oxg_plan_params {
+            max_distance: self.max_distance,
+            search_radius: self.search_radius,
+            resolution: pd.space.get_longest_valid_segment_length() * 0.1, // rrt_star.rs:83
+            goal_radius: pd.goal.radius(),
+            max_nodes: self.max_nodes as u64,
+            stop_at_goal: 1, // rrt_star.rs:285-288 returns at the first node that satisfies the goal
+            ..Default::default()
+        };
+        loop {
+            let elapsed = start_time.elapsed();
+            if elapsed > timeout {
+                return Err(PlanningError::Timeout); // rrt_star.rs:184-186
+            }
+            prm.timeout_s = (timeout - elapsed).as_secs_f64();
+            let stream = draw_stream(pd, self.goal_bias, self.chunk, &mut rng);
+            let mut r = ffi::oxg_plan_result::default();
+            check(unsafe {
+                ffi::oxg_rrt_star_solve(world, tree.0, &prm, pd.goal.target().values.as_ptr(),
+                                        stream.as_ptr(), self.chunk as u64, parents.as_mut_ptr(),
+                                        costs.as_mut_ptr(), &mut r)
+            });
+            if r.solved != 0 {
+                return Ok(Path(chain(tree, &parents, r.goal_node[0])));
+            }
+            if r.status == 3 || r.status == 2 {
+                return Err(PlanningError::Timeout);
+            }
+        }
+    }
+}
+
+/// A roadmap node as `PRM::get_roadmap` returns it (prm.rs:24-29, 82-84).
+#[derive(Clone)]
+pub struct GpuPrmNode {
+    pub state: RealVectorState,
+    pub edges: Vec<usize>,
+}
+
+/// `oxmpl::geometric::PRM` (prm.rs:48-308): the roadmap's states live in a GPU store, its edges in
+/// the lower-index CSR the library emits (`new_node.edges` at push time, prm.rs:135).
+pub struct GpuPRM<G: BallGoal> {
+    pub timeout: f64,
+    pub connection_radius: f64,
+    /// samples drawn per batch of the incremental build
+    pub batch: usize,
+    pub max_nodes: usize,
+    problem_def: Option<Arc<ProblemDefinition<RealVectorState, RealVectorStateSpace, G>>>,
+    checker: Option<(Arc<dyn StateValidityChecker<RealVectorState>>, ffi::oxg_world)>,
+    store: Option<Store>,
+    lower_off: Vec<u64>,
+    lower_idx: Vec<u32>,
+}
+
+impl<G: BallGoal> GpuPRM<G> {
+    /// prm.rs:70
+    pub fn new(timeout: f64, connection_radius: f64) -> Self {
+        Self { timeout, connection_radius, batch: 1 << 13, max_nodes: 1 << 22, problem_def: None,
+               checker: None, store: None, lower_off: vec![0], lower_idx: Vec::new() }
+    }
+    fn n_nodes(&self) -> usize { self.lower_off.len() - 1 }
+
+    /// prm.rs:88-90
+    pub fn set_problem_definition(
+        &mut self, pd: Arc<ProblemDefinition<RealVectorState, RealVectorStateSpace, G>>,
+    ) {
+        self.problem_def = Some(pd);
+    }
+
+    /// prm.rs:82-84: states plus symmetric edge lists (lower neighbours first, then the later nodes
+    /// that connected to this one, both ascending — the order the reference's lists grow in).
+    pub fn get_roadmap(&self) -> Vec<GpuPrmNode> {
+        let n = self.n_nodes();
+        let store = match self.store.as_ref() { Some(s) => s, None => return Vec::new() };
+        let mut nodes: Vec<GpuPrmNode> =
+            (0..n).map(|i| GpuPrmNode { state: store.get(i), edges: Vec::new() }).collect();
+        for i in 0..n {
+            for t in self.lower_off[i] as usize..self.lower_off[i + 1] as usize {
+                let j = self.lower_idx[t] as usize;
+                nodes[i].edges.push(j);
+            }
+        }
+        for i in 0..n {
+            for t in self.lower_off[i] as usize..self.lower_off[i + 1] as usize {
+                nodes[self.lower_idx[t] as usize].edges.push(i); // prm.rs:143-145
+            }
+        }
+        nodes
+    }
+
+    /// prm.rs:96-154, in batches: draw `batch` samples, keep the valid ones (prm.rs:123), append
+    /// them and let the library connect each to the earlier nodes within `connection_radius` whose
+    /// motion is valid (prm.rs:131-138) — identical to the one-at-a-time loop, because node i only
+    /// ever looks at nodes j < i.
+    pub fn construct_roadmap(&mut self) -> Result<(), PlanningError> {
+        if self.n_nodes() > 0 {
+            return Ok(()); // prm.rs:106-113: an existing roadmap is reused
+        }
+        let pd = self.problem_def.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
+        let world = self.checker.as_ref().ok_or(PlanningError::PlannerUninitialised)?.1;
+        let store = self.store.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
+        let dim = pd.space.dimension;
+        let sp = ffi::oxg_space_desc { n_real: dim as u32, n_so2: 0, w_real: 1.0, w_so2: 1.0 };
+        let resolution = pd.space.get_longest_valid_segment_length() * 0.1; // prm.rs:168
+        let start_time = Instant::now();
+        let mut rng = rand::rng(); // prm.rs:115
+        while start_time.elapsed().as_secs_f64() <= self.timeout && self.n_nodes() < self.max_nodes {
+            let mut rows = Vec::with_capacity(self.batch * dim);
+            for _ in 0..self.batch {
+                rows.extend_from_slice(&pd.space.sample_uniform(&mut rng).unwrap().values); // prm.rs:122
+            }
+            let mut ok = vec![0u8; self.batch];
+            check(unsafe { ffi::oxg_is_valid(world, &sp, rows.as_ptr(), self.batch as u64, ok.as_mut_ptr()) });
+            let keep: Vec<f64> = rows.chunks(dim).zip(&ok).filter(|(_, v)| **v != 0)
+                .flat_map(|(r, _)| r.iter().copied()).collect();
+            let nk = keep.len() / dim;
+            if nk == 0 {
+                continue;
+            }
+            let mut first = 0u64;
+            check(unsafe { ffi::oxg_store_append(store.0, keep.as_ptr(), nk as u64, &mut first) });
+            let mut off = vec![0u64; nk + 1];
+            let mut idx = vec![0u32; 64 * nk];
+            let mut st = ffi::oxg_prm_stats::default();
+            loop {
+                let rc = unsafe {
+                    ffi::oxg_prm_build_radius(world, store.0, self.connection_radius, resolution, first,
+                                              first + nk as u64, off.as_mut_ptr(), idx.as_mut_ptr(),
+                                              idx.len() as u64, &mut st)
+                };
+                if rc == ffi::OXG_E_CAPACITY {
+                    idx.resize(off[nk] as usize, 0);
+                    continue;
+                }
+                check(rc);
+                break;
+            }
+            let base = *self.lower_off.last().unwrap();
+            self.lower_off.extend(off[1..].iter().map(|o| base + o));
+            self.lower_idx.extend_from_slice(&idx[..off[nk] as usize]);
+        }
+        Ok(())
+    }
+}
+
+impl<G: BallGoal> Planner<RealVectorState, RealVectorStateSpace, G> for GpuPRM<G> {
+    fn setup(
+        &mut self,
+        problem_def: Arc<ProblemDefinition<RealVectorState, RealVectorStateSpace, G>>,
+        validity_checker: Arc<dyn StateValidityChecker<RealVectorState>>,
+    ) {
+        // prm.rs:217-225: remember the problem and the checker, clear the roadmap
+        let world = gpu_world_of(&validity_checker);
+        self.checker = Some((validity_checker, world));
+        self.store = Some(Store::new(problem_def.space.dimension));
+        self.lower_off = vec![0];
+        self.lower_idx.clear();
+        self.problem_def = Some(problem_def);
+    }
+
+    fn solve(&mut self, _timeout: Duration) -> Result<Path<RealVectorState>, PlanningError> {
+        let pd = self.problem_def.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
+        let world = self.checker.as_ref().ok_or(PlanningError::PlannerUninitialised)?.1;
+        let store = self.store.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
+        if self.n_nodes() == 0 {
+            return Err(PlanningError::UnsampledStateSpace); // prm.rs:239-241
+        }
+        let start = &pd.start_states[0];
+        let mut path = vec![0u32; self.n_nodes()];
+        let mut r = ffi::oxg_prm_query_result::default();
+        check(unsafe {
+            ffi::oxg_prm_solve(world, store.0, self.lower_off.as_ptr(), self.lower_idx.as_ptr(),
+                               self.connection_radius, pd.space.get_longest_valid_segment_length() * 0.1,
+                               start.values.as_ptr(), pd.goal.target().values.as_ptr(), pd.goal.radius(),
+                               path.as_mut_ptr(), path.len() as u32, &mut r)
+        });
+        match r.status {
+            0 => {
+                // reconstruct_path (prm.rs:189-208): the start state, then the roadmap nodes
+                let mut states = vec![start.clone()];
+                states.extend(path[..r.path_len as usize].iter().map(|i| store.get(*i as usize)));
+                Ok(Path(states))
+            }
+            2 => Err(PlanningError::InvalidStartState), // prm.rs:243-246
+            3 => Err(PlanningError::UnsampledStateSpace),
+            _ => Err(PlanningError::NoSolutionFound), // prm.rs:266-268, 304
         }
     }
 }

@@ -413,6 +413,21 @@ class PRM:
             ok = self.vc.cones.check_motion(np.repeat(q, len(nb), axis=0), rows[nb], res) \
                 if len(nb) else np.empty(0, np.uint8)
             return self._search(start, rows, nb, ok, mk)
+        goal = self.pd.goal
+        if hasattr(goal, "target") and hasattr(goal, "radius"):
+            # ball goal: the whole query runs in the library (oxg_prm_solve: start connection, goal
+            # scan, symmetrised adjacency and the reference-order BFS on the device)
+            lower = [[j for j in e if j < i] for i, e in enumerate(self.edges)]
+            off = np.zeros(len(lower) + 1, dtype=np.uint64)
+            off[1:] = np.cumsum([len(e) for e in lower])
+            idx = np.fromiter((j for e in lower for j in e), dtype=np.uint32, count=int(off[-1]))
+            status, path, _ = api.prm_solve(self.vc.world, self.store, off, idx, self.connection_radius,
+                                            res, start.values, goal.target.values, float(goal.radius))
+            if status == 2:
+                raise PlanningError(PlanningError.INVALID_START)
+            if status != 0:
+                raise PlanningError(PlanningError.NO_SOLUTION)
+            return Path([start] + [mk(rows[i]) for i in path])
         off, nb = self.store.radius(q, self.connection_radius)              # prm.rs:249-256
         ok = self.vc.world.check_motion(sp._space(), np.repeat(q, len(nb), axis=0), rows[nb], res) \
             if len(nb) else np.empty(0, np.uint8)

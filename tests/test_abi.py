@@ -156,3 +156,33 @@ def test_build_is_deterministic_for_the_scan_kernels():
     m = re.search(r"knn_rv_dot_kernelILi7ELi2E\w*:\s*\n\s*REG:(\d+)", out)
     assert m, "knn_rv_dot_kernel<7,2> not found in oxg_nn.o"
     assert int(m.group(1)) == 168
+
+
+def test_rust_crate_builds_every_source_it_calls_into():
+    """bindings/oxmpl-cuda (uncompiled here: no cargo/rustc): build.rs must compile exactly the
+    translation units of csrc/Makefile, every `ffi::oxg_*` function lib.rs calls must be declared
+    in ffi.rs AND defined in one of those units, and the planner types its docs promise must exist."""
+    crate = os.path.join(ROOT, "bindings", "oxmpl-cuda")
+    build_rs = open(os.path.join(crate, "build.rs")).read()
+    lib_rs = open(os.path.join(crate, "src", "lib.rs")).read()
+    ffi_rs = open(os.path.join(crate, "src", "ffi.rs")).read()
+    mk = open(os.path.join(ROOT, "oxmpl_b200", "csrc", "Makefile")).read()
+    mk_srcs = sorted(re.search(r"^SRCS := (.*)$", mk, flags=re.M).group(1).split())
+    rs_srcs = sorted(set(re.findall(r'"(oxg_[a-z0-9_]+\.cu)"', build_rs)))
+    assert rs_srcs == mk_srcs
+    assert "--split-compile" not in re.sub(r"//.*", "", build_rs)
+    defined = {}
+    for src in mk_srcs:
+        text = open(os.path.join(ROOT, "oxmpl_b200", "csrc", src)).read()
+        for name in re.findall(r"^(?:extern \"C\" )?(?:int|uint64_t|const char\*) (oxg_[a-z0-9_]+)\(", text, flags=re.M):
+            defined[name] = src
+    declared = set(re.findall(r"pub fn (oxg_[a-z0-9_]+)\s*\(", ffi_rs))
+    used = set(re.findall(r"ffi::(oxg_[a-z0-9_]+)\s*\(", lib_rs))
+    assert used, "lib.rs calls nothing?"
+    for name in sorted(used):
+        assert name in declared, f"lib.rs calls ffi::{name}, which ffi.rs does not declare"
+        assert name in defined, f"lib.rs calls ffi::{name}, which no source compiled by build.rs defines"
+    for ty in ("GpuValidityChecker", "GpuRRT", "GpuRRTConnect", "GpuRRTStar", "GpuPRM", "GpuConeChecker"):
+        assert re.search(rf"pub struct {ty}\b", lib_rs), f"{ty} is documented but not defined"
+        assert re.search(rf"impl(<[^>]*>)? (Planner<[^>]*>|StateValidityChecker<[^>]*>) for {ty}\b", lib_rs), ty
+    assert "set_gpu_checker" not in lib_rs           # setup() takes the checker it is given
