@@ -391,11 +391,16 @@ impl<G: BallGoal> Planner<RealVectorState, RealVectorStateSpace, G> for GpuRRTSt
             prm.timeout_s = (timeout - elapsed).as_secs_f64();
             let stream = draw_stream(pd, self.goal_bias, self.chunk, &mut rng);
             let mut r = ffi::oxg_plan_result::default();
-            check(unsafe {
+            let rc = unsafe {
                 ffi::oxg_rrt_star_solve(world, tree.0, &prm, pd.goal.target().values.as_ptr(),
                                         stream.as_ptr(), self.chunk as u64, parents.as_mut_ptr(),
                                         costs.as_mut_ptr(), &mut r)
-            });
+            };
+            if rc == ffi::OXG_E_CAPACITY {
+                // more than OXG_RRT_STAR_MAX_NEIGHBOURS nodes inside search_radius (include/oxg.h)
+                return Err(PlanningError::NoSolutionFound);
+            }
+            check(rc);
             if r.solved != 0 {
                 return Ok(Path(chain(tree, &parents, r.goal_node[0])));
             }

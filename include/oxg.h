@@ -261,7 +261,15 @@ int oxg_prm_solve_knn(oxg_world w, oxg_store s, const uint32_t* idx, const uint8
  *  - The reference loops until a wall-clock timeout; here a solve ends when it is solved, the
  *    stream is consumed, a tree holds max_nodes states, or timeout_s (if > 0) elapses.
  * status: 0 solved, 1 stream exhausted, 2 tree full, 3 timeout (PlanningError::Timeout).
+ *
+ * Limit (RRT* only): one iteration may find at most OXG_RRT_STAR_MAX_NEIGHBOURS tree nodes inside
+ * search_radius (find_neighbours, rrt_star.rs:121-131, is unbounded; the kernel keeps the
+ * neighbour list of an iteration in shared memory).  A denser neighbourhood ends the solve with
+ * OXG_E_CAPACITY; the tree, parents, costs and *out describe the iterations completed before it,
+ * and the solve can be continued with a smaller search_radius.  The host mirrors report it as
+ * PlanningError::NoSolutionFound with the library's message.
  */
+#define OXG_RRT_STAR_MAX_NEIGHBOURS 2048
 typedef struct oxg_plan_params {
   double max_distance;  /* RRT::new(max_distance, ..) rrt.rs:75, rrt_connect.rs:86, rrt_star.rs:65 */
   double search_radius; /* RRTStar::new(.., .., search_radius); ignored by RRT / RRT-Connect        */

@@ -361,8 +361,10 @@ class RRTStar {
       prm.timeout_s = left;
       const std::vector<double> stream = detail::draw_stream(*pd_, goal_bias, chunk, rng);
       oxg_plan_result r{};
-      check(oxg_rrt_star_solve(vc_->handle(), tree_->h(), &prm, pd_->goal->target.data(),
-                               stream.data(), chunk, parents_.data(), costs_.data(), &r));
+      const int rc = oxg_rrt_star_solve(vc_->handle(), tree_->h(), &prm, pd_->goal->target.data(),
+                                        stream.data(), chunk, parents_.data(), costs_.data(), &r);
+      if (rc == OXG_E_CAPACITY) throw PlanningError::no_solution();  // OXG_RRT_STAR_MAX_NEIGHBOURS (oxg.h)
+      check(rc);
       last_ = r;
       if (r.solved) return detail::trace(*tree_, parents_, r.goal_node[0], dim);
       if (r.status == 3 || r.status == 2) throw PlanningError::timeout();

@@ -90,6 +90,8 @@ class Oracle:
             "orc_prm_radius": (u64, [w, sp, d, d, vp, u64, vp, vp, vp, u64, C.POINTER(u64),
                                      C.POINTER(u64)]),
             "orc_prm_knn": (None, [w, sp, vp, u64, u32, d, u64, u64, vp, vp, vp, cnt]),
+            "orc_prm_solve": (C.c_int, [w, sp, vp, u64, vp, vp, d, d, vp, C.POINTER(OrcGoal), vp, u32,
+                                        C.POINTER(u32)]),
             "orc_so3_distance": (d, [vp, vp]),
             "orc_so3_interpolate": (None, [vp, vp, d, vp]),
             "orc_so3_nn1_batch": (None, [vp, u64, vp, u64, vp, vp]),
@@ -304,11 +306,9 @@ class Oracle:
         g = OrcGoal(C.c_void_p(tg.ctypes.data), float(goal_radius))
         path = np.empty(max(rows.shape[0], 1), dtype=np.uint32)
         plen = C.c_uint32(0)
-        self.lib.orc_prm_solve.restype = C.c_int
-        status = self.lib.orc_prm_solve(C.byref(w), C.byref(sp), _p(rows), C.c_uint64(rows.shape[0]),
-                                        _p(off), _p(idx), C.c_double(connection_radius),
-                                        C.c_double(resolution), _p(st), C.byref(g), _p(path),
-                                        C.c_uint32(path.shape[0]), C.byref(plen))
+        status = self.lib.orc_prm_solve(C.byref(w), C.byref(sp), _p(rows), rows.shape[0], _p(off),
+                                        _p(idx), connection_radius, resolution, _p(st), C.byref(g),
+                                        _p(path), path.shape[0], C.byref(plen))
         return int(status), path[: plen.value].copy()
 
     def rrt(self, w, sp, start, goal_target, goal_radius, max_distance, resolution, samples,

@@ -85,6 +85,98 @@ class GpuValidityChecker:
         return self.world.is_valid(self._space, rows)
 
 
+def _so2_normalise(v: float) -> float:
+    """SO2State::normalise (oxmpl/src/base/states/so2_state.rs:55-59):
+    ``(value + PI).rem_euclid(2.0 * PI) - PI`` — ``%`` on f64 is C fmod (exact), rem_euclid adds
+    ``|rhs|`` when the remainder is negative."""
+    r = math.fmod(v + math.pi, 2.0 * math.pi)
+    if r < 0.0:
+        r = r + abs(2.0 * math.pi)
+    return r - math.pi
+
+
+class SO2State:
+    """oxmpl_py.base.SO2State(value) (oxmpl-py/src/base/so2_state.rs): an angle, normalised to
+    [-pi, pi) on construction as ``SO2State::new`` does (so2_state.rs:34-38)."""
+
+    __slots__ = ("value",)
+
+    def __init__(self, value: float):
+        self.value = _so2_normalise(float(value))
+
+    @property
+    def values(self):
+        return [self.value]
+
+    def __repr__(self):
+        return f"SO2State(value={self.value})"
+
+
+class SO2StateSpace:
+    """oxmpl_py.base.SO2StateSpace(bounds=None); host arithmetic restates
+    oxmpl/src/base/spaces/so2_state_space.rs:57-79,97-122,161-170 in Python floats."""
+
+    dimension = 1
+
+    def __init__(self, bounds=None):
+        if bounds is None:
+            bounds = (-math.pi, math.pi)
+        lo, hi = float(bounds[0]), float(bounds[1])
+        if lo >= hi:
+            raise ValueError("InvalidBound: lower bound must be less than upper bound")
+        self.bounds = (lo, hi)
+        self._fraction = 0.05
+
+    def distance(self, state1: SO2State, state2: SO2State) -> float:
+        diff = state1.value - state2.value                      # so2_state_space.rs:97-101
+        return abs(_so2_normalise(diff))
+
+    def interpolate(self, frm: SO2State, to: SO2State, t: float) -> SO2State:
+        diff = _so2_normalise(to.value) - _so2_normalise(frm.value)   # so2_state_space.rs:107-122
+        if diff > math.pi:
+            diff -= 2.0 * math.pi
+        elif diff < -math.pi:
+            diff += 2.0 * math.pi
+        return SO2State(frm.value + diff * t)
+
+    def get_maximum_extent(self) -> float:
+        return math.pi
+
+    def set_longest_valid_segment_fraction(self, fraction: float):
+        self._fraction = fraction if 0.0 < fraction <= 1.0 else (0.0 if fraction <= 0.0 else 1.0)
+
+    def get_longest_valid_segment_length(self) -> float:
+        return self.get_maximum_extent() * self._fraction
+
+    def satisfies_bounds(self, state: SO2State) -> bool:
+        v = _so2_normalise(state.value)
+        return self.bounds[0] <= v <= self.bounds[1]
+
+    def sample_uniform(self, rng: random.Random) -> SO2State:
+        return SO2State(rng.uniform(self.bounds[0], self.bounds[1]))
+
+    def _space(self) -> api.Space:
+        return api.Space.so2()
+
+
+class GpuIntervalChecker:
+    """Declarative ``StateValidityChecker<SO2State>``: forbidden angle intervals ``(lo, hi)``; a
+    state is invalid iff ``lo <= normalise(angle) <= hi`` for one of them (the reference's SO2
+    fixture, oxmpl/tests/rrt_so2ss_tests.rs:17-27 / oxmpl-py/tests/test_rrt_so2ss.py:24-34)."""
+
+    dimension = 0
+
+    def __init__(self, intervals):
+        self.world = api.World(0, so2_intervals=[(0, float(lo), float(hi)) for lo, hi in intervals])
+        self._space = api.Space.so2()
+
+    def __call__(self, state: SO2State) -> bool:
+        return bool(self.world.is_valid(self._space, np.asarray([state.values]))[0])
+
+    def is_valid_batch(self, rows) -> np.ndarray:
+        return self.world.is_valid(self._space, rows)
+
+
 class SO3State:
     """oxmpl_py.base.SO3State(x, y, z, w) (oxmpl-py/src/base/so3_state.rs): a unit quaternion."""
 
@@ -195,6 +287,15 @@ class ProblemDefinition:
 
     @staticmethod
     def from_real_vector(space, start_state, goal) -> "ProblemDefinition":
+        for attr in ("target", "radius", "is_satisfied", "sample_goal"):
+            if not hasattr(goal, attr):
+                raise TypeError(f"goal must provide `{attr}` (a ball goal: target + radius)")
+        return ProblemDefinition(space, start_state, goal)
+
+    @staticmethod
+    def from_so2(space, start_state, goal) -> "ProblemDefinition":
+        """oxmpl-py/src/base/problem_definition.rs: an SO2 problem; the fused kernels test the goal
+        as the ball ``distance(state, target) <= radius``, so the goal must expose both."""
         for attr in ("target", "radius", "is_satisfied", "sample_goal"):
             if not hasattr(goal, attr):
                 raise TypeError(f"goal must provide `{attr}` (a ball goal: target + radius)")

@@ -43,7 +43,7 @@ namespace oxg {
 
 constexpr int PL_THREADS = 512;
 constexpr int PL_WARPS = PL_THREADS / 32;
-constexpr int NBR_CAP = 2048;  // neighbours of one RRT* iteration (OXG_E_CAPACITY beyond)
+constexpr int NBR_CAP = OXG_RRT_STAR_MAX_NEIGHBOURS;  // neighbours of one RRT* iteration (OXG_E_CAPACITY beyond; include/oxg.h)
 constexpr unsigned long long MAX_STEPS = 1ull << 24;  // steps of one motion (reference: unbounded)
 
 enum { MODE_RRT = 0, MODE_CONNECT = 1, MODE_STAR = 2 };
@@ -1183,7 +1183,8 @@ int plan_stage(oxg_world w, oxg_store t0, oxg_store t1, const oxg_plan_params* p
   out->ctas = G;
   for (int i = 0; i < 8; ++i) out->phase_ms[i] = (double)h.phase_ns[i] * 1e-6;
   if (h.status == ST_E_NEIGHBOURS) {
-    set_error("more than %d states inside search_radius in one RRT* iteration", NBR_CAP);
+    set_error("more than %d tree nodes inside search_radius in one RRT* iteration "
+              "(OXG_RRT_STAR_MAX_NEIGHBOURS, include/oxg.h): reduce search_radius", NBR_CAP);
     return OXG_E_CAPACITY;
   }
   if (h.status == ST_E_STEPS) {

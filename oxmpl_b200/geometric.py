@@ -14,15 +14,25 @@ from collections import deque
 import numpy as np
 
 from . import api
-from .base import (GpuConeChecker, GpuValidityChecker, Path, PlanningError, ProblemDefinition,
-                   RealVectorState, SO3State, SO3StateSpace)
+from .base import (GpuConeChecker, GpuIntervalChecker, GpuValidityChecker, Path, PlanningError,
+                   ProblemDefinition, RealVectorState, SO2State, SO2StateSpace, SO3State, SO3StateSpace)
 
 
-def _checker(validity) -> GpuValidityChecker:
-    if not isinstance(validity, GpuValidityChecker):
-        raise TypeError("the GPU planners take a declarative GpuValidityChecker, not a Python "
+def _checker(validity, space=None):
+    want = GpuIntervalChecker if isinstance(space, SO2StateSpace) else GpuValidityChecker
+    if not isinstance(validity, want):
+        raise TypeError(f"the GPU planners take a declarative {want.__name__}, not a Python "
                         "callback (oxmpl_b200 has no CPU fallback)")
     return validity
+
+
+def _state_maker(space):
+    """Row of the store -> the space's state type."""
+    if isinstance(space, SO2StateSpace):
+        return lambda r: SO2State(r[0])
+    if isinstance(space, SO3StateSpace):
+        return lambda r: SO3State(*r)
+    return RealVectorState
 
 
 class _TreePlanner:
@@ -39,7 +49,7 @@ class _TreePlanner:
         self.tree = None
 
     def setup(self, validity):
-        self.vc = _checker(validity)
+        self.vc = _checker(validity, self.pd.space)
         self.tree = api.StateStore(self.pd.space._space(), capacity=1024)
         self.tree.append(np.asarray([self.pd.start_state.values]))   # rrt.rs:147-155
 
@@ -56,9 +66,9 @@ class _TreePlanner:
         return self.pd.space.get_longest_valid_segment_length() * 0.1   # rrt.rs:97
 
     def _trace(self, store, parents, node):
-        rows, out = store.read(), []
+        rows, out, mk = store.read(), [], _state_maker(self.pd.space)
         while node >= 0:
-            out.append(RealVectorState(rows[node]))
+            out.append(mk(rows[node]))
             node = int(parents[node])
         return out[::-1]
 
@@ -235,11 +245,16 @@ class RRTStar(_TreePlanner):
             left = timeout_secs - (time.perf_counter() - t0)
             if left <= 0:
                 raise PlanningError(PlanningError.TIMEOUT)
-            parents, costs, r = api.rrt_star_solve(
-                self.vc.world, self.tree, self._stream(self.chunk), self.max_distance,
-                self.search_radius, self._resolution(), self.max_nodes,
-                goal_target=self.pd.goal.target.values, goal_radius=self.pd.goal.radius,
-                stop_at_goal=True, timeout_s=left)
+            try:
+                parents, costs, r = api.rrt_star_solve(
+                    self.vc.world, self.tree, self._stream(self.chunk), self.max_distance,
+                    self.search_radius, self._resolution(), self.max_nodes,
+                    goal_target=self.pd.goal.target.values, goal_radius=self.pd.goal.radius,
+                    stop_at_goal=True, timeout_s=left)
+            except api._lib.OxgError as e:
+                if e.code == api._lib.OXG_E_CAPACITY:   # OXG_RRT_STAR_MAX_NEIGHBOURS (include/oxg.h)
+                    raise PlanningError(PlanningError.NO_SOLUTION + " " + str(e)) from e
+                raise
             if r["solved"]:
                 return Path(self._trace(self.tree, parents, r["goal_node"][0]))
             if r["status"] in ("timeout", "tree_full"):
@@ -337,7 +352,7 @@ class PRM:
                                 "callback (oxmpl_b200 has no CPU fallback)")
             self.vc = validity
         else:
-            self.vc = _checker(validity)
+            self.vc = _checker(validity, self.pd.space)
         self.store = api.StateStore(self.pd.space._space(), capacity=1024)
         self.edges = []                                       # prm.rs:224
 
@@ -407,7 +422,7 @@ class PRM:
         sp, res = self.pd.space, self.pd.space.get_longest_valid_segment_length() * 0.1
         rows = self.store.read()
         q = np.asarray([start.values])
-        mk = (lambda r: SO3State(*r)) if self.so3 else RealVectorState
+        mk = _state_maker(self.pd.space)
         if self.so3:
             off, nb = self.store.so3_radius(q, self.connection_radius)      # prm.rs:249-256
             ok = self.vc.cones.check_motion(np.repeat(q, len(nb), axis=0), rows[nb], res) \

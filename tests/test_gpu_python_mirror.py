@@ -359,3 +359,92 @@ def test_rrt_star_so3ss_and_tree_matches_oracle_loop(oxg, orc):
     assert planner.t.parents == parents
     np.testing.assert_array_equal(np.asarray(planner.t.costs).view(np.uint64),
                                   np.asarray(costs).view(np.uint64))
+
+
+# ---------------------------------------------------------------------------------------------
+# SO2: oxmpl-py/tests/test_{rrt,rrt_connect,rrt_star,prm}_so2ss.py — forbidden zone [-0.5, 0.5],
+# start -pi/2, goal pi/2 +- 0.1; the callback is_angle_valid is kept as the independent check.
+# ---------------------------------------------------------------------------------------------
+class AngleGoalRegion:                   # oxmpl-py/tests/test_rrt_so2ss.py:9-21
+    def __init__(self, space, target_angle, radius):
+        from oxmpl_b200.base import SO2State
+        self.space = space
+        self.target = SO2State(target_angle)
+        self.radius = radius
+        self.rng = random.Random(456)
+
+    def is_satisfied(self, state):
+        return self.space.distance(self.target, state) <= self.radius
+
+    def sample_goal(self):
+        from oxmpl_b200.base import SO2State
+        return SO2State(self.target.value + self.rng.uniform(-self.radius, self.radius))
+
+
+def is_angle_valid(state):               # oxmpl-py/tests/test_rrt_so2ss.py:24-34
+    return not (-0.5 <= state.value <= 0.5)
+
+
+def _so2_problem():
+    from oxmpl_b200.base import GpuIntervalChecker, SO2State, SO2StateSpace
+    space = SO2StateSpace()
+    start = SO2State(-math.pi / 2.0)
+    goal = AngleGoalRegion(space, target_angle=math.pi / 2.0, radius=0.1)
+    return space, start, goal, ProblemDefinition.from_so2(space, start, goal), GpuIntervalChecker([(-0.5, 0.5)])
+
+
+def _check_so2(path, space, start, goal):
+    assert len(path.states) > 1
+    assert space.distance(path.states[0], start) < 1e-9
+    assert goal.is_satisfied(path.states[-1])
+    for s in path.states:
+        assert is_angle_valid(s), s.value
+
+
+def test_so2_state_and_space_follow_the_reference(orc):
+    from oxmpl_b200.base import SO2State, SO2StateSpace
+    assert SO2State(3.0 * math.pi / 2.0).value == -math.pi / 2.0       # so2_state.rs:80-87, exactly
+    assert abs(SO2State(5.0 * math.pi).value + math.pi) < 1e-9          # so2_state.rs:28-32
+    space = SO2StateSpace()
+    assert space.get_maximum_extent() == math.pi
+    rng = random.Random(3)
+    for _ in range(300):
+        a, b, t = rng.uniform(-7, 7), rng.uniform(-7, 7), rng.random()
+        sa, sb = SO2State(a), SO2State(b)
+        sp_o = orc.space(0, 1)
+        assert space.distance(sa, sb) == orc.distance(sp_o, [sa.value], [sb.value])
+        assert space.interpolate(sa, sb, t).value == orc.interpolate(sp_o, [sa.value], [sb.value], t)[0]
+
+
+@pytest.mark.parametrize("planner_name", ["RRT", "RRTConnect", "RRTStar"])
+def test_tree_planners_find_path_in_so2ss(planner_name):
+    from oxmpl_b200 import geometric
+    space, start, goal, pd, checker = _so2_problem()
+    kw = dict(max_distance=0.5, goal_bias=0.05, problem_definition=pd)
+    if planner_name == "RRTStar":
+        kw["search_radius"] = 0.25
+    planner = getattr(geometric, planner_name)(**kw)
+    with pytest.raises(TypeError):
+        planner.setup(is_angle_valid)                # a Python callback is not a GPU checker
+    planner.setup(checker)
+    _check_so2(planner.solve(timeout_secs=5.0), space, start, goal)
+
+
+def test_prm_finds_path_in_so2ss():
+    space, start, goal, pd, checker = _so2_problem()
+    planner = PRM(timeout=5.0, connection_radius=0.5, problem_definition=pd)
+    planner.setup(checker)
+    planner.construct_roadmap(max_samples=4000)
+    _check_so2(planner.solve(timeout_secs=5.0), space, start, goal)
+
+
+def test_rrt_star_dense_neighbourhood_is_a_planning_error():
+    """More than OXG_RRT_STAR_MAX_NEIGHBOURS tree nodes inside search_radius (include/oxg.h): the
+    mirror reports the reference's NoSolutionFound with the library's explanation."""
+    space, start, goal, pd = _problem()
+    planner = RRTStar(max_distance=0.5, goal_bias=0.0, search_radius=1e9, problem_definition=pd)
+    planner.chunk = 6000
+    planner.setup(GpuValidityChecker(2, aabbs=[[20.0, 20.0, 21.0, 21.0]]))
+    planner.pd.goal.radius = 1e-12                   # never satisfied: the tree keeps growing
+    with pytest.raises(PlanningError, match="No solution found.*search_radius"):
+        planner.solve(timeout_secs=20.0)
