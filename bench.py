@@ -448,17 +448,24 @@ def run_ours(args):
         oxg.tuning_set("knn_tree", -1)
         allpairs = {"rows": wave_rows, "ms": float(np.median(t_ms))}
 
-    # ---- end-to-end through the host-buffer entry point -----------------------------------------
-    h_idx = torch.empty((n, k), dtype=torch.int32).pin_memory()
-    h_dist = torch.empty((n, k), dtype=torch.float64).pin_memory()
-    h_valid = torch.empty((n, k), dtype=torch.uint8).pin_memory()
+    # ---- end-to-end through the host-buffer entry points ----------------------------------------
+    # Every rank uploads ITS slice of the samples from pinned host memory (oxg_store_append_dist:
+    # the other slices arrive over NVLink), all ranks build, rank 0 reads the complete roadmap back.
+    want_host = rank == 0
+    h_idx = torch.empty((n, k), dtype=torch.int32).pin_memory() if want_host else None
+    h_dist = torch.empty((n, k), dtype=torch.float64).pin_memory() if want_host else None
+    h_valid = torch.empty((n, k), dtype=torch.uint8).pin_memory() if want_host else None
+    HP = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
     stats = PrmStats()
+    slice_ptr = rows_pinned[rb:re].data_ptr()
+    first = C.c_uint64(0)
 
     def e2e_step():
         st.clear()
-        st.append_ptr(rows_pinned.data_ptr(), n)                       # H2D: the samples
+        check(lib.oxg_store_append_dist(dctx.handle, st.handle, C.c_void_p(slice_ptr), re - rb,
+                                        C.byref(first)))                              # H2D: the samples
         check(lib.oxg_prm_build_knn_dist(dctx.handle, gw.handle, st.handle, k, float(res),
-                                         P(h_idx), P(h_dist), P(h_valid), C.byref(stats)))  # D2H: roadmap
+                                         HP(h_idx), HP(h_dist), HP(h_valid), C.byref(stats)))  # D2H: roadmap
 
     e2e_step()
     barrier()
@@ -470,7 +477,8 @@ def run_ours(args):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     clocks = sampler.stop() if rank == 0 else None
     # the roadmap the e2e path delivered must be the one the resident path holds
-    same = bool(torch.equal(h_idx, d_idx_all.cpu())) if world_size > 1 else None
+    # (d_idx_all still holds the last complete table of the resident-store loop at N > 1)
+    same = bool(torch.equal(h_idx, d_idx_all.cpu())) if (world_size > 1 and want_host) else None
 
     # ---- max over ranks ---------------------------------------------------------------------
     vals = torch.tensor([elapsed_ms, e2e_s, knn_phase_ms, float(n_checked_local)], dtype=torch.float64,
@@ -534,9 +542,10 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(n * DIM * 8),
                     "d2h_bytes_per_step": int(n * k * (4 + 8 + 1)),
                     "ms_per_step": e2e_s_max * 1e3,
-                    "path": "per rank: oxg_store_clear + oxg_store_append(pinned host rows) + "
-                            "oxg_prm_build_knn_dist(host outputs: the complete roadmap); wall clock "
-                            "around synchronous calls, max over ranks",
+                    "path": "oxg_store_clear + oxg_store_append_dist(each rank's slice of the pinned host "
+                            "rows; the other slices arrive over NVLink) + oxg_prm_build_knn_dist(rank 0 "
+                            "reads the complete roadmap into pinned host memory); the byte counts are the "
+                            "job's totals; wall clock around synchronous calls, max over ranks",
                     "roadmap_equals_resident_run": same},
             "gpu_launches": int(launches),
             "clocks": clocks,

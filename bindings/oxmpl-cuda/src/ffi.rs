@@ -138,6 +138,8 @@ extern "C" {
     pub fn oxg_dist_destroy(d: oxg_dist) -> c_int;
     pub fn oxg_dist_row_range(n: u64, rank: c_int, world_size: c_int, radius_mode: c_int,
                               row_begin: *mut u64, row_end: *mut u64) -> c_int;
+    pub fn oxg_store_append_dist(d: oxg_dist, s: oxg_store, rows_local: *const f64, n_local: u64,
+                                 first_index: *mut u64) -> c_int;
     pub fn oxg_prm_build_knn_dist(d: oxg_dist, w: oxg_world, s: oxg_store, k: u32, resolution: f64,
                                   idx: *mut u32, dist: *mut f64, valid: *mut u8,
                                   stats: *mut oxg_prm_stats) -> c_int;

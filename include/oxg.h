@@ -350,6 +350,10 @@ int oxg_store_stream(oxg_store s, void** out_stream);
  *                       (rank+1) n / world) (uniform work per row).  Radius mode:
  *                       [n sqrt(rank/world), n sqrt((rank+1)/world)) — node i scans the i
  *                       earlier nodes (prm.rs:131), so equal areas of the triangle balance it.
+ *  oxg_store_append_dist : collective append: every rank passes ITS slice of a common row set
+ *                       (any sizes); afterwards every rank's store holds all the rows in rank
+ *                       order.  Each slice crosses PCIe once and reaches the other ranks over
+ *                       NVLink (one broadcast per rank in a group call).
  *  oxg_prm_build_knn_dist      : oxg_prm_build_knn over all rows; idx/dist/valid are
  *                       [N][k] host arrays (each nullable: a rank that does not want the
  *                       roadmap on the host passes NULL).  Exchanges: one grouped
@@ -372,6 +376,8 @@ int oxg_dist_create(const void* unique_id_128, int rank, int world_size, oxg_dis
 int oxg_dist_destroy(oxg_dist d);
 int oxg_dist_row_range(uint64_t n, int rank, int world_size, int radius_mode,
                        uint64_t* row_begin, uint64_t* row_end);
+int oxg_store_append_dist(oxg_dist d, oxg_store s, const double* rows_local, uint64_t n_local,
+                          uint64_t* first_index);
 int oxg_prm_build_knn_dist(oxg_dist d, oxg_world w, oxg_store s, uint32_t k, double resolution,
                            uint32_t* idx, double* dist, uint8_t* valid, oxg_prm_stats* stats);
 int oxg_prm_build_knn_dist_dev(oxg_dist d, oxg_world w, oxg_store s, uint32_t k,

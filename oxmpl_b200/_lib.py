@@ -183,6 +183,7 @@ SIGNATURES = {
     "oxg_dist_create": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "oxg_dist_destroy": (C.c_int, [_vp]),
     "oxg_dist_row_range": (C.c_int, [_u64, C.c_int, C.c_int, C.c_int, C.POINTER(_u64), C.POINTER(_u64)]),
+    "oxg_store_append_dist": (C.c_int, [_vp, _vp, _pd, _u64, C.POINTER(_u64)]),
     "oxg_prm_build_knn_dist": (C.c_int, [_vp, _vp, _vp, _u32, _dbl, _pu32, _pd, _pu8, C.POINTER(PrmStats)]),
     "oxg_prm_build_knn_dist_dev": (C.c_int, [_vp, _vp, _vp, _u32, _dbl, _pu32, _pd, _pu8, _pu64]),
     "oxg_prm_build_radius_dist": (

@@ -212,6 +212,29 @@ static int store_grow(oxg_store_s* s, uint64_t capacity) {
   return OXG_OK;
 }
 
+// Appends the n row-major states waiting in B_STAGE (device) to the SoA store and its f32 mirror.
+int store_append_staged(oxg_store_s* s, uint64_t n) {
+  if (n == 0) return OXG_OK;
+  if (s->size + n > 0xFFFFFFF0ull) {
+    set_error("store would exceed the u32 index range");
+    return OXG_E_CAPACITY;
+  }
+  if (s->size + n > s->pitch) OXG_TRY(store_grow(s, std::max(s->size + n, s->pitch * 2)));
+  uint64_t total = n * s->dim;
+  int threads = 256;
+  int blocks = (int)std::min<uint64_t>((total + threads - 1) / threads, 148 * 16);
+  scatter_rows_kernel<<<blocks, threads, 0, s->stream>>>(s->buf[B_STAGE].as<double>(), n, s->dim,
+                                                         s->d_data, s->d_data32, s->pitch, s->size,
+                                                         s->d_maxabs);
+  OXG_LAUNCH_CHECK();
+  OXG_TRY(launch_norms(s, s->size, n));
+  // the caller may reuse its host rows immediately
+  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  s->size += n;
+  s->epoch += 1;
+  return OXG_OK;
+}
+
 }  // namespace oxg
 
 using namespace oxg;
@@ -373,23 +396,10 @@ int oxg_store_append(oxg_store s, const double* rows, uint64_t n, uint64_t* firs
     set_error("store would exceed the u32 index range");
     return OXG_E_CAPACITY;
   }
-  if (s->size + n > s->pitch) OXG_TRY(store_grow(s, std::max(s->size + n, s->pitch * 2)));
   size_t bytes = sizeof(double) * n * s->dim;
   OXG_TRY(s->buf[B_STAGE].ensure(bytes));
   OXG_CUDA_TRY(cudaMemcpyAsync(s->buf[B_STAGE].p, rows, bytes, cudaMemcpyHostToDevice, s->stream));
-  uint64_t total = n * s->dim;
-  int threads = 256;
-  int blocks = (int)std::min<uint64_t>((total + threads - 1) / threads, 148 * 16);
-  scatter_rows_kernel<<<blocks, threads, 0, s->stream>>>(s->buf[B_STAGE].as<double>(), n, s->dim,
-                                                         s->d_data, s->d_data32, s->pitch, s->size,
-                                                         s->d_maxabs);
-  OXG_LAUNCH_CHECK();
-  OXG_TRY(launch_norms(s, s->size, n));
-  // the caller may reuse `rows` immediately
-  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
-  s->size += n;
-  s->epoch += 1;
-  return OXG_OK;
+  return store_append_staged(s, n);
   OXG_API_END
 }
 

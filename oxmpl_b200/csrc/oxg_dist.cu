@@ -293,6 +293,52 @@ int oxg_dist_destroy(oxg_dist d) {
   return OXG_OK;
 }
 
+// Every rank contributes its own slice of a common row set; afterwards every rank's store holds
+// all rows, in rank order.  The slices cross PCIe once (each rank uploads only its own) and reach
+// the other ranks over NVLink (one broadcast per rank inside a group call).
+int oxg_store_append_dist(oxg_dist d, oxg_store s, const double* rows_local, uint64_t n_local,
+                          uint64_t* first_index) {
+  OXG_API_BEGIN
+  if (!d || !s || (!rows_local && n_local > 0)) {
+    set_error("NULL argument");
+    return OXG_E_NULL;
+  }
+  if (first_index) *first_index = s->size;
+  if (d->world == 1) return oxg_store_append(s, rows_local, n_local, first_index);
+  NcclApi* api = nccl_api();
+  if (!api) {
+    set_error("NCCL is not available in this process (libnccl.so.2 not found)");
+    return OXG_E_NCCL;
+  }
+  const int G = d->world;
+  // slice sizes of all ranks
+  OXG_TRY(d->cnt_all.ensure((size_t)G * sizeof(uint64_t)));
+  uint64_t* d_cnt = d->cnt_all.as<uint64_t>();
+  OXG_CUDA_TRY(cudaMemcpyAsync(d_cnt + d->rank, &n_local, sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+  OXG_NCCL_TRY(api, api->AllGather(d_cnt + d->rank, d_cnt, 1, ncclUint64, d->comm, s->stream));
+  std::vector<uint64_t> cnt(G);
+  OXG_CUDA_TRY(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)G * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  std::vector<uint64_t> off(G + 1, 0);
+  for (int g = 0; g < G; ++g) off[g + 1] = off[g] + cnt[g];
+  const uint64_t total = off[G];
+  if (total == 0) return OXG_OK;
+  const size_t row_bytes = sizeof(double) * s->dim;
+  OXG_TRY(s->buf[B_STAGE].ensure(total * row_bytes));
+  unsigned char* stage = s->buf[B_STAGE].as<unsigned char>();
+  if (n_local)
+    OXG_CUDA_TRY(cudaMemcpyAsync(stage + off[d->rank] * row_bytes, rows_local, n_local * row_bytes,
+                                 cudaMemcpyHostToDevice, s->stream));
+  OXG_NCCL_TRY(api, api->GroupStart());
+  for (int g = 0; g < G; ++g)
+    if (cnt[g])
+      OXG_NCCL_TRY(api, api->Broadcast(stage + off[g] * row_bytes, stage + off[g] * row_bytes,
+                                       cnt[g] * row_bytes, ncclUint8, g, d->comm, s->stream));
+  OXG_NCCL_TRY(api, api->GroupEnd());
+  return store_append_staged(s, total);
+  OXG_API_END
+}
+
 int oxg_dist_row_range(uint64_t n, int rank, int world_size, int radius_mode, uint64_t* row_begin,
                        uint64_t* row_end) {
   if (!row_begin || !row_end) {

@@ -290,6 +290,7 @@ int nn_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double r, const ui
                      bool limit_self, uint64_t self_base, bool want_dist, uint64_t* total);
 int nn_radius_nsplit(const oxg_store_s* s, uint64_t Q);
 int store_refresh_mirror(oxg_store_s* s, uint64_t first, uint64_t n);
+int store_append_staged(oxg_store_s* s, uint64_t n);  // rows already in B_STAGE (device, row-major)
 int nn_radius_offsets(oxg_store_s* s, uint64_t Q, uint64_t* d_out);
 
 // oxg_tree.cu: exact k-NN through the store's bounding-box hierarchy

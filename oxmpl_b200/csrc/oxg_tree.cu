@@ -360,28 +360,31 @@ __global__ void kd_choose_dim_kernel(KdRound r, int dim, const double* __restric
   }
 }
 
-// key = (segment << 32) | order-preserving 32-bit image of the split coordinate within the cell
-// (untouched segments keep their order: the position inside the segment).
+// key = (segment << sub_bits) | order-preserving sub_bits-bit image of the split coordinate
+// within the cell (untouched segments keep their order: the position inside the segment, which
+// fits because such a segment is at most one child's worth of states).  32-bit keys: a radix sort
+// of four 8-bit passes instead of six.
 __global__ void kd_keys_kernel(KdRound r, int dim, const double* __restrict__ db, uint64_t pitch, uint32_t n,
                                const uint32_t* __restrict__ order, const double* __restrict__ cell,
-                               const uint8_t* __restrict__ seg_dim, unsigned long long* __restrict__ keys) {
+                               const uint8_t* __restrict__ seg_dim, int sub_bits, uint32_t* __restrict__ keys) {
+  const uint32_t sub_max = (sub_bits >= 32) ? 0xFFFFFFFFu : ((1u << sub_bits) - 1u);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint32_t lo = 0, hi = r.n_seg;  // last segment with begin <= i
     while (hi - lo > 1) {
       const uint32_t mid = (lo + hi) >> 1;
       if (__ldg(r.begin + mid) <= i) lo = mid; else hi = mid;
     }
-    uint32_t sub = i - __ldg(r.begin + lo);
+    uint32_t sub = min(i - __ldg(r.begin + lo), sub_max);
     if (__ldg(r.parts + lo) > 1) {
       const int d = seg_dim[lo];
       const double c0 = cell[(size_t)lo * 2 * dim + d], c1 = cell[(size_t)lo * 2 * dim + dim + d];
       const double x = db[(uint64_t)d * pitch + order[i]];
       double t = (x - c0) / (c1 - c0);  // NaN (x NaN, or a zero-width cell) sorts last / together
-      t = fmin(fmax(t, 0.0), 1.0) * 4294967295.0;
-      sub = (t == t) ? (uint32_t)t : 0xFFFFFFFFu;
-      if (!(x == x)) sub = 0xFFFFFFFFu;
+      t = fmin(fmax(t, 0.0), 1.0) * (double)sub_max;
+      sub = (t == t) ? (uint32_t)t : sub_max;
+      if (!(x == x)) sub = sub_max;
     }
-    keys[i] = ((unsigned long long)lo << 32) | sub;
+    keys[i] = (sub_bits >= 32) ? sub : ((lo << sub_bits) | sub);
   }
 }
 
@@ -1006,14 +1009,14 @@ static int kd_order(oxg_store_s* s, StoreTree* t, const unsigned long long* boun
   OXG_TRY(t->kd_cell_a.ensure((size_t)max_seg * 2 * dim * sizeof(double)));
   OXG_TRY(t->kd_cell_b.ensure((size_t)max_seg * 2 * dim * sizeof(double)));
   OXG_TRY(t->kd_dim.ensure(max_seg));
-  OXG_TRY(t->kd_keys_a.ensure((size_t)n * sizeof(unsigned long long)));
-  OXG_TRY(t->kd_keys_b.ensure((size_t)n * sizeof(unsigned long long)));
+  OXG_TRY(t->kd_keys_a.ensure((size_t)n * sizeof(uint32_t)));
+  OXG_TRY(t->kd_keys_b.ensure((size_t)n * sizeof(uint32_t)));
   double* cell = t->kd_cell_a.as<double>();
   double* cell_next = t->kd_cell_b.as<double>();
   uint32_t* ord = t->vals.as<uint32_t>();
   uint32_t* ord_next = t->vals2.as<uint32_t>();
-  unsigned long long* keys = t->kd_keys_a.as<unsigned long long>();
-  unsigned long long* keys2 = t->kd_keys_b.as<unsigned long long>();
+  uint32_t* keys = t->kd_keys_a.as<uint32_t>();
+  uint32_t* keys2 = t->kd_keys_b.as<uint32_t>();
   kd_iota_kernel<<<grid_1d(n, 256), 256, 0, s->stream>>>(ord, n);
   OXG_LAUNCH_CHECK();
   kd_root_cell_kernel<<<1, 32, 0, s->stream>>>(bounds, dim, cell);
@@ -1021,17 +1024,24 @@ static int kd_order(oxg_store_s* s, StoreTree* t, const unsigned long long* boun
   for (const KdRound& r : dev_rounds) {
     kd_choose_dim_kernel<<<grid_1d(r.n_seg, 128), 128, 0, s->stream>>>(r, dim, cell, t->kd_dim.as<uint8_t>());
     OXG_LAUNCH_CHECK();
-    kd_keys_kernel<<<grid_1d(n, 256), 256, 0, s->stream>>>(r, dim, s->d_data, s->pitch, n, ord, cell,
-                                                          t->kd_dim.as<uint8_t>(), keys);
-    OXG_LAUNCH_CHECK();
-    int seg_bits = 1;
+    int seg_bits = 0;
     while ((1u << seg_bits) < r.n_seg && seg_bits < 31) ++seg_bits;
+    // the segment id takes seg_bits, the coordinate image the rest (at least 12 bits: the split
+    // only has to put equal COUNTS on each side, ties inside a 1/4096 slice of the cell are harmless)
+    const int sub_bits = std::max(12, 32 - seg_bits);
+    if (seg_bits + sub_bits > 32) {
+      set_error("too many segments for the 32-bit partition keys");
+      return OXG_E_INTERNAL;
+    }
+    kd_keys_kernel<<<grid_1d(n, 256), 256, 0, s->stream>>>(r, dim, s->d_data, s->pitch, n, ord, cell,
+                                                          t->kd_dim.as<uint8_t>(), sub_bits, keys);
+    OXG_LAUNCH_CHECK();
     size_t tmp_bytes = 0;
     OXG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, ord, ord_next, (int)n, 0,
-                                                 32 + seg_bits, s->stream));
+                                                 seg_bits + sub_bits, s->stream));
     OXG_TRY(t->tmp.ensure(tmp_bytes));
     OXG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(t->tmp.p, tmp_bytes, keys, keys2, ord, ord_next, (int)n, 0,
-                                                 32 + seg_bits, s->stream));
+                                                 seg_bits + sub_bits, s->stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     std::swap(ord, ord_next);
     kd_cells_kernel<<<grid_1d(r.n_child, 128), 128, 0, s->stream>>>(r, dim, s->d_data, s->pitch, n, ord, cell,
@@ -1114,6 +1124,7 @@ int tree_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exc
                     unsigned long long* d_stats) {
   int kind = g_tune_tree_kind.load();
   if (kind < 0) kind = (Q >= 32768 && s->size >= 65536) ? 1 : 0;
+  if (s->size > (1ull << 25)) kind = 0;  // 32-bit partition keys hold at most 2^20 leaf segments
   OXG_TRY(tree_build(s, kind == 1));
   StoreTree* t = tree_of(s);
   // queries in key order: neighbouring warps walk the same part of the hierarchy

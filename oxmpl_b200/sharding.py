@@ -74,6 +74,17 @@ class Dist:
                                      C.byref(rb), C.byref(re)))
         return rb.value, re.value
 
+    def append(self, store, rows_local) -> int:
+        """Collective append (``oxg_store_append_dist``): every rank passes its own slice; all
+        stores end up holding all rows in rank order.  Returns the first new index."""
+        from ._lib import check, lib
+
+        rows = np.ascontiguousarray(rows_local, dtype=np.float64)
+        first = C.c_uint64(0)
+        check(lib.oxg_store_append_dist(self._h, store.handle, C.c_void_p(rows.ctypes.data),
+                                        rows.shape[0], C.byref(first)))
+        return first.value
+
     def prm_build_knn(self, world, store, k: int, resolution: float, want_host: bool = True):
         """The sharded k-NN build -> the complete (idx[N,k], dist[N,k], valid[N,k], stats)."""
         from ._lib import PrmStats, check, lib

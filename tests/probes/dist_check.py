@@ -53,6 +53,18 @@ def main():
             print(f"rank {rank}/{world} n={nn}: knn build identical={same} ms={stats['knn_ms']:.2f} "
                   f"edges checked (all ranks)={int(checked)}", flush=True)
             ok = ok and same
+        # collective append: every rank uploads only its slice, the rest arrives over NVLink
+        st.clear()
+        rb, re = d.row_range(n)
+        d.append(st, rows[rb:re])
+        same = len(st) == n and np.array_equal(st.read().view(np.uint64), rows.view(np.uint64))
+        gi2, _, _, _ = d.prm_build_knn(gw, st, k, res)
+        st.clear()
+        st.append(rows)
+        ri2, _, _, _ = oxg.prm_build_knn(gw, st, k, res)
+        same = same and np.array_equal(gi2, ri2)
+        print(f"rank {rank}/{world}: sharded append identical={same}", flush=True)
+        ok = ok and same
         # radius mode on a smaller store (brute-force scans)
         st.clear()
         m = 20_001
