@@ -2017,7 +2017,10 @@ static int nn_knn_device_impl(oxg_store_s* s, StateView q, uint64_t Q, uint32_t 
     if (mode < 0) mode = env_int("OXG_KNN_TREE", -1);
     bool use = mode > 0;
     if (mode < 0)
-      use = p.n_db >= 16384 && (tree_is_current(s) ? Q >= 64 : (double)Q * (double)p.n_db >= 4.0e9);
+      // a current hierarchy answers any batch the few-query streaming kernels do not take; a fresh
+      // one (0.3 ms + 0.2 ns per state in key order) pays from ~2e8 pairs, where the all-pairs
+      // scan of a medium batch takes about as long (profiles/r02_medium_batches.json)
+      use = p.n_db >= 16384 && Q >= 64 && (tree_is_current(s) || (double)Q * (double)p.n_db >= 2.0e8);
     if (use) {
       OXG_TRY(tree_knn_device(s, q, Q, k, exclude_mode, d_exclude, self_base, d_idx, d_dist, nullptr));
       if (k == 1 && stored_first && exclude_mode == EXCL_NONE) {
