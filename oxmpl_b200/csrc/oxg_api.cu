@@ -1,6 +1,7 @@
 // oxg_api.cu — library plumbing: errors, device selection, the SoA state store and the
 // declarative world.  See include/oxg.h for the contract of each entry point.
 #include <cstdarg>
+#include <cstdlib>
 #include <vector>
 
 #include "oxg_internal.cuh"
@@ -477,6 +478,20 @@ static float f32_down(double v) {
   return f;
 }
 
+// OXG_WORLD_GRID=0 switches the planners' obstacle grid off (A/B measurements; same results).
+static bool env_grid_enabled() {
+  const char* v = getenv("OXG_WORLD_GRID");
+  return !(v && v[0] == '0');
+}
+
+static int upload_u32(uint32_t** dst, const std::vector<uint32_t>& h, cudaStream_t st) {
+  *dst = nullptr;
+  if (h.empty()) return OXG_OK;
+  OXG_CUDA_TRY(cudaMalloc((void**)dst, sizeof(uint32_t) * h.size()));
+  OXG_CUDA_TRY(cudaMemcpyAsync(*dst, h.data(), sizeof(uint32_t) * h.size(), cudaMemcpyHostToDevice, st));
+  return OXG_OK;
+}
+
 static int upload(double** dst, const std::vector<double>& h, cudaStream_t st) {
   *dst = nullptr;
   if (h.empty()) return OXG_OK;
@@ -605,6 +620,91 @@ int oxg_world_create(uint32_t dim, const double* spheres, uint64_t n_spheres, co
       }
     }
   }
+  // ---- uniform grid of the obstacles' bounding boxes over the first min(dim, 3) coordinates
+  // (used by the fused planner kernels: a state only meets the obstacles listed in its cell)
+  std::vector<uint32_t> g_off, g_ids;
+  {
+    const uint64_t n_obst = n_spheres + n_aabbs + n_capsules;
+    const uint32_t gd = std::min<uint32_t>(dim, 3);
+    bool ok = gd >= 1 && n_obst >= 64 && n_obst < 0x7FFFFFFFull && env_grid_enabled();
+    std::vector<double> bb(n_obst * 2 * gd);  // [lo.., hi..] per obstacle
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint64_t o = 0; o < n_obst && ok; ++o) {
+      for (uint32_t d = 0; d < gd; ++d) {
+        double a, b;
+        if (o < n_spheres) {
+          const double* s0 = spheres + o * (dim + 1);
+          const double r = std::fabs(s0[dim]) * (1.0 + 1e-9);
+          a = s0[d] - r;
+          b = s0[d] + r;
+        } else if (o < n_spheres + n_aabbs) {
+          const double* b0 = aabbs + (o - n_spheres) * 2 * dim;
+          a = b0[d];
+          b = b0[dim + d];
+        } else {
+          const double* c0 = capsules + (o - n_spheres - n_aabbs) * (2 * dim + 1);
+          const double r = std::fabs(c0[2 * dim]) * (1.0 + 1e-9);
+          a = std::fmin(c0[d], c0[dim + d]) - r;
+          b = std::fmax(c0[d], c0[dim + d]) + r;
+        }
+        if (!std::isfinite(a) || !std::isfinite(b)) ok = false;
+        if (a > b) std::swap(a, b);  // an inverted box hits nothing; any cell range is fine
+        bb[o * 2 * gd + d] = a;
+        bb[o * 2 * gd + gd + d] = b;
+        lo[d] = std::fmin(lo[d], a);
+        hi[d] = std::fmax(hi[d], b);
+      }
+    }
+    if (ok) {
+      const double per_dim = std::pow((double)n_obst, 1.0 / gd) * 1.5;
+      const uint32_t cap = gd == 1 ? 4096 : (gd == 2 ? 96 : 24);
+      uint64_t cells = 1;
+      for (uint32_t d = 0; d < gd; ++d) {
+        const double ext = hi[d] - lo[d];
+        uint32_t nc = (uint32_t)std::min<double>(cap, std::max(2.0, std::ceil(per_dim)));
+        if (!(ext > 0.0)) nc = 1;
+        w->grid_n[d] = nc;
+        w->grid_lo[d] = lo[d];
+        w->grid_inv[d] = ext > 0.0 ? (double)nc / ext : 0.0;
+        if (!std::isfinite(w->grid_inv[d])) ok = false;
+        cells *= nc;
+      }
+      if (ok) {
+        auto cell_of = [&](double x, uint32_t d) -> int64_t {  // the device uses the same formula
+          double c = std::floor((x - w->grid_lo[d]) * w->grid_inv[d]);
+          if (!(c == c)) c = 0.0;
+          c = std::fmin(std::fmax(c, 0.0), (double)(w->grid_n[d] - 1));
+          return (int64_t)c;
+        };
+        std::vector<uint32_t> count(cells + 1, 0);
+        auto for_cells = [&](uint64_t o, auto&& fn) {
+          int64_t a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
+          for (uint32_t d = 0; d < gd; ++d) {
+            a[d] = std::max<int64_t>(0, cell_of(bb[o * 2 * gd + d], d) - 1);
+            b[d] = std::min<int64_t>((int64_t)w->grid_n[d] - 1, cell_of(bb[o * 2 * gd + gd + d], d) + 1);
+          }
+          for (int64_t z = a[2]; z <= b[2]; ++z)
+            for (int64_t y = a[1]; y <= b[1]; ++y)
+              for (int64_t x = a[0]; x <= b[0]; ++x)
+                fn((uint64_t)((z * w->grid_n[1] + y) * w->grid_n[0] + x));
+        };
+        for (uint64_t o = 0; o < n_obst; ++o) for_cells(o, [&](uint64_t c) { count[c + 1]++; });
+        uint64_t total = 0;
+        for (uint64_t c = 0; c < cells; ++c) total += count[c + 1];
+        // worth it only when a cell's list fits one warp round: long lists (many obstacles in
+        // more dimensions than the grid has) are served better by the chunk sweep, which keeps 32
+        // obstacles per warp resident and streams the states past them
+        if (total < 0x7FFFFFFFull && total <= 24 * cells) {
+          g_off.assign(cells + 1, 0);
+          for (uint64_t c = 0; c < cells; ++c) g_off[c + 1] = g_off[c] + count[c + 1];
+          g_ids.assign(std::max<uint64_t>(total, 1), 0);
+          std::vector<uint32_t> fill(g_off.begin(), g_off.end() - 1);
+          for (uint64_t o = 0; o < n_obst; ++o) for_cells(o, [&](uint64_t c) { g_ids[fill[c]++] = (uint32_t)o; });
+          w->grid_dims = gd;
+        }
+      }
+    }
+  }
   int r = upload(&w->d_spheres, hs, w->stream);
   if (r == OXG_OK) r = upload(&w->d_aabbs, ha, w->stream);
   if (r == OXG_OK) r = upload(&w->d_capsules, hc, w->stream);
@@ -612,6 +712,10 @@ int oxg_world_create(uint32_t dim, const double* spheres, uint64_t n_spheres, co
   if (r == OXG_OK) r = upload32(&w->d_aabbs32, ha32, w->stream);
   if (r == OXG_OK) r = upload32(&w->d_capsules32, hc32, w->stream);
   if (r == OXG_OK) r = upload32(&w->d_capsules32p, hc32p, w->stream);
+  if (r == OXG_OK && w->grid_dims > 0) {
+    r = upload_u32(&w->d_grid_off, g_off, w->stream);
+    if (r == OXG_OK) r = upload_u32(&w->d_grid_ids, g_ids, w->stream);
+  }
   if (r == OXG_OK && cudaStreamSynchronize(w->stream) != cudaSuccess) {
     set_error("world upload failed");
     r = OXG_E_CUDA;
@@ -664,6 +768,8 @@ int oxg_world_destroy(oxg_world w) {
   if (w->d_capsules32p) cudaFree(w->d_capsules32p);
   if (w->d_so2_comp) cudaFree(w->d_so2_comp);
   if (w->d_so2_lohi) cudaFree(w->d_so2_lohi);
+  if (w->d_grid_off) cudaFree(w->d_grid_off);
+  if (w->d_grid_ids) cudaFree(w->d_grid_ids);
   for (auto& b : w->buf) b.release();
   if (w->stream) cudaStreamDestroy(w->stream);
   delete w;

@@ -201,6 +201,15 @@ struct oxg_world_s {
   uint32_t n_so2 = 0;
   uint32_t h_so2_comp[16];
   double h_so2_lohi[32];
+  // Uniform grid over the first min(dim, 3) coordinates (planner kernels): cell -> ids of the
+  // obstacles whose bounding box touches it (+-1 cell of margin).  ids: spheres, then aabbs, then
+  // capsules.  A conservative candidate list only — every candidate still takes the exact test.
+  uint32_t* d_grid_off = nullptr;  // [cells + 1]
+  uint32_t* d_grid_ids = nullptr;
+  uint32_t grid_dims = 0;
+  uint32_t grid_n[3] = {1, 1, 1};
+  double grid_lo[3] = {0, 0, 0};
+  double grid_inv[3] = {0, 0, 0};  // cells per unit length
   uint32_t* d_so2_comp = nullptr;
   double* d_so2_lohi = nullptr;
   oxg::DevBuf buf[4];
@@ -220,6 +229,11 @@ struct WorldView {
   uint32_t capsule32p_stride;
   uint32_t sphere32_stride, capsule32_stride;
   double wmax_spheres, wmax_capsules;
+  const uint32_t* grid_off;  // nullable
+  const uint32_t* grid_ids;
+  uint32_t grid_dims;
+  uint32_t grid_n[3];
+  double grid_lo[3], grid_inv[3];
   const uint32_t* so2_comp;
   const double* so2_lohi;
   uint32_t n_spheres, n_aabbs, n_capsules, n_so2;
@@ -240,6 +254,14 @@ inline WorldView world_view(const oxg_world_s* w) {
   v.capsule32_stride = w->capsule32_stride;
   v.wmax_spheres = w->wmax_spheres;
   v.wmax_capsules = w->wmax_capsules;
+  v.grid_off = w->d_grid_off;
+  v.grid_ids = w->d_grid_ids;
+  v.grid_dims = w->grid_dims;
+  for (int i = 0; i < 3; ++i) {
+    v.grid_n[i] = w->grid_n[i];
+    v.grid_lo[i] = w->grid_lo[i];
+    v.grid_inv[i] = w->grid_inv[i];
+  }
   v.so2_comp = w->d_so2_comp;
   v.so2_lohi = w->d_so2_lohi;
   v.n_spheres = (uint32_t)w->n_spheres;

@@ -219,6 +219,31 @@ __device__ __forceinline__ bool chunk_hit(const PlanParams& P, uint32_t c, uint3
   return v >= w.so2_lohi[2 * p] && v <= w.so2_lohi[2 * p + 1];
 }
 
+// Grid lookup (oxg_world_s::d_grid_*): the cell of a state in the first grid_dims coordinates,
+// clamped to the grid — the host registered every obstacle in all cells within one cell of its
+// bounding box with the same formula, so a state that an obstacle invalidates always finds it.
+__device__ __forceinline__ uint32_t grid_cell(const WorldView& w, const double* x) {
+  uint32_t cell = 0, mul = 1;
+  for (uint32_t d = 0; d < w.grid_dims; ++d) {
+    double c = floor((x[d] - w.grid_lo[d]) * w.grid_inv[d]);
+    if (!(c == c)) c = 0.0;
+    c = fmin(fmax(c, 0.0), (double)(w.grid_n[d] - 1));
+    cell += (uint32_t)c * mul;
+    mul *= w.grid_n[d];
+  }
+  return cell;
+}
+
+// Exact test of obstacle `id` (spheres, then aabbs, then capsules) against state x.
+__device__ __forceinline__ bool obstacle_hit(const WorldView& w, uint32_t id, const double* x) {
+  const int dim = (int)w.dim;
+  if (id < w.n_spheres) return sphere_hit_dev<0>(x, w.spheres + (size_t)id * w.sphere_stride, dim);
+  id -= w.n_spheres;
+  if (id < w.n_aabbs) return aabb_hit_dev<0>(x, w.aabbs + (size_t)id * w.aabb_stride, dim);
+  id -= w.n_aabbs;
+  return capsule_hit_dev<0>(x, w.capsules + (size_t)id * w.capsule_stride, dim);
+}
+
 // num_steps of check_motion (rrt.rs:95-97); 0/1 both mean "check `to` only".
 __device__ __forceinline__ unsigned long long motion_steps(double dist, double resolution) {
   return ceil_as_usize_dev(__ddiv_rn(dist, resolution));
@@ -455,6 +480,26 @@ __device__ void motion_tasks(const PlanParams& P, PlanShared& sh, double* st_buf
       if (d == 0) st_edge[sl] = e;
     }
     __syncthreads();
+    // ---- stage 2 with the world's grid: a warp per state, lanes over the obstacles of the
+    // state's cell (a handful instead of the whole world) and over the SO2 intervals
+    if (P.w.grid_off) {
+      const WorldView& w = P.w;
+      for (uint32_t sl = gw; sl < nb; sl += GW) {
+        const uint32_t e = st_edge[sl];
+        if (*reinterpret_cast<volatile uint32_t*>(&hit[e])) continue;
+        const double* x = st_buf + (size_t)sl * dim;
+        const uint32_t cell = grid_cell(w, x);
+        const uint32_t a = __ldg(w.grid_off + cell), b = __ldg(w.grid_off + cell + 1);
+        bool h = false;
+        for (uint32_t t = a + lane; t < b && !h; t += 32) h = obstacle_hit(w, __ldg(w.grid_ids + t), x);
+        for (uint32_t t = lane; t < w.n_so2 && !h; t += 32) {
+          const double v = so2_normalise_dev(x[P.n_real + w.so2_comp[t]]);
+          h = v >= w.so2_lohi[2 * t] && v <= w.so2_lohi[2 * t + 1];
+        }
+        if (__any_sync(0xFFFFFFFFu, h) && lane == 0) atomicOr(&hit[e], 1u);
+      }
+      continue;
+    }
     // ---- stage 2: obstacle chunk x state sweep
     for (uint32_t c = c0; c < n_oc; c += cstep) {
       uint32_t skip_e = OXG_INVALID_INDEX, tick = 0;
