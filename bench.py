@@ -46,7 +46,7 @@ DIM = 7
 SEED = 4
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this config, from the `ncu --set
 # full` captures summarised in profiles/ (None until captured for the current kernel)
-TREE_DRAM_BYTES_NCU = None
+TREE_DRAM_BYTES_NCU = 588114432  # profiles/r02_ncu_full_hot_kernels.csv (459.7 MB read + 128.5 MB written; captured at 821 776 nodes)
 ALLPAIRS_DRAM_BYTES_NCU = 2249420000  # profiles/r01_ncu_full_knn_rv_dot_7_2.csv (2.046 GB read + 0.204 GB written)
 
 
