@@ -46,13 +46,13 @@ constexpr int TREE_LEVELS = 5;       // 32^6 = 2^30 states at most (tree_support
 constexpr int TREE_KEY_BITS = 32;
 constexpr int TREE_MAX_DIM = 8;      // dimensions the tree kernels are instantiated for
 #ifndef OXG_TK_THREADS
-#define OXG_TK_THREADS 256
+#define OXG_TK_THREADS 128
 #endif
 #ifndef OXG_TK_MIN_CTAS
-#define OXG_TK_MIN_CTAS 3
+#define OXG_TK_MIN_CTAS 7
 #endif
 #ifndef OXG_TK_QPC
-#define OXG_TK_QPC 128
+#define OXG_TK_QPC 32
 #endif
 #ifndef OXG_TK_PERSISTENT
 #define OXG_TK_PERSISTENT 0
@@ -65,6 +65,9 @@ constexpr int TREE_MAX_DIM = 8;      // dimensions the tree kernels are instanti
 #endif
 #ifndef OXG_TK_MERGE_INLINE
 #define OXG_TK_MERGE_INLINE 1
+#endif
+#ifndef OXG_TK_F32_LEAF
+#define OXG_TK_F32_LEAF 1
 #endif
 #ifndef OXG_TK_MERGE_AT
 #define OXG_TK_MERGE_AT 12
@@ -83,10 +86,12 @@ struct TreePlan {  // device-resident quantisation plan, written by tree_plan_ke
   // translation- and scale-invariant
   double c[kMaxFastDim];
   double sc, sc2;
+  double mabs;  // >= |x'| of every stored coordinate inside the bounding box (box space)
 };
 
 struct TreeView {
   const double* pts;     // [n_leaves][D][32]
+  const float* pts32;    // the same states in box space, rounded to nearest (filter input only)
   const uint32_t* perm;  // [n_leaves*32] sorted position -> store index (pads: OXG_INVALID_INDEX)
   const double* boxes[TREE_LEVELS];  // level l nodes in groups of 32: [groups][2D][32]
   const float* boxes32[TREE_LEVELS]; // the same boxes in the plan's box space, rounded outward
@@ -103,6 +108,7 @@ struct StoreTree {
   cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr, ev_q0 = nullptr, ev_q1 = nullptr;
   bool have_build_ev = false, have_query_ev = false;
   uint64_t last_Q = 0;
+  DevBuf pts32;
   DevBuf pts, perm, keys, keys2, vals, vals2, plan, bounds, qorder, tmp;
   DevBuf boxes[TREE_LEVELS];
   DevBuf boxes32[TREE_LEVELS];
@@ -198,6 +204,7 @@ __global__ void tree_plan_kernel(const unsigned long long* __restrict__ bounds, 
     e = e > 100 ? 100 : (e < -100 ? -100 : e);
     plan->sc = ldexp(1.0, e);
     plan->sc2 = ldexp(1.0, 2 * e);
+    plan->mabs = half * plan->sc * 1.000001 + 1e-300;
   }
   for (int d = 0; d < dim; ++d) {
     const double lo = ord_decode(bounds[d]), hi = ord_decode(bounds[kMaxFastDim + d]);
@@ -248,7 +255,8 @@ __global__ void tree_keys_kernel(StateView v, uint32_t n, int dim, const TreePla
 template <int D>
 __global__ void tree_leaves_kernel(const double* __restrict__ db, uint64_t pitch, uint32_t n,
                                    const uint32_t* __restrict__ sorted, uint32_t n_leaves,
-                                   uint32_t n_slots, double* __restrict__ pts,
+                                   uint32_t n_slots, const TreePlan* __restrict__ plan,
+                                   double* __restrict__ pts, float* __restrict__ pts32,
                                    uint32_t* __restrict__ perm, double* __restrict__ boxes0) {
   const int lane = threadIdx.x & 31;
   const uint32_t leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -269,6 +277,7 @@ __global__ void tree_leaves_kernel(const double* __restrict__ db, uint64_t pitch
       const double x = (j != OXG_INVALID_INDEX) ? db[(uint64_t)d * pitch + j]
                                                 : __longlong_as_double(0x7FF8000000000000ll);
       pts[((uint64_t)leaf * D + d) * 32 + lane] = x;
+      pts32[((uint64_t)leaf * D + d) * 32 + lane] = __double2float_rn((x - plan->c[d]) * plan->sc);
       lo[d] = fmin(lo[d], x);  // fmin / fmax drop NaN
       hi[d] = fmax(hi[d], x);
     }
@@ -523,7 +532,14 @@ constexpr int TK_MERGE_AT = OXG_TK_MERGE_AT;  // buffered candidates that trigge
 
 template <int D>
 struct WarpQuery {
+#if OXG_TK_F32_LEAF
+  float q32[D];          // the query in box space, rounded to nearest (filter input only)
+  const double* qd;      // shared: the query itself (exact path)
+  float T32;             // filter threshold: a32 > T32 proves d2 > U
+  double M;              // >= every |coordinate| the filter sees, in box space
+#else
   double q[D];
+#endif
 #if OXG_TK_QBOX_SMEM
   const float* qbox;     // shared: the query in the box space, [0..D) rounded down, [D..2D) rounded up
 #else
@@ -551,13 +567,34 @@ __device__ __forceinline__ double tree_sqrt_le_upper(double sw) {
   return __dadd_ru(u, __dmul_ru(u, 8.8817841970012523e-16));  // 2^-50
 }
 
+// Threshold of the FP32 leaf filter (difference form, the bound of filter_threshold_dev in
+// oxg_nn.cu applied in box space).  With u = 2^-24, M >= |q'_d|, |p'_d| and a = 4uM: whenever the
+// exact scaled sum S' <= Ub, the FP32 evaluation a32 = sum fma(df, df, .), df = fl32(q32 - p32),
+// satisfies  a32 <= [S + 2a sqrt(D S) + 2 D a^2](1 + D 2^-22),  S = Ub (1 + 1e-5).  A pair with
+// a32 > T32 therefore has reference-order d2 > U (Ub already carries the 1e-12 of the f64
+// roundings); everything else, including NaN and overflow, takes the exact path.
+__device__ __forceinline__ float tree_filter_threshold(double Ub, double M, int D) {
+  const float inf = __int_as_float(0x7F800000);
+  if (!(Ub < 1.0e300) || !(M < 1.0e30)) return inf;
+  const double a = M * 2.384185791015625e-07 + 1e-37;  // 2^-22 M
+  const double S = Ub * 1.00001;
+  double T = S + 2.0 * a * sqrt((double)D * S) + 2.0 * (double)D * a * a + 1e-35;
+  T = T * (1.0 + (double)D * 2.384185791015625e-07);
+  if (!(T == T)) return inf;
+  return __double2float_ru(T);  // rounds up; overflows to +inf
+}
+
 template <int D>
 __device__ __forceinline__ void set_bound(const TreeKnnParams& p, WarpQuery<D>& w, double sk) {
   const double U = tree_sqrt_le_upper(sk);
   w.ub = (unsigned long long)__double_as_longlong(U);
   // box space: squared lengths scale by sc2 (a power of two); 1e-12 covers the roundings of the
   // reference-order evaluation (d2 >= true (1 - (D+2) 2^-53))
-  w.Uf = __double2float_ru(__dmul_ru(__dmul_ru(U, __ldg(&p.plan->sc2)), 1.0 + 1.0e-12));
+  const double Ub = __dmul_ru(__dmul_ru(U, __ldg(&p.plan->sc2)), 1.0 + 1.0e-12);
+  w.Uf = __double2float_ru(Ub);
+#if OXG_TK_F32_LEAF
+  w.T32 = tree_filter_threshold(Ub, w.M, D);
+#endif
 }
 
 // (s, j) pairs: lexicographic "a before b".
@@ -634,6 +671,62 @@ const TreeKnnParams& p, WarpQuery<D>& w) {
   if (w.have == w.k) set_bound<D>(p, w, __shfl_sync(0xFFFFFFFFu, w.my_s, w.k - 1));
 }
 
+#if OXG_TK_F32_LEAF
+// FP32 filter value of state `lane` of a leaf (box space; decides nothing, see tree_filter_threshold).
+template <int D>
+__device__ __forceinline__ float leaf_a32(const TreeKnnParams& p, const WarpQuery<D>& w, uint32_t leaf) {
+  const float* lp = p.t.pts32 + (uint64_t)leaf * (D * 32) + w.lane;
+  float pv[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) pv[d] = __ldg(lp + d * 32);
+  float a = 0.0f;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float df = w.q32[d] - pv[d];
+    a = __fmaf_rn(df, df, a);
+  }
+  return a;
+}
+
+// The states the filter could not discard are evaluated in the reference's operation order
+// (real_vector_state_space.rs:148-153) and go through the admission test; the survivors go to the
+// candidate buffer.
+template <int D>
+__device__ __forceinline__ void leaf_commit(const TreeKnnParams& p, WarpQuery<D>& w, uint32_t leaf, float a32) {
+  ++w.n_leaf;
+  if (__ballot_sync(0xFFFFFFFFu, !(a32 > w.T32)) == 0u) return;
+  double d2 = __longlong_as_double(0x7FF8000000000000ll);
+  if (!(a32 > w.T32)) {
+    const double* lp = p.t.pts + (uint64_t)leaf * (D * 32) + w.lane;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double df = __dsub_rn(w.qd[d], __ldg(lp + d * 32));
+      const double m = __dmul_rn(df, df);
+      d2 = (d == 0) ? m : __dadd_rn(d2, m);
+    }
+  }
+  // d2 >= +0 or NaN; every NaN pattern (pads, filtered lanes) compares above any ub as unsigned
+  bool pass = (unsigned long long)__double_as_longlong(d2) <= w.ub;
+  uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
+  if (m == 0) return;
+  int n = __popc(m);
+  if (w.bc + n > 32) {
+    merge_buffer<D>(p, w);
+    pass = (unsigned long long)__double_as_longlong(d2) <= w.ub;  // the bound moved
+    m = __ballot_sync(0xFFFFFFFFu, pass);
+    n = __popc(m);
+  }
+  if (pass) {
+    const int slot = w.bc + __popc(m & ((1u << w.lane) - 1u));
+    w.b_d2[slot] = d2;
+    w.b_j[slot] = __ldg(p.t.perm + (uint64_t)leaf * 32 + w.lane);
+  }
+  w.bc += n;
+  w.n_cand += n;
+  if (w.bc >= TK_MERGE_AT || w.have < w.k) merge_buffer<D>(p, w);
+}
+#define OXG_LEAF_EVAL leaf_a32
+#else
 // Reference-order squared distance of the query to state `lane` of a leaf
 // (real_vector_state_space.rs:148-153).
 template <int D>
@@ -678,6 +771,9 @@ __device__ __forceinline__ void leaf_commit(const TreeKnnParams& p, WarpQuery<D>
   if (w.bc >= TK_MERGE_AT || w.have < w.k) merge_buffer<D>(p, w);
 }
 
+#define OXG_LEAF_EVAL leaf_d2
+#endif
+
 // Tests the 32 children of `group` at level L and descends into the survivors, nearest first.
 template <int D, int L>
 struct Visit {
@@ -716,12 +812,12 @@ struct Visit {
         if (OXG_TK_TWO_LEAVES && r1 != 0xFFFFFFFFu) {
           const uint32_t c1 = r1 & 31u;
           cand &= ~(1u << c1);
-          const double da = leaf_d2<D>(p, w, child0 + c);
-          const double db = leaf_d2<D>(p, w, child0 + c1);
+          const auto da = OXG_LEAF_EVAL<D>(p, w, child0 + c);
+          const auto db = OXG_LEAF_EVAL<D>(p, w, child0 + c1);
           leaf_commit<D>(p, w, child0 + c, da);
           leaf_commit<D>(p, w, child0 + c1, db);
         } else {
-          leaf_commit<D>(p, w, child0 + c, leaf_d2<D>(p, w, child0 + c));
+          leaf_commit<D>(p, w, child0 + c, OXG_LEAF_EVAL<D>(p, w, child0 + c));
         }
       } else {
         Visit<D, L - 1>::run(p, w, child0 + c);
@@ -734,6 +830,9 @@ struct Visit {
 // warps of an SM work on neighbouring queries at the same time and share the leaves through L1.
 template <int D>
 __global__ void __launch_bounds__(TK_THREADS, OXG_TK_MIN_CTAS) tree_knn_kernel(const TreeKnnParams p) {
+#if OXG_TK_F32_LEAF
+  __shared__ double s_q[TK_THREADS / 32][D];
+#endif
   __shared__ double s_d2[TK_THREADS];
   __shared__ uint32_t s_j[TK_THREADS];
 #if OXG_TK_QBOX_SMEM
@@ -753,21 +852,37 @@ __global__ void __launch_bounds__(TK_THREADS, OXG_TK_MIN_CTAS) tree_knn_kernel(c
       WarpQuery<D> w;
       bool qnan = false;
       __syncwarp();
+#if OXG_TK_F32_LEAF
+      double mq = 0.0;
+#endif
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        w.q[d] = p.q.p[(uint64_t)qi * p.q.stride_i + (uint64_t)d * p.q.stride_d];
-        qnan = qnan || !(w.q[d] == w.q[d]);
+        const double qv = p.q.p[(uint64_t)qi * p.q.stride_i + (uint64_t)d * p.q.stride_d];
+        qnan = qnan || !(qv == qv);
         const double c = p.plan->c[d];
+#if OXG_TK_F32_LEAF
+        const double qs = (qv - c) * sc;
+        w.q32[d] = __double2float_rn(qs);
+        mq = fmax(mq, fabs(qs));
+        if (lane == 0) s_q[wid][d] = qv;
+#else
+        w.q[d] = qv;
+#endif
 #if OXG_TK_QBOX_SMEM
         if (lane == 0) {
-          s_qbox[wid][d] = __double2float_rd(__dmul_rd(__dsub_rd(w.q[d], c), sc));
-          s_qbox[wid][D + d] = __double2float_ru(__dmul_ru(__dsub_ru(w.q[d], c), sc));
+          s_qbox[wid][d] = __double2float_rd(__dmul_rd(__dsub_rd(qv, c), sc));
+          s_qbox[wid][D + d] = __double2float_ru(__dmul_ru(__dsub_ru(qv, c), sc));
         }
 #else
-        w.qbox[d] = __double2float_rd(__dmul_rd(__dsub_rd(w.q[d], c), sc));
-        w.qbox[D + d] = __double2float_ru(__dmul_ru(__dsub_ru(w.q[d], c), sc));
+        w.qbox[d] = __double2float_rd(__dmul_rd(__dsub_rd(qv, c), sc));
+        w.qbox[D + d] = __double2float_ru(__dmul_ru(__dsub_ru(qv, c), sc));
 #endif
       }
+#if OXG_TK_F32_LEAF
+      w.qd = s_q[wid];
+      w.M = fmax(mq, p.plan->mabs) * 1.000001;  // inf for a query far outside: the filter then passes everything
+      w.T32 = __int_as_float(0x7F800000);
+#endif
       __syncwarp();
 #if OXG_TK_QBOX_SMEM
       w.qbox = s_qbox[wid];
@@ -847,14 +962,16 @@ static int tree_build_levels(oxg_store_s* s, StoreTree* t, const uint32_t* sorte
     v.boxes32[l] = nullptr;
   }
   OXG_TRY(t->pts.ensure((size_t)n_leaves * D * 32 * sizeof(double)));
+  OXG_TRY(t->pts32.ensure((size_t)n_leaves * D * 32 * sizeof(float)));
+  v.pts32 = t->pts32.as<float>();
   OXG_TRY(t->perm.ensure((size_t)n_leaves * 32 * sizeof(uint32_t)));
   v.pts = t->pts.as<double>();
   v.perm = t->perm.as<uint32_t>();
   {
     const uint32_t slots = ((n_leaves + 31u) / 32u) * 32u;
     tree_leaves_kernel<D><<<(slots * 32u + 255u) / 256u, 256, 0, s->stream>>>(
-        s->d_data, s->pitch, n, sorted, n_leaves, slots, t->pts.as<double>(), t->perm.as<uint32_t>(),
-        t->boxes[0].as<double>());
+        s->d_data, s->pitch, n, sorted, n_leaves, slots, t->plan.as<TreePlan>(), t->pts.as<double>(),
+        t->pts32.as<float>(), t->perm.as<uint32_t>(), t->boxes[0].as<double>());
     OXG_LAUNCH_CHECK();
   }
   for (int l = 1; l <= lvl; ++l) {
@@ -894,6 +1011,7 @@ void tree_release(oxg_store_s* s) {
   if (!s->tree) return;
   StoreTree* t = static_cast<StoreTree*>(s->tree);
   t->pts.release();
+  t->pts32.release();
   t->perm.release();
   t->keys.release();
   t->keys2.release();
