@@ -409,12 +409,14 @@ uint64_t oxg_kernel_launches(int reset);
  * every batch instead of reusing it while the store is unchanged (benchmarks that must pay the
  * build inside the timed step), 1 = reuse (default).  "tree_kind": 0 = order the states by a space-filling key (cheapest build),
  * 1 = balanced partition order (a few ms per 1e6 states, about half the leaf visits per query),
- * -1 = by batch size (default).  "tree_stats": 1 = count the visited
- * leaves and time the query kernel for oxg_store_tree_stats (costs a few percent). */
+ * -1 = by batch size (default).  "tree_stats": 1 = time the hierarchy build and
+ * the query kernel for oxg_store_tree_stats, 2 = also count the visits (the counters cost the
+ * query kernel ~15 %), 0 = neither (default). */
 int oxg_tuning_set(const char* key, int64_t value);
 /* Counters of the most recent k-NN answered through the hierarchy with "tree_stats" on:
  * out8 = { build ms, query-kernel ms, leaves visited, 32-child box groups tested, candidates
- * admitted, list merges, stored states, queries }. */
+ * admitted, list merges, leaves whose states reached the exact f64 evaluation (the FP32 leaf
+ * filter discarded the others whole), queries }. */
 int oxg_store_tree_stats(oxg_store s, double* out8);
 
 #ifdef __cplusplus

@@ -184,7 +184,7 @@ class StateStore:
         out = (C.c_double * 8)()
         check(lib.oxg_store_tree_stats(self._h, out))
         names = ("build_ms", "query_kernel_ms", "leaves_visited", "box_groups_tested", "candidates",
-                 "merges", "stored_states", "queries")
+                 "merges", "exact_leaves", "queries")
         return dict(zip(names, [float(v) for v in out]))
 
     def stream(self) -> int:

@@ -291,7 +291,7 @@ int oxg_tuning_set(const char* key, int64_t value) {
     return OXG_OK;
   }
   if (strcmp(key, "tree_stats") == 0) {
-    g_tune_tree_stats.store(value ? 1 : 0);
+    g_tune_tree_stats.store(value <= 0 ? 0 : (value >= 2 ? 2 : 1));
     return OXG_OK;
   }
   set_error("unknown tuning key '%s'", key);

@@ -106,7 +106,7 @@ struct StoreTree {
   uint64_t size = 0;
   // measurement (oxg_tuning_set("tree_stats", 1) + oxg_store_tree_stats)
   cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr, ev_q0 = nullptr, ev_q1 = nullptr;
-  bool have_build_ev = false, have_query_ev = false;
+  bool have_build_ev = false, have_query_ev = false, have_counts = false;
   uint64_t last_Q = 0;
   DevBuf pts32;
   DevBuf pts, perm, keys, keys2, vals, vals2, plan, bounds, qorder, tmp;
@@ -525,7 +525,8 @@ struct TreeKnnParams {
   uint32_t* out_idx;   // [Q][k]
   double* out_dist;
   uint32_t qpc;               // consecutive key-ordered queries per CTA chunk
-  unsigned long long* stats;  // nullable: [0] leaves visited, [1] box groups tested, [2] candidates, [3] merges
+  unsigned long long* stats;  // nullable: [0] leaves visited, [1] box groups tested, [2] candidates, [3] merges,
+                              // [4] leaves that reached the exact f64 path
 };
 
 constexpr int TK_MERGE_AT = OXG_TK_MERGE_AT;  // buffered candidates that trigger a merge into the list
@@ -556,7 +557,7 @@ struct WarpQuery {
   uint32_t* b_j;
   uint32_t excl;
   int lane;
-  unsigned n_leaf, n_box, n_cand, n_merge;
+  unsigned n_leaf, n_box, n_cand, n_merge, n_exact;
 };
 
 // Upper bound of max{x : sqrt(x) <= sw}: any upper bound is correct here because admitted
@@ -695,6 +696,7 @@ template <int D>
 __device__ __forceinline__ void leaf_commit(const TreeKnnParams& p, WarpQuery<D>& w, uint32_t leaf, float a32) {
   ++w.n_leaf;
   if (__ballot_sync(0xFFFFFFFFu, !(a32 > w.T32)) == 0u) return;
+  ++w.n_exact;
   double d2 = __longlong_as_double(0x7FF8000000000000ll);
   if (!(a32 > w.T32)) {
     const double* lp = p.t.pts + (uint64_t)leaf * (D * 32) + w.lane;
@@ -842,7 +844,7 @@ __global__ void __launch_bounds__(TK_THREADS, OXG_TK_MIN_CTAS) tree_knn_kernel(c
   const int wid = threadIdx.x >> 5;
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   const double sc = p.plan->sc;
-  unsigned long long st_leaf = 0, st_box = 0, st_cand = 0, st_merge = 0;
+  unsigned long long st_leaf = 0, st_box = 0, st_cand = 0, st_merge = 0, st_exact = 0;
   const uint32_t n_chunks = (p.Q + p.qpc - 1) / p.qpc;
   for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     const uint32_t q_begin = chunk * p.qpc;
@@ -897,7 +899,7 @@ __global__ void __launch_bounds__(TK_THREADS, OXG_TK_MIN_CTAS) tree_knn_kernel(c
       w.b_d2 = s_d2 + wid * 32;
       w.b_j = s_j + wid * 32;
       w.lane = lane;
-      w.n_leaf = w.n_box = w.n_cand = w.n_merge = 0;
+      w.n_leaf = w.n_box = w.n_cand = w.n_merge = w.n_exact = 0;
       w.excl = OXG_INVALID_INDEX;
       if (p.exclude_mode == 1) w.excl = __ldg(p.exclude + qi);
       if (p.exclude_mode == 2) w.excl = p.self_base + qi;
@@ -920,6 +922,7 @@ __global__ void __launch_bounds__(TK_THREADS, OXG_TK_MIN_CTAS) tree_knn_kernel(c
       st_box += w.n_box;
       st_cand += w.n_cand;
       st_merge += w.n_merge;
+      st_exact += w.n_exact;
     }
   }
   if (p.stats && lane == 0) {
@@ -927,6 +930,7 @@ __global__ void __launch_bounds__(TK_THREADS, OXG_TK_MIN_CTAS) tree_knn_kernel(c
     atomicAdd(&p.stats[1], st_box);
     atomicAdd(&p.stats[2], st_cand);
     atomicAdd(&p.stats[3], st_merge);
+    atomicAdd(&p.stats[4], st_exact);
   }
 }
 
@@ -1048,14 +1052,18 @@ bool tree_is_current(const oxg_store_s* s) {
   return t && g_tune_tree_cache.load() != 0 && t->epoch == s->epoch && t->size == s->size;
 }
 
-static bool tree_stats_on() {
-  if (g_tune_tree_stats.load() > 0) return true;
-  static const bool env_on = [] {
-    const char* v = getenv("OXG_TREE_STATS");
-    return v && *v && *v != '0';
+// 0 = off, 1 = time the build and the query kernel (events only), 2 = also count visits (the
+// counters cost the query kernel ~15 %)
+static int tree_stats_level() {
+  const int v = g_tune_tree_stats.load();
+  if (v > 0) return v;
+  static const int env_level = [] {
+    const char* e = getenv("OXG_TREE_STATS");
+    return (e && *e) ? atoi(e) : 0;
   }();
-  return env_on;
+  return env_level;
 }
+static bool tree_stats_on() { return tree_stats_level() > 0; }
 
 static int tree_events(StoreTree* t) {
   if (t->ev_b0) return OXG_OK;
@@ -1180,7 +1188,7 @@ int tree_build(oxg_store_s* s, bool want_kd) {
   StoreTree* t = tree_of(s);
   if (tree_is_current(s) && (t->kind == 1 || !want_kd)) return OXG_OK;
   const uint32_t n = (uint32_t)s->size;
-  OXG_TRY(t->bounds.ensure((2 * kMaxFastDim + 4) * sizeof(unsigned long long)));
+  OXG_TRY(t->bounds.ensure((2 * kMaxFastDim + 8) * sizeof(unsigned long long)));
   OXG_TRY(t->plan.ensure(sizeof(TreePlan)));
   OXG_TRY(t->keys.ensure((size_t)n * sizeof(uint32_t)));
   OXG_TRY(t->keys2.ensure((size_t)n * sizeof(uint32_t)));
@@ -1282,8 +1290,10 @@ int tree_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exc
   const bool stats = tree_stats_on();
   if (stats && !d_stats) {
     OXG_TRY(tree_events(t));
-    p.stats = t->bounds.as<unsigned long long>() + 2 * kMaxFastDim;
-    OXG_CUDA_TRY(cudaMemsetAsync(p.stats, 0, 4 * sizeof(unsigned long long), s->stream));
+    if (tree_stats_level() >= 2) {
+      p.stats = t->bounds.as<unsigned long long>() + 2 * kMaxFastDim;
+      OXG_CUDA_TRY(cudaMemsetAsync(p.stats, 0, 8 * sizeof(unsigned long long), s->stream));
+    }
     OXG_CUDA_TRY(cudaEventRecord(t->ev_q0, s->stream));
   }
   int r = OXG_E_INTERNAL;
@@ -1291,6 +1301,7 @@ int tree_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exc
   if (stats && !d_stats && r == OXG_OK) {
     OXG_CUDA_TRY(cudaEventRecord(t->ev_q1, s->stream));
     t->have_query_ev = true;
+    t->have_counts = p.stats != nullptr;
     t->last_Q = Q;
   }
   return r;
@@ -1316,11 +1327,11 @@ extern "C" int oxg_store_tree_stats(oxg_store s, double* out8) {
   if (t->have_build_ev && cudaEventElapsedTime(&ms, t->ev_b0, t->ev_b1) == cudaSuccess) out8[0] = ms;
   OXG_CUDA_TRY(cudaEventElapsedTime(&ms, t->ev_q0, t->ev_q1));
   out8[1] = ms;
-  unsigned long long h[4] = {0, 0, 0, 0};
-  OXG_CUDA_TRY(cudaMemcpy(h, t->bounds.as<unsigned long long>() + 2 * kMaxFastDim, sizeof(h),
+  unsigned long long h[5] = {0, 0, 0, 0, 0};
+  if (t->have_counts)
+    OXG_CUDA_TRY(cudaMemcpy(h, t->bounds.as<unsigned long long>() + 2 * kMaxFastDim, sizeof(h),
                           cudaMemcpyDeviceToHost));
-  for (int i = 0; i < 4; ++i) out8[2 + i] = (double)h[i];
-  out8[6] = (double)t->size;
+  for (int i = 0; i < 5; ++i) out8[2 + i] = (double)h[i];
   out8[7] = (double)t->last_Q;
   return OXG_OK;
   OXG_API_END

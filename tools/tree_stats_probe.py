@@ -17,7 +17,7 @@ def main():
     lo, hi = np.asarray(worlds.PANDA_LO), np.asarray(worlds.PANDA_HI)
     rows = lo + (hi - lo) * rng.random((n, 7))
     oxg.tuning_set("knn_tree", 1)
-    oxg.tuning_set("tree_stats", 1)
+    oxg.tuning_set("tree_stats", 2)
     with oxg.StateStore(oxg.Space.real_vector(7)) as st:
         st.append(rows)
         for kind in (0, 1):
@@ -29,7 +29,7 @@ def main():
             q = s["queries"]
             print(f"kind={kind} build_ms={s['build_ms']:.3f} kernel_ms={s['query_kernel_ms']:.3f} "
                   f"leaves/q={s['leaves_visited'] / q:.1f} groups/q={s['box_groups_tested'] / q:.1f} "
-                  f"cand/q={s['candidates'] / q:.1f} merges/q={s['merges'] / q:.2f}", flush=True)
+                  f"cand/q={s['candidates'] / q:.1f} merges/q={s['merges'] / q:.2f} exact leaves/q={s['exact_leaves'] / q:.1f}", flush=True)
 
 
 if __name__ == "__main__":
