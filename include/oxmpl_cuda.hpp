@@ -517,73 +517,46 @@ class PRM {
     }
   }
 
-  Path solve(double timeout_s) {  // prm.rs:227-307
+  // prm.rs:227-307 through oxg_prm_solve: start validity, start connection, goal scan and the
+  // reference-order BFS all run in the library; the roadmap goes in as each node's lower-index
+  // neighbours (new_node.edges at push time, prm.rs:135).
+  Path solve(double timeout_s) {
     (void)timeout_s;
     if (!pd_ || !vc_) throw PlanningError::uninitialised();
     if (edges_.empty()) throw PlanningError::unsampled();
     const uint32_t dim = (uint32_t)pd_->space->dimension();
     const double res = pd_->space->get_longest_valid_segment_length() * 0.1;
     const State& start = pd_->start_states.at(0);
-    if (!vc_->is_valid(start)) throw PlanningError::invalid_start();  // prm.rs:244
     const uint64_t n = edges_.size();
-    // start connection (prm.rs:249-256): radius scan + check_motion(start, roadmap[i])
-    std::vector<uint64_t> off(2, 0);
-    std::vector<uint32_t> nb(std::max<uint64_t>(n, 1));
-    check(oxg_radius(store_->h(), start.data(), 1, connection_radius, nullptr, off.data(), nb.data(),
-                     nb.size(), nullptr));
-    nb.resize(off[1]);
-    std::vector<uint32_t> start_edges;
-    if (!nb.empty()) {
-      std::vector<double> from(nb.size() * dim), to(nb.size() * dim);
-      for (std::size_t e = 0; e < nb.size(); ++e) {
-        std::copy(start.begin(), start.end(), from.begin() + e * dim);
-        const State s = store_->read(nb[e], dim);
-        std::copy(s.begin(), s.end(), to.begin() + e * dim);
-      }
-      std::vector<uint8_t> ok(nb.size());
-      oxg_space_desc sp = pd_->space->desc();
-      check(oxg_check_motion(vc_->handle(), &sp, from.data(), to.data(), nb.size(), res, ok.data(), nullptr));
-      for (std::size_t e = 0; e < nb.size(); ++e)
-        if (ok[e]) start_edges.push_back(nb[e]);
-    }
-    // goal scan (prm.rs:259-264)
-    std::vector<double> all(n * dim);
-    check(oxg_store_read(store_->h(), 0, n, all.data()));
-    std::vector<uint8_t> is_goal(n, 0);
-    bool any_goal = false;
+    std::vector<uint64_t> off(n + 1, 0);
+    std::vector<uint32_t> lower;
     for (uint64_t i = 0; i < n; ++i) {
-      State s(all.begin() + i * dim, all.begin() + (i + 1) * dim);
-      if (pd_->goal->is_satisfied(*pd_->space, s)) is_goal[i] = 1, any_goal = true;
+      for (uint32_t j : edges_[i])
+        if (j < i) lower.push_back(j);
+      off[i + 1] = lower.size();
     }
-    if (!any_goal || start_edges.empty()) throw PlanningError::no_solution();
-    // BFS from the virtual start node (prm.rs:271-301)
-    const uint32_t START = 0xFFFFFFFFu;
-    std::unordered_map<uint32_t, uint32_t> parent;
-    std::deque<uint32_t> queue;
-    for (uint32_t j : start_edges)
-      if (!parent.count(j)) parent[j] = START, queue.push_back(j);
-    while (!queue.empty()) {
-      const uint32_t cur = queue.front();
-      queue.pop_front();
-      if (is_goal[cur]) {
-        Path p;
-        for (uint32_t i = cur; i != START; i = parent[i])
-          p.emplace_back(all.begin() + (uint64_t)i * dim, all.begin() + ((uint64_t)i + 1) * dim);
-        p.push_back(start);
-        std::reverse(p.begin(), p.end());
-        return p;
-      }
-      for (uint32_t j : edges_[cur])
-        if (!parent.count(j)) parent[j] = cur, queue.push_back(j);
-    }
-    throw PlanningError::no_solution();
+    std::vector<uint32_t> nodes(n);
+    oxg_prm_query_result r{};
+    check(oxg_prm_solve(vc_->handle(), store_->h(), off.data(), lower.data(), connection_radius, res,
+                        start.data(), pd_->goal->target.data(), pd_->goal->radius, nodes.data(),
+                        (uint32_t)nodes.size(), &r));
+    last_query_ = r;
+    if (r.status == 2) throw PlanningError::invalid_start();   // prm.rs:243-246
+    if (r.status == 3) throw PlanningError::unsampled();       // prm.rs:239-241
+    if (r.status != 0) throw PlanningError::no_solution();     // prm.rs:266-268, 304
+    Path p;                                                    // reconstruct_path, prm.rs:189-208
+    p.push_back(start);
+    for (uint32_t t = 0; t < r.path_len; ++t) p.push_back(store_->read(nodes[t], dim));
+    return p;
   }
+  const oxg_prm_query_result& last_query() const { return last_query_; }
 
  private:
   std::shared_ptr<ProblemDefinition> pd_;
   std::shared_ptr<GpuValidityChecker> vc_;
   std::unique_ptr<detail::Store> store_;
   std::vector<std::vector<uint32_t>> edges_;
+  oxg_prm_query_result last_query_{};
 };
 
 }  // namespace cuda

@@ -52,6 +52,10 @@ class RealVectorStateSpace:
             s = s + d * d
         return math.sqrt(s)
 
+    def interpolate(self, frm: RealVectorState, to: RealVectorState, t: float) -> RealVectorState:
+        # real_vector_state_space.rs:161-186: from + (to - from) * t, each operation rounded
+        return RealVectorState([f + (g - f) * t for f, g in zip(frm.values, to.values)])
+
     def get_maximum_extent(self) -> float:
         return api.real_vector_max_extent(self.bounds)
 
@@ -283,13 +287,18 @@ class ProblemDefinition:
 
     space: RealVectorStateSpace
     start_state: RealVectorState
-    goal: object   # needs .target (RealVectorState), .radius, .is_satisfied(), .sample_goal()
+    goal: object   # .is_satisfied(), .sample_goal(); ball goals also expose .target and .radius
 
     @staticmethod
     def from_real_vector(space, start_state, goal) -> "ProblemDefinition":
-        for attr in ("target", "radius", "is_satisfied", "sample_goal"):
+        """oxmpl-py/src/base/problem_definition.rs:51-77.  A ball goal (``target`` + ``radius``,
+        the CircularGoalRegion of the reference's tests) runs on the fused device loops; any other
+        goal object with ``is_satisfied(state)`` and ``sample_goal()`` is accepted too and makes
+        ``RRT`` take the unfused per-iteration path (``oxg_nn1`` -> steer -> ``oxg_check_motion``
+        -> append), one round trip per iteration."""
+        for attr in ("is_satisfied", "sample_goal"):
             if not hasattr(goal, attr):
-                raise TypeError(f"goal must provide `{attr}` (a ball goal: target + radius)")
+                raise TypeError(f"goal must provide `{attr}`")
         return ProblemDefinition(space, start_state, goal)
 
     @staticmethod

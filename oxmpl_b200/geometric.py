@@ -164,11 +164,42 @@ class RRT(_TreePlanner):
                     return Path(out[::-1])
         raise PlanningError(PlanningError.TIMEOUT)
 
+    def _solve_unfused(self, timeout_secs: float) -> Path:
+        """rrt.rs:170-225 one iteration at a time, for goals the device cannot test (anything but a
+        ball): oxg_nn1 -> steer on the host (rrt.rs:200-208) -> oxg_check_motion -> append -> the
+        user's ``is_satisfied``."""
+        pd, space = self.pd, self.pd.space
+        sp, res = space._space(), self._resolution()
+        nodes, parents = [pd.start_state], [-1]
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 <= timeout_secs:
+            q_rand = pd.goal.sample_goal() if self.rng.random() < self.goal_bias \
+                else space.sample_uniform(self.rng)
+            idx, dist = self.tree.nn1(np.asarray([q_rand.values]))
+            near, min_dist = int(idx[0]), float(dist[0])
+            q_near = nodes[near]
+            q_new = space.interpolate(q_near, q_rand, self.max_distance / min_dist) \
+                if min_dist > self.max_distance else q_rand
+            if self.vc.world.check_motion(sp, np.asarray([q_near.values]), np.asarray([q_new.values]),
+                                          res)[0]:
+                self.tree.append(np.asarray([q_new.values]))
+                nodes.append(q_new)
+                parents.append(near)
+                if pd.goal.is_satisfied(q_new):
+                    out, node = [], len(nodes) - 1
+                    while node >= 0:
+                        out.append(nodes[node])
+                        node = parents[node]
+                    return Path(out[::-1])
+        raise PlanningError(PlanningError.TIMEOUT)
+
     def solve(self, timeout_secs: float) -> Path:
         if self.vc is None:
             raise PlanningError(PlanningError.UNINITIALISED)
         if isinstance(self.pd.space, SO3StateSpace):
             return self._solve_so3(timeout_secs)
+        if not (hasattr(self.pd.goal, "target") and hasattr(self.pd.goal, "radius")):
+            return self._solve_unfused(timeout_secs)
         t0 = time.perf_counter()
         while True:
             left = timeout_secs - (time.perf_counter() - t0)
@@ -245,6 +276,9 @@ class RRTStar(_TreePlanner):
             left = timeout_secs - (time.perf_counter() - t0)
             if left <= 0:
                 raise PlanningError(PlanningError.TIMEOUT)
+            if not (hasattr(self.pd.goal, "target") and hasattr(self.pd.goal, "radius")):
+                raise TypeError("the fused RRT* loop tests a ball goal (target + radius); use RRT for "
+                                "other goal objects")
             try:
                 parents, costs, r = api.rrt_star_solve(
                     self.vc.world, self.tree, self._stream(self.chunk), self.max_distance,

@@ -186,3 +186,30 @@ def test_rust_crate_builds_every_source_it_calls_into():
         assert re.search(rf"pub struct {ty}\b", lib_rs), f"{ty} is documented but not defined"
         assert re.search(rf"impl(<[^>]*>)? (Planner<[^>]*>|StateValidityChecker<[^>]*>) for {ty}\b", lib_rs), ty
     assert "set_gpu_checker" not in lib_rs           # setup() takes the checker it is given
+
+
+def test_round2_entry_points_validate_their_arguments():
+    """The new entry points reject bad arguments before touching the device (so this runs on CPU)."""
+    from oxmpl_b200 import _lib
+    from oxmpl_b200._lib import lib
+
+    assert lib.oxg_tuning_set(None, 1) == _lib.OXG_E_NULL
+    assert lib.oxg_tuning_set(b"no_such_switch", 1) == _lib.OXG_E_ARG
+    assert b"no_such_switch" in lib.oxg_last_error()
+    for key in (b"knn_tree", b"tree_kind", b"tree_cache", b"tree_stats"):
+        assert lib.oxg_tuning_set(key, 1) == 0
+    assert lib.oxg_tuning_set(b"knn_tree", -1) == 0 and lib.oxg_tuning_set(b"tree_kind", -1) == 0
+    assert lib.oxg_tuning_set(b"tree_stats", 0) == 0
+    out8 = (C.c_double * 8)()
+    assert lib.oxg_store_tree_stats(None, out8) == _lib.OXG_E_NULL
+    r = _lib.PrmQueryResult()
+    assert lib.oxg_prm_solve(None, None, None, None, 0.5, 0.1, None, None, 0.5, None, 0, C.byref(r)) == _lib.OXG_E_NULL
+    assert lib.oxg_prm_solve_knn(None, None, None, None, 10, 0.5, 0.1, None, None, 0.5, None, 0,
+                                 C.byref(r)) == _lib.OXG_E_NULL
+    first = C.c_uint64(0)
+    assert lib.oxg_store_append_dist(None, None, None, 0, C.byref(first)) == _lib.OXG_E_NULL
+    assert lib.oxg_prm_build_knn_dist(None, None, None, 10, 0.1, None, None, None, None) == _lib.OXG_E_NULL
+    assert lib.oxg_prm_build_radius_dist(None, None, None, 0.5, 0.1, None, None, 0, None) == _lib.OXG_E_NULL
+    uid = C.create_string_buffer(128)
+    assert lib.oxg_dist_unique_id(None) == _lib.OXG_E_NULL
+    assert lib.oxg_dist_unique_id(uid) in (0, _lib.OXG_E_NCCL)     # NCCL may be absent on a CPU box

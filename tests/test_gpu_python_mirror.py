@@ -448,3 +448,31 @@ def test_rrt_star_dense_neighbourhood_is_a_planning_error():
     planner.pd.goal.radius = 1e-12                   # never satisfied: the tree keeps growing
     with pytest.raises(PlanningError, match="No solution found.*search_radius"):
         planner.solve(timeout_secs=20.0)
+
+
+def test_rrt_accepts_a_goal_that_is_not_a_ball():
+    """A reference-style user Goal with an arbitrary is_satisfied (here: a half-plane) has no device
+    form; RRT then runs the unfused per-iteration path through the same C-ABI entry points."""
+    class RightEdgeGoal:
+        def __init__(self):
+            self.rng = random.Random(9)
+
+        def is_satisfied(self, state):
+            return state.values[0] >= 9.0
+
+        def sample_goal(self):
+            return RealVectorState([self.rng.uniform(9.0, 10.0), self.rng.uniform(0.0, 10.0)])
+
+    space = RealVectorStateSpace(dimension=2, bounds=[(0.0, 10.0), (0.0, 10.0)])
+    start = RealVectorState([1.0, 5.0])
+    goal = RightEdgeGoal()
+    pd = ProblemDefinition.from_real_vector(space, start, goal)
+    planner = RRT(max_distance=0.5, goal_bias=0.05, problem_definition=pd)
+    planner.setup(GpuValidityChecker(2, aabbs=WALL))
+    path = planner.solve(timeout_secs=20.0)
+    assert len(path.states) > 1 and space.distance(path.states[0], start) < 1e-9
+    assert goal.is_satisfied(path.states[-1])
+    for s in path.states:
+        assert is_state_valid(s), s.values
+    for a, b in zip(path.states[:-1], path.states[1:]):
+        assert space.distance(a, b) <= 0.5 + 1e-9
