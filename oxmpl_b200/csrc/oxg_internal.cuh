@@ -168,6 +168,7 @@ struct oxg_store_s {
   oxg::DevBuf buf[oxg::B_COUNT];  // named scratch arenas, see enum StoreBuf
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   uint64_t epoch = 0;        // bumped whenever the contents change (append, clear, planner growth)
+  uint32_t last_radius_nsplit = 1;  // slices per query of the most recent nn_radius_device call
   void* tree = nullptr;      // oxg::StoreTree, the bounding-box hierarchy of oxg_tree.cu (lazy)
 };
 
@@ -323,6 +324,8 @@ int tree_build(oxg_store_s* s, bool want_kd);
 int tree_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclude_mode,
                     const uint32_t* d_exclude, uint64_t self_base, uint32_t* d_idx, double* d_dist,
                     unsigned long long* d_stats);
+int tree_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double U, const uint32_t* d_idx_limit,
+                       bool limit_self, uint64_t self_base, bool want_dist, uint64_t* total);
 // runtime tuning switches (oxg_tuning_set): -1 = automatic
 extern std::atomic<int> g_tune_knn_tree;
 extern std::atomic<int> g_tune_tree_cache;  // 0 = rebuild the hierarchy for every batch

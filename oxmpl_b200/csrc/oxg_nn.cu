@@ -2277,9 +2277,21 @@ int nn_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double r, const ui
   } else {
     memcpy(&p.r_bits, &thr, sizeof(double));
   }
+  // Exact spatial pruning (oxg_tree.cu), as for k-NN: low-dimensional RealVector stores, enough
+  // pairs to pay for the hierarchy or a hierarchy that is still current.
+  if (tree_supported(s, 1) && Q >= 64 && p.n_db >= 16384) {
+    int mode = g_tune_knn_tree.load();
+    if (mode < 0) mode = env_int("OXG_KNN_TREE", -1);
+    const bool use = mode > 0 || (mode < 0 && (tree_is_current(s) || (double)Q * (double)p.n_db >= 2.0e8));
+    if (use) {
+      s->last_radius_nsplit = 1;
+      return tree_radius_device(s, q, Q, thr, d_idx_limit, limit_self, self_base, want_dist, total);
+    }
+  }
   const RadiusPlan pl = radius_plan(s, Q);
   p.nsplit = pl.nsplit;
   p.split_len = pl.split_len;
+  s->last_radius_nsplit = pl.nsplit;
 
   size_t ncounts = (size_t)Q * p.nsplit + 1;
   OXG_TRY(s->buf[B_OFFSETS].ensure(ncounts * sizeof(uint64_t)));
@@ -2378,7 +2390,7 @@ int nn_radius_nsplit(const oxg_store_s* s, uint64_t Q) { return (int)radius_plan
 
 // Compacts B_OFFSETS (per-slice offsets) into per-query CSR offsets in `d_out` (Q+1 entries).
 int nn_radius_offsets(oxg_store_s* s, uint64_t Q, uint64_t* d_out) {
-  uint32_t nsplit = (uint32_t)nn_radius_nsplit(s, Q);
+  uint32_t nsplit = s->last_radius_nsplit;
   int threads = 256;
   pick_offsets_kernel<<<(unsigned)((Q + 1 + threads - 1) / threads), threads, 0, s->stream>>>(
       s->buf[B_OFFSETS].as<uint64_t>(), Q, nsplit, d_out);

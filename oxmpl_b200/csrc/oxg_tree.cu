@@ -32,6 +32,7 @@
 // skipped only if  lb (1 - 1e-13) > U  where U >= max{x : sqrt(x) <= s_kth}.  NaN coordinates
 // never enter a box (fmin/fmax drop them) and never enter a list (d2 != d2), as in the scans.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstdlib>
@@ -935,6 +936,166 @@ __global__ void __launch_bounds__(TK_THREADS, OXG_TK_MIN_CTAS) tree_knn_kernel(c
 }
 
 // ---------------------------------------------------------------------------------------
+// radius search through the hierarchy: all i with distance(query, stored_i) < r (strict), the
+// scans of rrt_star.rs:121-131, prm.rs:131-138 and prm.rs:249-256.  Same certified pruning with a
+// fixed bound U = max{x : sqrt(x) < r}; a count pass and a fill pass (the fill emits
+// (query << 32 | index) keys, one radix sort puts every row in ascending index order).
+// ---------------------------------------------------------------------------------------
+struct TreeRadiusParams {
+  TreeView t;
+  const TreePlan* plan;
+  StateView q;
+  uint32_t Q;
+  const uint32_t* qorder;
+  unsigned long long ub;       // bits of U (admission: bits(d2) <= ub)
+  double U;
+  const uint32_t* idx_limit;   // nullable
+  int limit_self;              // limit of query qi = self_base + qi
+  uint32_t self_base;
+  uint32_t n_db;
+  uint64_t* counts;            // count pass: hits per query; fill pass: exclusive offsets
+  unsigned long long* keys;    // fill pass
+  double* dist;                // fill pass, nullable
+  uint32_t qpc;
+};
+
+template <int D>
+struct RadiusQuery {
+  float q32[D];
+  const double* qd;
+  const float* qbox;
+  float T32, Uf;
+  unsigned long long ub;
+  uint32_t limit, qi;
+  uint64_t base;     // fill: first output slot of this query
+  uint32_t found;
+  int lane;
+};
+
+template <int D, bool FILL>
+__device__ __forceinline__ void radius_leaf(const TreeRadiusParams& p, RadiusQuery<D>& w, uint32_t leaf) {
+  const float* lp32 = p.t.pts32 + (uint64_t)leaf * (D * 32) + w.lane;
+  float a = 0.0f;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float df = w.q32[d] - __ldg(lp32 + d * 32);
+    a = __fmaf_rn(df, df, a);
+  }
+  const bool maybe = !(a > w.T32);
+  if (__ballot_sync(0xFFFFFFFFu, maybe) == 0u) return;
+  bool hit = false;
+  double d2 = 0.0;
+  uint32_t j = OXG_INVALID_INDEX;
+  if (maybe) {
+    const double* lp = p.t.pts + (uint64_t)leaf * (D * 32) + w.lane;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double df = __dsub_rn(w.qd[d], __ldg(lp + d * 32));
+      const double m = __dmul_rn(df, df);
+      d2 = (d == 0) ? m : __dadd_rn(d2, m);
+    }
+    j = __ldg(p.t.perm + (uint64_t)leaf * 32 + w.lane);
+    // NaN patterns compare above any ub as unsigned; pads carry NaN coordinates
+    hit = (unsigned long long)__double_as_longlong(d2) <= w.ub && j < w.limit;
+  }
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+  if (FILL && hit) {
+    const uint64_t pos = w.base + w.found + __popc(m & ((1u << w.lane) - 1u));
+    p.keys[pos] = ((unsigned long long)w.qi << 32) | j;
+    if (p.dist) p.dist[pos] = sqrt(d2);
+  }
+  w.found += __popc(m);
+}
+
+template <int D, int L, bool FILL>
+struct VisitRadius {
+  static __device__ __forceinline__ void run(const TreeRadiusParams& p, RadiusQuery<D>& w, uint32_t group) {
+    const uint32_t child0 = group * 32u;
+    const float* bp = p.t.boxes32[L] + (uint64_t)group * (2 * D * 32) + w.lane;
+    float lb = 0.0f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float lo = __ldg(bp + d * 32), hi = __ldg(bp + (D + d) * 32);
+      const float t = fmaxf(fmaxf(__fsub_rd(lo, w.qbox[D + d]), __fsub_rd(w.qbox[d], hi)), 0.0f);
+      lb = __fadd_rd(lb, __fmul_rd(t, t));
+    }
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, child0 + (uint32_t)w.lane < p.t.count[L] && !(lb > w.Uf));
+    while (m) {
+      const uint32_t c = __ffs(m) - 1;
+      m &= m - 1;
+      if constexpr (L == 0)
+        radius_leaf<D, FILL>(p, w, child0 + c);
+      else
+        VisitRadius<D, L - 1, FILL>::run(p, w, child0 + c);
+    }
+  }
+};
+
+template <int D, bool FILL>
+__global__ void __launch_bounds__(TK_THREADS, OXG_TK_MIN_CTAS) tree_radius_kernel(const TreeRadiusParams p) {
+  __shared__ double s_q[TK_THREADS / 32][D];
+  __shared__ float s_qbox[TK_THREADS / 32][2 * D];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const double sc = p.plan->sc;
+  const uint32_t n_chunks = (p.Q + p.qpc - 1) / p.qpc;
+  for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const uint32_t q_begin = chunk * p.qpc;
+    const uint32_t q_end = min(p.Q, q_begin + p.qpc);
+    for (uint32_t wq = q_begin + wid; wq < q_end; wq += TK_THREADS / 32) {
+      const uint32_t qi = p.qorder ? __ldg(p.qorder + wq) : wq;
+      RadiusQuery<D> w;
+      bool qnan = false;
+      double mq = 0.0;
+      __syncwarp();
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const double qv = p.q.p[(uint64_t)qi * p.q.stride_i + (uint64_t)d * p.q.stride_d];
+        qnan = qnan || !(qv == qv);
+        const double c = p.plan->c[d];
+        const double qs = (qv - c) * sc;
+        w.q32[d] = __double2float_rn(qs);
+        mq = fmax(mq, fabs(qs));
+        if (lane == 0) {
+          s_q[wid][d] = qv;
+          s_qbox[wid][d] = __double2float_rd(__dmul_rd(__dsub_rd(qv, c), sc));
+          s_qbox[wid][D + d] = __double2float_ru(__dmul_ru(__dsub_ru(qv, c), sc));
+        }
+      }
+      __syncwarp();
+      w.qd = s_q[wid];
+      w.qbox = s_qbox[wid];
+      w.lane = lane;
+      w.qi = qi;
+      w.ub = p.ub;
+      w.found = 0;
+      w.limit = p.limit_self ? p.self_base + qi : (p.idx_limit ? __ldg(p.idx_limit + qi) : p.n_db);
+      w.base = FILL ? p.counts[qi] : 0;
+      const double Ub = __dmul_ru(__dmul_ru(p.U, __ldg(&p.plan->sc2)), 1.0 + 1.0e-12);
+      w.Uf = __double2float_ru(Ub);
+      w.T32 = tree_filter_threshold(Ub, fmax(mq, p.plan->mabs) * 1.000001, D);
+      if (!qnan && w.limit > 0) {
+        switch (p.t.top) {
+          case 0: VisitRadius<D, 0, FILL>::run(p, w, 0); break;
+          case 1: VisitRadius<D, 1, FILL>::run(p, w, 0); break;
+          case 2: VisitRadius<D, 2, FILL>::run(p, w, 0); break;
+          case 3: VisitRadius<D, 3, FILL>::run(p, w, 0); break;
+          default: VisitRadius<D, 4, FILL>::run(p, w, 0); break;
+        }
+      }
+      if (!FILL && lane == 0) p.counts[qi] = w.found;
+    }
+  }
+}
+
+__global__ void tree_radius_unpack_kernel(const unsigned long long* __restrict__ keys, uint64_t n,
+                                          uint32_t* __restrict__ idx) {
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+       t += (uint64_t)gridDim.x * blockDim.x)
+    idx[t] = (uint32_t)(keys[t] & 0xFFFFFFFFull);
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 static unsigned grid_1d(uint64_t n, int threads, unsigned cap = 148u * 16u) {
@@ -1305,6 +1466,123 @@ int tree_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exc
     t->last_Q = Q;
   }
   return r;
+}
+
+template <int D>
+static int launch_tree_radius(TreeRadiusParams p, bool fill, cudaStream_t st) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned warps = TK_THREADS / 32;
+  unsigned qpc = (unsigned)((p.Q + (unsigned)sms * OXG_TK_MIN_CTAS - 1) / ((unsigned)sms * OXG_TK_MIN_CTAS));
+  qpc = ((qpc + warps - 1) / warps) * warps;
+  p.qpc = std::max(warps, std::min<unsigned>(qpc, TK_QPC));
+  const unsigned grid = (p.Q + p.qpc - 1) / p.qpc;
+  if (fill)
+    tree_radius_kernel<D, true><<<grid, TK_THREADS, 0, st>>>(p);
+  else
+    tree_radius_kernel<D, false><<<grid, TK_THREADS, 0, st>>>(p);
+  OXG_LAUNCH_CHECK();
+  return OXG_OK;
+}
+
+// Radius search of Q device-resident queries through the hierarchy (same contract as
+// nn_radius_device with one slice per query): exclusive offsets (Q + 1) in B_OFFSETS, ascending
+// indices in B_PIDX, distances in B_PDIST.  `U` = max{x : sqrt(x) < r} (negative: no hits).
+int tree_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double U, const uint32_t* d_idx_limit,
+                       bool limit_self, uint64_t self_base, bool want_dist, uint64_t* total) {
+  *total = 0;
+  int kind = g_tune_tree_kind.load();
+  if (kind < 0) kind = (Q >= 8192 && Q >= s->size / 64 && s->size >= 65536) ? 1 : 0;
+  if (s->size > (1ull << 25)) kind = 0;
+  OXG_TRY(tree_build(s, kind == 1));
+  StoreTree* t = tree_of(s);
+  OXG_TRY(s->buf[B_OFFSETS].ensure((Q + 1) * sizeof(uint64_t)));
+  OXG_TRY(s->buf[B_COUNTS].ensure((Q + 1) * sizeof(uint64_t)));
+  uint64_t* counts = s->buf[B_COUNTS].as<uint64_t>();
+  uint64_t* offsets = s->buf[B_OFFSETS].as<uint64_t>();
+  OXG_CUDA_TRY(cudaMemsetAsync(counts, 0, (Q + 1) * sizeof(uint64_t), s->stream));
+  if (!(U >= 0.0)) {  // r <= 0 or NaN: nothing is within the radius
+    OXG_CUDA_TRY(cudaMemsetAsync(offsets, 0, (Q + 1) * sizeof(uint64_t), s->stream));
+    OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return OXG_OK;
+  }
+  OXG_TRY(t->qorder.ensure((size_t)Q * 4 * sizeof(uint32_t)));
+  uint32_t* qk = t->qorder.as<uint32_t>();
+  uint32_t* qk2 = qk + Q;
+  uint32_t* qv = qk + 2 * Q;
+  uint32_t* qv2 = qk + 3 * Q;
+  tree_keys_kernel<<<grid_1d(Q, 256), 256, 0, s->stream>>>(q, (uint32_t)Q, (int)s->dim,
+                                                           t->plan.as<TreePlan>(), qk, qv);
+  OXG_LAUNCH_CHECK();
+  OXG_TRY(sort_pairs(s, t, qk, qk2, qv, qv2, (uint32_t)Q));
+  TreeRadiusParams p;
+  memset(&p, 0, sizeof(p));
+  p.t = t->view;
+  p.plan = t->plan.as<TreePlan>();
+  p.q = q;
+  p.Q = (uint32_t)Q;
+  p.qorder = qv2;
+  p.U = U;
+  memcpy(&p.ub, &U, sizeof(double));
+  p.idx_limit = d_idx_limit;
+  p.limit_self = limit_self ? 1 : 0;
+  p.self_base = (uint32_t)self_base;
+  p.n_db = (uint32_t)s->size;
+  p.counts = counts;
+  int r = OXG_E_INTERNAL;
+  OXG_TREE_DISPATCH_D(s->dim, r = (launch_tree_radius<DD>(p, false, s->stream)));
+  OXG_TRY(r);
+  size_t tmp_bytes = 0;
+  OXG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, offsets, (int)(Q + 1), s->stream));
+  OXG_TRY(t->tmp.ensure(tmp_bytes));
+  OXG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(t->tmp.p, tmp_bytes, counts, offsets, (int)(Q + 1), s->stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  uint64_t tot = 0;
+  OXG_CUDA_TRY(cudaMemcpyAsync(&tot, offsets + Q, sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  *total = tot;
+  if (tot == 0) return OXG_OK;
+  if (tot > 0x7FFFFFF0ull) {
+    set_error("radius result of %llu entries is too large for one batch", (unsigned long long)tot);
+    return OXG_E_ARG;
+  }
+  OXG_TRY(s->buf[B_PIDX].ensure(tot * sizeof(uint32_t)));
+  OXG_TRY(t->kd_keys_a.ensure(tot * sizeof(unsigned long long)));
+  OXG_TRY(t->kd_keys_b.ensure(tot * sizeof(unsigned long long)));
+  unsigned long long* keys = t->kd_keys_a.as<unsigned long long>();
+  unsigned long long* keys2 = t->kd_keys_b.as<unsigned long long>();
+  double* dist_tmp = nullptr;
+  if (want_dist) {
+    OXG_TRY(s->buf[B_PDIST].ensure(tot * sizeof(double)));
+    OXG_TRY(t->keys.ensure(tot * sizeof(double)));
+    dist_tmp = t->keys.as<double>();
+  }
+  p.counts = offsets;
+  p.keys = keys;
+  p.dist = dist_tmp;
+  OXG_TREE_DISPATCH_D(s->dim, r = (launch_tree_radius<DD>(p, true, s->stream)));
+  OXG_TRY(r);
+  // rows in ascending index order: one sort of (query << 32 | index); the query part already
+  // places every key inside its row's slot range
+  int qbits = 1;
+  while ((1ull << qbits) < Q && qbits < 32) ++qbits;
+  tmp_bytes = 0;
+  if (want_dist) {
+    OXG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, dist_tmp,
+                                                 s->buf[B_PDIST].as<double>(), (int)tot, 0, 32 + qbits, s->stream));
+    OXG_TRY(t->tmp.ensure(tmp_bytes));
+    OXG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(t->tmp.p, tmp_bytes, keys, keys2, dist_tmp,
+                                                 s->buf[B_PDIST].as<double>(), (int)tot, 0, 32 + qbits, s->stream));
+  } else {
+    OXG_CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, keys2, (int)tot, 0, 32 + qbits, s->stream));
+    OXG_TRY(t->tmp.ensure(tmp_bytes));
+    OXG_CUDA_TRY(cub::DeviceRadixSort::SortKeys(t->tmp.p, tmp_bytes, keys, keys2, (int)tot, 0, 32 + qbits, s->stream));
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  tree_radius_unpack_kernel<<<grid_1d(tot, 256), 256, 0, s->stream>>>(keys2, tot, s->buf[B_PIDX].as<uint32_t>());
+  OXG_LAUNCH_CHECK();
+  return OXG_OK;
 }
 
 }  // namespace oxg

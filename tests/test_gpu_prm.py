@@ -241,3 +241,46 @@ def test_row_shards_of_the_full_build_equal_the_full_table(oxg, orc, concurrent,
             i2, d2, v2, _ = oxg.prm_build_knn(gw, st, k, res, 1000, 1000 + rows_q)
             assert np.array_equal(i2, idx[1000:1000 + rows_q]), rows_q
             assert np.array_equal(d2.view(np.uint64), dist[1000:1000 + rows_q].view(np.uint64))
+
+
+def test_radius_prm_full_size_two_algorithms_one_roadmap(oxg, orc):
+    """The reference's own PRM (radius mode, prm.rs:117-146) at 1 000 000 nodes: the hierarchy and the
+    all-pairs radius kernels must emit the same CSR, and sampled rows must equal the oracle's
+    `new_node.edges` (radius scan over the earlier nodes + check_motion(q_i, q_j))."""
+    n, d, radius = 1_000_000, 7, 0.75
+    lo, hi = worlds.PANDA_LO, worlds.PANDA_HI
+    caps = worlds.capsule_world(4, lo, hi, 256)
+    sp, sp_o = oxg.Space.real_vector(d), orc.space(d)
+    res = oxg.motion_resolution(oxg.real_vector_max_extent(list(zip(lo, hi))))
+    rng = np.random.default_rng(4)
+    with oxg.World(d, capsules=caps) as gw, oxg.StateStore(sp, capacity=n) as st:
+        s = lo + (hi - lo) * rng.random((n + n // 3, d))
+        rows = np.ascontiguousarray(s[gw.is_valid(sp, s).astype(bool)][:n])
+        assert len(rows) == n
+        st.append(rows)
+        off, idx, stats = oxg.prm_build_radius(gw, st, radius, res)
+        oxg.tuning_set("knn_tree", 0)
+        try:
+            off2, idx2, _ = oxg.prm_build_radius(gw, st, radius, res)
+        finally:
+            oxg.tuning_set("knn_tree", -1)
+    np.testing.assert_array_equal(off, off2)
+    np.testing.assert_array_equal(idx, idx2)
+    assert stats["n_candidates"] > 4_000_000 and off[-1] > 0.95 * stats["n_candidates"]
+    # rows are ascending and strictly below their own index
+    starts = off[:-1].astype(np.int64)
+    row_of = np.repeat(np.arange(n, dtype=np.int64), np.diff(off).astype(np.int64))
+    assert (idx.astype(np.int64) < row_of).all()
+    inner = np.ones(len(idx), dtype=bool)
+    inner[starts[starts < len(idx)]] = False
+    assert (np.diff(idx.astype(np.int64))[inner[1:]] > 0).all()
+    # sampled rows against the oracle
+    ow, keep = orc.world(d, capsules=caps)
+    pick = np.sort(np.random.default_rng(5).choice(n, size=256, replace=False))
+    ooff, oidx = orc.radius(sp_o, rows, rows[pick], radius, idx_limit=pick.astype(np.uint32))
+    for t, i in enumerate(pick):
+        cand = oidx[int(ooff[t]):int(ooff[t + 1])]
+        if len(cand):
+            ok, _ = orc.check_motion(ow, sp_o, np.repeat(rows[i:i + 1], len(cand), axis=0), rows[cand], res)
+            cand = cand[ok.astype(bool)]
+        np.testing.assert_array_equal(idx[int(off[i]):int(off[i + 1])], cand)

@@ -158,3 +158,67 @@ def test_tree_equals_all_pairs_scan_on_a_prm_table(oxg, orc):
     oi, od = orc.knn(orc.space(7), rows, rows[pick], 10, exclude=pick.astype(np.uint32))
     np.testing.assert_array_equal(ti[pick], oi)
     np.testing.assert_array_equal(td[pick].view(np.uint64), od.view(np.uint64))
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 7, 8])
+@pytest.mark.parametrize("n", [20000, 33000])
+def test_tree_radius_uniform(oxg, orc, tree_on, d, n):
+    """The radius scans (rrt_star.rs:121-131, prm.rs:131-138) through the hierarchy: strict `<`,
+    ascending indices, optional per-query index limits, distances bit for bit."""
+    rows = uniform_states(500 + d, n, [-1.0] * d, [2.0] * d)
+    queries = np.vstack([uniform_states(600 + d, 80, [-1.5] * d, [2.5] * d), rows[:40]])
+    sp_o = orc.space(d)
+    r = 3.0 * (200.0 / n) ** (1.0 / d)
+    with oxg.StateStore(oxg.Space.real_vector(d)) as st:
+        st.append(rows)
+        off, idx, dist = st.radius(queries, r, want_dist=True)
+        ooff, oidx, odist = orc.radius(sp_o, rows, queries, r, want_dist=True)
+        np.testing.assert_array_equal(off, ooff)
+        np.testing.assert_array_equal(idx, oidx)
+        np.testing.assert_array_equal(dist.view(np.uint64), odist.view(np.uint64))
+        assert off[-1] > 0
+        lim = np.random.default_rng(d).integers(0, n, size=len(queries)).astype(np.uint32)
+        off, idx = st.radius(queries, r, idx_limit=lim)
+        ooff, oidx = orc.radius(sp_o, rows, queries, r, idx_limit=lim)
+        np.testing.assert_array_equal(off, ooff)
+        np.testing.assert_array_equal(idx, oidx)
+        for bad in (0.0, -1.0, float("nan")):
+            off, idx = st.radius(queries, bad)
+            assert off[-1] == 0 and len(idx) == 0
+
+
+def test_tree_radius_boundary_and_ties(oxg, orc, tree_on):
+    """States exactly at distance r are excluded (strict `<`), one ulp inside are included; the
+    lattice makes whole shells tie."""
+    rng = np.random.default_rng(77)
+    rows = rng.integers(0, 30, size=(40000, 3)).astype(np.float64)
+    queries = np.vstack([rows[:100], rng.integers(0, 30, size=(60, 3)).astype(np.float64)])
+    sp_o = orc.space(3)
+    with oxg.StateStore(oxg.Space.real_vector(3)) as st:
+        st.append(rows)
+        for r in (1.0, np.nextafter(1.0, 2.0), float(np.sqrt(2.0)), float(np.nextafter(np.sqrt(2.0), 2.0)), 3.0):
+            off, idx = st.radius(queries, r)
+            ooff, oidx = orc.radius(sp_o, rows, queries, r)
+            np.testing.assert_array_equal(off, ooff)
+            np.testing.assert_array_equal(idx, oidx)
+
+
+def test_radius_prm_through_the_hierarchy_equals_the_oracle(oxg, orc, tree_on):
+    """Reference-faithful PRM rows (node i joins the earlier nodes within the radius whose motion is
+    valid, prm.rs:131-138) with the neighbour phase answered by the hierarchy."""
+    from oxmpl_b200 import worlds
+
+    n, d = 24000, 7
+    lo, hi = worlds.PANDA_LO, worlds.PANDA_HI
+    caps = worlds.capsule_world(4, lo, hi, 64)
+    sp, sp_o = oxg.Space.real_vector(d), orc.space(d)
+    res = oxg.motion_resolution(oxg.real_vector_max_extent(list(zip(lo, hi))))
+    samples = lo + (hi - lo) * np.random.default_rng(9).random((n, d))
+    ow, keep = orc.world(d, capsules=caps)
+    o_rows, o_off, o_idx, _, _ = orc.prm_radius(ow, sp_o, 1.6, res, samples)
+    with oxg.World(d, capsules=caps) as gw, oxg.StateStore(sp) as st:
+        st.append(o_rows)
+        off, idx, stats = oxg.prm_build_radius(gw, st, 1.6, res)
+    np.testing.assert_array_equal(off, o_off)
+    np.testing.assert_array_equal(idx, o_idx)
+    assert off[-1] > 10000
