@@ -84,6 +84,8 @@ struct oxg_dist_s {
   int world = 1;
   int device = 0;
   oxg::DevBuf idx_all, dist_all, valid_all, counters, pad, pad2, off_all, cnt_all;
+  cudaStream_t copy_stream = nullptr;  // D2H of the neighbour table while the edge phase runs
+  cudaEvent_t ev_knn = nullptr;
 };
 
 namespace oxg {
@@ -185,7 +187,8 @@ static int all_gather_rows(NcclApi* api, oxg_dist_s* d, cudaStream_t st, uint64_
 // every rank; d_counters[0..1] = motion checks executed / valid on THIS rank.
 static int prm_build_knn_dist_dev(oxg_dist_s* d, oxg_world_s* w, oxg_store_s* s, uint32_t k,
                                   double resolution, uint32_t* d_idx_all, double* d_dist_all,
-                                  uint8_t* d_valid_all, uint64_t* d_counters) {
+                                  uint8_t* d_valid_all, uint64_t* d_counters,
+                                  cudaEvent_t after_neighbours = nullptr) {
   NcclApi* api = nccl_api();
   if (d->world > 1 && !api) {
     set_error("NCCL is not available in this process (libnccl.so.2 not found)");
@@ -200,6 +203,7 @@ static int prm_build_knn_dist_dev(oxg_dist_s* d, oxg_world_s* w, oxg_store_s* s,
                            {d_dist_all, k * (uint32_t)sizeof(double), &d->pad2}};
     OXG_TRY(all_gather_rows(api, d, s->stream, n, items, 2));
   }
+  if (after_neighbours) OXG_CUDA_TRY(cudaEventRecord(after_neighbours, s->stream));  // idx / dist are final
   OXG_TRY(oxg_prm_edges_dev(w, s, d_idx_all, k, resolution, rb, re, d_valid_all, d_counters));
   if (d->world > 1) {
     GatherItem item = {d_valid_all, k * (uint32_t)sizeof(uint8_t), &d->pad};
@@ -281,6 +285,8 @@ int oxg_dist_destroy(oxg_dist d) {
     NcclApi* api = nccl_api();
     if (api) api->CommDestroy(d->comm);
   }
+  if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
+  if (d->ev_knn) cudaEventDestroy(d->ev_knn);
   d->idx_all.release();
   d->dist_all.release();
   d->valid_all.release();
@@ -398,15 +404,24 @@ int oxg_prm_build_knn_dist(oxg_dist d, oxg_world w, oxg_store s, uint32_t k, dou
   double* d_dist = d->dist_all.as<double>();
   uint8_t* d_valid = d->valid_all.as<uint8_t>();
   uint64_t* d_cnt = d->counters.as<uint64_t>();
+  // the neighbour table goes to the host on a second stream while the edge phase runs
+  if (!d->copy_stream) {
+    OXG_CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    OXG_CUDA_TRY(cudaEventCreateWithFlags(&d->ev_knn, cudaEventDisableTiming));
+  }
   OXG_CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
-  OXG_TRY(prm_build_knn_dist_dev(d, w, s, k, resolution, d_idx, d_dist, d_valid, d_cnt));
+  OXG_TRY(prm_build_knn_dist_dev(d, w, s, k, resolution, d_idx, d_dist, d_valid, d_cnt, d->ev_knn));
   OXG_CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+  OXG_CUDA_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_knn, 0));
   uint64_t h_cnt[2] = {0, 0};
-  if (idx) OXG_CUDA_TRY(cudaMemcpyAsync(idx, d_idx, slots * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-  if (dist) OXG_CUDA_TRY(cudaMemcpyAsync(dist, d_dist, slots * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (idx)
+    OXG_CUDA_TRY(cudaMemcpyAsync(idx, d_idx, slots * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->copy_stream));
+  if (dist)
+    OXG_CUDA_TRY(cudaMemcpyAsync(dist, d_dist, slots * sizeof(double), cudaMemcpyDeviceToHost, d->copy_stream));
   if (valid) OXG_CUDA_TRY(cudaMemcpyAsync(valid, d_valid, slots, cudaMemcpyDeviceToHost, s->stream));
   OXG_CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, s->stream));
   OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(d->copy_stream));
   if (stats) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->ev0, s->ev1);
