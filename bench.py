@@ -46,7 +46,11 @@ DIM = 7
 SEED = 4
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this config, from the `ncu --set
 # full` captures summarised in profiles/ (None until captured for the current kernel)
-TREE_DRAM_BYTES_NCU = 588114432  # profiles/r02_ncu_full_hot_kernels.csv (459.7 MB read + 128.5 MB written; captured at 821 776 nodes)
+TREE_DRAM_BYTES_NCU = 661177344  # profiles/r02_ncu_full_hot_kernels.csv (532.4 MB read + 128.8 MB written; captured at 821 776 nodes)
+# the same capture: share of tree_knn_kernel's L1 sector requests that hit L1 (the rest go to L2),
+# and the L2 read sectors it caused (x 32 B = 73.8 GB for 821 776 queries)
+TREE_L1_HIT_NCU = 0.2456
+TREE_L2_READ_BYTES_PER_QUERY_NCU = 2305868772 * 32 / 821776
 ALLPAIRS_DRAM_BYTES_NCU = 2249420000  # profiles/r01_ncu_full_knn_rv_dot_7_2.csv (2.046 GB read + 0.204 GB written)
 
 
@@ -516,14 +520,30 @@ def run_ours(args):
         f32_ops = (tstats["leaves_visited"] * 2.0 * DIM + tstats["box_groups_tested"] * 5.0 * DIM) * 32.0
         f64_ops = tstats["exact_leaves"] * 32.0 * (3.0 * DIM - 1.0)
         t_pipes_ms = (f32_ops / peak32_ops + f64_ops / peak64_ops) * 1e3
+        # Memory side.  The store and its hierarchy are L2-resident by design (the leaf copies and
+        # boxes of config 4 are ~120 MB of the 126 MB L2, DRAM traffic 0.66 GB per launch), so the
+        # memory roofline is the L2, not HBM.  Bytes the warps request: per visited leaf D x 32 f32,
+        # per exact leaf D x 32 f64, per box group 2D x 32 f32, per candidate one 32-byte sector of
+        # `perm`; the ncu capture in profiles/ gives the share that hits L1.
+        req_bytes = (tstats["leaves_visited"] * DIM * 32 * 4.0 + tstats["exact_leaves"] * DIM * 32 * 8.0 +
+                     tstats["box_groups_tested"] * 2 * DIM * 32 * 4.0 + tstats["candidates"] * 32.0)
+        # achieved: the L2 read traffic ncu measured per query (the counter-based estimate
+        # req_bytes x (1 - L1 hit rate) is ~9 % higher; the smaller figure is reported)
+        l2_bytes = min(req_bytes * (1.0 - TREE_L1_HIT_NCU), TREE_L2_READ_BYTES_PER_QUERY_NCU * q_n)
+        l2_peak_bps, _ = oxg.l2_peak()
         roof = {
-            "kernel": "oxg::tree_knn_kernel<7>", "bound": "fp32+fp64 pipes (latency-bound in practice)",
-            "achieved": (f32_ops + f64_ops) / (kern_ms * 1e-3) / 1e12,
-            "peak": (f32_ops + f64_ops) / (t_pipes_ms * 1e-3) / 1e12,
-            "unit": "T lane-operations/s (executed FP32 filter / box operations + f64 exact operations; "
-                    "peak = the same mix at the measured FP32 and unfused-FP64 issue rates)",
-            "frac": t_pipes_ms / kern_ms, "traffic": TREE_DRAM_BYTES_NCU,
-            "launch_ms": kern_ms, "executed_f32_lane_ops": f32_ops, "executed_f64_lane_ops": f64_ops,
+            "kernel": "oxg::tree_knn_kernel<7>", "bound": "l2",
+            "achieved": l2_bytes / (kern_ms * 1e-3) / 1e9, "peak": l2_peak_bps / 1e9, "unit": "GB/s",
+            "frac": l2_bytes / (kern_ms * 1e-3) / l2_peak_bps, "traffic": TREE_DRAM_BYTES_NCU,
+            "launch_ms": kern_ms,
+            "requested_bytes_per_launch": req_bytes, "l1_hit_rate_ncu": TREE_L1_HIT_NCU,
+            "l2_read_bytes_per_query_ncu": TREE_L2_READ_BYTES_PER_QUERY_NCU,
+            "requested_bytes_per_query": req_bytes / q_n,
+            "pipes": {"what": "time the executed FP32 (leaf filter, box tests) and f64 (exact leaves) "
+                              "lane-operations would need at the measured pipe peaks / kernel time",
+                      "frac": t_pipes_ms / kern_ms, "executed_f32_lane_ops": f32_ops,
+                      "executed_f64_lane_ops": f64_ops, "fp32_peak_tops": peak32_ops / 1e12,
+                      "fp64_peak_tops": peak64_ops / 1e12},
             "leaves_visited_per_query": tstats["leaves_visited"] / q_n,
             "exact_leaves_per_query": tstats["exact_leaves"] / q_n,
             "box_groups_per_query": tstats["box_groups_tested"] / q_n,
@@ -531,13 +551,13 @@ def run_ours(args):
             "pairs_evaluated_fraction_of_all_pairs": tstats["leaves_visited"] * 32.0 / (q_n * n),
             "all_pairs_equivalent_tflops": 3.0 * DIM * float(rows_rank0) * float(n) / (kern_ms * 1e-3) / 1e12,
             "hierarchy_build_ms": tstats["build_ms"],
-            "peak_source": "oxg_fp32_peak() / oxg_fp64_peak(): packed-FP32 lane rate and unfused DADD/DMUL "
-                           "issue rate measured in this run (MEASURED_PEAKS.json holds HBM and bf16-tensor "
-                           "figures only; the store is L2-resident and separately rounded f64 sums have no "
-                           "tensor-core form)",
-            "note": "an irregular traversal: ~100 dependent steps per query, 1.1 % of the all-pairs pair "
-                    "count; ncu (profiles/): issue slots ~60 %, L2 hit 99 %, stalls on L2 latency and "
-                    "dependent chains — neither pipe is the limiter",
+            "peak_source": "oxg_l2_peak(): all SMs reading a 48 MB L2-resident buffer with coalesced 16-byte "
+                           "ld.global.cg, measured in this run (MEASURED_PEAKS.json's HBM figure, "
+                           "%s GB/s, does not bound an L2-resident working set; the pipe peaks are "
+                           "oxg_fp32_peak / oxg_fp64_peak)" % _measured_hbm(),
+            "note": "an irregular traversal of ~100 dependent steps per query over 1.1 % of the all-pairs "
+                    "pair count: L2 latency, not bandwidth or arithmetic, limits it (ncu: long-scoreboard "
+                    "stalls 5.0 per issue, issue slots 59 %, L2 hit 99 %)",
             "hbm_peak_gbs_measured": _measured_hbm(),
         }
         line = {

@@ -151,6 +151,7 @@ extern "C" {
                                      idx: *mut u32, cap: u64, stats: *mut oxg_prm_stats) -> c_int;
     pub fn oxg_fp64_peak(out_ops_per_s: *mut f64, out_ms: *mut f64) -> c_int;
     pub fn oxg_fp32_peak(out_ops_per_s: *mut f64, out_ms: *mut f64) -> c_int;
+    pub fn oxg_l2_peak(out_bytes_per_s: *mut f64, out_ms: *mut f64) -> c_int;
     pub fn oxg_kernel_launches(reset: c_int) -> u64;
     pub fn oxg_tuning_set(key: *const std::os::raw::c_char, value: i64) -> c_int;
     pub fn oxg_store_tree_stats(s: oxg_store, out8: *mut f64) -> c_int;

@@ -401,6 +401,10 @@ int oxg_fp64_peak(double* out_ops_per_s, double* out_ms);
  * subtract + packed FMA, FADD2/FFMA2), in lane-instructions per second (an FMA counts once;
  * the mix's flop rate is 1.5x this figure). */
 int oxg_fp32_peak(double* out_ops_per_s, double* out_ms);
+/* oxg_l2_peak: bytes per second all SMs read from an L2-resident buffer with coalesced 16-byte
+ * loads that bypass L1 — the memory roofline of kernels whose working set (store + hierarchy) is
+ * L2-resident by design. */
+int oxg_l2_peak(double* out_bytes_per_s, double* out_ms);
 uint64_t oxg_kernel_launches(int reset);
 /* A/B switches for measurements; every setting runs hand-written sm_100a kernels and gives
  * bit-identical results.  "knn_tree": 1 = always answer oxg_knn / oxg_prm_build_knn through the

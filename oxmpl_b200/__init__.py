@@ -14,6 +14,7 @@ from .api import (  # noqa: F401
     fp32_peak,
     fp64_peak,
     kernel_launches,
+    l2_peak,
     motion_resolution,
     prm_build_knn,
     prm_build_radius,

@@ -191,6 +191,7 @@ SIGNATURES = {
     "oxg_store_last_scan_ms": (C.c_int, [_vp, C.POINTER(_dbl)]),
     "oxg_fp64_peak": (C.c_int, [C.POINTER(_dbl), C.POINTER(_dbl)]),
     "oxg_fp32_peak": (C.c_int, [C.POINTER(_dbl), C.POINTER(_dbl)]),
+    "oxg_l2_peak": (C.c_int, [C.POINTER(_dbl), C.POINTER(_dbl)]),
     "oxg_kernel_launches": (_u64, [C.c_int]),
     "oxg_tuning_set": (C.c_int, [C.c_char_p, C.c_int64]),
     "oxg_store_tree_stats": (C.c_int, [_vp, C.POINTER(_dbl)]),

@@ -103,6 +103,14 @@ def fp32_peak():
     return ops.value, ms.value
 
 
+def l2_peak():
+    """(bytes per second all SMs read from an L2-resident buffer, kernel ms) on the current GPU."""
+    bps = C.c_double(0.0)
+    ms = C.c_double(0.0)
+    check(lib.oxg_l2_peak(C.byref(bps), C.byref(ms)))
+    return bps.value, ms.value
+
+
 def kernel_launches(reset: bool = False) -> int:
     return int(lib.oxg_kernel_launches(1 if reset else 0))
 

@@ -49,9 +49,77 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float2* __restrict__ out
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// L2 read bandwidth: every CTA streams through the same L2-resident buffer with coalesced 16-byte
+// loads that bypass L1 (ld.global.cg), the access shape of a warp reading a leaf of the
+// bounding-box hierarchy.  The buffer (48 MB) fits the 126 MB L2 and is touched once before timing.
+__global__ void __launch_bounds__(256) l2_peak_kernel(const float4* __restrict__ buf, size_t n_vec, int passes,
+                                                      float4* __restrict__ out) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int p = 0; p < passes; ++p) {
+    // a different starting offset per pass and CTA, so that CTAs do not march in lock step
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x + (size_t)p * 7919u * blockDim.x) % n_vec;
+    for (size_t t = 0; t < n_vec / stride; ++t) {
+      const float4 v = __ldcg(buf + i);
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+      i += stride;
+      if (i >= n_vec) i -= n_vec;
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 }  // namespace oxg
 
 using namespace oxg;
+
+// Bytes per second read from L2 by all SMs (the store and its hierarchy are L2-resident by design,
+// so this — not HBM — is the memory roofline of the batched neighbour kernels).
+extern "C" int oxg_l2_peak(double* out_bytes_per_s, double* out_ms) {
+  OXG_API_BEGIN
+  if (!out_bytes_per_s) {
+    set_error("out_bytes_per_s is NULL");
+    return OXG_E_NULL;
+  }
+  const size_t bytes = 48ull << 20, n_vec = bytes / sizeof(float4);
+  const int blocks = 148 * 8, threads = 256, passes = 128;
+  float4 *d_buf = nullptr, *d_out = nullptr;
+  OXG_CUDA_TRY(cudaMalloc((void**)&d_buf, bytes));
+  if (cudaMalloc((void**)&d_out, sizeof(float4) * blocks * threads) != cudaSuccess) {
+    cudaFree(d_buf);
+    set_error("cudaMalloc failed");
+    return OXG_E_CUDA;
+  }
+  cudaMemset(d_buf, 0, bytes);
+  cudaEvent_t e0, e1;
+  OXG_CUDA_TRY(cudaEventCreate(&e0));
+  OXG_CUDA_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    OXG_CUDA_TRY(cudaEventRecord(e0, 0));
+    l2_peak_kernel<<<blocks, threads>>>(d_buf, n_vec, passes, d_out);
+    OXG_LAUNCH_CHECK();
+    OXG_CUDA_TRY(cudaEventRecord(e1, 0));
+    OXG_CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    OXG_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_buf);
+  cudaFree(d_out);
+  const size_t per_thread = n_vec / ((size_t)blocks * threads);
+  const double total = (double)per_thread * blocks * threads * passes * sizeof(float4);
+  *out_bytes_per_s = total / (best * 1e-3);
+  if (out_ms) *out_ms = best;
+  return OXG_OK;
+  OXG_API_END
+}
+
 
 // Lane-instructions per second of the FADD2+FFMA2 mix (a packed instruction counts as two
 // lane-instructions; an FMA counts once).  Flop rate of the mix = 1.5 x this figure.
