@@ -601,6 +601,23 @@ __device__ __forceinline__ int knn_scan_tile(const ScanParams& p, uint32_t sp_ad
   int passed = 0;
 #pragma unroll 1
   for (int j = 0; j < cnt; j += 8) {
+    // A step can defer at most 8 candidates per query: make room BEFORE the step (one rarely taken
+    // branch with the only call sites of the exact path), so the step's body is pure arithmetic
+    // and stores and ptxas does not have to keep the call's operands live across it.
+    {
+      bool full = false;
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) full = full || ncand[a] > CAND_CAP - 8;
+      if (full) {
+#pragma unroll
+        for (int a = 0; a < QPT; ++a) {
+          const int li = a * NN_THREADS + tid;
+          thr[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ, 1, g_list[a],
+                                    g_ilist[a], &s_have[li], &s_ubits[li], thr[a]);
+          ncand[a] = 0;
+        }
+      }
+    }
     const uint32_t row = sp_addr + (uint32_t)j * 4u;
     float2 acc[QPT][4];
     if (DOT) {
@@ -661,13 +678,7 @@ __device__ __forceinline__ int knn_scan_tile(const ScanParams& p, uint32_t sp_ad
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           if (av[e] > (DOT ? thr[a].dot : thr[a].diff)) continue;
-          if (ncand[a] == CAND_CAP) {  // buffer full: drain this query now
-            thr[a] = knn_drain_f32<D>(p, qi[a], n1, excl[a], s_cand + li, ncand[a], NQ, 1, g_list[a],
-                                      g_ilist[a], &s_have[li], &s_ubits[li], thr[a]);
-            ncand[a] = 0;
-            if (av[e] > (DOT ? thr[a].dot : thr[a].diff)) continue;
-          }
-          s_cand[li + ncand[a] * NQ] = base + j + e;
+          s_cand[li + ncand[a] * NQ] = base + j + e;  // room for 8 was made at the top of the step
           ++ncand[a];
           ++passed;
         }
