@@ -160,6 +160,11 @@ extern "C" {
     pub fn oxg_so3_nn1(s: oxg_store, queries: *const f64, q: u64, idx: *mut u32, dist: *mut f64) -> c_int;
     pub fn oxg_so3_radius(s: oxg_store, queries: *const f64, q: u64, r: f64, offsets: *mut u64,
                           idx: *mut u32, cap: u64, dist: *mut f64) -> c_int;
+    pub fn oxg_so3_knn(s: oxg_store, queries: *const f64, q: u64, k: u32, exclude_idx: *const u32,
+                       idx: *mut u32, dist: *mut f64) -> c_int;
+    pub fn oxg_so3_rrt_solve(tree: oxg_store, cones: oxg_so3_cones, params: *const oxg_plan_params,
+                             goal_target: *const f64, samples: *const f64, n_samples: u64,
+                             parents: *mut i64, out: *mut oxg_plan_result) -> c_int;
     pub fn oxg_so3_cones_create(cones: *const f64, n_cones: u64, out: *mut oxg_so3_cones) -> c_int;
     pub fn oxg_so3_cones_destroy(cones: oxg_so3_cones) -> c_int;
     pub fn oxg_so3_is_valid(cones: oxg_so3_cones, states: *const f64, q: u64, out: *mut u8) -> c_int;

@@ -44,6 +44,16 @@ int oxg_so3_nn1(oxg_store store, const double* queries /* row-major Q x 4 */, ui
 int oxg_so3_radius(oxg_store store, const double* queries, uint64_t q, double r, uint64_t* offsets,
                    uint32_t* idx, uint64_t cap, double* dist);
 
+/* k nearest stored quaternions by (distance(query, stored), index) ascending -- oxg_knn's contract
+ * (oxg.h; not in the reference, SURVEY F1, semantics pinned by oracle/) under the SO3 metric.
+ * The device finds the k-th largest a of every query; the host turns it into the low end of its
+ * acos plateau; a second device pass gathers the states at or above it (normally exactly k) with
+ * their a; distances and the final order come from the host's libm.  k <= 32.  exclude_idx
+ * (nullable, one per query) removes that stored index; states whose a is NaN never enter; rows
+ * are padded with OXG_INVALID_INDEX / +inf. */
+int oxg_so3_knn(oxg_store store, const double* queries /* row-major Q x 4 */, uint64_t q, uint32_t k,
+                const uint32_t* exclude_idx, uint32_t* idx /* q x k */, double* dist /* q x k */);
+
 /* Declarative form of the reference's SO3 validity fixture (ForbiddenConeChecker,
  * oxmpl/tests/rrt_so3ss_tests.rs:46-56): a state is valid iff distance(centre_c, state) > angle_c
  * for every cone c.  cones is row-major n x 5: (x, y, z, w, angle). */
@@ -59,6 +69,22 @@ int oxg_so3_is_valid(oxg_so3_cones cones, const double* states /* row-major Q x 
  * valid[e] = 1/0; first_invalid (nullable) = 0 when valid, else the 1-based failing step. */
 int oxg_so3_check_motion(oxg_so3_cones cones, const double* from, const double* to, uint64_t e,
                          double resolution, uint8_t* valid, uint32_t* first_invalid);
+
+/* RRT::solve (rrt.rs:158-227) over SO3 for a whole pre-drawn sample stream -- the SO3 counterpart
+ * of oxg_rrt_solve (oxg.h; same params / result / status codes; search_radius and stop_at_goal are
+ * ignored).  `tree` holds the start state at index 0 (or a tree grown by an earlier call, with its
+ * parents[] passed back in); the goal is the ball distance(state, goal_target) <= goal_radius
+ * (SO3GoalRegion, oxmpl/tests/rrt_so3ss_tests.rs:58-68; NULL target or radius < 0: no goal test).
+ * SLERP needs libm, so the loop's steering runs on the host, and the scans and cone tests run on
+ * the device for a CHUNK of samples at a time against the tree as it stood when the chunk began;
+ * samples are committed in order and a chunk is cut at the first sample whose nearest node would
+ * have been a node added inside the chunk (checked exactly), so the tree, parents and iteration
+ * count are those of the one-sample-at-a-time loop.  out->ctas reports the number of chunks,
+ * out->motion_checks_executed the motion checks launched (speculative ones included),
+ * out->device_ms the wall time of the call.  parents: in/out, max_nodes entries. */
+int oxg_so3_rrt_solve(oxg_store tree, oxg_so3_cones cones, const oxg_plan_params* params,
+                      const double* goal_target /* 4 */, const double* samples /* n x 4 */,
+                      uint64_t n_samples, int64_t* parents, oxg_plan_result* out);
 
 #ifdef __cplusplus
 }

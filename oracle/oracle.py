@@ -96,7 +96,10 @@ class Oracle:
             "orc_so3_interpolate": (None, [vp, vp, d, vp]),
             "orc_so3_nn1_batch": (None, [vp, u64, vp, u64, vp, vp]),
             "orc_so3_radius": (u64, [vp, u64, vp, d, vp, vp, u64]),
+            "orc_so3_knn_batch": (None, [vp, u64, vp, u64, C.c_uint32, vp, vp, vp]),
             "orc_so3_is_valid": (C.c_int, [vp, u64, vp]),
+            "orc_so3_rrt": (u64, [vp, u64, vp, d, d, d, vp, u64, u64, vp, vp, C.POINTER(C.c_int),
+                                  C.POINTER(u64)]),
             "orc_so3_check_motion": (C.c_int, [vp, u64, vp, vp, d, C.POINTER(u32)]),
             "orc_build_info": (C.c_int, []),
             "orc_probe_mul_add": (d, [d, d, d]),
@@ -225,6 +228,15 @@ class Oracle:
         self.lib.orc_so3_nn1_batch(_p(rows), rows.shape[0], _p(q), q.shape[0], _p(idx), _p(dist))
         return idx, dist
 
+    def so3_knn(self, rows, queries, k, exclude=None):
+        rows, q = _f64(rows), _f64(np.atleast_2d(queries))
+        idx = np.empty((q.shape[0], k), dtype=np.uint32)
+        dist = np.empty((q.shape[0], k), dtype=np.float64)
+        ex = None if exclude is None else np.ascontiguousarray(exclude, dtype=np.uint32)
+        self.lib.orc_so3_knn_batch(_p(rows), rows.shape[0], _p(q), q.shape[0], k, _p(ex), _p(idx),
+                                   _p(dist))
+        return idx, dist
+
     def so3_radius(self, rows, queries, r):
         rows, q = _f64(rows), _f64(np.atleast_2d(queries))
         N = rows.shape[0]
@@ -241,6 +253,22 @@ class Oracle:
         idx = np.concatenate(idxs) if idxs else np.empty(0, np.uint32)
         dist = np.concatenate(dists) if dists else np.empty(0, np.float64)
         return offsets, idx, dist
+
+    def so3_rrt(self, cones, start, samples, max_distance, resolution, max_nodes, goal_target=None,
+                goal_radius=-1.0):
+        """RRT::solve over SO3 -> (tree rows, parents, solved, iters)."""
+        cones = _f64(np.reshape(cones, (-1, 5)))
+        s = _f64(np.atleast_2d(samples))
+        tree = np.zeros((max_nodes, 4), dtype=np.float64)
+        tree[0] = start
+        parents = np.full(max_nodes, -1, dtype=np.int64)
+        g = None if goal_target is None else _f64(goal_target)
+        solved, iters = C.c_int(0), C.c_uint64(0)
+        n = self.lib.orc_so3_rrt(_p(cones), cones.shape[0], _p(g), float(goal_radius),
+                                 float(max_distance), float(resolution), _p(s), s.shape[0],
+                                 int(max_nodes), _p(tree), _p(parents), C.byref(solved),
+                                 C.byref(iters))
+        return tree[:n].copy(), parents[:n].copy(), bool(solved.value), int(iters.value)
 
     def so3_is_valid(self, cones, states):
         cones, st = _f64(np.reshape(cones, (-1, 5))), _f64(np.atleast_2d(states))

@@ -743,6 +743,40 @@ void orc_so3_nn1_batch(const double* rows, uint64_t N, const double* queries, ui
   }
 }
 
+// k-NN over SO3 -- orc_knn's definition (the reference has no k-NN) with
+// SO3StateSpace::distance(q, store[i]), so3_state_space.rs:102-112.
+void orc_so3_knn_batch(const double* rows, uint64_t N, const double* queries, uint64_t Q, uint32_t k,
+                       const uint32_t* exclude, uint32_t* idx, double* dist) {
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int64_t qi = 0; qi < (int64_t)Q; ++qi) {
+    const double* q = queries + (uint64_t)qi * 4;
+    uint32_t* out_idx = idx + (uint64_t)qi * k;
+    double* out_dist = dist + (uint64_t)qi * k;
+    const uint32_t ex = exclude ? exclude[qi] : 0xFFFFFFFFu;
+    uint32_t have = 0;
+    for (uint32_t e = 0; e < k; ++e) {
+      out_idx[e] = 0xFFFFFFFFu;
+      out_dist[e] = std::numeric_limits<double>::infinity();
+    }
+    if (k == 0) continue;
+    for (uint64_t i = 0; i < N; ++i) {
+      if ((uint32_t)i == ex) continue;
+      double d = orc_so3_distance(q, rows + i * 4);
+      if (!(d == d)) continue;
+      if (have == k && !(d < out_dist[k - 1])) continue;
+      uint32_t pos = have < k ? have : k - 1;
+      while (pos > 0 && d < out_dist[pos - 1]) {
+        out_dist[pos] = out_dist[pos - 1];
+        out_idx[pos] = out_idx[pos - 1];
+        --pos;
+      }
+      out_dist[pos] = d;
+      out_idx[pos] = (uint32_t)i;
+      if (have < k) ++have;
+    }
+  }
+}
+
 // radius loop of rrt_star.rs:121-131 with distance(q, store[i]) < r; returns the count, writes
 // at most cap entries (ascending index).
 uint64_t orc_so3_radius(const double* rows, uint64_t N, const double* q, double r, uint32_t* idx,
@@ -873,5 +907,49 @@ int orc_build_info(void) {
 // A contraction-sensitive probe: returns a*b+c computed with separate roundings.  With
 // a = 1+2^-27, b = 1+2^-27, c = -1 an FMA gives 2^-26 + 2^-54, separate ops give 2^-26.
 double orc_probe_mul_add(double a, double b, double c) { return a * b + c; }
+
+// RRT::solve over SO3 -- rrt.rs:158-227 with SO3StateSpace::distance / interpolate and the
+// ForbiddenConeChecker / SO3GoalRegion fixtures (oxmpl/tests/rrt_so3ss_tests.rs:46-68); same
+// conventions as orc_rrt.  goal_target NULL: no goal test.
+uint64_t orc_so3_rrt(const double* cones, uint64_t n_cones, const double* goal_target,
+                     double goal_radius, double max_distance, double resolution,
+                     const double* samples, uint64_t n_samples, uint64_t max_nodes,
+                     double* tree_states, int64_t* parents, int* solved, uint64_t* iters) {
+  uint64_t n = 1;
+  parents[0] = -1;
+  *solved = 0;
+  uint64_t it = 0;
+  for (; it < n_samples && n < max_nodes; ++it) {
+    const double* q_rand = samples + it * 4;
+    uint32_t near = 0;
+    double min_dist = orc_so3_distance(tree_states, q_rand);  // rrt.rs:187-196
+    for (uint64_t i = 1; i < n; ++i) {
+      double d = orc_so3_distance(tree_states + i * 4, q_rand);
+      if (d < min_dist) {
+        min_dist = d;
+        near = (uint32_t)i;
+      }
+    }
+    const double* q_near = tree_states + (uint64_t)near * 4;
+    double q_new[4];
+    if (min_dist > max_distance) {  // rrt.rs:200-208
+      orc_so3_interpolate(q_near, q_rand, max_distance / min_dist, q_new);
+    } else {
+      std::memcpy(q_new, q_rand, sizeof(q_new));
+    }
+    if (orc_so3_check_motion(cones, n_cones, q_near, q_new, resolution, nullptr) == 1) {
+      std::memcpy(tree_states + n * 4, q_new, sizeof(q_new));
+      parents[n] = near;
+      ++n;
+      if (goal_target && orc_so3_distance(q_new, goal_target) <= goal_radius) {
+        *solved = 1;
+        ++it;
+        break;
+      }
+    }
+  }
+  *iters = it;
+  return n;
+}
 
 }  // extern "C"

@@ -198,6 +198,11 @@ SIGNATURES = {
     # include/oxg_so3.h
     "oxg_so3_nn1": (C.c_int, [_vp, _pd, _u64, _pu32, _pd]),
     "oxg_so3_radius": (C.c_int, [_vp, _pd, _u64, _dbl, _pu64, _pu32, _u64, _pd]),
+    "oxg_so3_knn": (C.c_int, [_vp, _pd, _u64, C.c_uint32, _pu32, _pu32, _pd]),
+    "oxg_so3_rrt_solve": (
+        C.c_int,
+        [_vp, _vp, C.POINTER(PlanParams), _pd, _pd, _u64, _vp, C.POINTER(PlanResult)],
+    ),
     "oxg_so3_cones_create": (C.c_int, [_pd, _u64, C.POINTER(_vp)]),
     "oxg_so3_cones_destroy": (C.c_int, [_vp]),
     "oxg_so3_is_valid": (C.c_int, [_vp, _pd, _u64, _pu8]),

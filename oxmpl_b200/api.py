@@ -251,6 +251,17 @@ class StateStore:
         check(lib.oxg_so3_nn1(self._h, _ptr(q), q.shape[0], _ptr(idx), _ptr(dist)))
         return idx, dist
 
+    def so3_knn(self, queries, k: int, exclude=None):
+        """k nearest stored quaternions by (SO3 distance, index) ascending (``oxg_so3_knn``)."""
+        q = _f64(np.atleast_2d(queries), 4)
+        ex = None if exclude is None else np.ascontiguousarray(exclude, dtype=np.uint32)
+        if ex is not None and ex.shape != (q.shape[0],):
+            raise ValueError("exclude needs one index per query")
+        idx = np.empty((q.shape[0], k), dtype=np.uint32)
+        dist = np.empty((q.shape[0], k), dtype=np.float64)
+        check(lib.oxg_so3_knn(self._h, _ptr(q), q.shape[0], int(k), _ptr(ex), _ptr(idx), _ptr(dist)))
+        return idx, dist
+
     def so3_radius(self, queries, r: float, want_dist: bool = False):
         """Radius scan ``distance(query, stored) < r`` over SO3 -> CSR (offsets, idx[, dist])."""
         q = _f64(np.atleast_2d(queries), 4)
@@ -503,6 +514,24 @@ def rrt_solve(world: World, tree: StateStore, samples, max_distance: float, reso
     check(lib.oxg_rrt_solve(world.handle, tree.handle, C.byref(prm), _ptr(g), _ptr(s), s.shape[0],
                             _ptr(parents), C.byref(res)))
     return parents[: int(res.n_nodes[0])].copy(), _plan_result(res)
+
+
+def so3_rrt_solve(cones: "So3Cones", tree: StateStore, samples, max_distance: float, resolution: float,
+                  max_nodes: int, goal_target=None, goal_radius: float = -1.0, timeout_s: float = 0.0,
+                  parents=None):
+    """RRT::solve over SO3 (``oxg_so3_rrt_solve``): speculative chunks of samples per device call,
+    results those of the one-sample-at-a-time loop.  ``parents`` continues an earlier call's tree.
+    Returns (parents i64[n], result dict); ``result["ctas"]`` is the number of chunks."""
+    s = _f64(np.atleast_2d(samples), 4)
+    g = None if goal_target is None else _f64(goal_target)
+    prm = _plan_params(max_distance, resolution, max_nodes, goal_radius, timeout_s=timeout_s)
+    par = np.full(max_nodes, -1, dtype=np.int64)
+    if parents is not None:
+        par[: len(parents)] = parents
+    res = _lib.PlanResult()
+    check(lib.oxg_so3_rrt_solve(tree.handle, cones._h, C.byref(prm), _ptr(g), _ptr(s), s.shape[0],
+                                _ptr(par), C.byref(res)))
+    return par[: int(res.n_nodes[0])].copy(), _plan_result(res)
 
 
 def rrt_connect_solve(world: World, start_tree: StateStore, goal_tree: StateStore, samples,

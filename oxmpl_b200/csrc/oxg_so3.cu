@@ -4,6 +4,9 @@
 // The device works only on a = |q1 . q2| (exactly reproducible); everything that involves libm
 // (acos, sin) runs on the host with the caller's libm, and every distance comparison is turned into
 // an exact threshold on `a` by a monotone search over f64 bit patterns.  See the header.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <limits>
 #include <vector>
@@ -35,8 +38,11 @@ struct So3Params {
   uint32_t nsplit;
   const double* queries;  // device, row-major Q x 4
   uint64_t Q;
-  const double* thr;  // MODE_FIRST: per-query threshold on a
-  double thr_all;     // radius kernels: one threshold
+  const double* thr;  // MODE_FIRST / k-NN gather: per-query threshold on a (radius: nullable)
+  double thr_all;     // radius kernels: one threshold (used when thr is NULL)
+  const uint32_t* exclude;  // k-NN: per-query stored index left out (nullable)
+  uint32_t k;               // k-NN: list length (<= 32)
+  double* part_a;           // k-NN: [Q][nsplit][SO3_WARPS][32] descending partial lists
   long long* part_key;  // [Q][nsplit] bits of the best a (MODE_BEST)
   uint32_t* part_idx;   // [Q][nsplit]
   uint32_t* counts;         // radius: [Q][nsplit]
@@ -60,6 +66,94 @@ __device__ __forceinline__ void so3_stage_queries(const So3Params& p, double (*s
     const int a = threadIdx.x >> 2, c = threadIdx.x & 3;
     s_q[a][c] = a < qn ? p.queries[(q0 + a) * 4 + c] : 0.0;  // qn <= SO3_QC
   }
+}
+
+// Per-query threshold (p.thr, else the common p.thr_all) and excluded index (p.exclude, else none).
+__device__ __forceinline__ void so3_stage_limits(const So3Params& p, double* s_thr, uint32_t* s_ex,
+                                                 uint64_t q0, int qn) {
+  if (threadIdx.x < SO3_QC) {
+    const int a = threadIdx.x;
+    s_thr[a] = a < qn && p.thr ? p.thr[q0 + a] : p.thr_all;
+    s_ex[a] = a < qn && p.exclude ? p.exclude[q0 + a] : 0xFFFFFFFFu;
+  }
+}
+
+// Inserts x into a warp's descending list (lane l holds the (l+1)-th largest value seen, -1 =
+// empty; equal values are all kept: the list is a multiset) and returns the new k-th largest.
+__device__ __forceinline__ double so3_list_insert(double& mine, double x, int lane, uint32_t k) {
+  const int pos = __popc(__ballot_sync(0xFFFFFFFFu, mine >= x));  // entries >= x form a prefix
+  const double up = __shfl_up_sync(0xFFFFFFFFu, mine, 1);
+  if (lane == pos) mine = x;
+  else if (lane > pos) mine = up;
+  return __shfl_sync(0xFFFFFFFFu, mine, (int)k - 1);
+}
+
+// k-NN, pass 1: the k largest a of every (query, slice, warp), NaN and the excluded index left
+// out.  Only the VALUE of the k-th largest a of a query is needed (see oxg_so3_knn): the states
+// that can be among the k nearest are those with a >= the low end of its acos plateau.
+template <int QN>
+__global__ void __launch_bounds__(SO3_THREADS) so3_kth_kernel(const So3Params p) {
+  __shared__ double s_q[SO3_QC][4];
+  __shared__ double s_thr[SO3_QC];
+  __shared__ uint32_t s_ex[SO3_QC];
+  const uint64_t q0 = (uint64_t)blockIdx.x * QN;
+  const int qn = (int)min((uint64_t)QN, p.Q - q0);
+  so3_stage_queries(p, s_q, q0, qn);
+  so3_stage_limits(p, s_thr, s_ex, q0, qn);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n0 = blockIdx.y * p.split_len;
+  const uint32_t n1 = min(p.n, n0 + p.split_len);
+  double list[QN], kth[QN];
+#pragma unroll
+  for (int a = 0; a < QN; ++a) list[a] = kth[a] = -1.0;
+  for (uint32_t base = n0; base < n1; base += SO3_THREADS) {
+    const uint32_t i = base + threadIdx.x;
+    const bool live = i < n1;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[c] = __ldg(p.col[c] + i);
+    }
+#pragma unroll
+    for (int a = 0; a < QN; ++a) {
+      const double v = so3_absdot(s, s_q[a]);
+      // strict: once the list is full an equal value cannot change the k-th largest
+      uint32_t bal = __ballot_sync(0xFFFFFFFFu, live && a < qn && i != s_ex[a] && v > kth[a]);
+      while (bal) {
+        const int src = __ffs(bal) - 1;
+        bal &= bal - 1;
+        const double x = __shfl_sync(0xFFFFFFFFu, v, src);
+        if (x > kth[a]) kth[a] = so3_list_insert(list[a], x, lane, p.k);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < QN; ++a) {
+    if (a < qn)
+      p.part_a[((((size_t)(q0 + a) * p.nsplit + blockIdx.y) * SO3_WARPS) + warp) * 32 + lane] = list[a];
+  }
+}
+
+// k-NN, pass 1 merge: one warp per query folds the partial lists; out_a[q] = the k-th largest a,
+// or -1 when fewer than k states qualify.
+__global__ void __launch_bounds__(128) so3_kth_final_kernel(const So3Params p) {
+  const uint64_t q = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (q >= p.Q) return;
+  const int lane = threadIdx.x & 31;
+  const double* src = p.part_a + (size_t)q * p.nsplit * SO3_WARPS * 32;
+  double list = -1.0, kth = -1.0;
+  for (uint32_t r = 0; r < p.nsplit * SO3_WARPS; ++r) {
+    const double v = src[(size_t)r * 32 + lane];
+    uint32_t bal = __ballot_sync(0xFFFFFFFFu, v > kth);
+    while (bal) {
+      const int from = __ffs(bal) - 1;
+      bal &= bal - 1;
+      const double x = __shfl_sync(0xFFFFFFFFu, v, from);
+      if (x > kth) kth = so3_list_insert(list, x, lane, p.k);
+    }
+  }
+  if (lane == 0) p.out_a[q] = kth;
 }
 
 // MODE_BEST : per (query, slice) the largest a, lowest index on ties.  The hot loop compares a as
@@ -229,10 +323,13 @@ __global__ void __launch_bounds__(128) so3_final_kernel(const So3Params p) {
 template <bool FILL, int QN>
 __global__ void __launch_bounds__(SO3_THREADS) so3_radius_kernel(const So3Params p) {
   __shared__ double s_q[SO3_QC][4];
+  __shared__ double s_thr[SO3_QC];
+  __shared__ uint32_t s_ex[SO3_QC];
   __shared__ uint32_t s_w[SO3_QC][SO3_WARPS];
   const uint64_t q0 = (uint64_t)blockIdx.x * QN;
   const int qn = (int)min((uint64_t)QN, p.Q - q0);
   so3_stage_queries(p, s_q, q0, qn);
+  so3_stage_limits(p, s_thr, s_ex, q0, qn);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n0 = blockIdx.y * p.split_len;
@@ -253,7 +350,7 @@ __global__ void __launch_bounds__(SO3_THREADS) so3_radius_kernel(const So3Params
 #pragma unroll
     for (int a = 0; a < QN; ++a) {
       v[a] = so3_absdot(s, s_q[a]);
-      bal[a] = __ballot_sync(0xFFFFFFFFu, live && a < qn && v[a] >= p.thr_all);
+      bal[a] = __ballot_sync(0xFFFFFFFFu, live && a < qn && v[a] >= s_thr[a] && i != s_ex[a]);
     }
     if (!FILL) {
 #pragma unroll
@@ -464,6 +561,56 @@ void launch_so3_radius(int qn, dim3 grid, cudaStream_t st, const So3Params& p) {
   }
 }
 
+// Count and fill passes of so3_radius_kernel for the thresholds / exclusions set in p.  On return
+// offsets[q] .. offsets[q + 1] delimit query q's hits (ascending index) in p.out_idx = B_PIDX and,
+// if want_a, their a in p.out_a = B_PDIST (both still on the device, fill enqueued on the stream).
+int so3_gather(oxg_store_s* s, So3Params& p, int qn, bool want_a, uint64_t* offsets, uint64_t cap,
+               uint64_t* total_out) {
+  const uint64_t Q = p.Q;
+  const size_t np = (size_t)Q * p.nsplit;
+  OXG_TRY(s->buf[B_COUNTS].ensure(np * sizeof(uint32_t)));
+  OXG_TRY(s->buf[B_OFFSETS].ensure(np * sizeof(uint64_t)));
+  p.counts = s->buf[B_COUNTS].as<uint32_t>();
+  const uint64_t qchunks = (Q + qn - 1) / qn;
+  dim3 grid((unsigned)qchunks, p.nsplit);
+  OXG_CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+  launch_so3_radius<false>(qn, grid, s->stream, p);
+  OXG_LAUNCH_CHECK();
+  std::vector<uint32_t> counts(np);
+  OXG_CUDA_TRY(cudaMemcpyAsync(counts.data(), p.counts, np * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                               s->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  std::vector<uint64_t> slice_off(np);
+  uint64_t total = 0;
+  offsets[0] = 0;
+  for (uint64_t q = 0; q < Q; ++q) {
+    for (uint32_t sl = 0; sl < p.nsplit; ++sl) {
+      slice_off[q * p.nsplit + sl] = total;
+      total += counts[q * p.nsplit + sl];
+    }
+    offsets[q + 1] = total;
+  }
+  *total_out = total;
+  if (total > cap) {
+    set_error("radius result needs %llu entries, capacity is %llu", (unsigned long long)total,
+              (unsigned long long)cap);
+    return OXG_E_CAPACITY;
+  }
+  if (total == 0) return OXG_OK;
+  OXG_CUDA_TRY(cudaMemcpyAsync(s->buf[B_OFFSETS].p, slice_off.data(), np * sizeof(uint64_t),
+                               cudaMemcpyHostToDevice, s->stream));
+  OXG_TRY(s->buf[B_PIDX].ensure(total * sizeof(uint32_t)));
+  if (want_a) OXG_TRY(s->buf[B_PDIST].ensure(total * sizeof(double)));
+  p.offsets = s->buf[B_OFFSETS].as<uint64_t>();
+  p.out_idx = s->buf[B_PIDX].as<uint32_t>();
+  p.out_a = want_a ? s->buf[B_PDIST].as<double>() : nullptr;
+  launch_so3_radius<true>(qn, grid, s->stream, p);
+  OXG_LAUNCH_CHECK();
+  OXG_CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+  // slice_off is pageable host memory: the copy above is staged before the call returns
+  return OXG_OK;
+}
+
 int so3_upload(oxg_store_s* s, StoreBuf which, const void* src, size_t bytes) {
   OXG_TRY(s->buf[which].ensure(bytes));
   OXG_CUDA_TRY(cudaMemcpyAsync(s->buf[which].p, src, bytes, cudaMemcpyHostToDevice, s->stream));
@@ -555,6 +702,98 @@ int oxg_so3_nn1(oxg_store s, const double* queries, uint64_t Q, uint32_t* idx, d
   OXG_API_END
 }
 
+int oxg_so3_knn(oxg_store s, const double* queries, uint64_t Q, uint32_t k, const uint32_t* exclude_idx,
+                uint32_t* idx, double* dist) {
+  OXG_API_BEGIN
+  OXG_TRY(so3_check_store(s));
+  if ((Q > 0 && !queries) || (Q > 0 && k > 0 && (!idx || !dist))) {
+    set_error("NULL argument");
+    return OXG_E_NULL;
+  }
+  if (k > 32) {
+    set_error("SO3 k-NN supports k <= 32 (got %u)", k);
+    return OXG_E_ARG;
+  }
+  if (Q > 0x3FFFFFFFull) {
+    set_error("too many queries in one call");
+    return OXG_E_ARG;
+  }
+  if (Q == 0 || k == 0) return OXG_OK;
+  for (uint64_t i = 0; i < Q * k; ++i) {
+    idx[i] = OXG_INVALID_INDEX;
+    dist[i] = std::numeric_limits<double>::infinity();
+  }
+  if (s->size == 0) return OXG_OK;
+  OXG_CUDA_TRY(cudaSetDevice(s->device));
+  OXG_TRY(so3_upload(s, B_QUERY, queries, Q * 4 * sizeof(double)));
+  if (exclude_idx) OXG_TRY(so3_upload(s, B_AUX, exclude_idx, Q * sizeof(uint32_t)));
+  So3Params p{};
+  const int qn = so3_qn(Q);
+  so3_plan(s, Q, p, qn);
+  p.queries = s->buf[B_QUERY].as<double>();
+  p.exclude = exclude_idx ? s->buf[B_AUX].as<uint32_t>() : nullptr;
+  p.k = k;
+  // pass 1: A_k = the k-th largest a of every query (-1: fewer than k candidates)
+  OXG_TRY(s->buf[B_PDIST].ensure((size_t)Q * p.nsplit * SO3_WARPS * 32 * sizeof(double)));
+  OXG_TRY(s->buf[B_ODIST].ensure(Q * sizeof(double)));
+  p.part_a = s->buf[B_PDIST].as<double>();
+  p.out_a = s->buf[B_ODIST].as<double>();
+  const uint64_t qchunks = (Q + qn - 1) / qn;
+  dim3 grid((unsigned)qchunks, p.nsplit);
+  switch (qn) {
+    case 1: so3_kth_kernel<1><<<grid, SO3_THREADS, 0, s->stream>>>(p); break;
+    case 2: so3_kth_kernel<2><<<grid, SO3_THREADS, 0, s->stream>>>(p); break;
+    case 4: so3_kth_kernel<4><<<grid, SO3_THREADS, 0, s->stream>>>(p); break;
+    default: so3_kth_kernel<SO3_QC><<<grid, SO3_THREADS, 0, s->stream>>>(p); break;
+  }
+  OXG_LAUNCH_CHECK();
+  so3_kth_final_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, s->stream>>>(p);
+  OXG_LAUNCH_CHECK();
+  std::vector<double> thr(Q);
+  OXG_CUDA_TRY(cudaMemcpyAsync(thr.data(), p.out_a, Q * sizeof(double), cudaMemcpyDeviceToHost,
+                               s->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  // Host: the k-th smallest distance is f(A_k); every state at most that far has
+  // a >= min{x : f(x) == f(A_k)} (f is non-increasing), and nothing else can be in the list.
+  const double clamp_lo = std::nextafter(1.0 - 1e-9, 2.0);  // f == 0 from here up
+  for (uint64_t q = 0; q < Q; ++q) {
+    const double av = thr[q];
+    if (av < 0.0) thr[q] = 0.0;  // fewer than k candidates: all of them (NaN a never passes)
+    else if (av > 1.0 - 1e-9) thr[q] = clamp_lo;
+    else thr[q] = so3_plateau_low(av);
+  }
+  // pass 2: gather those states (ascending index) with their a
+  OXG_TRY(so3_upload(s, B_AUX2, thr.data(), Q * sizeof(double)));
+  p.thr = s->buf[B_AUX2].as<double>();
+  std::vector<uint64_t> off(Q + 1);
+  uint64_t total = 0;
+  OXG_TRY(so3_gather(s, p, qn, true, off.data(), ~0ull, &total));
+  if (total == 0) return OXG_OK;
+  std::vector<uint32_t> hi(total);
+  std::vector<double> ha(total);
+  OXG_CUDA_TRY(cudaMemcpyAsync(hi.data(), p.out_idx, total * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                               s->stream));
+  OXG_CUDA_TRY(cudaMemcpyAsync(ha.data(), p.out_a, total * sizeof(double), cudaMemcpyDeviceToHost,
+                               s->stream));
+  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  // Host: distances from libm; stable order by distance keeps the ascending index inside a tie.
+  std::vector<uint32_t> order;
+  for (uint64_t q = 0; q < Q; ++q) {
+    const uint64_t b = off[q], n = off[q + 1] - off[q];
+    for (uint64_t e = 0; e < n; ++e) ha[b + e] = so3_f(ha[b + e]);
+    order.resize(n);
+    for (uint64_t e = 0; e < n; ++e) order[e] = (uint32_t)e;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](uint32_t x, uint32_t y) { return ha[b + x] < ha[b + y]; });
+    for (uint64_t e = 0; e < n && e < k; ++e) {
+      idx[q * k + e] = hi[b + order[e]];
+      dist[q * k + e] = ha[b + order[e]];
+    }
+  }
+  return OXG_OK;
+  OXG_API_END
+}
+
 int oxg_so3_radius(oxg_store s, const double* queries, uint64_t Q, double r, uint64_t* offsets,
                    uint32_t* idx, uint64_t cap, double* dist) {
   OXG_API_BEGIN
@@ -582,44 +821,9 @@ int oxg_so3_radius(oxg_store s, const double* queries, uint64_t Q, double r, uin
   so3_plan(s, Q, p, qn);
   p.queries = s->buf[B_QUERY].as<double>();
   p.thr_all = thr;
-  const size_t np = (size_t)Q * p.nsplit;
-  OXG_TRY(s->buf[B_COUNTS].ensure(np * sizeof(uint32_t)));
-  OXG_TRY(s->buf[B_OFFSETS].ensure(np * sizeof(uint64_t)));
-  p.counts = s->buf[B_COUNTS].as<uint32_t>();
-  const uint64_t qchunks = (Q + qn - 1) / qn;
-  dim3 grid((unsigned)qchunks, p.nsplit);
-  OXG_CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
-  launch_so3_radius<false>(qn, grid, s->stream, p);
-  OXG_LAUNCH_CHECK();
-  std::vector<uint32_t> counts(np);
-  OXG_CUDA_TRY(cudaMemcpyAsync(counts.data(), p.counts, np * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                               s->stream));
-  OXG_CUDA_TRY(cudaStreamSynchronize(s->stream));
-  std::vector<uint64_t> slice_off(np);
   uint64_t total = 0;
-  for (uint64_t q = 0; q < Q; ++q) {
-    for (uint32_t sl = 0; sl < p.nsplit; ++sl) {
-      slice_off[q * p.nsplit + sl] = total;
-      total += counts[q * p.nsplit + sl];
-    }
-    offsets[q + 1] = total;
-  }
-  if (total > cap || (total > 0 && !idx)) {
-    set_error("radius result needs %llu entries, capacity is %llu", (unsigned long long)total,
-              (unsigned long long)cap);
-    return OXG_E_CAPACITY;
-  }
+  OXG_TRY(so3_gather(s, p, qn, dist != nullptr, offsets, idx ? cap : 0, &total));
   if (total == 0) return OXG_OK;
-  OXG_CUDA_TRY(cudaMemcpyAsync(s->buf[B_OFFSETS].p, slice_off.data(), np * sizeof(uint64_t),
-                               cudaMemcpyHostToDevice, s->stream));
-  OXG_TRY(s->buf[B_PIDX].ensure(total * sizeof(uint32_t)));
-  if (dist) OXG_TRY(s->buf[B_PDIST].ensure(total * sizeof(double)));
-  p.offsets = s->buf[B_OFFSETS].as<uint64_t>();
-  p.out_idx = s->buf[B_PIDX].as<uint32_t>();
-  p.out_a = dist ? s->buf[B_PDIST].as<double>() : nullptr;
-  launch_so3_radius<true>(qn, grid, s->stream, p);
-  OXG_LAUNCH_CHECK();
-  OXG_CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
   OXG_CUDA_TRY(cudaMemcpyAsync(idx, p.out_idx, total * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                s->stream));
   if (dist)
@@ -772,6 +976,119 @@ int oxg_so3_check_motion(oxg_so3_cones c, const double* from, const double* to, 
     valid[e] = bad == 0;
     if (first_invalid) first_invalid[e] = bad;
   }
+  return OXG_OK;
+  OXG_API_END
+}
+
+// RRT over SO3 (rrt.rs:158-227) on a pre-drawn sample stream.  The loop is sequential -- the
+// nearest node of sample j may be a node that sample j-1 added -- but most samples' nearest node is
+// an OLD one, so it runs in speculative chunks: one 1-NN launch and one cone launch serve m
+// samples against the tree as it stood when the chunk began; the samples are then committed in
+// order, and the first one whose nearest node turns out to be a node added earlier in the same
+// chunk (host test on <= m new nodes, the same distance function) ends the chunk and is redone
+// at the head of the next.  The result is the sequential loop's, iteration for iteration.
+int oxg_so3_rrt_solve(oxg_store tree, oxg_so3_cones cones, const oxg_plan_params* params,
+                      const double* goal_target, const double* samples, uint64_t n_samples,
+                      int64_t* parents, oxg_plan_result* out) {
+  OXG_API_BEGIN
+  OXG_TRY(so3_check_store(tree));
+  if (!cones || !params || !out || !parents || (n_samples > 0 && !samples)) {
+    set_error("NULL argument");
+    return OXG_E_NULL;
+  }
+  if (!(params->resolution > 0.0)) {
+    set_error("resolution must be > 0 (the reference loop would not terminate)");
+    return OXG_E_RESOLUTION;
+  }
+  if (tree->size == 0) {
+    set_error("the tree must hold the start state at index 0");
+    return OXG_E_EMPTY;
+  }
+  if (params->max_nodes < tree->size || params->max_nodes > 0x3FFFFFFFull) {
+    set_error("max_nodes must lie in [tree size, 2^30)");
+    return OXG_E_ARG;
+  }
+  const auto t_begin = std::chrono::steady_clock::now();
+  *out = oxg_plan_result{};
+  out->goal_node[0] = out->goal_node[1] = -1;
+  const bool has_goal = goal_target && params->goal_radius >= 0.0;
+  const double maxd = params->max_distance;
+  uint64_t n = tree->size;
+  std::vector<double> nodes(n * 4);
+  OXG_TRY(oxg_store_read(tree, 0, n, nodes.data()));
+  nodes.reserve(std::min<uint64_t>(params->max_nodes, n + n_samples) * 4);
+  uint64_t cursor = 0, chunk = 8, chunks = 0;
+  std::vector<uint32_t> near;
+  std::vector<double> dist, from, to;
+  std::vector<uint8_t> valid;
+  int status = 1;
+  while (cursor < n_samples) {
+    if (n >= params->max_nodes) {
+      status = 2;
+      break;
+    }
+    if (params->timeout_s > 0.0 &&
+        std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count() >
+            params->timeout_s) {
+      status = 3;
+      break;
+    }
+    const uint64_t m = std::min<uint64_t>({chunk, n_samples - cursor, params->max_nodes - n});
+    const double* q = samples + cursor * 4;
+    near.resize(m);
+    dist.resize(m);
+    from.resize(m * 4);
+    to.resize(m * 4);
+    valid.resize(m);
+    OXG_TRY(oxg_so3_nn1(tree, q, m, near.data(), dist.data()));
+    for (uint64_t j = 0; j < m; ++j) {  // steering, rrt.rs:200-208
+      const double* qn = nodes.data() + (size_t)near[j] * 4;
+      std::copy(qn, qn + 4, from.begin() + j * 4);
+      if (dist[j] > maxd) so3_interpolate_host(qn, q + j * 4, maxd / dist[j], to.data() + j * 4);
+      else std::copy(q + j * 4, q + j * 4 + 4, to.begin() + j * 4);
+    }
+    OXG_TRY(oxg_so3_check_motion(cones, from.data(), to.data(), m, params->resolution, valid.data(),
+                                 nullptr));
+    ++chunks;
+    const uint64_t n_before = n;
+    uint64_t done = 0;
+    bool solved = false;
+    for (; done < m && !solved; ++done) {
+      bool stale = false;  // a node of this chunk is strictly nearer than the old tree's winner
+      for (uint64_t p = n_before; p < n && !stale; ++p)
+        stale = so3_distance_host(nodes.data() + p * 4, q + done * 4) < dist[done];
+      if (stale) break;
+      ++out->motion_checks;
+      if (!valid[done]) continue;
+      nodes.insert(nodes.end(), to.begin() + done * 4, to.begin() + done * 4 + 4);
+      parents[n] = near[done];
+      ++n;
+      if (has_goal && so3_distance_host(to.data() + done * 4, goal_target) <= params->goal_radius) {
+        solved = true;
+        out->goal_node[0] = (int64_t)n - 1;
+      }
+    }
+    out->motion_checks_executed += m;
+    cursor += done;
+    if (n > n_before) {
+      uint64_t first = 0;
+      OXG_TRY(oxg_store_append(tree, nodes.data() + n_before * 4, n - n_before, &first));
+    }
+    if (solved) {
+      status = 0;
+      break;
+    }
+    // a chunk that committed everything earns a longer one; a cut one restarts near its length
+    chunk = done == m ? std::min<uint64_t>(chunk * 2, 1024) : std::max<uint64_t>(done, 4);
+  }
+  if (status == 1 && n >= params->max_nodes && cursor < n_samples) status = 2;
+  out->n_nodes[0] = n;
+  out->iters = cursor;
+  out->solved = status == 0;
+  out->status = status;
+  out->ctas = (int32_t)std::min<uint64_t>(chunks, 0x7FFFFFFF);
+  out->device_ms =
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
   return OXG_OK;
   OXG_API_END
 }

@@ -137,8 +137,43 @@ class RRT(_TreePlanner):
         self.nodes = [self.pd.start_state]
         self.parents = [-1]
 
+    so3_chunk = 1024
+
+    def _solve_so3_chunked(self, timeout_secs: float) -> Path:
+        """Ball goal: ``oxg_so3_rrt_solve`` consumes a pre-drawn stream in speculative chunks (one
+        1-NN launch + one cone launch per chunk instead of per iteration, include/oxg_so3.h)."""
+        pd, res = self.pd, self._resolution()
+        par = np.asarray(self.parents, dtype=np.int64)
+        t0 = time.perf_counter()
+        while True:
+            left = timeout_secs - (time.perf_counter() - t0)
+            if left <= 0:
+                raise PlanningError(PlanningError.TIMEOUT)
+            stream = np.empty((self.so3_chunk, 4))
+            for i in range(self.so3_chunk):                        # rrt.rs:177-184, ahead of time
+                q = pd.goal.sample_goal() if self.rng.random() < self.goal_bias \
+                    else pd.space.sample_uniform(self.rng)
+                stream[i] = q.values
+            par, r = api.so3_rrt_solve(self.vc.cones, self.tree, stream, self.max_distance, res,
+                                       self.max_nodes, goal_target=pd.goal.target.values,
+                                       goal_radius=pd.goal.radius, timeout_s=left, parents=par)
+            for row in self.tree.read(len(self.nodes)):
+                self.nodes.append(SO3State(*row))
+            self.parents = [int(v) for v in par]
+            self.last_result = r
+            if r["solved"]:
+                out, node = [], r["goal_node"][0]
+                while node >= 0:
+                    out.append(self.nodes[node])
+                    node = self.parents[node]
+                return Path(out[::-1])
+            if r["status"] in ("timeout", "tree_full"):
+                raise PlanningError(PlanningError.TIMEOUT)
+
     def _solve_so3(self, timeout_secs: float) -> Path:
         pd, space = self.pd, self.pd.space
+        if hasattr(pd.goal, "target") and hasattr(pd.goal, "radius"):
+            return self._solve_so3_chunked(timeout_secs)
         res = self._resolution()
         t0 = time.perf_counter()
         while time.perf_counter() - t0 <= timeout_secs:          # rrt.rs:170-225

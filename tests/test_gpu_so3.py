@@ -99,6 +99,90 @@ def test_so3_nn1_plateaus_clamp_and_nan(oxg, orc):
     assert idx[0] == oidx[0] == expected and idx[1] == oidx[1]
 
 
+@pytest.mark.parametrize("n,q,k", [(1, 1, 1), (5, 3, 8), (255, 3, 10), (20000, 50, 10), (5003, 3001, 4),
+                                   (300000, 9, 32), (70000, 1, 10), (33, 40, 32)])
+def test_so3_knn_random(oxg, orc, n, q, k):
+    rng = np.random.default_rng(n + q + k)
+    rows, qs = _unit(rng, n), _unit(rng, q)
+    qs[::7] = rows[rng.integers(0, n, size=len(qs[::7]))]        # exact members (distance 0)
+    with _store(oxg, rows) as st:
+        idx, dist = st.so3_knn(qs, k)
+        ex = rng.integers(0, n, size=q).astype(np.uint32)
+        ex[::3] = 0xFFFFFFFF
+        idx_e, dist_e = st.so3_knn(qs, k, exclude=ex)
+        i1, d1 = st.so3_nn1(qs)
+    oidx, odist = orc.so3_knn(rows, qs, k)
+    np.testing.assert_array_equal(idx, oidx)
+    np.testing.assert_array_equal(_bits(dist), _bits(odist))
+    oidx, odist = orc.so3_knn(rows, qs, k, exclude=ex)
+    np.testing.assert_array_equal(idx_e, oidx)
+    np.testing.assert_array_equal(_bits(dist_e), _bits(odist))
+    np.testing.assert_array_equal(idx[:, 0], i1)                   # the list starts at the 1-NN
+    np.testing.assert_array_equal(_bits(dist[:, 0]), _bits(d1))
+
+
+def test_so3_knn_plateaus_clamp_nan_and_duplicates(oxg, orc):
+    plat = _plateau(0.3, width=5)
+    cases = []
+    # members of one acos plateau order by index, not by a; the k-th sits inside the plateau
+    cases.append([plat[4], 0.1, plat[0], plat[3], 0.31, plat[1], plat[2], 0.29])
+    cases.append([0.1, plat[-2], 0.2, plat[-1]])
+    # next to a = 0 everything rounds to acos = pi/2
+    cases.append([0.0, 1e-30, 1e-20, 1e-18, 5e-324, 0.5, 1e-200])
+    # clamp region: distance 0 for every a > 1 - 1e-9 (+inf and values above 1 too)
+    cases.append([0.5, 1.0 - 1e-10, 1.0, 0.9999999995, np.inf, 7.0, 1.0 - 1e-9,
+                  np.nextafter(1.0 - 1e-9, 2.0)])
+    # NaN never enters, wherever it sits
+    cases.append([np.nan, 0.9, 1.0, np.nan, 0.3])
+    cases.append([np.nan, np.nan])
+    # duplicates of the k-th value
+    cases.append([0.7, 0.2, 0.7, 0.7, 0.9, 0.7, 0.1, 0.7])
+    cases.append([-0.7, 0.6, -0.6, 0.7])
+    for xs in cases:
+        rows = _x_rows(xs)
+        for k in (1, 2, 3, 4, len(xs), len(xs) + 3):
+            if k > 32:
+                continue
+            with _store(oxg, rows) as st:
+                idx, dist = st.so3_knn(E1, k)
+                idx_e, dist_e = st.so3_knn(E1, k, exclude=np.array([2], np.uint32))
+            oidx, odist = orc.so3_knn(rows, E1, k)
+            np.testing.assert_array_equal(idx, oidx, err_msg=f"{xs} k={k}")
+            np.testing.assert_array_equal(_bits(dist), _bits(odist), err_msg=f"{xs} k={k}")
+            oidx, odist = orc.so3_knn(rows, E1, k, exclude=np.array([2], np.uint32))
+            np.testing.assert_array_equal(idx_e, oidx, err_msg=f"{xs} k={k} excl")
+            np.testing.assert_array_equal(_bits(dist_e), _bits(odist), err_msg=f"{xs} k={k} excl")
+    # a plateau spread over a large store that spans many slices and warps
+    rng = np.random.default_rng(11)
+    xs = rng.uniform(-0.29, 0.29, size=90001)
+    for pos, v in zip((60000, 123, 40000, 89999, 7), (plat[4], -plat[3], plat[0], plat[2], plat[1])):
+        xs[pos] = v
+    rows = _x_rows(xs)
+    rows[:, 1:] = rng.normal(size=(len(xs), 3))
+    qs = np.vstack([E1, -E1])
+    with _store(oxg, rows) as st:
+        for k in (1, 3, 5, 6, 10):
+            idx, dist = st.so3_knn(qs, k)
+            oidx, odist = orc.so3_knn(rows, qs, k)
+            np.testing.assert_array_equal(idx, oidx)
+            np.testing.assert_array_equal(_bits(dist), _bits(odist))
+
+
+def test_so3_knn_errors_and_empty(oxg):
+    with oxg.StateStore(oxg.Space.real_vector(4)) as st:
+        idx, dist = st.so3_knn(E1, 3)                               # empty store: padded rows
+        assert (idx == 0xFFFFFFFF).all() and np.isinf(dist).all()
+        st.append(_x_rows([0.5, 0.4]))
+        with pytest.raises(oxg.OxgError):
+            st.so3_knn(E1, 33)
+        idx, dist = st.so3_knn(E1, 3)
+        assert idx.tolist() == [[0, 1, 0xFFFFFFFF]] and np.isinf(dist[0, 2])
+    with oxg.StateStore(oxg.Space.real_vector(3)) as st:
+        st.append(np.zeros((2, 3)))
+        with pytest.raises(oxg.OxgError):
+            st.so3_knn(E1, 1)
+
+
 @pytest.mark.parametrize("r", [0.3, 1.0, math.pi / 2, 2.0, 0.0, -1.0, float("nan"), 4.5e-5, 1e-300])
 def test_so3_radius_random(oxg, orc, r):
     rng = np.random.default_rng(21)
@@ -206,3 +290,69 @@ def test_so3_check_motion_matches_oracle(oxg, orc):
     with pytest.raises(oxg.OxgError) as e:
         c.check_motion(frm[:1], to[:1], 0.0)
     assert e.value.code == -5                                      # OXG_E_RESOLUTION
+
+
+def _so3_problem(rng, n_cones, n_samples, goal_bias=0.05):
+    cones = np.hstack([_unit(rng, n_cones), rng.uniform(0.2, 0.5, size=(n_cones, 1))])
+    start = np.array([0.0, 0.0, 0.0, 1.0])
+    goal = _unit(rng, 1)[0]
+    samples = _unit(rng, n_samples)
+    samples[rng.random(n_samples) < goal_bias] = goal
+    return cones, start, goal, samples
+
+
+@pytest.mark.parametrize("seed,max_distance,n_cones", [(1, 0.5, 1), (2, 0.2, 3), (3, 0.05, 2), (4, 2.0, 6)])
+def test_so3_rrt_chunked_loop_is_the_sequential_loop(oxg, orc, seed, max_distance, n_cones):
+    """oxg_so3_rrt_solve runs speculative chunks; tree, parents, iteration count and outcome must
+    be the one-sample-at-a-time loop's (orc_so3_rrt), bit for bit."""
+    rng = np.random.default_rng(seed)
+    cones, start, goal, samples = _so3_problem(rng, n_cones, 3000, goal_bias=0.0)
+    while not orc.so3_is_valid(cones, start[None])[0]:
+        cones, start, goal, samples = _so3_problem(rng, n_cones, 3000, goal_bias=0.0)
+    c = oxg.So3Cones(cones)
+    otree, opar, osolved, oiters = orc.so3_rrt(cones, start, samples, max_distance, RES, 4000)
+    with _store(oxg, start[None]) as st:
+        par, r = oxg.so3_rrt_solve(c, st, samples, max_distance, RES, 4000)
+        rows = st.read(0, len(st))
+    assert r["iters"] == oiters == 3000 and not r["solved"] and r["status"] == "samples_exhausted"
+    np.testing.assert_array_equal(par, opar)
+    np.testing.assert_array_equal(_bits(rows), _bits(otree))
+    assert len(par) > 100
+    assert r["ctas"] < r["iters"] / 4, r                            # it really ran in chunks
+
+
+def test_so3_rrt_goal_continuation_and_capacity(oxg, orc):
+    rng = np.random.default_rng(8)
+    cones, start, goal, samples = _so3_problem(rng, 2, 4000, goal_bias=0.05)
+    while not orc.so3_is_valid(cones, goal[None])[0] or not orc.so3_is_valid(cones, start[None])[0]:
+        cones, start, goal, samples = _so3_problem(rng, 2, 4000, goal_bias=0.05)
+    c = oxg.So3Cones(cones)
+    otree, opar, osolved, oiters = orc.so3_rrt(cones, start, samples, 0.3, RES, 4000, goal, 0.1)
+    assert osolved
+    with _store(oxg, start[None]) as st:
+        par, r = oxg.so3_rrt_solve(c, st, samples, 0.3, RES, 4000, goal_target=goal, goal_radius=0.1)
+        rows = st.read(0, len(st))
+    assert r["solved"] and r["iters"] == oiters and r["goal_node"][0] == len(opar) - 1
+    np.testing.assert_array_equal(par, opar)
+    np.testing.assert_array_equal(_bits(rows), _bits(otree))
+    # the same stream in two calls (the second continues the first call's tree)
+    cut = oiters // 2
+    with _store(oxg, start[None]) as st:
+        p1, r1 = oxg.so3_rrt_solve(c, st, samples[:cut], 0.3, RES, 4000, goal_target=goal,
+                                   goal_radius=0.1)
+        assert not r1["solved"] and r1["iters"] == cut
+        p2, r2 = oxg.so3_rrt_solve(c, st, samples[cut:], 0.3, RES, 4000, goal_target=goal,
+                                   goal_radius=0.1, parents=p1)
+        rows = st.read(0, len(st))
+    assert r2["solved"] and r2["iters"] == oiters - cut
+    np.testing.assert_array_equal(p2, opar)
+    np.testing.assert_array_equal(_bits(rows), _bits(otree))
+    # capacity: the loop stops when the tree holds max_nodes states
+    otree, opar, osolved, oiters = orc.so3_rrt(cones, start, samples, 0.3, RES, 50)
+    with _store(oxg, start[None]) as st:
+        par, r = oxg.so3_rrt_solve(c, st, samples, 0.3, RES, 50)
+    assert r["status"] == "tree_full" and r["iters"] == oiters and len(par) == 50
+    np.testing.assert_array_equal(par, opar)
+    with oxg.StateStore(oxg.Space.real_vector(4)) as st:
+        with pytest.raises(oxg.OxgError):
+            oxg.so3_rrt_solve(c, st, samples, 0.3, RES, 50)         # no start state

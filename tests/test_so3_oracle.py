@@ -85,3 +85,25 @@ def test_so3_check_motion_steps(orc):
     assert abs(int(first[0]) - want) <= 1
     valid, first = orc.so3_check_motion([[1.0, 0.0, 0.0, 0.0, 0.05]], ident, to, res)
     assert valid[0] == 1 and first[0] == 0
+
+
+def test_so3_knn_is_the_sorted_scan(orc):
+    """orc.so3_knn = the k smallest (distance, index) pairs of the pure-Python metric; its first
+    column is the 1-NN scan's winner."""
+    rng = np.random.default_rng(5)
+    rows, qs = _unit(rng, 400), _unit(rng, 7)
+    rows[10] = rows[3]                                  # duplicate state: index 3 comes first
+    qs[0] = rows[3]
+    ex = np.array([3, 0xFFFFFFFF, 1, 2, 0xFFFFFFFF, 5, 399], np.uint32)
+    for k, exclude in ((1, None), (6, None), (6, ex)):
+        idx, dist = orc.so3_knn(rows, qs, k, exclude=exclude)
+        for q in range(len(qs)):
+            pairs = sorted((_py_distance(qs[q], rows[i]), i) for i in range(len(rows))
+                           if exclude is None or i != exclude[q])[:k]
+            assert idx[q].tolist() == [i for _, i in pairs]
+            assert dist[q].tolist() == [d for d, _ in pairs]
+    i1, d1 = orc.so3_nn1(rows, qs)
+    idx, dist = orc.so3_knn(rows, qs, 3)
+    assert (idx[:, 0] == i1).all() and (dist[:, 0] == d1).all()
+    idx, dist = orc.so3_knn(rows[:2], qs[:1], 4)        # padding
+    assert idx[0, 2:].tolist() == [0xFFFFFFFF] * 2 and np.isinf(dist[0, 2:]).all()
