@@ -1403,7 +1403,11 @@ static int launch_tree_knn(TreeKnnParams p, cudaStream_t st) {
   // warp so that they spread over the machine; large ones TK_QPC neighbouring queries per CTA so
   // that its warps share leaves through L1.
   const unsigned warps = TK_THREADS / 32;
-  unsigned qpc = (unsigned)((p.Q + (unsigned)sms * OXG_TK_MIN_CTAS - 1) / ((unsigned)sms * OXG_TK_MIN_CTAS));
+  // ... and never fewer than ~16 waves of CTAs, so the last wave is short (measured on a 125 000-query
+  // shard of the 1e6-node build: 2.14 ms against 2.30 ms with 32 queries per CTA)
+  const unsigned waves = 16;
+  const unsigned slots = (unsigned)sms * OXG_TK_MIN_CTAS * waves;
+  unsigned qpc = (unsigned)((p.Q + slots - 1) / slots);
   qpc = ((qpc + warps - 1) / warps) * warps;
   p.qpc = std::max(warps, std::min<unsigned>(qpc, TK_QPC));
   const unsigned chunks = (p.Q + p.qpc - 1) / p.qpc;
