@@ -165,6 +165,10 @@ extern "C" {
     pub fn oxg_so3_rrt_solve(tree: oxg_store, cones: oxg_so3_cones, params: *const oxg_plan_params,
                              goal_target: *const f64, samples: *const f64, n_samples: u64,
                              parents: *mut i64, out: *mut oxg_plan_result) -> c_int;
+    pub fn oxg_so3_rrt_connect_solve(start_tree: oxg_store, goal_tree: oxg_store, cones: oxg_so3_cones,
+                                     params: *const oxg_plan_params, goal_target: *const f64,
+                                     samples: *const f64, n_samples: u64, start_parents: *mut i64,
+                                     goal_parents: *mut i64, out: *mut oxg_plan_result) -> c_int;
     pub fn oxg_so3_cones_create(cones: *const f64, n_cones: u64, out: *mut oxg_so3_cones) -> c_int;
     pub fn oxg_so3_cones_destroy(cones: oxg_so3_cones) -> c_int;
     pub fn oxg_so3_is_valid(cones: oxg_so3_cones, states: *const f64, q: u64, out: *mut u8) -> c_int;

@@ -86,6 +86,20 @@ int oxg_so3_rrt_solve(oxg_store tree, oxg_so3_cones cones, const oxg_plan_params
                       const double* goal_target /* 4 */, const double* samples /* n x 4 */,
                       uint64_t n_samples, int64_t* parents, oxg_plan_result* out);
 
+/* RRTConnect::solve (rrt_connect.rs:227-309, extend :121-159) over SO3 -- the counterpart of
+ * oxg_rrt_connect_solve, run in speculative chunks like oxg_so3_rrt_solve.  Both growth cases
+ * (start tree or goal tree extends towards q_rand; the other tree then extends towards the new
+ * node) are prepared for every sample of a chunk in six launches; samples are committed in order
+ * with the case the tree sizes dictate, and a chunk is cut at the first sample one of whose scans
+ * would have found a node added inside the chunk.  goal_tree holds the goal state at index 0
+ * (rrt_connect.rs:201-216).  out->goal_node = the joined nodes (start tree, goal tree), [1] = -1
+ * when the start tree reached the goal ball itself (:271-274); n_nodes[0/1] = tree sizes.
+ * start_parents / goal_parents: in/out, max_nodes entries each. */
+int oxg_so3_rrt_connect_solve(oxg_store start_tree, oxg_store goal_tree, oxg_so3_cones cones,
+                              const oxg_plan_params* params, const double* goal_target,
+                              const double* samples, uint64_t n_samples, int64_t* start_parents,
+                              int64_t* goal_parents, oxg_plan_result* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,10 @@ class Oracle:
             "orc_so3_radius": (u64, [vp, u64, vp, d, vp, vp, u64]),
             "orc_so3_knn_batch": (None, [vp, u64, vp, u64, C.c_uint32, vp, vp, vp]),
             "orc_so3_is_valid": (C.c_int, [vp, u64, vp]),
+            "orc_so3_rrt_connect": (C.c_int, [vp, u64, vp, d, d, d, vp, u64, u64, vp, vp,
+                                              C.POINTER(u64), vp, vp, C.POINTER(u64),
+                                              C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                              C.POINTER(u64)]),
             "orc_so3_rrt": (u64, [vp, u64, vp, d, d, d, vp, u64, u64, vp, vp, C.POINTER(C.c_int),
                                   C.POINTER(u64)]),
             "orc_so3_check_motion": (C.c_int, [vp, u64, vp, vp, d, C.POINTER(u32)]),
@@ -269,6 +273,29 @@ class Oracle:
                                  int(max_nodes), _p(tree), _p(parents), C.byref(solved),
                                  C.byref(iters))
         return tree[:n].copy(), parents[:n].copy(), bool(solved.value), int(iters.value)
+
+    def so3_rrt_connect(self, cones, start, goal_root, samples, max_distance, resolution, max_nodes,
+                        goal_target=None, goal_radius=-1.0):
+        """RRTConnect::solve over SO3 -> dict(start_tree, start_parents, goal_tree, goal_parents,
+        solved, conn, iters)."""
+        cones = _f64(np.reshape(cones, (-1, 5)))
+        s = _f64(np.atleast_2d(samples))
+        ta = np.zeros((max_nodes, 4), dtype=np.float64)
+        tb = np.zeros((max_nodes, 4), dtype=np.float64)
+        ta[0], tb[0] = start, goal_root
+        pa = np.full(max_nodes, -1, dtype=np.int64)
+        pb = np.full(max_nodes, -1, dtype=np.int64)
+        g = None if goal_target is None else _f64(goal_target)
+        na, nb, iters = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        cs, cg = C.c_int64(-1), C.c_int64(-1)
+        solved = self.lib.orc_so3_rrt_connect(_p(cones), cones.shape[0], _p(g), float(goal_radius),
+                                              float(max_distance), float(resolution), _p(s),
+                                              s.shape[0], int(max_nodes), _p(ta), _p(pa),
+                                              C.byref(na), _p(tb), _p(pb), C.byref(nb),
+                                              C.byref(cs), C.byref(cg), C.byref(iters))
+        return {"start_tree": ta[:na.value].copy(), "start_parents": pa[:na.value].copy(),
+                "goal_tree": tb[:nb.value].copy(), "goal_parents": pb[:nb.value].copy(),
+                "solved": bool(solved), "conn": (cs.value, cg.value), "iters": int(iters.value)}
 
     def so3_is_valid(self, cones, states):
         cones, st = _f64(np.reshape(cones, (-1, 5))), _f64(np.atleast_2d(states))

@@ -952,4 +952,86 @@ uint64_t orc_so3_rrt(const double* cones, uint64_t n_cones, const double* goal_t
   return n;
 }
 
+// RRTConnect::solve over SO3 -- rrt_connect.rs:227-309 with extend :121-159; conventions of
+// orc_rrt_connect, fixtures of orc_so3_rrt.
+static int so3_rc_extend(const double* cones, uint64_t n_cones, double* tree, int64_t* parents,
+                         uint64_t* n, uint64_t cap, const double* q_target, double max_distance,
+                         double resolution, bool* reached, uint64_t* new_idx) {
+  uint32_t near = 0;
+  double min_dist = orc_so3_distance(tree, q_target);  // rrt_connect.rs:128-136
+  for (uint64_t i = 1; i < *n; ++i) {
+    double d = orc_so3_distance(tree + i * 4, q_target);
+    if (d < min_dist) {
+      min_dist = d;
+      near = (uint32_t)i;
+    }
+  }
+  double q_near[4], q_new[4];
+  std::memcpy(q_near, tree + (uint64_t)near * 4, sizeof(q_near));
+  if (min_dist > max_distance) {
+    orc_so3_interpolate(q_near, q_target, max_distance / min_dist, q_new);
+    *reached = false;
+  } else {
+    std::memcpy(q_new, q_target, sizeof(q_new));
+    *reached = true;
+  }
+  if (*n >= cap) return 0;
+  if (orc_so3_check_motion(cones, n_cones, q_near, q_new, resolution, nullptr) == 1) {
+    std::memcpy(tree + (*n) * 4, q_new, sizeof(q_new));
+    parents[*n] = near;
+    *new_idx = *n;
+    ++(*n);
+    return 1;
+  }
+  return 0;
+}
+
+int orc_so3_rrt_connect(const double* cones, uint64_t n_cones, const double* goal_target,
+                        double goal_radius, double max_distance, double resolution,
+                        const double* samples, uint64_t n_samples, uint64_t max_nodes,
+                        double* start_tree, int64_t* start_parents, uint64_t* n_start,
+                        double* goal_tree, int64_t* goal_parents, uint64_t* n_goal,
+                        int64_t* conn_start, int64_t* conn_goal, uint64_t* iters) {
+  *n_start = 1;
+  *n_goal = 1;
+  start_parents[0] = -1;
+  goal_parents[0] = -1;
+  *conn_start = -1;
+  *conn_goal = -1;
+  uint64_t it = 0;
+  int solved = 0;
+  for (; it < n_samples && *n_start < max_nodes && *n_goal < max_nodes; ++it) {
+    bool growing_start = *n_start <= *n_goal;  // rrt_connect.rs:249-254
+    double* ta = growing_start ? start_tree : goal_tree;
+    int64_t* pa = growing_start ? start_parents : goal_parents;
+    uint64_t* na = growing_start ? n_start : n_goal;
+    double* tb = growing_start ? goal_tree : start_tree;
+    int64_t* pb = growing_start ? goal_parents : start_parents;
+    uint64_t* nb = growing_start ? n_goal : n_start;
+    bool reached_a, reached_b;
+    uint64_t idx_a, idx_b;
+    if (!so3_rc_extend(cones, n_cones, ta, pa, na, max_nodes, samples + it * 4, max_distance,
+                       resolution, &reached_a, &idx_a))
+      continue;
+    const double* q_new = ta + idx_a * 4;
+    if (growing_start && goal_target && orc_so3_distance(q_new, goal_target) <= goal_radius) {
+      *conn_start = (int64_t)idx_a;  // :271-274
+      solved = 1;
+      ++it;
+      break;
+    }
+    if (so3_rc_extend(cones, n_cones, tb, pb, nb, max_nodes, q_new, max_distance, resolution,
+                      &reached_b, &idx_b) &&
+        reached_b) {  // :280
+      *conn_start = (int64_t)(growing_start ? idx_a : idx_b);
+      *conn_goal = (int64_t)(growing_start ? idx_b : idx_a);
+      solved = 1;
+      ++it;
+      break;
+    }
+  }
+  *iters = it;
+  return solved;
+}
+
 }  // extern "C"

@@ -24,6 +24,7 @@ from .api import (  # noqa: F401
     rrt_connect_solve,
     rrt_solve,
     rrt_star_solve,
+    so3_rrt_connect_solve,
     so3_rrt_solve,
     tuning_set,
 )

@@ -203,6 +203,10 @@ SIGNATURES = {
         C.c_int,
         [_vp, _vp, C.POINTER(PlanParams), _pd, _pd, _u64, _vp, C.POINTER(PlanResult)],
     ),
+    "oxg_so3_rrt_connect_solve": (
+        C.c_int,
+        [_vp, _vp, _vp, C.POINTER(PlanParams), _pd, _pd, _u64, _vp, _vp, C.POINTER(PlanResult)],
+    ),
     "oxg_so3_cones_create": (C.c_int, [_pd, _u64, C.POINTER(_vp)]),
     "oxg_so3_cones_destroy": (C.c_int, [_vp]),
     "oxg_so3_is_valid": (C.c_int, [_vp, _pd, _u64, _pu8]),

@@ -534,6 +534,28 @@ def so3_rrt_solve(cones: "So3Cones", tree: StateStore, samples, max_distance: fl
     return par[: int(res.n_nodes[0])].copy(), _plan_result(res)
 
 
+def so3_rrt_connect_solve(cones: "So3Cones", start_tree: StateStore, goal_tree: StateStore, samples,
+                          max_distance: float, resolution: float, max_nodes: int, goal_target=None,
+                          goal_radius: float = -1.0, timeout_s: float = 0.0, start_parents=None,
+                          goal_parents=None):
+    """RRTConnect::solve over SO3 (``oxg_so3_rrt_connect_solve``), speculative chunks.
+    Returns (start_parents, goal_parents, result dict)."""
+    s = _f64(np.atleast_2d(samples), 4)
+    g = None if goal_target is None else _f64(goal_target)
+    prm = _plan_params(max_distance, resolution, max_nodes, goal_radius, timeout_s=timeout_s)
+    pa = np.full(max_nodes, -1, dtype=np.int64)
+    pb = np.full(max_nodes, -1, dtype=np.int64)
+    if start_parents is not None:
+        pa[: len(start_parents)] = start_parents
+    if goal_parents is not None:
+        pb[: len(goal_parents)] = goal_parents
+    res = _lib.PlanResult()
+    check(lib.oxg_so3_rrt_connect_solve(start_tree.handle, goal_tree.handle, cones._h, C.byref(prm),
+                                        _ptr(g), _ptr(s), s.shape[0], _ptr(pa), _ptr(pb),
+                                        C.byref(res)))
+    return pa[: int(res.n_nodes[0])].copy(), pb[: int(res.n_nodes[1])].copy(), _plan_result(res)
+
+
 def rrt_connect_solve(world: World, start_tree: StateStore, goal_tree: StateStore, samples,
                       max_distance: float, resolution: float, max_nodes: int, goal_target=None,
                       goal_radius: float = -1.0, timeout_s: float = 0.0):

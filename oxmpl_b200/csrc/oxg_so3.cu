@@ -1093,4 +1093,198 @@ int oxg_so3_rrt_solve(oxg_store tree, oxg_so3_cones cones, const oxg_plan_params
   OXG_API_END
 }
 
+// RRT-Connect over SO3 (rrt_connect.rs:227-309, extend :121-159) in speculative chunks, like
+// oxg_so3_rrt_solve.  Which tree an iteration grows depends on the sizes the earlier iterations
+// left, so both cases are prepared for every sample of a chunk: extend 1 (1-NN of q_rand in tree
+// c, steer, motion check) for c = start and c = goal, then extend 2 (1-NN of that q_new in the
+// other tree, steer, motion check) for the edges that survived -- six launches per chunk.  The
+// commit pass walks the samples in order, picks the case the sizes dictate, and cuts the chunk at
+// the first sample one of whose two scans is beaten by a node added inside the chunk.
+int oxg_so3_rrt_connect_solve(oxg_store start_tree, oxg_store goal_tree, oxg_so3_cones cones,
+                              const oxg_plan_params* params, const double* goal_target,
+                              const double* samples, uint64_t n_samples, int64_t* start_parents,
+                              int64_t* goal_parents, oxg_plan_result* out) {
+  OXG_API_BEGIN
+  OXG_TRY(so3_check_store(start_tree));
+  OXG_TRY(so3_check_store(goal_tree));
+  if (!cones || !params || !out || !start_parents || !goal_parents || (n_samples > 0 && !samples)) {
+    set_error("NULL argument");
+    return OXG_E_NULL;
+  }
+  if (start_tree == goal_tree) {
+    set_error("the two trees must be different stores");
+    return OXG_E_ARG;
+  }
+  if (!(params->resolution > 0.0)) {
+    set_error("resolution must be > 0 (the reference loop would not terminate)");
+    return OXG_E_RESOLUTION;
+  }
+  if (start_tree->size == 0 || goal_tree->size == 0) {
+    set_error("each tree must hold its root state at index 0");
+    return OXG_E_EMPTY;
+  }
+  const uint64_t cap = params->max_nodes;
+  if (cap < start_tree->size || cap < goal_tree->size || cap > 0x3FFFFFFFull) {
+    set_error("max_nodes must lie in [tree size, 2^30)");
+    return OXG_E_ARG;
+  }
+  const auto t_begin = std::chrono::steady_clock::now();
+  *out = oxg_plan_result{};
+  out->goal_node[0] = out->goal_node[1] = -1;
+  const bool has_goal = goal_target && params->goal_radius >= 0.0;
+  const double maxd = params->max_distance;
+  oxg_store tr[2] = {start_tree, goal_tree};
+  int64_t* par[2] = {start_parents, goal_parents};
+  uint64_t n[2];
+  std::vector<double> nodes[2];
+  for (int c = 0; c < 2; ++c) {
+    n[c] = tr[c]->size;
+    nodes[c].resize(n[c] * 4);
+    OXG_TRY(oxg_store_read(tr[c], 0, n[c], nodes[c].data()));
+  }
+  // steering of extend (rrt.rs:200-208 as used by rrt_connect.rs:138-146); returns `reached`
+  auto steer = [maxd](const double* q_near, const double* target, double d, double* q_new) {
+    if (d > maxd) {
+      so3_interpolate_host(q_near, target, maxd / d, q_new);
+      return false;
+    }
+    std::copy(target, target + 4, q_new);
+    return true;
+  };
+  uint64_t cursor = 0, chunk = 8, chunks = 0;
+  std::vector<uint32_t> near1[2], near2[2], pos2[2];
+  std::vector<double> dist1[2], dist2[2], from, to1[2], q2[2], to2[2];
+  std::vector<uint8_t> valid1, valid2, reached2[2];
+  std::vector<double> to;
+  int status = 1;
+  while (cursor < n_samples) {
+    if (n[0] >= cap || n[1] >= cap) {
+      status = 2;
+      break;
+    }
+    if (params->timeout_s > 0.0 &&
+        std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count() >
+            params->timeout_s) {
+      status = 3;
+      break;
+    }
+    const uint64_t m = std::min<uint64_t>({chunk, n_samples - cursor, cap - std::max(n[0], n[1])});
+    const double* q = samples + cursor * 4;
+    // extend 1 for both cases: edges [0, m) grow the start tree, [m, 2m) the goal tree
+    from.resize(2 * m * 4);
+    to.resize(2 * m * 4);
+    valid1.resize(2 * m);
+    for (int c = 0; c < 2; ++c) {
+      near1[c].resize(m);
+      dist1[c].resize(m);
+      OXG_TRY(oxg_so3_nn1(tr[c], q, m, near1[c].data(), dist1[c].data()));
+      for (uint64_t j = 0; j < m; ++j) {
+        const double* qn = nodes[c].data() + (size_t)near1[c][j] * 4;
+        std::copy(qn, qn + 4, from.begin() + (c * m + j) * 4);
+        steer(qn, q + j * 4, dist1[c][j], to.data() + (c * m + j) * 4);
+      }
+    }
+    OXG_TRY(oxg_so3_check_motion(cones, from.data(), to.data(), 2 * m, params->resolution,
+                                 valid1.data(), nullptr));
+    to1[0].assign(to.begin(), to.begin() + m * 4);
+    to1[1].assign(to.begin() + m * 4, to.end());
+    // extend 2: the new node of case c is the target of the OTHER tree
+    uint64_t e2 = 0, cnt[2];
+    for (int c = 0; c < 2; ++c) {
+      pos2[c].assign(m, 0xFFFFFFFFu);
+      q2[c].clear();
+      for (uint64_t j = 0; j < m; ++j)
+        if (valid1[c * m + j]) {
+          pos2[c][j] = (uint32_t)(q2[c].size() / 4);
+          q2[c].insert(q2[c].end(), to1[c].begin() + j * 4, to1[c].begin() + j * 4 + 4);
+        }
+      cnt[c] = q2[c].size() / 4;
+      e2 += cnt[c];
+    }
+    from.resize(e2 * 4);
+    to.resize(e2 * 4);
+    valid2.resize(e2);
+    for (int c = 0, base = 0; c < 2; base += (int)cnt[c], ++c) {
+      near2[c].resize(cnt[c]);
+      dist2[c].resize(cnt[c]);
+      reached2[c].resize(cnt[c]);
+      if (cnt[c] == 0) continue;
+      const int o = 1 - c;
+      OXG_TRY(oxg_so3_nn1(tr[o], q2[c].data(), cnt[c], near2[c].data(), dist2[c].data()));
+      for (uint64_t e = 0; e < cnt[c]; ++e) {
+        const double* qn = nodes[o].data() + (size_t)near2[c][e] * 4;
+        std::copy(qn, qn + 4, from.begin() + (base + e) * 4);
+        reached2[c][e] = steer(qn, q2[c].data() + e * 4, dist2[c][e], to.data() + (base + e) * 4);
+      }
+    }
+    if (e2 > 0)
+      OXG_TRY(oxg_so3_check_motion(cones, from.data(), to.data(), e2, params->resolution,
+                                   valid2.data(), nullptr));
+    ++chunks;
+    out->motion_checks_executed += 2 * m + e2;
+    // commit in order
+    const uint64_t n_before[2] = {n[0], n[1]};
+    auto beaten = [&](int t, const double* target, double d) {  // by a node added in this chunk
+      for (uint64_t p = n_before[t]; p < n[t]; ++p)
+        if (so3_distance_host(nodes[t].data() + p * 4, target) < d) return true;
+      return false;
+    };
+    uint64_t done = 0;
+    bool solved = false;
+    while (done < m && !solved && n[0] < cap && n[1] < cap) {
+      const int c = n[0] <= n[1] ? 0 : 1, o = 1 - c;  // rrt_connect.rs:249-254
+      const uint64_t j = done;
+      const bool ok1 = valid1[c * m + j] != 0;
+      const uint64_t e = ok1 ? pos2[c][j] : 0;
+      if (beaten(c, q + j * 4, dist1[c][j])) break;
+      if (ok1 && beaten(o, to1[c].data() + j * 4, dist2[c][e])) break;
+      ++done;
+      ++out->motion_checks;
+      if (!ok1) continue;
+      const double* q_new = to1[c].data() + j * 4;
+      nodes[c].insert(nodes[c].end(), q_new, q_new + 4);
+      par[c][n[c]] = near1[c][j];
+      const int64_t idx_a = (int64_t)n[c]++;
+      if (c == 0 && has_goal && so3_distance_host(q_new, goal_target) <= params->goal_radius) {
+        solved = true;  // rrt_connect.rs:271-274
+        out->goal_node[0] = idx_a;
+        break;
+      }
+      ++out->motion_checks;
+      const uint64_t g = (c == 0 ? 0 : cnt[0]) + e;
+      if (!valid2[g]) continue;
+      nodes[o].insert(nodes[o].end(), to.begin() + g * 4, to.begin() + g * 4 + 4);
+      par[o][n[o]] = near2[c][e];
+      const int64_t idx_b = (int64_t)n[o]++;
+      if (reached2[c][e]) {  // rrt_connect.rs:280
+        solved = true;
+        out->goal_node[0] = c == 0 ? idx_a : idx_b;
+        out->goal_node[1] = c == 0 ? idx_b : idx_a;
+      }
+    }
+    cursor += done;
+    for (int c = 0; c < 2; ++c)
+      if (n[c] > n_before[c]) {
+        uint64_t first = 0;
+        OXG_TRY(oxg_store_append(tr[c], nodes[c].data() + n_before[c] * 4, n[c] - n_before[c], &first));
+      }
+    if (solved) {
+      status = 0;
+      break;
+    }
+    chunk = done == m ? std::min<uint64_t>(chunk * 2, 1024) : std::max<uint64_t>(done, 4);
+  }
+  if (status == 1 && cursor < n_samples) status = 2;
+  out->n_nodes[0] = n[0];
+  out->n_nodes[1] = n[1];
+  out->iters = cursor;
+  out->solved = status == 0;
+  out->status = status;
+  out->ctas = (int32_t)std::min<uint64_t>(chunks, 0x7FFFFFFF);
+  out->device_ms =
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  return OXG_OK;
+  OXG_API_END
+}
+
 }  // extern "C"

@@ -342,8 +342,46 @@ class RRTConnect(_TreePlanner):
             return None
         return reached, t.push(q_new, near)
 
+    so3_chunk = 1024
+
+    def _solve_so3_chunked(self, timeout_secs: float) -> Path:
+        """Ball goal: ``oxg_so3_rrt_connect_solve`` on a pre-drawn stream (speculative chunks, six
+        launches per chunk instead of four synchronous calls per iteration)."""
+        pd, res = self.pd, self._resolution()
+        pa = np.asarray(self.ta.parents, dtype=np.int64)
+        pb = np.asarray(self.tb.parents, dtype=np.int64)
+        t0 = time.perf_counter()
+        while True:
+            left = timeout_secs - (time.perf_counter() - t0)
+            if left <= 0:
+                raise PlanningError(PlanningError.TIMEOUT)
+            stream = np.empty((self.so3_chunk, 4))
+            for i in range(self.so3_chunk):                        # rrt_connect.rs:256-262
+                q = pd.goal.sample_goal() if self.rng.random() < self.goal_bias \
+                    else pd.space.sample_uniform(self.rng)
+                stream[i] = q.values
+            pa, pb, r = api.so3_rrt_connect_solve(
+                self.vc.cones, self.ta.store, self.tb.store, stream, self.max_distance, res,
+                self.max_nodes, goal_target=pd.goal.target.values, goal_radius=pd.goal.radius,
+                timeout_s=left, start_parents=pa, goal_parents=pb)
+            for t, par in ((self.ta, pa), (self.tb, pb)):
+                for row in t.store.read(len(t.nodes)):
+                    t.nodes.append(SO3State(*row))
+                    t.costs.append(0.0)
+                t.parents = [int(v) for v in par]
+            self.last_result = r
+            if r["solved"]:
+                s_idx, g_idx = r["goal_node"]
+                if g_idx < 0:
+                    return Path(self.ta.path_to(s_idx))
+                return Path(self.ta.path_to(s_idx) + self.tb.path_to(g_idx)[::-1][1:])
+            if r["status"] in ("timeout", "tree_full"):
+                raise PlanningError(PlanningError.TIMEOUT)
+
     def _solve_so3(self, timeout_secs: float) -> Path:
         pd, space = self.pd, self.pd.space
+        if hasattr(pd.goal, "target") and hasattr(pd.goal, "radius"):
+            return self._solve_so3_chunked(timeout_secs)
         t0 = time.perf_counter()
         while time.perf_counter() - t0 <= timeout_secs:
             grow_start = len(self.ta.nodes) <= len(self.tb.nodes)          # rrt_connect.rs:249-254

@@ -356,3 +356,70 @@ def test_so3_rrt_goal_continuation_and_capacity(oxg, orc):
     with oxg.StateStore(oxg.Space.real_vector(4)) as st:
         with pytest.raises(oxg.OxgError):
             oxg.so3_rrt_solve(c, st, samples, 0.3, RES, 50)         # no start state
+
+
+@pytest.mark.parametrize("seed,max_distance,n_cones,goal_radius",
+                         [(1, 0.5, 1, -1.0), (2, 0.2, 3, -1.0), (3, 0.05, 2, -1.0), (4, 1.0, 2, 0.05),
+                          (5, 0.3, 4, 0.1)])
+def test_so3_rrt_connect_chunked_loop_is_the_sequential_loop(oxg, orc, seed, max_distance, n_cones,
+                                                             goal_radius):
+    """Both trees, their parents, the joined nodes and the iteration count of the chunked
+    RRT-Connect equal the sequential loop's (orc_so3_rrt_connect)."""
+    rng = np.random.default_rng(100 + seed)
+    while True:
+        cones, start, goal, samples = _so3_problem(rng, n_cones, 2500, goal_bias=0.05)
+        if orc.so3_is_valid(cones, np.vstack([start, goal])).all():
+            break
+    c = oxg.So3Cones(cones)
+    gt = goal if goal_radius >= 0 else None
+    # an unreachable "connection" keeps the loops running when no goal is set: forbid `reached`
+    # by never letting the trees meet only if max_distance is small; otherwise compare as is
+    o = orc.so3_rrt_connect(cones, start, goal, samples, max_distance, RES, 3000, gt, goal_radius)
+    with _store(oxg, start[None]) as sa, _store(oxg, goal[None]) as sb:
+        pa, pb, r = oxg.so3_rrt_connect_solve(c, sa, sb, samples, max_distance, RES, 3000,
+                                              goal_target=gt, goal_radius=goal_radius)
+        ra, rb = sa.read(), sb.read()
+    assert r["solved"] == o["solved"] and r["iters"] == o["iters"]
+    np.testing.assert_array_equal(pa, o["start_parents"])
+    np.testing.assert_array_equal(pb, o["goal_parents"])
+    np.testing.assert_array_equal(_bits(ra), _bits(o["start_tree"]))
+    np.testing.assert_array_equal(_bits(rb), _bits(o["goal_tree"]))
+    if o["solved"]:
+        assert r["goal_node"] == o["conn"]
+    assert r["iters"] <= 8 or r["ctas"] < r["iters"]
+    # the same stream in two calls continues the same trees
+    cut = max(1, o["iters"] // 2)
+    with _store(oxg, start[None]) as sa, _store(oxg, goal[None]) as sb:
+        pa1, pb1, r1 = oxg.so3_rrt_connect_solve(c, sa, sb, samples[:cut], max_distance, RES, 3000,
+                                                 goal_target=gt, goal_radius=goal_radius)
+        if not r1["solved"]:
+            pa2, pb2, r2 = oxg.so3_rrt_connect_solve(c, sa, sb, samples[cut:], max_distance, RES, 3000,
+                                                     goal_target=gt, goal_radius=goal_radius,
+                                                     start_parents=pa1, goal_parents=pb1)
+            assert r1["iters"] + r2["iters"] == o["iters"] and r2["solved"] == o["solved"]
+            np.testing.assert_array_equal(pa2, o["start_parents"])
+            np.testing.assert_array_equal(pb2, o["goal_parents"])
+            np.testing.assert_array_equal(_bits(sb.read()), _bits(o["goal_tree"]))
+
+
+def test_so3_rrt_connect_small_steps(oxg, orc):
+    """Small steps: hundreds of iterations in which the node added last is usually the nearest one
+    of the next scan, so chunks are cut early and often."""
+    rng = np.random.default_rng(77)
+    while True:
+        cones, start, goal, samples = _so3_problem(rng, 3, 6000, goal_bias=0.0)
+        if orc.so3_is_valid(cones, np.vstack([start, goal])).all():
+            break
+    c = oxg.So3Cones(cones)
+    o = orc.so3_rrt_connect(cones, start, goal, samples, 0.02, RES, 1500)
+    with _store(oxg, start[None]) as sa, _store(oxg, goal[None]) as sb:
+        pa, pb, r = oxg.so3_rrt_connect_solve(c, sa, sb, samples, 0.02, RES, 1500)
+        ra, rb = sa.read(), sb.read()
+    assert r["solved"] == o["solved"] and r["iters"] == o["iters"]
+    np.testing.assert_array_equal(pa, o["start_parents"])
+    np.testing.assert_array_equal(pb, o["goal_parents"])
+    np.testing.assert_array_equal(_bits(ra), _bits(o["start_tree"]))
+    np.testing.assert_array_equal(_bits(rb), _bits(o["goal_tree"]))
+    if not o["solved"]:
+        assert r["status"] in ("tree_full", "samples_exhausted")
+    assert r["ctas"] <= r["iters"], r      # tiny steps: the newest node is usually the nearest one

@@ -84,6 +84,19 @@ def rrt_loop(rng):
         rec["per_iteration_calls"] = {"iters_per_s": round(n_loop / dt), "nodes": len(nodes)}
         rec["same_tree_prefix"] = bool((st.read().view(np.uint64) ==
                                         rows_chunked[: len(nodes)].view(np.uint64)).all())
+    # RRT-Connect, no goal ball, trees rooted at antipodal-ish states; 0.3 rad steps
+    goal_root = np.array([[0.0, 1.0, 0.0, 0.0]])
+    for md in (0.3, 0.05):
+        with oxg.StateStore(oxg.Space.real_vector(4)) as sa, oxg.StateStore(oxg.Space.real_vector(4)) as sb:
+            sa.append(start)
+            sb.append(goal_root)
+            t0 = time.perf_counter()
+            pa, pb, r = oxg.so3_rrt_connect_solve(c, sa, sb, samples, md, res, 30000)
+            dt = time.perf_counter() - t0
+            rec[f"connect_chunked_step{md}"] = {
+                "iters": r["iters"], "iters_per_s": round(r["iters"] / dt), "chunks": r["ctas"],
+                "solved": r["solved"], "nodes": [len(pa), len(pb)],
+                "motion_checks": r["motion_checks"], "launched": r["motion_checks_executed"]}
     return rec
 
 
