@@ -11,6 +11,10 @@
 //! * [`GpuPRM`] is `oxmpl::geometric::PRM` (prm.rs:70-154, 227-307): `construct_roadmap` batches
 //!   the incremental radius build through `oxg_prm_build_radius`, `solve` runs the start
 //!   connection, the goal scan and the reference-order BFS on the device (`oxg_prm_solve`).
+//! * [`GpuConeChecker`], [`GpuSo3RRT`] and [`GpuSo3RRTConnect`] cover `SO3StateSpace`
+//!   (oxmpl/tests/{rrt,rrt_connect}_so3ss_tests.rs): cone validity on the device, and the two
+//!   planner loops on `oxg_so3_rrt_solve` / `oxg_so3_rrt_connect_solve` (include/oxg_so3.h), which
+//!   scan and motion-check a chunk of samples per launch and commit them in the reference's order.
 //!
 //! `Planner::setup` receives `Arc<dyn StateValidityChecker<S>>` like every reference planner.
 //! The GPU planners need the checker's device handle, and a trait object cannot be downcast, so
@@ -599,7 +603,10 @@ impl GpuConeChecker {
     }
 }
 impl Drop for GpuConeChecker {
-    fn drop(&mut self) { unsafe { ffi::oxg_so3_cones_destroy(self.cones); } }
+    fn drop(&mut self) {
+        registry().lock().unwrap().retain(|_, c| *c != self.cones as usize);
+        unsafe { ffi::oxg_so3_cones_destroy(self.cones); }
+    }
 }
 impl StateValidityChecker<oxmpl::base::state::SO3State> for GpuConeChecker {
     fn is_valid(&self, state: &oxmpl::base::state::SO3State) -> bool {
@@ -608,4 +615,232 @@ impl StateValidityChecker<oxmpl::base::state::SO3State> for GpuConeChecker {
         check(unsafe { ffi::oxg_so3_is_valid(self.cones, v.as_ptr(), 1, &mut out) });
         out != 0
     }
+}
+
+impl GpuConeChecker {
+    /// Wraps the checker for `Planner::setup` and registers its device handle (see
+    /// `GpuValidityChecker::into_arc`).
+    pub fn into_arc(self) -> Arc<Self> {
+        let arc = Arc::new(self);
+        registry().lock().unwrap().insert(Arc::as_ptr(&arc) as *const u8 as usize, arc.cones as usize);
+        arc
+    }
+}
+fn gpu_cones_of(vc: &Arc<dyn StateValidityChecker<oxmpl::base::state::SO3State>>) -> ffi::oxg_so3_cones {
+    let key = Arc::as_ptr(vc) as *const u8 as usize;
+    match registry().lock().unwrap().get(&key) {
+        Some(c) => *c as ffi::oxg_so3_cones,
+        None => panic!(
+            "oxmpl-cuda SO3 planners need a GpuConeChecker created with into_arc() (no CPU fallback)"
+        ),
+    }
+}
+
+/// The ball goal of oxmpl/tests/rrt_so3ss_tests.rs:58-68 (`distance(state, target) <= radius`).
+pub trait So3BallGoal: Goal<oxmpl::base::state::SO3State>
+    + GoalSampleableRegion<oxmpl::base::state::SO3State>
+{
+    fn target(&self) -> &oxmpl::base::state::SO3State;
+    fn radius(&self) -> f64;
+}
+
+type So3 = oxmpl::base::state::SO3State;
+type So3Space = oxmpl::base::space::SO3StateSpace;
+
+fn so3_row(s: &So3) -> [f64; 4] { [s.x, s.y, s.z, s.w] }
+
+struct So3Store(ffi::oxg_store);
+impl So3Store {
+    fn new(root: &So3) -> Self {
+        let sp = ffi::oxg_space_desc { n_real: 4, n_so2: 0, w_real: 1.0, w_so2: 1.0 };
+        let mut s = std::ptr::null_mut();
+        check(unsafe { ffi::oxg_store_create(&sp, 1024, &mut s) });
+        let (row, mut first) = (so3_row(root), 0u64);
+        check(unsafe { ffi::oxg_store_append(s, row.as_ptr(), 1, &mut first) });
+        So3Store(s)
+    }
+    fn get(&self, i: usize) -> So3 {
+        let mut v = [0.0f64; 4];
+        check(unsafe { ffi::oxg_store_read(self.0, i as u64, 1, v.as_mut_ptr()) });
+        So3 { x: v[0], y: v[1], z: v[2], w: v[3] }
+    }
+    fn chain(&self, parents: &[i64], last: i64) -> Vec<So3> {
+        let (mut states, mut i) = (Vec::new(), last);
+        while i >= 0 {
+            states.push(self.get(i as usize));
+            i = parents[i as usize];
+        }
+        states.reverse();
+        states
+    }
+}
+impl Drop for So3Store {
+    fn drop(&mut self) { unsafe { ffi::oxg_store_destroy(self.0); } }
+}
+
+fn so3_stream<G: So3BallGoal>(
+    pd: &ProblemDefinition<So3, So3Space, G>, goal_bias: f64, chunk: usize, rng: &mut impl Rng,
+) -> Vec<f64> {
+    let mut stream = Vec::with_capacity(chunk * 4);
+    for _ in 0..chunk {
+        let q = if rng.random_bool(goal_bias) {
+            pd.goal.sample_goal(rng).unwrap()
+        } else {
+            pd.space.sample_uniform(rng).unwrap()
+        };
+        stream.extend_from_slice(&so3_row(&q));
+    }
+    stream
+}
+
+/// `oxmpl::geometric::RRT` over `SO3StateSpace` (rrt.rs:63-227; oxmpl/tests/rrt_so3ss_tests.rs):
+/// `oxg_so3_rrt_solve` consumes a pre-drawn stream in speculative chunks and returns the tree the
+/// one-sample-at-a-time loop builds.
+pub struct GpuSo3RRT<G: So3BallGoal> {
+    pub max_distance: f64,
+    pub goal_bias: f64,
+    pub chunk: usize,
+    pub max_nodes: usize,
+    problem_def: Option<Arc<ProblemDefinition<So3, So3Space, G>>>,
+    cones: Option<(Arc<dyn StateValidityChecker<So3>>, ffi::oxg_so3_cones)>,
+    tree: Option<So3Store>,
+}
+impl<G: So3BallGoal> GpuSo3RRT<G> {
+    pub fn new(max_distance: f64, goal_bias: f64) -> Self {
+        Self { max_distance, goal_bias, chunk: 1 << 12, max_nodes: 1 << 20, problem_def: None,
+               cones: None, tree: None }
+    }
+}
+impl<G: So3BallGoal> Planner<So3, So3Space, G> for GpuSo3RRT<G> {
+    fn setup(&mut self, problem_def: Arc<ProblemDefinition<So3, So3Space, G>>,
+             validity_checker: Arc<dyn StateValidityChecker<So3>>) {
+        let cones = gpu_cones_of(&validity_checker);
+        self.cones = Some((validity_checker, cones));
+        self.tree = Some(So3Store::new(&problem_def.start_states[0])); // rrt.rs:147-155
+        self.problem_def = Some(problem_def);
+    }
+
+    fn solve(&mut self, timeout: Duration) -> Result<Path<So3>, PlanningError> {
+        let pd = self.problem_def.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
+        let cones = self.cones.as_ref().ok_or(PlanningError::PlannerUninitialised)?.1;
+        let tree = self.tree.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
+        let (start_time, mut rng) = (Instant::now(), rand::rng());
+        let mut parents = vec![-1i64; self.max_nodes];
+        let mut prm = ffi::oxg_plan_params {
+            max_distance: self.max_distance,
+            resolution: pd.space.get_longest_valid_segment_length() * 0.1, // rrt.rs:97
+            goal_radius: pd.goal.radius(),
+            max_nodes: self.max_nodes as u64,
+            stop_at_goal: 1,
+            ..Default::default()
+        };
+        let target = so3_row(pd.goal.target());
+        loop {
+            let elapsed = start_time.elapsed();
+            if elapsed > timeout {
+                return Err(PlanningError::Timeout);
+            }
+            prm.timeout_s = (timeout - elapsed).as_secs_f64();
+            let stream = so3_stream(pd, self.goal_bias, self.chunk, &mut rng);
+            let mut r = ffi::oxg_plan_result::default();
+            check(unsafe {
+                ffi::oxg_so3_rrt_solve(tree.0, cones, &prm, target.as_ptr(), stream.as_ptr(),
+                                       self.chunk as u64, parents.as_mut_ptr(), &mut r)
+            });
+            if r.solved != 0 {
+                return Ok(Path(tree.chain(&parents, r.goal_node[0])));
+            }
+            if r.status == 3 || r.status == 2 {
+                return Err(PlanningError::Timeout);
+            }
+        }
+    }
+}
+
+/// `oxmpl::geometric::RRTConnect` over `SO3StateSpace` (rrt_connect.rs:63-310;
+/// oxmpl/tests/rrt_connect_so3ss_tests.rs) on `oxg_so3_rrt_connect_solve`.
+pub struct GpuSo3RRTConnect<G: So3BallGoal> {
+    pub max_distance: f64,
+    pub goal_bias: f64,
+    pub chunk: usize,
+    pub max_nodes: usize,
+    problem_def: Option<Arc<ProblemDefinition<So3, So3Space, G>>>,
+    cones: Option<(Arc<dyn StateValidityChecker<So3>>, ffi::oxg_so3_cones)>,
+    start_tree: Option<So3Store>,
+    goal_tree: Option<So3Store>,
+}
+impl<G: So3BallGoal> GpuSo3RRTConnect<G> {
+    pub fn new(max_distance: f64, goal_bias: f64) -> Self {
+        Self { max_distance, goal_bias, chunk: 1 << 12, max_nodes: 1 << 20, problem_def: None,
+               cones: None, start_tree: None, goal_tree: None }
+    }
+}
+impl<G: So3BallGoal> Planner<So3, So3Space, G> for GpuSo3RRTConnect<G> {
+    fn setup(&mut self, problem_def: Arc<ProblemDefinition<So3, So3Space, G>>,
+             validity_checker: Arc<dyn StateValidityChecker<So3>>) {
+        let cones = gpu_cones_of(&validity_checker);
+        self.cones = Some((validity_checker, cones));
+        self.start_tree = Some(So3Store::new(&problem_def.start_states[0]));
+        // rrt_connect.rs:201-216: the goal tree is rooted at one sampled goal state
+        let goal_root = problem_def.goal.sample_goal(&mut rand::rng()).unwrap();
+        self.goal_tree = Some(So3Store::new(&goal_root));
+        self.problem_def = Some(problem_def);
+    }
+
+    fn solve(&mut self, timeout: Duration) -> Result<Path<So3>, PlanningError> {
+        let pd = self.problem_def.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
+        let cones = self.cones.as_ref().ok_or(PlanningError::PlannerUninitialised)?.1;
+        let ta = self.start_tree.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
+        let tb = self.goal_tree.as_ref().ok_or(PlanningError::PlannerUninitialised)?;
+        let (start_time, mut rng) = (Instant::now(), rand::rng());
+        let mut pa = vec![-1i64; self.max_nodes];
+        let mut pb = vec![-1i64; self.max_nodes];
+        let mut prm = ffi::oxg_plan_params {
+            max_distance: self.max_distance,
+            resolution: pd.space.get_longest_valid_segment_length() * 0.1,
+            goal_radius: pd.goal.radius(),
+            max_nodes: self.max_nodes as u64,
+            stop_at_goal: 1,
+            ..Default::default()
+        };
+        let target = so3_row(pd.goal.target());
+        loop {
+            let elapsed = start_time.elapsed();
+            if elapsed > timeout {
+                return Err(PlanningError::Timeout);
+            }
+            prm.timeout_s = (timeout - elapsed).as_secs_f64();
+            let stream = so3_stream(pd, self.goal_bias, self.chunk, &mut rng);
+            let mut r = ffi::oxg_plan_result::default();
+            check(unsafe {
+                ffi::oxg_so3_rrt_connect_solve(ta.0, tb.0, cones, &prm, target.as_ptr(),
+                                               stream.as_ptr(), self.chunk as u64, pa.as_mut_ptr(),
+                                               pb.as_mut_ptr(), &mut r)
+            });
+            if r.solved != 0 {
+                // rrt_connect.rs:288-304: start-side chain, then the goal-side chain reversed
+                let mut states = ta.chain(&pa, r.goal_node[0]);
+                if r.goal_node[1] >= 0 {
+                    let mut tail = tb.chain(&pb, r.goal_node[1]);
+                    tail.reverse();
+                    states.extend(tail.into_iter().skip(1));
+                }
+                return Ok(Path(states));
+            }
+            if r.status == 3 || r.status == 2 {
+                return Err(PlanningError::Timeout);
+            }
+        }
+    }
+}
+
+/// k nearest stored quaternions (`oxg_so3_knn`): rows of (index, distance), ascending.
+pub fn so3_knn(store: ffi::oxg_store, queries: &[So3], k: usize) -> (Vec<u32>, Vec<f64>) {
+    let rows: Vec<f64> = queries.iter().flat_map(so3_row).collect();
+    let (mut idx, mut dist) = (vec![0u32; queries.len() * k], vec![0.0f64; queries.len() * k]);
+    check(unsafe {
+        ffi::oxg_so3_knn(store, rows.as_ptr(), queries.len() as u64, k as u32, std::ptr::null(),
+                         idx.as_mut_ptr(), dist.as_mut_ptr())
+    });
+    (idx, dist)
 }

@@ -137,6 +137,12 @@ struct SO3ProblemDefinition {
   std::vector<SO3State> start_states;
   std::function<bool(const SO3State&)> goal_is_satisfied;   // Goal::is_satisfied
   std::function<SO3State(std::mt19937_64&)> sample_goal;    // GoalSampleableRegion::sample_goal
+  // Optional: the goal as the ball distance(state, goal_target) <= goal_radius (SO3GoalRegion,
+  // oxmpl/tests/rrt_so3ss_tests.rs:58-68).  When set, SO3RRT::solve runs the library's chunked
+  // loop (oxg_so3_rrt_solve) instead of one call per step of every iteration.
+  bool ball_goal = false;
+  SO3State goal_target;
+  double goal_radius = 0.0;
 };
 
 class SO3RRT {
@@ -163,6 +169,7 @@ class SO3RRT {
     std::bernoulli_distribution coin(goal_bias);
     const auto t0 = detail::Clock::now();
     const double res = pd_->space->get_longest_valid_segment_length() * 0.1;  // rrt.rs:97
+    if (pd_->ball_goal) return solve_chunked(timeout_s, res, rng, coin);
     while (detail::seconds_since(t0) <= timeout_s) {
       const SO3State q_rand = coin(rng) ? pd_->sample_goal(rng) : pd_->space->sample_uniform(rng);
       const auto q = q_rand.values();
@@ -189,8 +196,59 @@ class SO3RRT {
     throw PlanningError::timeout();
   }
   uint64_t tree_size() const { return nodes_.size(); }
+  uint64_t chunks() const { return chunks_; }      // device round trips of the last chunked solve
+  uint64_t iterations() const { return iters_; }
 
  private:
+  // rrt.rs:158-227 on oxg_so3_rrt_solve: the per-iteration draw (rrt.rs:177-184) does not depend
+  // on the tree, so `kStream` iterations are drawn ahead and handed to the library at once.
+  SO3Path solve_chunked(double timeout_s, double res, std::mt19937_64& rng,
+                        std::bernoulli_distribution& coin) {
+    constexpr uint64_t kStream = 4096, kMaxNodes = 1u << 20;
+    const auto t0 = detail::Clock::now();
+    std::vector<int64_t> parents(kMaxNodes, -1);
+    std::copy(parents_.begin(), parents_.end(), parents.begin());
+    oxg_plan_params prm{};
+    prm.max_distance = max_distance;
+    prm.resolution = res;
+    prm.goal_radius = pd_->goal_radius;
+    prm.max_nodes = kMaxNodes;
+    prm.stop_at_goal = 1;
+    const auto target = pd_->goal_target.values();
+    std::vector<double> stream(kStream * 4);
+    chunks_ = iters_ = 0;
+    for (;;) {
+      const double left = timeout_s - detail::seconds_since(t0);
+      if (left <= 0.0) throw PlanningError::timeout();
+      prm.timeout_s = left;
+      for (uint64_t i = 0; i < kStream; ++i) {
+        const SO3State q = coin(rng) ? pd_->sample_goal(rng) : pd_->space->sample_uniform(rng);
+        const auto v = q.values();
+        std::copy(v.begin(), v.end(), stream.begin() + i * 4);
+      }
+      oxg_plan_result r{};
+      check(oxg_so3_rrt_solve(tree_->h(), vc_->handle(), &prm, target.data(), stream.data(), kStream,
+                              parents.data(), &r));
+      chunks_ += (uint64_t)r.ctas;
+      iters_ += r.iters;
+      std::vector<double> rows((r.n_nodes[0] - nodes_.size()) * 4);
+      if (!rows.empty())
+        check(oxg_store_read(tree_->h(), nodes_.size(), rows.size() / 4, rows.data()));
+      for (std::size_t i = 0; i < rows.size(); i += 4)
+        nodes_.push_back(SO3State{rows[i], rows[i + 1], rows[i + 2], rows[i + 3]});
+      parents_.assign(parents.begin(), parents.begin() + (std::ptrdiff_t)nodes_.size());
+      if (r.solved) {
+        SO3Path p;
+        for (int64_t i = r.goal_node[0]; i >= 0; i = parents_[(std::size_t)i])
+          p.push_back(nodes_[(std::size_t)i]);
+        std::reverse(p.begin(), p.end());
+        return p;
+      }
+      if (r.status == 2 || r.status == 3) throw PlanningError::timeout();
+    }
+  }
+
+  uint64_t chunks_ = 0, iters_ = 0;
   std::shared_ptr<SO3ProblemDefinition> pd_;
   std::shared_ptr<GpuConeChecker> vc_;
   std::unique_ptr<detail::Store> tree_;

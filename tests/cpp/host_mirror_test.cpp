@@ -239,6 +239,28 @@ int main() {
       std::printf("  FAILED: %s\n", e.what());
       ++g_failures;
     }
+    // the same problem with the goal declared as a ball: the library's chunked loop, same draws
+    // -> same tree as the per-iteration loop above
+    {
+      auto pd2 = std::make_shared<SO3ProblemDefinition>(*pd);
+      pd2->ball_goal = true;
+      pd2->goal_target = target;
+      pd2->goal_radius = goal_radius;
+      SO3RRT chunked(0.5, 0.0);
+      chunked.setup(pd2, vc);
+      try {
+        const SO3Path path = chunked.solve(20.0);
+        EXPECT(path.size() > 1 && pd->goal_is_satisfied(path.back()));
+        EXPECT(chunked.tree_size() == planner.tree_size());
+        EXPECT(chunked.chunks() < chunked.iterations());
+        std::printf("  so3_rrt chunked: %zu states, tree %llu, %llu iterations in %llu chunks\n", path.size(),
+                    (unsigned long long)chunked.tree_size(), (unsigned long long)chunked.iterations(),
+                    (unsigned long long)chunked.chunks());
+      } catch (const std::exception& e) {
+        std::printf("  FAILED: %s\n", e.what());
+        ++g_failures;
+      }
+    }
     SO3RRT fresh(0.5, 0.0);
     bool threw = false;
     try {
