@@ -1314,9 +1314,15 @@ static int kd_order(oxg_store_s* s, StoreTree* t, const unsigned long long* boun
     OXG_LAUNCH_CHECK();
     int seg_bits = 0;
     while ((1u << seg_bits) < r.n_seg && seg_bits < 31) ++seg_bits;
-    // the segment id takes seg_bits, the coordinate image the rest (at least 12 bits: the split
-    // only has to put equal COUNTS on each side, ties inside a 1/4096 slice of the cell are harmless)
-    const int sub_bits = std::max(12, 32 - seg_bits);
+    // the segment id takes seg_bits, the coordinate image at least 12 bits (the split only has to
+    // put equal COUNTS on each side, ties inside a 1/4096 slice of the cell are harmless) and no
+    // more than fills whole 8-bit sort passes: 2 passes for the first rounds, 3 for the middle
+    // ones, instead of 4 for every round
+#ifndef OXG_KD_MIN_SUB
+#define OXG_KD_MIN_SUB 12
+#endif
+    const int key_bits = std::min(32, std::max(16, (seg_bits + OXG_KD_MIN_SUB + 7) / 8 * 8));
+    const int sub_bits = std::max(12, key_bits - seg_bits);
     if (seg_bits + sub_bits > 32) {
       set_error("too many segments for the 32-bit partition keys");
       return OXG_E_INTERNAL;
