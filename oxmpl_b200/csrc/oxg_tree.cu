@@ -71,7 +71,7 @@ constexpr int TREE_MAX_DIM = 8;      // dimensions the tree kernels are instanti
 #define OXG_TK_F32_LEAF 1
 #endif
 #ifndef OXG_TK_MERGE_AT
-#define OXG_TK_MERGE_AT 12
+#define OXG_TK_MERGE_AT 8
 #endif
 constexpr int TK_THREADS = OXG_TK_THREADS;  // query kernel: warps per CTA x 32
 constexpr int TK_QPC = OXG_TK_QPC;          // consecutive (key-ordered) queries per chunk
@@ -532,7 +532,9 @@ struct TreeKnnParams {
 
 constexpr int TK_MERGE_AT = OXG_TK_MERGE_AT;  // buffered candidates that trigger a merge into the list
 
-template <int D>
+// STATS: the per-query counters of oxg_store_tree_stats (a measurement build of the kernel: the
+// counters cost registers the 7-CTA budget does not have).
+template <int D, bool STATS = false>
 struct WarpQuery {
 #if OXG_TK_F32_LEAF
   float q32[D];          // the query in box space, rounded to nearest (filter input only)
@@ -586,8 +588,8 @@ __device__ __forceinline__ float tree_filter_threshold(double Ub, double M, int 
   return __double2float_ru(T);  // rounds up; overflows to +inf
 }
 
-template <int D>
-__device__ __forceinline__ void set_bound(const TreeKnnParams& p, WarpQuery<D>& w, double sk) {
+template <int D, bool S>
+__device__ __forceinline__ void set_bound(const TreeKnnParams& p, WarpQuery<D, S>& w, double sk) {
   const double U = tree_sqrt_le_upper(sk);
   w.ub = (unsigned long long)__double_as_longlong(U);
   // box space: squared lengths scale by sc2 (a power of two); 1e-12 covers the roundings of the
@@ -607,13 +609,13 @@ __device__ __forceinline__ bool pair_before(double sa, uint32_t ja, double sb, u
 // Merges the buffered candidates into the sorted list: bitonic sort of the buffer across the
 // lanes, min-exchange against the reversed list, bitonic merge.  Order is the exact
 // (sqrt(d2), index) one, so visiting order never shows in the result.
-template <int D>
+template <int D, bool S>
 #if OXG_TK_MERGE_INLINE
 __device__ __forceinline__ void merge_buffer(
 #else
 __device__ __noinline__ void merge_buffer(
 #endif
-const TreeKnnParams& p, WarpQuery<D>& w) {
+const TreeKnnParams& p, WarpQuery<D, S>& w) {
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   __syncwarp();
   double s = inf;
@@ -627,10 +629,14 @@ const TreeKnnParams& p, WarpQuery<D>& w) {
     }
   }
   __syncwarp();
+  const int filled = w.bc;
   w.bc = 0;
-  ++w.n_merge;
+  if constexpr (S) ++w.n_merge;
+  // lanes >= filled hold +inf, so once k2 / 2 >= filled the lower half is sorted ascending and the
+  // upper half is all sentinels: the remaining stages would not move anything
 #pragma unroll
   for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+    if (k2 > 2 && (k2 >> 1) >= filled) break;
 #pragma unroll
     for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
       const double so = __shfl_xor_sync(0xFFFFFFFFu, s, j2);
@@ -670,13 +676,13 @@ const TreeKnnParams& p, WarpQuery<D>& w) {
     w.my_i = OXG_INVALID_INDEX;
   }
   w.have = __popc(__ballot_sync(0xFFFFFFFFu, w.my_i != OXG_INVALID_INDEX));
-  if (w.have == w.k) set_bound<D>(p, w, __shfl_sync(0xFFFFFFFFu, w.my_s, w.k - 1));
+  if (w.have == w.k) set_bound(p, w, __shfl_sync(0xFFFFFFFFu, w.my_s, w.k - 1));
 }
 
 #if OXG_TK_F32_LEAF
 // FP32 filter value of state `lane` of a leaf (box space; decides nothing, see tree_filter_threshold).
-template <int D>
-__device__ __forceinline__ float leaf_a32(const TreeKnnParams& p, const WarpQuery<D>& w, uint32_t leaf) {
+template <int D, bool S>
+__device__ __forceinline__ float leaf_a32(const TreeKnnParams& p, const WarpQuery<D, S>& w, uint32_t leaf) {
   const float* lp = p.t.pts32 + (uint64_t)leaf * (D * 32) + w.lane;
   float pv[D];
 #pragma unroll
@@ -693,11 +699,11 @@ __device__ __forceinline__ float leaf_a32(const TreeKnnParams& p, const WarpQuer
 // The states the filter could not discard are evaluated in the reference's operation order
 // (real_vector_state_space.rs:148-153) and go through the admission test; the survivors go to the
 // candidate buffer.
-template <int D>
-__device__ __forceinline__ void leaf_commit(const TreeKnnParams& p, WarpQuery<D>& w, uint32_t leaf, float a32) {
-  ++w.n_leaf;
+template <int D, bool S>
+__device__ __forceinline__ void leaf_commit(const TreeKnnParams& p, WarpQuery<D, S>& w, uint32_t leaf, float a32) {
+  if constexpr (S) ++w.n_leaf;
   if (__ballot_sync(0xFFFFFFFFu, !(a32 > w.T32)) == 0u) return;
-  ++w.n_exact;
+  if constexpr (S) ++w.n_exact;
   double d2 = __longlong_as_double(0x7FF8000000000000ll);
   if (!(a32 > w.T32)) {
     const double* lp = p.t.pts + (uint64_t)leaf * (D * 32) + w.lane;
@@ -714,7 +720,7 @@ __device__ __forceinline__ void leaf_commit(const TreeKnnParams& p, WarpQuery<D>
   if (m == 0) return;
   int n = __popc(m);
   if (w.bc + n > 32) {
-    merge_buffer<D>(p, w);
+    merge_buffer(p, w);
     pass = (unsigned long long)__double_as_longlong(d2) <= w.ub;  // the bound moved
     m = __ballot_sync(0xFFFFFFFFu, pass);
     n = __popc(m);
@@ -725,15 +731,15 @@ __device__ __forceinline__ void leaf_commit(const TreeKnnParams& p, WarpQuery<D>
     w.b_j[slot] = __ldg(p.t.perm + (uint64_t)leaf * 32 + w.lane);
   }
   w.bc += n;
-  w.n_cand += n;
-  if (w.bc >= TK_MERGE_AT || w.have < w.k) merge_buffer<D>(p, w);
+  if constexpr (S) w.n_cand += n;
+  if (w.bc >= TK_MERGE_AT || w.have < w.k) merge_buffer(p, w);
 }
 #define OXG_LEAF_EVAL leaf_a32
 #else
 // Reference-order squared distance of the query to state `lane` of a leaf
 // (real_vector_state_space.rs:148-153).
-template <int D>
-__device__ __forceinline__ double leaf_d2(const TreeKnnParams& p, const WarpQuery<D>& w, uint32_t leaf) {
+template <int D, bool S>
+__device__ __forceinline__ double leaf_d2(const TreeKnnParams& p, const WarpQuery<D, S>& w, uint32_t leaf) {
   const double* lp = p.t.pts + (uint64_t)leaf * (D * 32) + w.lane;
   double pv[D];
 #pragma unroll
@@ -749,17 +755,17 @@ __device__ __forceinline__ double leaf_d2(const TreeKnnParams& p, const WarpQuer
 }
 
 // Admission test of a leaf's 32 distances; the survivors go to the candidate buffer.
-template <int D>
-__device__ __forceinline__ void leaf_commit(const TreeKnnParams& p, WarpQuery<D>& w, uint32_t leaf,
+template <int D, bool S>
+__device__ __forceinline__ void leaf_commit(const TreeKnnParams& p, WarpQuery<D, S>& w, uint32_t leaf,
                                             double d2) {
   // d2 >= +0 or NaN; every NaN pattern (pads included) compares above any ub as unsigned
   bool pass = (unsigned long long)__double_as_longlong(d2) <= w.ub;
   uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
-  ++w.n_leaf;
+  if constexpr (S) ++w.n_leaf;
   if (m == 0) return;
   int n = __popc(m);
   if (w.bc + n > 32) {
-    merge_buffer<D>(p, w);
+    merge_buffer(p, w);
     pass = (unsigned long long)__double_as_longlong(d2) <= w.ub;  // the bound moved
     m = __ballot_sync(0xFFFFFFFFu, pass);
     n = __popc(m);
@@ -770,17 +776,21 @@ __device__ __forceinline__ void leaf_commit(const TreeKnnParams& p, WarpQuery<D>
     w.b_j[slot] = __ldg(p.t.perm + (uint64_t)leaf * 32 + w.lane);
   }
   w.bc += n;
-  w.n_cand += n;
-  if (w.bc >= TK_MERGE_AT || w.have < w.k) merge_buffer<D>(p, w);
+  if constexpr (S) w.n_cand += n;
+  if (w.bc >= TK_MERGE_AT || w.have < w.k) merge_buffer(p, w);
 }
 
 #define OXG_LEAF_EVAL leaf_d2
 #endif
 
 // Tests the 32 children of `group` at level L and descends into the survivors, nearest first.
+// Every lane owns one child: `mine` says it is still to be visited, and the lane whose key equals
+// the warp minimum is the one being visited (keys carry the lane in their low bits, so they are
+// unique) -- no lane index is needed inside the loop.
 template <int D, int L>
 struct Visit {
-  static __device__ __forceinline__ void run(const TreeKnnParams& p, WarpQuery<D>& w, uint32_t group) {
+  template <bool S>
+  static __device__ __forceinline__ void run(const TreeKnnParams& p, WarpQuery<D, S>& w, uint32_t group) {
     const uint32_t child0 = group * 32u;
     const float* bp = p.t.boxes32[L] + (uint64_t)group * (2 * D * 32) + w.lane;
     // certified lower bound in the box space: boxes rounded outward, the query bracketed, every
@@ -797,30 +807,29 @@ struct Visit {
       const float t = fmaxf(fmaxf(__fsub_rd(blo[d], w.qbox[D + d]), __fsub_rd(w.qbox[d], bhi[d])), 0.0f);
       lb = __fadd_rd(lb, __fmul_rd(t, t));
     }
-    ++w.n_box;
+    if constexpr (S) ++w.n_box;
     const uint32_t key = (__float_as_uint(lb) & 0xFFFFFFE0u) | (uint32_t)w.lane;
-    uint32_t cand = __ballot_sync(0xFFFFFFFFu, child0 + (uint32_t)w.lane < p.t.count[L]);
+    bool mine = child0 + (uint32_t)w.lane < p.t.count[L];
     for (;;) {
-      const bool alive = ((cand >> w.lane) & 1u) && !(lb > w.Uf);
-      cand = __ballot_sync(0xFFFFFFFFu, alive);
-      if (!cand) break;
+      const bool alive = mine && !(lb > w.Uf);
       const uint32_t r = __reduce_min_sync(0xFFFFFFFFu, alive ? key : 0xFFFFFFFFu);
+      if (r == 0xFFFFFFFFu) break;
       const uint32_t c = r & 31u;
-      cand &= ~(1u << c);
+      if (key == r) mine = false;
       if constexpr (L == 0) {
         // two leaves per round: both loads are in flight before either is consumed
         const uint32_t r1 = OXG_TK_TWO_LEAVES
-                                ? __reduce_min_sync(0xFFFFFFFFu, (alive && (uint32_t)w.lane != c) ? key : 0xFFFFFFFFu)
+                                ? __reduce_min_sync(0xFFFFFFFFu, (alive && key != r) ? key : 0xFFFFFFFFu)
                                 : 0xFFFFFFFFu;
         if (OXG_TK_TWO_LEAVES && r1 != 0xFFFFFFFFu) {
           const uint32_t c1 = r1 & 31u;
-          cand &= ~(1u << c1);
-          const auto da = OXG_LEAF_EVAL<D>(p, w, child0 + c);
-          const auto db = OXG_LEAF_EVAL<D>(p, w, child0 + c1);
-          leaf_commit<D>(p, w, child0 + c, da);
-          leaf_commit<D>(p, w, child0 + c1, db);
+          if (key == r1) mine = false;
+          const auto da = OXG_LEAF_EVAL(p, w, child0 + c);
+          const auto db = OXG_LEAF_EVAL(p, w, child0 + c1);
+          leaf_commit(p, w, child0 + c, da);
+          leaf_commit(p, w, child0 + c1, db);
         } else {
-          leaf_commit<D>(p, w, child0 + c, OXG_LEAF_EVAL<D>(p, w, child0 + c));
+          leaf_commit(p, w, child0 + c, OXG_LEAF_EVAL(p, w, child0 + c));
         }
       } else {
         Visit<D, L - 1>::run(p, w, child0 + c);
@@ -831,7 +840,7 @@ struct Visit {
 
 // Persistent CTAs: chunks of TK_QPC key-ordered queries are dealt round-robin to the CTAs, so all
 // warps of an SM work on neighbouring queries at the same time and share the leaves through L1.
-template <int D>
+template <int D, bool STATS>
 __global__ void __launch_bounds__(TK_THREADS, OXG_TK_MIN_CTAS) tree_knn_kernel(const TreeKnnParams p) {
 #if OXG_TK_F32_LEAF
   __shared__ double s_q[TK_THREADS / 32][D];
@@ -845,14 +854,14 @@ __global__ void __launch_bounds__(TK_THREADS, OXG_TK_MIN_CTAS) tree_knn_kernel(c
   const int wid = threadIdx.x >> 5;
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   const double sc = p.plan->sc;
-  unsigned long long st_leaf = 0, st_box = 0, st_cand = 0, st_merge = 0, st_exact = 0;
+  [[maybe_unused]] unsigned long long st_leaf = 0, st_box = 0, st_cand = 0, st_merge = 0, st_exact = 0;
   const uint32_t n_chunks = (p.Q + p.qpc - 1) / p.qpc;
   for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     const uint32_t q_begin = chunk * p.qpc;
     const uint32_t q_end = min(p.Q, q_begin + p.qpc);
     for (uint32_t wq = q_begin + wid; wq < q_end; wq += TK_THREADS / 32) {
       const uint32_t qi = p.qorder ? __ldg(p.qorder + wq) : wq;
-      WarpQuery<D> w;
+      WarpQuery<D, STATS> w;
       bool qnan = false;
       __syncwarp();
 #if OXG_TK_F32_LEAF
@@ -912,21 +921,23 @@ __global__ void __launch_bounds__(TK_THREADS, OXG_TK_MIN_CTAS) tree_knn_kernel(c
           case 3: Visit<D, 3>::run(p, w, 0); break;
           default: Visit<D, 4>::run(p, w, 0); break;
         }
-        if (w.bc > 0) merge_buffer<D>(p, w);
+        if (w.bc > 0) merge_buffer(p, w);
       }
       if (lane < (int)p.k) {
         const uint64_t o = (uint64_t)qi * p.k + lane;
         p.out_idx[o] = w.my_i;
         p.out_dist[o] = w.my_s;
       }
-      st_leaf += w.n_leaf;
-      st_box += w.n_box;
-      st_cand += w.n_cand;
-      st_merge += w.n_merge;
-      st_exact += w.n_exact;
+      if constexpr (STATS) {
+        st_leaf += w.n_leaf;
+        st_box += w.n_box;
+        st_cand += w.n_cand;
+        st_merge += w.n_merge;
+        st_exact += w.n_exact;
+      }
     }
   }
-  if (p.stats && lane == 0) {
+  if (STATS && p.stats && lane == 0) {
     atomicAdd(&p.stats[0], st_leaf);
     atomicAdd(&p.stats[1], st_box);
     atomicAdd(&p.stats[2], st_cand);
@@ -1418,7 +1429,10 @@ static int launch_tree_knn(TreeKnnParams p, cudaStream_t st) {
   p.qpc = std::max(warps, std::min<unsigned>(qpc, TK_QPC));
   const unsigned chunks = (p.Q + p.qpc - 1) / p.qpc;
   const unsigned grid = OXG_TK_PERSISTENT ? std::max(1u, std::min(chunks, (unsigned)sms * OXG_TK_MIN_CTAS)) : chunks;
-  tree_knn_kernel<D><<<grid, TK_THREADS, 0, st>>>(p);
+  if (p.stats)
+    tree_knn_kernel<D, true><<<grid, TK_THREADS, 0, st>>>(p);
+  else
+    tree_knn_kernel<D, false><<<grid, TK_THREADS, 0, st>>>(p);
   OXG_LAUNCH_CHECK();
   return OXG_OK;
 }
