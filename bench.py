@@ -46,11 +46,14 @@ DIM = 7
 SEED = 4
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this config, from the `ncu --set
 # full` captures summarised in profiles/ (None until captured for the current kernel)
-TREE_DRAM_BYTES_NCU = 661177344  # profiles/r02_ncu_full_hot_kernels.csv (532.4 MB read + 128.8 MB written; captured at 821 776 nodes)
+TREE_DRAM_BYTES_NCU = 913045248  # profiles/r02c_ncu_full_hot_kernels.csv (753.9 MB read + 159.2 MB written; 1e6 queries)
 # the same capture: share of tree_knn_kernel's L1 sector requests that hit L1 (the rest go to L2),
-# and the L2 read sectors it caused (x 32 B = 73.8 GB for 821 776 queries)
-TREE_L1_HIT_NCU = 0.2456
-TREE_L2_READ_BYTES_PER_QUERY_NCU = 2305868772 * 32 / 821776
+# the L2 read sectors it caused (x 32 B = 86.4 GB for 1e6 queries), the issue-slot utilisation and
+# the executed warp instructions
+TREE_L1_HIT_NCU = 0.2180
+TREE_L2_READ_BYTES_PER_QUERY_NCU = 2700565645 * 32 / 1000000
+TREE_ISSUE_ACTIVE_NCU = 0.708
+TREE_WARP_INSTRUCTIONS_NCU = 8113218346
 ALLPAIRS_DRAM_BYTES_NCU = 2249420000  # profiles/r01_ncu_full_knn_rv_dot_7_2.csv (2.046 GB read + 0.204 GB written)
 
 
@@ -555,9 +558,16 @@ def run_ours(args):
                            "ld.global.cg, measured in this run (MEASURED_PEAKS.json's HBM figure, "
                            "%s GB/s, does not bound an L2-resident working set; the pipe peaks are "
                            "oxg_fp32_peak / oxg_fp64_peak)" % _measured_hbm(),
-            "note": "an irregular traversal of ~100 dependent steps per query over 1.1 % of the all-pairs "
-                    "pair count: L2 latency, not bandwidth or arithmetic, limits it (ncu: long-scoreboard "
-                    "stalls 5.0 per issue, issue slots 59 %, L2 hit 99 %)",
+            "issue_slots": {"what": "smsp__issue_active of the ncu capture in profiles/ (same workload): the "
+                                    "share of the schedulers' issue cycles the kernel uses; the executed "
+                                    "warp instructions per query are the quantity left to shrink",
+                            "frac_ncu": TREE_ISSUE_ACTIVE_NCU,
+                            "warp_instructions_per_query_ncu": TREE_WARP_INSTRUCTIONS_NCU / 1e6},
+            "note": "an irregular traversal of ~95 dependent steps per query over 1.0 % of the all-pairs "
+                    "pair count; the working set is L2-resident, so the memory roofline is the L2's. "
+                    "ncu: issue slots 71 %, long-scoreboard stalls 2.6 per issue, L2 hit 98 % -- the "
+                    "kernel is bound by instruction issue first and L2 latency second, not by bandwidth "
+                    "or arithmetic",
             "hbm_peak_gbs_measured": _measured_hbm(),
         }
         line = {

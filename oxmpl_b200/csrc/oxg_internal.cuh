@@ -141,6 +141,9 @@ enum StoreBuf {
   B_PARENT,     // planner trees: parent index of every node (i64, -1 = root)
   B_COST,       // RRT*: cost-to-come of every node (f64)
   B_PLAN,       // planner kernels: control block, barrier scratch, per-CTA neighbour lists
+  B_EROW,       // PRM edge phase: owner row of every candidate edge
+  B_ROWCNT,     // PRM edge phase: per-row count of obstacle pairs that survive the row cull
+  B_ROWLIST,    // PRM edge phase: those pairs
   B_COUNT
 };
 
@@ -303,10 +306,29 @@ int nn_knn_device(oxg_store_s* s, StateView q, uint64_t Q, uint32_t k, int exclu
 // E_dev (nullable): the edge count is read from device memory at kernel start (E is then
 // only an upper bound used to size the grid), so a producer kernel can feed the check without
 // a host round-trip.
+// Row cull (PRM k-NN build): every candidate edge owned by row r lies inside the ball around
+// state r whose radius is r's longest candidate edge, so the obstacles that ball cannot touch are
+// ruled out once per row instead of once per edge.  e_row[e] = owner row of edge e (relative to
+// the first row of the lists), row_cnt[r] = surviving capsule pairs of row r (kRowCullOverflow:
+// too many, the edge takes the full pass), row_list[r * kRowCullCap ..] = their pair indices.
+constexpr uint32_t kRowCullCap = 64;
+constexpr uint16_t kRowCullOverflow = 0xFFFF;
+struct RowCull {
+  const uint32_t* e_row = nullptr;
+  const uint16_t* row_cnt = nullptr;
+  const uint16_t* row_list = nullptr;
+};
 int motion_check_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t stream,
                         StateView from, StateView to, const uint32_t* d_from_idx,
                         const uint32_t* d_to_idx, uint64_t E, const uint64_t* E_dev,
-                        double resolution, uint8_t* d_valid, uint32_t* d_first_invalid);
+                        double resolution, uint8_t* d_valid, uint32_t* d_first_invalid,
+                        const RowCull* row_cull = nullptr);
+// Fills the row lists for rows [row_begin, row_end) of the store (their candidates are
+// d_idx[(row - base_row) * k ..]); *enabled = false when this world / space / size does not take
+// the row-cull path (nothing is written then).
+int prm_row_cull_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t stream, StateView st,
+                        const uint32_t* d_idx, uint32_t k, uint64_t base_row, uint64_t row_begin,
+                        uint64_t row_end, uint16_t* row_cnt, uint16_t* row_list, bool* enabled);
 int is_valid_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t stream,
                     StateView st, uint64_t Q, uint8_t* d_out);
 int nn_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double r, const uint32_t* d_idx_limit,

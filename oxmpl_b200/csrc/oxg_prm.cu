@@ -27,7 +27,8 @@ __global__ void prm_mark_edges_kernel(const uint32_t* __restrict__ idx, uint32_t
                                       uint64_t avail_begin, uint64_t avail_end, uint64_t row_begin,
                                       uint64_t row_end, uint8_t* __restrict__ valid,
                                       uint32_t* __restrict__ e_from, uint32_t* __restrict__ e_to,
-                                      uint32_t* __restrict__ e_slot, uint64_t* __restrict__ counters) {
+                                      uint32_t* __restrict__ e_slot, uint32_t* __restrict__ e_row,
+                                      uint64_t* __restrict__ counters) {
   const uint64_t nslots = (row_end - row_begin) * k;
   for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nslots;
        u += (uint64_t)gridDim.x * blockDim.x) {
@@ -56,6 +57,7 @@ __global__ void prm_mark_edges_kernel(const uint32_t* __restrict__ idx, uint32_t
       e_from[pos] = (uint32_t)(i > j ? i : j);
       e_to[pos] = (uint32_t)(i > j ? j : i);
       e_slot[pos] = (uint32_t)t;
+      if (e_row) e_row[pos] = (uint32_t)(i - row_begin);  // owner row, for the row cull
     }
   }
 }
@@ -128,12 +130,28 @@ static int prm_edges(const oxg_world_s* w, oxg_store_s* s, const uint32_t* d_idx
   uint32_t* e_slot = s->buf[B_AUX3].as<uint32_t>();
   uint8_t* e_valid = s->buf[B_TMP].as<uint8_t>();
   OXG_CUDA_TRY(cudaMemsetAsync(d_counters, 0, 2 * sizeof(uint64_t), s->stream));
+  // Row cull: the obstacles no candidate edge of a row can touch are ruled out once per row
+  // (oxg_internal.cuh); the edge kernel then starts from the row's short list.
+  OXG_TRY(s->buf[B_ROWCNT].ensure(rows * sizeof(uint16_t)));
+  OXG_TRY(s->buf[B_ROWLIST].ensure(rows * kRowCullCap * sizeof(uint16_t)));
+  bool row_cull = false;
+  OXG_TRY(prm_row_cull_device(w, s->space, s->stream, store_view(s), d_idx, k, base_row, row_begin, row_end,
+                              s->buf[B_ROWCNT].as<uint16_t>(), s->buf[B_ROWLIST].as<uint16_t>(), &row_cull));
+  uint32_t* e_row = nullptr;
+  if (row_cull) {
+    OXG_TRY(s->buf[B_EROW].ensure(nslots * sizeof(uint32_t)));
+    e_row = s->buf[B_EROW].as<uint32_t>();
+  }
   prm_mark_edges_kernel<<<grid_for(nslots, 256), 256, 0, s->stream>>>(
-      d_idx, k, base_row, avail_begin, avail_end, row_begin, row_end, d_valid, e_from, e_to, e_slot,
+      d_idx, k, base_row, avail_begin, avail_end, row_begin, row_end, d_valid, e_from, e_to, e_slot, e_row,
       d_counters);
   OXG_LAUNCH_CHECK();
+  RowCull rc;
+  rc.e_row = e_row;
+  rc.row_cnt = s->buf[B_ROWCNT].as<uint16_t>();
+  rc.row_list = s->buf[B_ROWLIST].as<uint16_t>();
   OXG_TRY(motion_check_device(w, s->space, s->stream, store_view(s), store_view(s), e_from, e_to,
-                              nslots, d_counters, resolution, e_valid, nullptr));
+                              nslots, d_counters, resolution, e_valid, nullptr, row_cull ? &rc : nullptr));
   prm_scatter_valid_kernel<<<grid_for(nslots, 256), 256, 0, s->stream>>>(e_valid, e_slot, d_counters,
                                                                         d_valid);
   OXG_LAUNCH_CHECK();

@@ -150,6 +150,7 @@ struct MotionParams {
   uint8_t* valid;
   uint32_t* first_invalid;  // nullable
   uint32_t world_smem_bytes;  // dynamic shared memory available for the staged f32 mirrors
+  RowCull rc;                 // motion_cull_kernel: per-row survivor lists (all null: full pass)
 };
 
 template <int DT, int L>
@@ -329,10 +330,44 @@ __global__ void __launch_bounds__(128, 6) motion_cull_kernel(const MotionParams 
       }
       cnt += __popc(b);
     }
-    for (uint32_t i0 = 0; i0 < n_cap; i0 += 2 * L) {
+    // capsules: the pairs the owner row's ball could not rule out (row cull), else all of them
+    bool all_caps = live;
+    if (p.rc.row_cnt) {
+      const uint32_t row = live ? __ldg(p.rc.e_row + e) : 0u;
+      const uint32_t rcnt = live ? (uint32_t)__ldg(p.rc.row_cnt + row) : 0u;
+      all_caps = live && rcnt == kRowCullOverflow;
+      const uint32_t mine = all_caps ? 0u : rcnt;
+      const uint16_t* rl = p.rc.row_list + (size_t)row * kRowCullCap;
+      const uint32_t most = __reduce_max_sync(FULL, mine);
+      for (uint32_t s0 = 0; s0 < most; s0 += L) {
+        const uint32_t sidx = s0 + lane_g;
+        unsigned mh = 0;
+        uint32_t i = 0;
+        if (sidx < mine) {
+          i = 2u * (uint32_t)__ldg(rl + sidx);
+          mh = capsule_pair_fat_maybe_hit32_s<DT>(mf, sm_cap + (i >> 1) * w.capsule32p_stride * 4u, tol.a2_c,
+                                                  tol.ce_c, ft);
+          if (i + 1 >= n_cap) mh &= 1u;
+        }
+        const unsigned b0 = (__ballot_sync(FULL, (mh & 1u) != 0) >> group_shift) & GMASK;
+        const unsigned b1 = (__ballot_sync(FULL, (mh & 2u) != 0) >> group_shift) & GMASK;
+        if (mh & 1u) {
+          const unsigned pos = cnt + __popc(b0 & below);
+          if (pos < CULL_CAP) my_list[pos] = (uint16_t)(n_sph + n_box + i);
+        }
+        cnt += __popc(b0);
+        if (mh & 2u) {
+          const unsigned pos = cnt + __popc(b1 & below);
+          if (pos < CULL_CAP) my_list[pos] = (uint16_t)(n_sph + n_box + i + 1);
+        }
+        cnt += __popc(b1);
+      }
+    }
+    const uint32_t n_cap_walk = __any_sync(FULL, all_caps) ? n_cap : 0u;
+    for (uint32_t i0 = 0; i0 < n_cap_walk; i0 += 2 * L) {
       const uint32_t i = i0 + 2 * lane_g;
       unsigned mh = 0;
-      if (live && i < n_cap)
+      if (all_caps && i < n_cap)
         mh = capsule_pair_fat_maybe_hit32_s<DT>(mf, sm_cap + (i >> 1) * w.capsule32p_stride * 4u, tol.a2_c,
                                                 tol.ce_c, ft);
       if (i + 1 >= n_cap) mh &= 1u;
@@ -408,6 +443,88 @@ __global__ void __launch_bounds__(128, 6) motion_cull_kernel(const MotionParams 
       if (p.first_invalid)
         p.first_invalid[e] = first_bad > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)first_bad;
     }
+  }
+}
+
+
+// Row cull of the PRM k-NN build (see RowCull in oxg_internal.cuh): one warp per row.  The ball is
+// centred on the row's state; its radius is the longest of the row's candidate edges, computed
+// with the same reference-order distance the edge kernel uses, so every interpolated state of
+// every owned edge lies inside it and the certified fat test (FatTol) may discard for all of them.
+struct RowCullParams {
+  WorldView w;
+  StateView st;
+  const uint32_t* idx;
+  uint32_t k;
+  uint64_t base_row, row_begin, row_end;
+  uint16_t* row_cnt;
+  uint16_t* row_list;
+  uint32_t world_smem_bytes;
+};
+
+template <int DT>
+__global__ void __launch_bounds__(128, 6) prm_row_cull_kernel(const RowCullParams p) {
+  extern __shared__ __align__(16) unsigned char world_smem[];
+  uint32_t sm_sph = 0, sm_cap = 0;
+  stage_world32(p.w, p.world_smem_bytes, world_smem, &sm_sph, &sm_cap);
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned below = (1u << lane) - 1u;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const WorldView& w = p.w;
+  const uint32_t n_cap = w.n_capsules, n_pairs = (n_cap + 1) / 2;
+  const double inf = __longlong_as_double(0x7FF0000000000000ll);
+  FatTol ft;
+  ft.sqrt_d = __double2float_ru(sqrt((double)DT) * 1.000001);
+  ft.inv_sqrt_d = __double2float_ru(1.000001 / sqrt((double)DT));
+  for (uint64_t r = p.row_begin + warp; r < p.row_end; r += nwarps) {
+    double x[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) x[d] = p.st.p[r * p.st.stride_i + (uint64_t)d * p.st.stride_d];
+    // longest candidate edge of the row: lane s takes slot s (k <= 32)
+    double dj = 0.0;
+    if (lane < p.k) {
+      const uint32_t j = __ldg(p.idx + (r - p.base_row) * p.k + lane);
+      if (j != OXG_INVALID_INDEX) {
+        double y[DT];
+#pragma unroll
+        for (int d = 0; d < DT; ++d) y[d] = p.st.p[(uint64_t)j * p.st.stride_i + (uint64_t)d * p.st.stride_d];
+        dj = sqrt(rv_sumsq_dev<DT>(x, y, DT));
+      }
+    }
+    const bool odd = __any_sync(FULL, !(dj == dj));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dj = fmax(dj, __shfl_xor_sync(FULL, dj, o));
+    const double R = odd ? inf : dj;
+    double ms = 0.0;
+    float mf[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+      ms = fmax(ms, fabs(x[d]));
+      if (!(x[d] == x[d])) ms = __longlong_as_double(0x7FF8000000000000ll);
+      mf[d] = __double2float_rn(x[d]);
+    }
+    ms = ms + R;  // every coordinate of every state of the row's edges is within R of x
+    const EdgeTol tol = edge_tol_dev(ms * 1.0000001, w.wmax_spheres, w.wmax_capsules, DT);
+    ft.rho = __double2float_ru(R * 1.00001 + ms * 1.0e-6 + 1e-37);  // NaN / inf: nothing is culled
+    uint16_t* out = p.row_list + (size_t)(r - p.row_begin) * kRowCullCap;
+    unsigned cnt = 0;
+    for (uint32_t q0 = 0; q0 < n_pairs; q0 += 32) {
+      const uint32_t q = q0 + lane;
+      unsigned mh = 0;
+      if (q < n_pairs) {
+        mh = capsule_pair_fat_maybe_hit32_s<DT>(mf, sm_cap + q * w.capsule32p_stride * 4u, tol.a2_c, tol.ce_c, ft);
+        if (2 * q + 1 >= n_cap) mh &= 1u;
+      }
+      const unsigned b = __ballot_sync(FULL, mh != 0);
+      if (mh) {
+        const unsigned pos = cnt + __popc(b & below);
+        if (pos < kRowCullCap) out[pos] = (uint16_t)q;
+      }
+      cnt += __popc(b);
+    }
+    if (lane == 0) p.row_cnt[r - p.row_begin] = cnt > kRowCullCap ? kRowCullOverflow : (uint16_t)cnt;
   }
 }
 
@@ -589,7 +706,8 @@ int is_valid_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t
 int motion_check_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t stream,
                         StateView from, StateView to, const uint32_t* d_from_idx,
                         const uint32_t* d_to_idx, uint64_t E, const uint64_t* E_dev,
-                        double resolution, uint8_t* d_valid, uint32_t* d_first_invalid) {
+                        double resolution, uint8_t* d_valid, uint32_t* d_first_invalid,
+                        const RowCull* row_cull) {
   OXG_TRY(check_world_space(w, sp));
   if (!(resolution > 0.0)) {
     set_error("motion resolution must be > 0 (got %g): the reference loop would not terminate",
@@ -634,6 +752,7 @@ int motion_check_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStre
     return !(v && v[0] == '0');
   }();
   if (cull_on && stage > 0 && !wide && w->n_so2 == 0 && n_obst >= 16 && n_obst <= 60000) {
+    if (row_cull) p.rc = *row_cull;
     OXG_DISPATCH_FAST_DT(fast_dim(sp), (motion_cull_kernel<DD, 4><<<blocks, threads, stage, stream>>>(p)));
     OXG_LAUNCH_CHECK();
     return OXG_OK;
@@ -644,6 +763,43 @@ int motion_check_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStre
     OXG_DISPATCH_DT(fast_dim(sp), (motion_kernel<DD, 4><<<blocks, threads, stage, stream>>>(p)));
   }
   OXG_LAUNCH_CHECK();
+  return OXG_OK;
+}
+
+// The row lists are only consumed by motion_cull_kernel: the conditions below are the ones under
+// which motion_check_device takes that kernel for the same world / space / edge count.
+int prm_row_cull_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t stream, StateView st,
+                        const uint32_t* d_idx, uint32_t k, uint64_t base_row, uint64_t row_begin,
+                        uint64_t row_end, uint16_t* row_cnt, uint16_t* row_list, bool* enabled) {
+  *enabled = false;
+  static const bool on = [] {
+    const char* v = getenv("OXG_ROW_CULL");
+    const char* c = getenv("OXG_MOTION_CULL");
+    return !(v && v[0] == '0') && !(c && c[0] == '0');
+  }();
+  const uint64_t rows = row_end - row_begin;
+  const uint64_t n_obst = w->n_spheres + w->n_aabbs + w->n_capsules + w->n_so2;
+  size_t stage = (size_t)w->n_spheres * w->sphere32_stride * 4 +
+                 (size_t)((w->n_capsules + 1) / 2) * w->capsule32p_stride * 4;
+  if (!on || rows == 0 || k == 0 || k > 32 || fast_dim(sp) == 0 || fast_dim(sp) > kMaxFastDim ||
+      stage == 0 || stage > 40 * 1024 || w->n_so2 != 0 || w->n_capsules < 64 || n_obst > 60000 ||
+      rows * k < 148ull * 64)
+    return OXG_OK;
+  RowCullParams p;
+  p.w = world_view(w);
+  p.st = st;
+  p.idx = d_idx;
+  p.k = k;
+  p.base_row = base_row;
+  p.row_begin = row_begin;
+  p.row_end = row_end;
+  p.row_cnt = row_cnt;
+  p.row_list = row_list;
+  p.world_smem_bytes = (uint32_t)stage;
+  const unsigned blocks = (unsigned)std::min<uint64_t>((rows + 3) / 4, 148ull * 16);
+  OXG_DISPATCH_FAST_DT(fast_dim(sp), (prm_row_cull_kernel<DD><<<blocks, 128, stage, stream>>>(p)));
+  OXG_LAUNCH_CHECK();
+  *enabled = true;
   return OXG_OK;
 }
 
