@@ -415,7 +415,9 @@ uint64_t oxg_kernel_launches(int reset);
  * 1 = balanced partition order (a few ms per 1e6 states, about half the leaf visits per query),
  * -1 = by batch size (default).  "tree_stats": 1 = time the hierarchy build and
  * the query kernel for oxg_store_tree_stats, 2 = also count the visits (the counters cost the
- * query kernel ~15 %), 0 = neither (default). */
+ * query kernel ~15 %), 0 = neither (default).  "row_cull": 0 = the k-NN PRM edge phase tests every
+ * obstacle against every edge's own ball only, 1 = it first rules obstacles out once per row
+ * (default). */
 int oxg_tuning_set(const char* key, int64_t value);
 /* Counters of the most recent k-NN answered through the hierarchy with "tree_stats" on:
  * out8 = { build ms, query-kernel ms, leaves visited, 32-child box groups tested, candidates

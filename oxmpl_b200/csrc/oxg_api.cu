@@ -15,6 +15,7 @@ std::atomic<int> g_tune_knn_tree{-1};
 std::atomic<int> g_tune_tree_cache{1};
 std::atomic<int> g_tune_tree_stats{0};
 std::atomic<int> g_tune_tree_kind{-1};
+std::atomic<int> g_tune_row_cull{1};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -292,6 +293,10 @@ int oxg_tuning_set(const char* key, int64_t value) {
   }
   if (strcmp(key, "tree_stats") == 0) {
     g_tune_tree_stats.store(value <= 0 ? 0 : (value >= 2 ? 2 : 1));
+    return OXG_OK;
+  }
+  if (strcmp(key, "row_cull") == 0) {
+    g_tune_row_cull.store(value ? 1 : 0);
     return OXG_OK;
   }
   set_error("unknown tuning key '%s'", key);

@@ -352,6 +352,7 @@ int tree_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double U, const 
 extern std::atomic<int> g_tune_knn_tree;
 extern std::atomic<int> g_tune_tree_cache;  // 0 = rebuild the hierarchy for every batch
 extern std::atomic<int> g_tune_tree_kind;   // -1 auto, 0 space-filling key order, 1 balanced partition
+extern std::atomic<int> g_tune_row_cull;    // 0 = the PRM edge phase culls per edge only
 extern std::atomic<int> g_tune_tree_stats;  // 1 = count visits and time the query kernel
 
 }  // namespace oxg

@@ -781,7 +781,7 @@ int prm_row_cull_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStre
   const uint64_t n_obst = w->n_spheres + w->n_aabbs + w->n_capsules + w->n_so2;
   size_t stage = (size_t)w->n_spheres * w->sphere32_stride * 4 +
                  (size_t)((w->n_capsules + 1) / 2) * w->capsule32p_stride * 4;
-  if (!on || rows == 0 || k == 0 || k > 32 || fast_dim(sp) == 0 || fast_dim(sp) > kMaxFastDim ||
+  if (!on || g_tune_row_cull.load() == 0 || rows == 0 || k == 0 || k > 32 || fast_dim(sp) == 0 || fast_dim(sp) > kMaxFastDim ||
       stage == 0 || stage > 40 * 1024 || w->n_so2 != 0 || w->n_capsules < 64 || n_obst > 60000 ||
       rows * k < 148ull * 64)
     return OXG_OK;

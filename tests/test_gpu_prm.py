@@ -42,6 +42,45 @@ def test_prm_radius_matches_incremental_reference(oxg, orc):
     gw.close()
 
 
+@pytest.mark.parametrize("n_caps,scale,offset", [(256, 1.0, 0.0), (64, 1.0, 0.0), (300, 1e-12, 0.0),
+                                                 (256, 1.0, 1.0e5), (500, 1.0, 0.0)])
+def test_row_cull_never_changes_the_validity_table(oxg, orc, n_caps, scale, offset):
+    """The edge phase rules obstacles out once per row (ball around the row's state, radius = its
+    longest candidate edge) before the per-edge cull.  The validity table must be the one the
+    per-edge-only path gives, and the oracle's, for thin, dense, tiny-scale and far-offset worlds
+    (at 6000 states the rows' balls are wide: with 256+ capsules most rows overflow
+    their lists and take the full pass, with 64 none does)."""
+    sp, sp_o = oxg.Space.real_vector(7), orc.space(7)
+    lo, hi = np.asarray(worlds.PANDA_LO), np.asarray(worlds.PANDA_HI)
+    caps = worlds.capsule_world(9, worlds.PANDA_LO, worlds.PANDA_HI, n_caps)
+    caps[:, :14] = caps[:, :14] * scale + offset
+    caps[:, 14] *= scale
+    gw = oxg.World(7, capsules=caps)
+    ow, keep = orc.world(7, capsules=caps)
+    rows = uniform_states(45, 6000, worlds.PANDA_LO, worlds.PANDA_HI) * scale + offset
+    rows[17] = rows[16]                                   # duplicate state: zero-length edge
+    res = oxg.motion_resolution(oxg.real_vector_max_extent(list(zip(lo * scale, hi * scale))))
+    with oxg.StateStore(sp) as st:
+        st.append(rows)
+        oxg.tuning_set("row_cull", 0)
+        try:
+            idx0, dist0, valid0, stats0 = oxg.prm_build_knn(gw, st, 10, res)
+        finally:
+            oxg.tuning_set("row_cull", 1)
+        idx1, dist1, valid1, stats1 = oxg.prm_build_knn(gw, st, 10, res)
+    np.testing.assert_array_equal(idx0, idx1)
+    np.testing.assert_array_equal(valid0, valid1)
+    assert stats0["n_edges_valid"] == stats1["n_edges_valid"]
+    oi, od, ov = orc.prm_knn(ow, sp_o, rows[:1500], 10, res)  # oracle on a prefix store ...
+    with oxg.StateStore(sp) as st:
+        st.append(rows[:1500])
+        idx2, dist2, valid2, _ = oxg.prm_build_knn(gw, st, 10, res)
+    np.testing.assert_array_equal(idx2, oi)
+    np.testing.assert_array_equal(valid2, ov)
+    assert 0 < int((valid1 == 1).sum()) < valid1.size
+    gw.close()
+
+
 @pytest.mark.parametrize("n,k", [(3000, 10), (9, 10), (513, 4)])
 def test_prm_knn_matches_oracle(oxg, orc, n, k):
     sp, sp_o = oxg.Space.real_vector(7), orc.space(7)
