@@ -323,12 +323,15 @@ int motion_check_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStre
                         const uint32_t* d_to_idx, uint64_t E, const uint64_t* E_dev,
                         double resolution, uint8_t* d_valid, uint32_t* d_first_invalid,
                         const RowCull* row_cull = nullptr);
-// Fills the row lists for rows [row_begin, row_end) of the store (their candidates are
-// d_idx[(row - base_row) * k ..]); *enabled = false when this world / space / size does not take
-// the row-cull path (nothing is written then).
+// Fills the row lists for rows [row_begin, row_end) of the store.  k-NN mode: the row's candidates
+// are d_idx[(row - base_row) * k ..] and the ball's radius is the longest of them; radius mode
+// (d_idx == nullptr): every candidate is shorter than fixed_radius.  n_edges = the edge count the
+// motion check will be launched with.  *enabled = false when this world / space / size does not
+// take the row-cull path (nothing is written then).
 int prm_row_cull_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t stream, StateView st,
                         const uint32_t* d_idx, uint32_t k, uint64_t base_row, uint64_t row_begin,
-                        uint64_t row_end, uint16_t* row_cnt, uint16_t* row_list, bool* enabled);
+                        uint64_t row_end, double fixed_radius, uint64_t n_edges, uint16_t* row_cnt,
+                        uint16_t* row_list, bool* enabled);
 int is_valid_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t stream,
                     StateView st, uint64_t Q, uint8_t* d_out);
 int nn_radius_device(oxg_store_s* s, StateView q, uint64_t Q, double r, const uint32_t* d_idx_limit,

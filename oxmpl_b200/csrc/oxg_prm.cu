@@ -136,7 +136,8 @@ static int prm_edges(const oxg_world_s* w, oxg_store_s* s, const uint32_t* d_idx
   OXG_TRY(s->buf[B_ROWLIST].ensure(rows * kRowCullCap * sizeof(uint16_t)));
   bool row_cull = false;
   OXG_TRY(prm_row_cull_device(w, s->space, s->stream, store_view(s), d_idx, k, base_row, row_begin, row_end,
-                              s->buf[B_ROWCNT].as<uint16_t>(), s->buf[B_ROWLIST].as<uint16_t>(), &row_cull));
+                              0.0, nslots, s->buf[B_ROWCNT].as<uint16_t>(),
+                              s->buf[B_ROWLIST].as<uint16_t>(), &row_cull));
   uint32_t* e_row = nullptr;
   if (row_cull) {
     OXG_TRY(s->buf[B_EROW].ensure(nslots * sizeof(uint32_t)));
@@ -161,10 +162,14 @@ static int prm_edges(const oxg_world_s* w, oxg_store_s* s, const uint32_t* d_idx
 // ---- radius mode helpers ------------------------------------------------------------------
 // from-index of every candidate hit: the query row that owns it.
 __global__ void expand_rows_kernel(const uint64_t* __restrict__ row_off, uint64_t rows,
-                                   uint64_t row_begin, uint32_t* __restrict__ e_from) {
+                                   uint64_t row_begin, uint32_t* __restrict__ e_from,
+                                   uint32_t* __restrict__ e_row) {
   for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < rows;
        q += (uint64_t)gridDim.x * blockDim.x)
-    for (uint64_t t = row_off[q]; t < row_off[q + 1]; ++t) e_from[t] = (uint32_t)(row_begin + q);
+    for (uint64_t t = row_off[q]; t < row_off[q + 1]; ++t) {
+      e_from[t] = (uint32_t)(row_begin + q);
+      if (e_row) e_row[t] = (uint32_t)q;  // owner row, for the row cull
+    }
 }
 
 __global__ void count_valid_rows_kernel(const uint64_t* __restrict__ row_off, uint64_t rows,
@@ -344,10 +349,26 @@ int oxg_prm_build_radius(oxg_world w, oxg_store s, double connection_radius, dou
     uint32_t* e_from = s->buf[B_AUX2].as<uint32_t>();
     uint32_t* e_to = s->buf[B_PIDX].as<uint32_t>();
     uint8_t* e_valid = s->buf[B_STAGE].as<uint8_t>();
-    expand_rows_kernel<<<grid_for(rows, 128), 128, 0, s->stream>>>(d_row_off, rows, row_begin, e_from);
+    // row cull (oxg_internal.cuh): every candidate of row i is closer than connection_radius
+    OXG_TRY(s->buf[B_ROWCNT].ensure(rows * sizeof(uint16_t)));
+    OXG_TRY(s->buf[B_ROWLIST].ensure(rows * kRowCullCap * sizeof(uint16_t)));
+    bool row_cull = false;
+    OXG_TRY(prm_row_cull_device(w, s->space, s->stream, store_view(s), nullptr, 0, 0, row_begin, row_end,
+                                connection_radius, total, s->buf[B_ROWCNT].as<uint16_t>(),
+                                s->buf[B_ROWLIST].as<uint16_t>(), &row_cull));
+    uint32_t* e_row = nullptr;
+    if (row_cull) {
+      OXG_TRY(s->buf[B_EROW].ensure(total * sizeof(uint32_t)));
+      e_row = s->buf[B_EROW].as<uint32_t>();
+    }
+    expand_rows_kernel<<<grid_for(rows, 128), 128, 0, s->stream>>>(d_row_off, rows, row_begin, e_from, e_row);
     OXG_LAUNCH_CHECK();
+    RowCull rc;
+    rc.e_row = e_row;
+    rc.row_cnt = s->buf[B_ROWCNT].as<uint16_t>();
+    rc.row_list = s->buf[B_ROWLIST].as<uint16_t>();
     OXG_TRY(motion_check_device(w, s->space, s->stream, store_view(s), store_view(s), e_from, e_to,
-                                total, nullptr, resolution, e_valid, nullptr));
+                                total, nullptr, resolution, e_valid, nullptr, row_cull ? &rc : nullptr));
     uint64_t* d_counts = s->buf[B_COUNTS].as<uint64_t>();
     uint64_t* d_out_off = s->buf[B_AUX3].as<uint64_t>();
     count_valid_rows_kernel<<<grid_for(rows + 1, 128), 128, 0, s->stream>>>(d_row_off, rows, e_valid,

@@ -457,6 +457,7 @@ struct RowCullParams {
   const uint32_t* idx;
   uint32_t k;
   uint64_t base_row, row_begin, row_end;
+  double fixed_radius;  // idx == nullptr: every candidate edge of every row is shorter than this
   uint16_t* row_cnt;
   uint16_t* row_list;
   uint32_t world_smem_bytes;
@@ -483,10 +484,10 @@ __global__ void __launch_bounds__(128, 6) prm_row_cull_kernel(const RowCullParam
 #pragma unroll
     for (int d = 0; d < DT; ++d) x[d] = p.st.p[r * p.st.stride_i + (uint64_t)d * p.st.stride_d];
     // longest candidate edge of the row
-    double R = 0.0;
-    bool odd = false;
-    const uint32_t* slots = p.idx + (r - p.base_row) * p.k;
-    for (uint32_t sl = 0; sl < p.k; ++sl) {
+    double R = p.idx ? 0.0 : p.fixed_radius;
+    bool odd = !(R == R);
+    const uint32_t* slots = p.idx ? p.idx + (r - p.base_row) * p.k : nullptr;
+    for (uint32_t sl = 0; slots && sl < p.k; ++sl) {
       const uint32_t j = __ldg(slots + sl);
       if (j == OXG_INVALID_INDEX) continue;
       double y[DT];
@@ -765,7 +766,8 @@ int motion_check_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStre
 // which motion_check_device takes that kernel for the same world / space / edge count.
 int prm_row_cull_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStream_t stream, StateView st,
                         const uint32_t* d_idx, uint32_t k, uint64_t base_row, uint64_t row_begin,
-                        uint64_t row_end, uint16_t* row_cnt, uint16_t* row_list, bool* enabled) {
+                        uint64_t row_end, double fixed_radius, uint64_t n_edges, uint16_t* row_cnt,
+                        uint16_t* row_list, bool* enabled) {
   *enabled = false;
   static const bool on = [] {
     const char* v = getenv("OXG_ROW_CULL");
@@ -776,9 +778,9 @@ int prm_row_cull_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStre
   const uint64_t n_obst = w->n_spheres + w->n_aabbs + w->n_capsules + w->n_so2;
   size_t stage = (size_t)w->n_spheres * w->sphere32_stride * 4 +
                  (size_t)((w->n_capsules + 1) / 2) * w->capsule32p_stride * 4;
-  if (!on || g_tune_row_cull.load() == 0 || rows == 0 || k == 0 || k > 32 || fast_dim(sp) == 0 || fast_dim(sp) > kMaxFastDim ||
-      stage == 0 || stage > 40 * 1024 || w->n_so2 != 0 || w->n_capsules < 64 || n_obst > 60000 ||
-      rows * k < 148ull * 64)
+  if (!on || g_tune_row_cull.load() == 0 || rows == 0 || (d_idx && (k == 0 || k > 32)) || fast_dim(sp) == 0 ||
+      fast_dim(sp) > kMaxFastDim || stage == 0 || stage > 40 * 1024 || w->n_so2 != 0 || w->n_capsules < 64 ||
+      n_obst > 60000 || n_edges < 148ull * 64)
     return OXG_OK;
   RowCullParams p;
   p.w = world_view(w);
@@ -788,6 +790,7 @@ int prm_row_cull_device(const oxg_world_s* w, const oxg_space_desc& sp, cudaStre
   p.base_row = base_row;
   p.row_begin = row_begin;
   p.row_end = row_end;
+  p.fixed_radius = fixed_radius;
   p.row_cnt = row_cnt;
   p.row_list = row_list;
   p.world_smem_bytes = (uint32_t)stage;

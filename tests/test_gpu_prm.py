@@ -71,6 +71,19 @@ def test_row_cull_never_changes_the_validity_table(oxg, orc, n_caps, scale, offs
     np.testing.assert_array_equal(idx0, idx1)
     np.testing.assert_array_equal(valid0, valid1)
     assert stats0["n_edges_valid"] == stats1["n_edges_valid"]
+    # the radius build takes the same lists with the connection radius as every row's ball
+    radius = float(np.sort(dist1[:, 3])[len(dist1) // 2])       # ~4 earlier neighbours per node
+    with oxg.StateStore(sp) as st:
+        st.append(rows)
+        oxg.tuning_set("row_cull", 0)
+        try:
+            off0, nbr0, rs0 = oxg.prm_build_radius(gw, st, radius, res)
+        finally:
+            oxg.tuning_set("row_cull", 1)
+        off1, nbr1, rs1 = oxg.prm_build_radius(gw, st, radius, res)
+    np.testing.assert_array_equal(off0, off1)
+    np.testing.assert_array_equal(nbr0, nbr1)
+    assert rs1["n_candidates"] > 148 * 64 and 0 < rs1["n_edges_valid"] <= rs1["n_candidates"]
     oi, od, ov = orc.prm_knn(ow, sp_o, rows[:1500], 10, res)  # oracle on a prefix store ...
     with oxg.StateStore(sp) as st:
         st.append(rows[:1500])
