@@ -46,14 +46,14 @@ DIM = 7
 SEED = 4
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this config, from the `ncu --set
 # full` captures summarised in profiles/ (None until captured for the current kernel)
-TREE_DRAM_BYTES_NCU = 913045248  # profiles/r02c_ncu_full_hot_kernels.csv (753.9 MB read + 159.2 MB written; 1e6 queries)
+TREE_DRAM_BYTES_NCU = 904850688  # profiles/r02_ncu_full_hot_kernels.csv (746.5 MB read + 158.4 MB written; 1e6 queries)
 # the same capture: share of tree_knn_kernel's L1 sector requests that hit L1 (the rest go to L2),
-# the L2 read sectors it caused (x 32 B = 86.4 GB for 1e6 queries), the issue-slot utilisation and
+# the L2 read sectors it caused (x 32 B = 81.6 GB for 1e6 queries), the issue-slot utilisation and
 # the executed warp instructions
-TREE_L1_HIT_NCU = 0.2180
-TREE_L2_READ_BYTES_PER_QUERY_NCU = 2700565645 * 32 / 1000000
-TREE_ISSUE_ACTIVE_NCU = 0.708
-TREE_WARP_INSTRUCTIONS_NCU = 8113218346
+TREE_L1_HIT_NCU = 0.2256
+TREE_L2_READ_BYTES_PER_QUERY_NCU = 2551546522 * 32 / 1000000
+TREE_ISSUE_ACTIVE_NCU = 0.712
+TREE_WARP_INSTRUCTIONS_NCU = 7987274268
 ALLPAIRS_DRAM_BYTES_NCU = 2249420000  # profiles/r01_ncu_full_knn_rv_dot_7_2.csv (2.046 GB read + 0.204 GB written)
 
 
@@ -565,7 +565,7 @@ def run_ours(args):
                             "warp_instructions_per_query_ncu": TREE_WARP_INSTRUCTIONS_NCU / 1e6},
             "note": "an irregular traversal of ~95 dependent steps per query over 1.0 % of the all-pairs "
                     "pair count; the working set is L2-resident, so the memory roofline is the L2's. "
-                    "ncu: issue slots 71 %, long-scoreboard stalls 2.6 per issue, L2 hit 98 % -- the "
+                    "ncu: issue slots 71 %, long-scoreboard stalls 2.5 per issue, L2 hit 98 % -- the "
                     "kernel is bound by instruction issue first and L2 latency second, not by bandwidth "
                     "or arithmetic",
             "hbm_peak_gbs_measured": _measured_hbm(),

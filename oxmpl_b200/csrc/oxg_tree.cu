@@ -71,7 +71,7 @@ constexpr int TREE_MAX_DIM = 8;      // dimensions the tree kernels are instanti
 #define OXG_TK_F32_LEAF 1
 #endif
 #ifndef OXG_TK_MERGE_AT
-#define OXG_TK_MERGE_AT 8
+#define OXG_TK_MERGE_AT 4
 #endif
 constexpr int TK_THREADS = OXG_TK_THREADS;  // query kernel: warps per CTA x 32
 constexpr int TK_QPC = OXG_TK_QPC;          // consecutive (key-ordered) queries per chunk
